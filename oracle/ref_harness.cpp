@@ -1,0 +1,238 @@
+// TEST INFRASTRUCTURE — C-callable harness over the UNMODIFIED reference library.
+//
+// Links the reference's own src/*.cpp objects (compiled in place from
+// /root/reference, CPU libtorch; see Makefile) and exposes their public
+// functions to ctypes with plain pointers in the reference's AoS layout
+// ({X,Y,9} row-major, fp64).  Used by tests/ to pin oracle/lbm_oracle.c and to
+// generate tests/golden/*.  No arithmetic of its own: every number comes out of
+// a reference function.
+#include <torch/torch.h>
+#include <toml++/toml.hpp>
+
+#include <cstring>
+#include <iostream>
+#include <string>
+
+#include "src/colour.hpp"
+#include "src/differential.hpp"
+#include "src/domain.hpp"
+#include "src/ibm.hpp"
+#include "src/params.hpp"
+#include "src/solver.hpp"
+
+namespace
+{
+thread_local std::string g_err;
+
+torch::Tensor wrap(const double* p, std::initializer_list<int64_t> shape)
+{
+  return torch::from_blob(const_cast<double*>(p), shape, torch::TensorOptions().dtype(torch::kDouble)).clone();
+}
+
+void copy_out(const torch::Tensor& t, double* out)
+{
+  auto c = t.contiguous().to(torch::kDouble);
+  std::memcpy(out, c.data_ptr<double>(), sizeof(double) * c.numel());
+}
+
+// Sets the default dtype like every reference main() does (e.g. test/cylinder_test.cpp:41) and
+// mutes the reference's std::cout chatter for the duration of a call.
+struct dtype_guard
+{
+  std::ios_base::iostate saved;
+  dtype_guard() : saved(std::cout.rdstate())
+  {
+    torch::set_default_dtype(caffe2::scalarTypeToTypeMeta(torch::kDouble));
+    std::cout.setstate(std::ios_base::failbit);
+  }
+  ~dtype_guard() { std::cout.clear(saved); }
+};
+}  // namespace
+
+#define REF_TRY try { dtype_guard guard__;
+#define REF_CATCH \
+  } catch (const std::exception& e) { g_err = e.what(); return 1; } \
+  return 0;
+
+extern "C"
+{
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void ref_set_num_threads(int n) { at::set_num_threads(n); }
+int ref_get_num_threads() { return at::get_num_threads(); }
+
+// solver::E, solver::c (src/solver.cpp:12-21)
+int ref_constants(double* w9, double* c18)
+{
+  REF_TRY
+  copy_out(solver::E, w9);
+  copy_out(solver::c, c18);
+  REF_CATCH
+}
+
+// src/solver.cpp:23-26
+int ref_calc_rho(const double* f, int X, int Y, double* rho)
+{
+  REF_TRY
+  auto tf = wrap(f, {X, Y, 9});
+  auto r = torch::zeros({X, Y, 1});
+  solver::calc_rho(r, tf);
+  copy_out(r, rho);
+  REF_CATCH
+}
+
+// src/solver.cpp:34-37
+int ref_calc_u(const double* f, const double* rho, int X, int Y, double* u)
+{
+  REF_TRY
+  auto tf = wrap(f, {X, Y, 9});
+  auto tr = wrap(rho, {X, Y, 1});
+  auto tu = torch::zeros({X, Y, 2});
+  solver::calc_u(tu, tf, tr);
+  copy_out(tu, u);
+  REF_CATCH
+}
+
+// src/solver.cpp:28-31
+int ref_calc_incomp_u(const double* f, int X, int Y, double* u)
+{
+  REF_TRY
+  auto tf = wrap(f, {X, Y, 9});
+  auto tu = torch::zeros({X, Y, 2});
+  solver::calc_incomp_u(tu, tf);
+  copy_out(tu, u);
+  REF_CATCH
+}
+
+// src/solver.cpp:51-62
+int ref_equilibrium(const double* u, const double* rho, int X, int Y, double* feq)
+{
+  REF_TRY
+  auto tu = wrap(u, {X, Y, 2});
+  auto tr = wrap(rho, {X, Y, 1});
+  auto fe = torch::zeros({X, Y, 9});
+  solver::equilibrium(fe, tu, tr);
+  copy_out(fe, feq);
+  REF_CATCH
+}
+
+// src/solver.cpp:39-49
+int ref_incomp_equilibrium(const double* u, const double* rho, int X, int Y, double* feq)
+{
+  REF_TRY
+  auto tu = wrap(u, {X, Y, 2});
+  auto tr = wrap(rho, {X, Y, 1});
+  auto fe = torch::zeros({X, Y, 9});
+  solver::incomp_equilibrium(fe, tu, tr);
+  copy_out(fe, feq);
+  REF_CATCH
+}
+
+// src/solver.cpp:65-74
+int ref_collision(const double* f, const double* feq, double omega, int X, int Y, double* fcoll)
+{
+  REF_TRY
+  auto tf = wrap(f, {X, Y, 9});
+  auto te = wrap(feq, {X, Y, 9});
+  auto tc = torch::zeros({X, Y, 9});
+  solver::collision(tc, tf, te, omega);
+  copy_out(tc, fcoll);
+  REF_CATCH
+}
+
+// src/solver.cpp:76-131
+int ref_advect(const double* f, int X, int Y, double* g)
+{
+  REF_TRY
+  auto tf = wrap(f, {X, Y, 9});
+  auto tg = torch::zeros({X, Y, 9});
+  solver::advect(tg, tf);
+  copy_out(tg, g);
+  REF_CATCH
+}
+
+// src/differential.cpp:23-39 ; out_x, out_y are {R,C}
+int ref_differential(const double* psi, int R, int C, double* out_x, double* out_y)
+{
+  REF_TRY
+  static differential D{};
+  auto tp = wrap(psi, {R, C});
+  copy_out(D.x(tp), out_x);
+  copy_out(D.y(tp), out_y);
+  REF_CATCH
+}
+
+// src/params.cpp:7-120.  out[] = {fp.nu, fp.u, fp.l, fp.rho_0, fp.Re,
+//   lp.tau, lp.omega, lp.Re, lp.nu, lp.l, lp.dx, lp.dt, lp.T, lp.u, lp.X, lp.Y,
+//   sp.stop_time, sp.snapshot_period, sp.total_steps, sp.snapshot_steps, sp.total_snapshots}
+// (the simulation block is filled only when with_simulation != 0).
+int ref_params(const char* toml_path, int with_simulation, double* out)
+{
+  REF_TRY
+  toml::table tbl = toml::parse_file(toml_path);
+  const params::flow fp{tbl};
+  const params::lattice lp{tbl, fp};
+  int k = 0;
+  out[k++] = fp.nu; out[k++] = fp.u; out[k++] = fp.l; out[k++] = fp.rho_0; out[k++] = fp.Re;
+  out[k++] = lp.tau; out[k++] = lp.omega; out[k++] = lp.Re; out[k++] = lp.nu; out[k++] = lp.l;
+  out[k++] = lp.dx; out[k++] = lp.dt; out[k++] = lp.T; out[k++] = lp.u; out[k++] = lp.X; out[k++] = lp.Y;
+  if (with_simulation)
+  {
+    const params::simulation sp{tbl, lp};
+    out[k++] = sp.stop_time; out[k++] = sp.snapshot_period; out[k++] = sp.total_steps;
+    out[k++] = sp.snapshot_steps; out[k++] = sp.total_snapshots;
+  }
+  REF_CATCH
+}
+
+// src/colour.cpp:11-64.  out[] = {rho_0, alpha, A, nu, mu, beta, cs2, ics2, rlx, phi[9], eta[9]}
+int ref_colour(const char* toml_path, const char* table_name, double* out)
+{
+  REF_TRY
+  toml::table tbl = toml::parse_file(toml_path);
+  const torch::Tensor E = solver::c;
+  colour k{tbl[table_name], 2, 2, E};
+  int n = 0;
+  out[n++] = k.rho_0; out[n++] = k.alpha; out[n++] = k.A; out[n++] = k.nu; out[n++] = k.mu;
+  out[n++] = k.beta; out[n++] = k.cs2; out[n++] = k.ics2; out[n++] = k.rlx;
+  copy_out(k.phi, out + n); n += 9;
+  copy_out(k.eta.index({0, 0}), out + n);
+  REF_CATCH
+}
+
+// src/ibm.cpp:60-190.  roi[4] = {row_start,row_stop,col_start,col_stop};
+// F_out must hold (row_stop-row_start)*(col_stop-col_start)*2 doubles; pass
+// F_out = nullptr to query the ROI only.
+int ref_ibm_force(const char* toml_path, const char* name, const double* u, const double* rho,
+                  int X, int Y, long* roi, double* F_out)
+{
+  REF_TRY
+  toml::table tbl = toml::parse_file(toml_path);
+  ibm ib{tbl, name, torch::kCPU};
+  roi[0] = ib.rows.start().maybe_as_int().value();
+  roi[1] = ib.rows.stop().maybe_as_int().value();
+  roi[2] = ib.cols.start().maybe_as_int().value();
+  roi[3] = ib.cols.stop().maybe_as_int().value();
+  if (F_out)
+  {
+    auto tu = wrap(u, {X, Y, 2});
+    auto tr = wrap(rho, {X, Y, 1});
+    auto F = ib.eulerian_force_density(tu, tr);
+    copy_out(F, F_out);
+  }
+  REF_CATCH
+}
+
+// struct domain (src/domain.cpp:3-12): shapes of the five buffers, 15 ints.
+int ref_domain_shapes(int R, int C, long* shapes15)
+{
+  REF_TRY
+  domain d{R, C};
+  const torch::Tensor* ts[5] = {&d.adve_f, &d.equi_f, &d.coll_f, &d.m_0, &d.m_1};
+  for (int i = 0; i < 5; i++)
+    for (int j = 0; j < 3; j++) shapes15[3 * i + j] = ts[i]->size(j);
+  REF_CATCH
+}
+
+}  // extern "C"
