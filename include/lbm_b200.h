@@ -1,0 +1,310 @@
+/* lbm_b200.h — C ABI of the B200-native D2Q9 lattice-Boltzmann time step.
+ *
+ * Drop-in boundary for the hot path of cristian-jfv/lattice-boltzmann-method: the reference has no
+ * FFI layer of its own (its callable surface is C++ on torch::Tensor: src/solver.hpp:8-36,
+ * src/domain.hpp:5-15, src/colour.hpp:9-42, src/differential.hpp:6-53, src/ibm.hpp:9-34,
+ * src/params.hpp:9-49, plus the loop bodies of test/<driver>.cpp), so this header is what a cgo-/ctypes-/
+ * C++-side binding of that surface binds to.  Each entry point cites the reference interface it
+ * replaces.  INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - every function returns an lbm_status (0 = ok); lbm_last_error() gives the message of the
+ *     last failure on the calling thread.  No C++ exception crosses this boundary (the reference
+ *     throws std::runtime_error / c10::Error instead: src/params.cpp:13, src/colour.cpp:45).
+ *   - "AoS" buffers use the reference layout: fp64, shape {X,Y,Q} row-major, axis 0 = x ("rows"),
+ *     axis 1 = y ("columns"), Q innermost (src/domain.cpp:7-11).  Direction order and weights are
+ *     solver::c / solver::E (src/solver.cpp:12-21).
+ *   - host pointers unless a name ends in _dev.  The caller owns host buffers, the library owns
+ *     all device memory.  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with LBM_ERR_CUDA.
+ *   - one lbm_domain = one slab (rows [x0,x1) of the global grid) on one GPU, the unit the
+ *     reference calls `struct domain` (src/domain.hpp:5-15, test/decompose_domain.cpp:101-104).
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lbm_domain lbm_domain;
+
+typedef enum
+{
+  LBM_OK = 0,
+  LBM_ERR_INVALID = 1,     /* bad argument / inconsistent description */
+  LBM_ERR_CUDA = 2,        /* CUDA runtime failure or no device */
+  LBM_ERR_CONFIG = 3,      /* missing / malformed TOML key (message mirrors the reference's) */
+  LBM_ERR_UNSUPPORTED = 4, /* valid request outside what this build implements */
+  LBM_ERR_COMM = 5         /* NCCL failure */
+} lbm_status;
+
+const char* lbm_last_error(void);
+/* library version string, e.g. "lbm_b200 0.1 (sm_100a)" */
+const char* lbm_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Models (one fused collide+stream kernel family per model)
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum
+{
+  LBM_MODEL_BGK = 0,     /* single lattice: drivers 10-14 (test/horizontal_poiseuille_test.cpp, cylinder_test.cpp,
+                            free_stream_test.cpp, specular_boundary_test.cpp, gravity_test.cpp) */
+  LBM_MODEL_BGK_ADE = 1, /* fluid + advection-diffusion lattice: test/rectangle_sedimentation_test.cpp */
+  LBM_MODEL_MRTCG = 2,   /* MRT colour gradient: test/mrtcg_rayleigh_taylor.cpp, test/mrtcg_static_droplet.cpp */
+  LBM_MODEL_RK = 3       /* Rothman-Keller droplet: test/rk_static_droplet_test.cpp */
+} lbm_model;
+
+typedef enum
+{
+  LBM_EQ_COMPRESSIBLE = 0,  /* solver::equilibrium        src/solver.cpp:51-62 */
+  LBM_EQ_INCOMPRESSIBLE = 1 /* solver::incomp_equilibrium src/solver.cpp:39-49 */
+} lbm_equilibrium_kind;
+
+typedef enum
+{
+  LBM_FORCE_NONE = 0,
+  LBM_FORCE_UNIFORM = 1, /* test/gravity_test.cpp:143-160: u += Fg, source term with ics2=1/3, ics4=1/9 */
+  LBM_FORCE_IBM = 2      /* test/cylinder_test.cpp:110-127: ROI force field from the immersed boundary */
+} lbm_force_kind;
+
+typedef struct
+{
+  double rho_0, alpha, A, nu, beta; /* [red]/[blue] tables: src/colour.cpp:11-21 */
+} lbm_colour_desc;
+
+typedef struct
+{
+  int model;          /* lbm_model */
+  int X, Y;           /* GLOBAL grid (rows, columns) */
+  int x0, x1;         /* rows of the global grid owned by this domain, [x0,x1); x0=0,x1=X for one GPU */
+  int device;         /* CUDA device ordinal */
+  /* --- BGK / BGK_ADE */
+  double omega;       /* 1/tau (params::lattice::omega, src/params.cpp:57) */
+  int equilibrium;    /* lbm_equilibrium_kind */
+  int force;          /* lbm_force_kind */
+  double Fg[2];       /* LBM_FORCE_UNIFORM; MRTCG: gravity vector (mrtcg_rayleigh_taylor.cpp:403) */
+  double w_s;         /* BGK_ADE: settling velocity added to BOTH components (rectangle_sedimentation_test.cpp:125) */
+  double omega_g;     /* BGK_ADE: relaxation of the second lattice (lp.omega/1.0, :131) */
+  /* --- MRTCG / RK */
+  lbm_colour_desc red, blue;
+  double sigma;       /* MRTCG: [general].sigma (RT) or 0.1 (droplet) */
+  double delta;       /* interface half-width of the relaxation blend: 0.1 (MRTCG), 0.98 (RK) */
+  int add_force;      /* MRTCG: 1 = RT driver (:463-464), 0 = droplet driver (source not added) */
+} lbm_config;
+
+/* fills *cfg with zeros and the defaults (model BGK, compressible, no force, delta 0.1, device 0) */
+void lbm_config_default(lbm_config* cfg);
+
+/* replaces `domain::domain(R,C,Q)` (src/domain.cpp:3-12) and the per-driver tensor allocations
+ * (e.g. test/cylinder_test.cpp:49-53): allocates the SoA device state of one slab. */
+int lbm_create(const lbm_config* cfg, lbm_domain** out);
+int lbm_destroy(lbm_domain* d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Boundary conditions.  The reference writes them as ordered slice assignments after
+ * solver::advect (post-stream, e.g. test/horizontal_poiseuille_test.cpp:146-152) or on f_coll
+ * before it (pre-stream, e.g. :140, rectangle_sedimentation_test.cpp:138-141).  An lbm_bc_op is
+ * ONE such assignment; ops are applied in the order added, so later ops win where regions
+ * overlap, exactly like the reference.  Slices use torch semantics (negative = from the end,
+ * LBM_END = "None").  Coordinates are GLOBAL; each slab keeps the part it owns.
+ * ---------------------------------------------------------------------------------------------- */
+#define LBM_END 2147483647
+
+typedef enum
+{
+  /* post-stream: f_adve[region, dst_q] = coef * f_coll[src_node(region), src_q] + cst */
+  LBM_BC_LINEAR = 0,
+  /* post-stream anti-bounce-back with a fixed wall velocity (test/cylinder_test.cpp:135-154):
+   *   f_adve[region, opp(src_q)] = -f_coll[region, src_q] + (2 + 9 (c.uw)^2 - 3 uw.uw) w     */
+  LBM_BC_ABB_FIXED = 1,
+  /* same with uw = 1.5 u[.., -1] - 0.5 u[.., -2] of the previous moments
+   * (test/rectangle_sedimentation_test.cpp:163-172); region must be a column                      */
+  LBM_BC_ABB_EXTRAPOLATED = 2,
+  /* ADE inlet (rectangle_sedimentation_test.cpp:204-218): lattice 1,
+   *   g_adve[region, opp(src_q)] = -g_coll[region, src_q] + 2 geq_q(u + w_s, C_w[x])               */
+  LBM_BC_ADE_INLET = 3,
+  /* pre-stream pressure-periodic rows (test/horizontal_poiseuille_test.cpp:25-45):
+   *   f_coll[row] = feq(rho_bc, u[src_row]) + f_coll[src_row] - f_equi[src_row]                    */
+  LBM_BC_PRESSURE_PERIODIC = 4,
+  /* pre-stream copy (zero gradient, rectangle_sedimentation_test.cpp:138-141):
+   *   f_coll[region, :] = f_coll[src_node(region), :]                                              */
+  LBM_BC_COPY_PRE = 5
+} lbm_bc_kind;
+
+typedef enum
+{
+  LBM_SRC_SAME_NODE = 0, /* f_coll at the node being written */
+  LBM_SRC_SHIFT = 1,     /* node + (src_a, src_b) */
+  LBM_SRC_ROW = 2,       /* same column, absolute row src_a (negative = from the end) */
+  LBM_SRC_COL = 3        /* same row, absolute column src_a (negative = from the end) */
+} lbm_bc_src;
+
+typedef struct
+{
+  int kind;                 /* lbm_bc_kind */
+  int lattice;              /* 0 = f / red, 1 = g / blue, -1 = both lattices */
+  int x_begin, x_end;       /* row slice   [x_begin, x_end) */
+  int y_begin, y_end;       /* column slice [y_begin, y_end) */
+  int dst_q;                /* population written; -1 = all nine, each from the same q of the source */
+  int src_q;                /* population read */
+  int src_mode;             /* lbm_bc_src */
+  int src_a, src_b;
+  double coef, cst;         /* LBM_BC_LINEAR */
+  double uw[2];             /* LBM_BC_ABB_FIXED */
+  double rho_bc;            /* LBM_BC_PRESSURE_PERIODIC */
+  const double* per_row;    /* LBM_BC_ADE_INLET: C_w[X] (global rows), copied at add time */
+} lbm_bc_op;
+
+void lbm_bc_op_default(lbm_bc_op* op);
+int lbm_bc_clear(lbm_domain* d);
+int lbm_bc_add(lbm_domain* d, const lbm_bc_op* op);
+/* compiles the op list into per-node programs (must be called once before stepping) */
+int lbm_bc_commit(lbm_domain* d);
+/* bit-exact introspection of the compiled masks ("boundary-node masks ... bit-exact"):
+ * for lattice l, mask[(x*Y + y)*9 + q] = 1 + index of the post-stream op that owns (x,y,q), 0 = plain pull.
+ * x runs over the slab's own rows.  */
+int lbm_bc_get_mask(lbm_domain* d, int lattice, int32_t* mask);
+
+/* Ready-made rule lists: each one is the ordered list of slice assignments of one reference driver,
+ * expressed with lbm_bc_add and committed (lbm_bc_clear + adds + lbm_bc_commit).
+ *   lbm_preset_poiseuille        test/horizontal_poiseuille_test.cpp:140,146-152 (also gravity_test.cpp:163-176,
+ *                                decompose_domain.cpp:155-178 once the slabs are linked)
+ *   lbm_preset_specular_channel  test/specular_boundary_test.cpp:116,122-128
+ *   lbm_preset_free_stream       test/free_stream_test.cpp:106-134, test/cylinder_test.cpp:135-163
+ *   lbm_preset_sedimentation     test/rectangle_sedimentation_test.cpp:138-141,150-196,204-236
+ *   lbm_preset_mrtcg             test/mrtcg_rayleigh_taylor.cpp:495-533
+ *   lbm_preset_rk                test/rk_static_droplet_test.cpp:204-211                              */
+int lbm_preset_poiseuille(lbm_domain* d, double rho_in, double rho_out);
+int lbm_preset_specular_channel(lbm_domain* d, double rho_in, double rho_out);
+int lbm_preset_free_stream(lbm_domain* d, double uwx, double uwy);
+int lbm_preset_sedimentation(lbm_domain* d, double u_lb, const double* C_w, int R23, int C28, int C38);
+int lbm_preset_mrtcg(lbm_domain* d);
+int lbm_preset_rk(lbm_domain* d);
+/* fully periodic box (solver::advect alone): no rules */
+int lbm_preset_periodic(lbm_domain* d);
+
+/* ------------------------------------------------------------------------------------------------
+ * State import / export in the reference layout
+ * ---------------------------------------------------------------------------------------------- */
+/* f_adve of one lattice, AoS {x1-x0, Y, 9}  (replaces direct tensor access, e.g. cylinder_test.cpp:86) */
+int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos);
+int lbm_get_f(lbm_domain* d, int lattice, double* f_aos);
+/* moments of the CURRENT post-stream state, as the next loop iteration of the reference would
+ * compute them: rho {X,Y,1} (solver::calc_rho), u {X,Y,2} (calc_u / calc_incomp_u, plus the
+ * model's force shift).  Either pointer may be NULL.  BGK_ADE: lattice 1 gives C in rho.          */
+int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u);
+/* two-phase fields of the current state: phase {X,Y} (eval_phase_field), rho_r, rho_b {X,Y}     */
+int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b);
+/* two-phase models carry u between steps (mrtcg_rayleigh_taylor.cpp:476-477); initial value.      */
+int lbm_set_u(lbm_domain* d, const double* u_aos);
+/* initial condition helpers that mirror the drivers' own initialisation:
+ *   BGK       f = incomp_equilibrium(u0, rho0)              (cylinder_test.cpp:86)
+ *   two-phase adv_f = eq(rho_r, rho_b, u)                   (mrtcg_rayleigh_taylor.cpp:407-410)     */
+int lbm_init_equilibrium(lbm_domain* d, int lattice, int equilibrium_kind, const double* rho, const double* u);
+int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, const double* u);
+
+/* ------------------------------------------------------------------------------------------------
+ * Immersed boundary (src/ibm.hpp:21-34, src/ibm.cpp:60-190)
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces `ibm ib{tbl, name, dev}`: marker coordinates in GLOBAL lattice units */
+int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n_markers, int m_max);
+/* ib.rows / ib.cols: roi = {row_start,row_stop,col_start,col_stop} */
+int lbm_ibm_get_roi(lbm_domain* d, long* roi4);
+/* last Eulerian force density F {roi_rows, roi_cols, 2} computed inside lbm_step (cylinder_test.cpp:110) */
+int lbm_ibm_get_force(lbm_domain* d, double* F_aos);
+/* stand-alone ibm::eulerian_force_density(u, rho) on AoS inputs {X,Y,2}, {X,Y,1} (src/ibm.cpp:158-190) */
+int lbm_ibm_force(lbm_domain* d, const double* u_aos, const double* rho_aos, double* F_aos);
+
+/* ------------------------------------------------------------------------------------------------
+ * Time stepping — replaces the loop body of each driver
+ * ---------------------------------------------------------------------------------------------- */
+/* advance n_steps; asynchronous on the domain's stream */
+int lbm_step(lbm_domain* d, int n_steps);
+int lbm_synchronize(lbm_domain* d);
+/* device time of the last lbm_step call in milliseconds (CUDA events on the domain's stream) */
+int lbm_last_step_ms(lbm_domain* d, float* ms);
+/* number of kernels launched by this domain so far */
+int lbm_kernel_launches(lbm_domain* d, long long* n);
+/* the cudaStream_t the domain runs on (as void*) */
+int lbm_get_stream(lbm_domain* d, void** stream);
+/* capture one step into a CUDA graph and replay it in lbm_step (launch-bound small grids) */
+int lbm_use_graph(lbm_domain* d, int enable);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU slabs (test/decompose_domain.cpp:181-187 generalised to P slabs along axis 0)
+ * ---------------------------------------------------------------------------------------------- */
+#define LBM_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id, the launcher broadcasts it (torch.distributed / MPI / file) */
+int lbm_comm_unique_id(char id[LBM_UNIQUE_ID_BYTES]);
+/* joins the slab ring: neighbours are rank-1 and rank+1 (periodic, like solver::advect) */
+int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank);
+/* single-process alternative: link two domains on the same host process; ghost rows are exchanged with
+ * cudaMemcpyPeerAsync (what decompose_domain.cpp's "bind" does between tensors) */
+int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper);
+/* bit-exact decomposition indexing: rows [x0,x1) for `rank` of `n_ranks` over X rows */
+int lbm_decompose_rows(int X, int n_ranks, int rank, int* x0, int* x1);
+
+/* ------------------------------------------------------------------------------------------------
+ * Granular operators, one-to-one with namespace solver (src/solver.hpp:11-36) and class
+ * differential (src/differential.hpp:48-51), on AoS host buffers; each runs a CUDA kernel.
+ * ---------------------------------------------------------------------------------------------- */
+int lbm_calc_rho(const double* f, int X, int Y, double* rho);
+int lbm_calc_u(const double* f, const double* rho, int X, int Y, double* u);
+int lbm_calc_incomp_u(const double* f, int X, int Y, double* u);
+int lbm_equilibrium(const double* u, const double* rho, int X, int Y, double* feq);
+int lbm_incomp_equilibrium(const double* u, const double* rho, int X, int Y, double* feq);
+int lbm_collision(const double* f, const double* feq, double omega, int X, int Y, double* fcoll);
+int lbm_advect(const double* f, int X, int Y, double* g);
+/* 5x5 isotropic differences, replicate padding: dx along axis 0, dy along axis 1 */
+int lbm_differential(const double* psi, int R, int C, double* dx, double* dy);
+/* the RK driver's 3x3 operator (test/rk_static_droplet_test.cpp:48-107): its "x" is along axis 1 */
+int lbm_differential3(const double* psi, int R, int C, double* dx, double* dy);
+
+/* ------------------------------------------------------------------------------------------------
+ * parameters.toml surface (src/params.cpp, src/colour.cpp) — host-only scalar code
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+  /* params::flow (src/params.cpp:7-29) */
+  double flow_nu, flow_u, flow_l, flow_rho_0, flow_Re;
+  /* params::lattice (src/params.cpp:31-66) */
+  double tau, omega, Re, nu, dx, dt, u;
+  int l, T, X, Y;
+  /* params::simulation (src/params.cpp:95-120); valid only when has_simulation */
+  int has_simulation;
+  double stop_time, snapshot_period;
+  int total_steps, snapshot_steps, total_snapshots;
+  char file_prefix[256];
+} lbm_params;
+
+/* parses [flow], [lattice] and, when require_simulation != 0, [simulation]; a missing key gives
+ * LBM_ERR_CONFIG with the reference's message "<key> not defined in parameters file" */
+int lbm_params_from_toml(const char* path, int require_simulation, lbm_params* out);
+
+typedef struct
+{
+  double rho_0, alpha, A, nu, mu, beta, cs2, ics2, rlx; /* src/colour.cpp:11-39 */
+  double phi[9], eta[9];                                /* :49-64 */
+} lbm_colour;
+int lbm_colour_from_toml(const char* path, const char* table, lbm_colour* out);
+
+typedef struct
+{
+  int rows, columns, time_steps, nr_snapshots, period_snapshots; /* mrtcg_rayleigh_taylor.cpp:103-117 */
+  int has_general;
+  double sigma, gravity_magnitude;                              /* :360-361 */
+  char name[256];                                               /* :362 */
+} lbm_two_phase_params;
+int lbm_two_phase_from_toml(const char* path, int require_general, lbm_two_phase_params* out);
+
+/* boundary file `[name] x=[..] y=[..]` (src/ibm.cpp:78-102).  Call with xs=ys=NULL to get the count. */
+int lbm_markers_from_toml(const char* path, const char* name, double* xs, double* ys, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,792 @@
+// lbm_domain.cu — C ABI: domain life cycle, boundary compiler, state import/export and the
+// step sequencing of the single-phase family.  See include/lbm_b200.h for the contract.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "lbm_internal.hpp"
+
+namespace lbm
+{
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...)
+{
+  char b[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(b, sizeof(b), fmt, ap);
+  va_end(ap);
+  g_error = b;
+}
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// small kernels used only by the import / export paths
+// ------------------------------------------------------------------------------------------------
+__global__ void k_export_aos(const double* __restrict__ f, double* __restrict__ aos, const SlabGeom g)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++) aos[n * 9 + q] = f[q * g.plane + o];
+}
+
+// moments of an AoS post-stream state, with the conventions of the model's driver
+__global__ void k_moments_aos(const double* __restrict__ aos, long long n_nodes, int incompressible, double sx,
+                              double sy, double* __restrict__ rho_out, double* __restrict__ u_out)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  double f[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) f[q] = aos[n * 9 + q];
+  double rho, jx, jy;
+  moments(f, rho, jx, jy);
+  if (rho_out) rho_out[n] = rho;
+  if (u_out)
+  {
+    double ux = incompressible ? jx : jx / rho;
+    double uy = incompressible ? jy : jy / rho;
+    u_out[2 * n] = ux + sx;
+    u_out[2 * n + 1] = uy + sy;
+  }
+}
+
+__global__ void k_init_equilibrium(double* __restrict__ f, const SlabGeom g, int incompressible,
+                                   const double* __restrict__ rho, const double* __restrict__ u)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const long long o = node_off(g, x, y);
+  const double r = rho[n], ux = u[2 * n], uy = u[2 * n + 1];
+  const double uu = ux * ux + uy * uy;
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+    f[q * g.plane + o] = incompressible ? feq_incomp(q, r, ux, uy) : feq_comp(q, r, ux, uy, uu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int EQ, int FORCE, bool ADE>
+static int launch_bgk(lbm_domain* d, int row_begin, int row_end, bool do_interior, bool do_boundary)
+{
+  const int s = d->cur, t = d->cur ^ 1;
+  BgkParams p;
+  p.omega = d->cfg.omega;
+  p.omega_g = d->cfg.omega_g;
+  p.Fg0 = d->cfg.Fg[0];
+  p.Fg1 = d->cfg.Fg[1];
+  p.w_s = d->cfg.w_s;
+  p.roi_r0 = (int)d->ibm.r0; p.roi_r1 = (int)d->ibm.r1; p.roi_c0 = (int)d->ibm.c0; p.roi_c1 = (int)d->ibm.c1;
+  p.Fx = d->ibm.d_Fx;
+  p.Fy = d->ibm.d_Fy;
+  if (do_interior && d->npairs > 0 && row_end > row_begin)
+  {
+    dim3 grid(cdiv(d->npairs, 128), row_end - row_begin);
+    k_bgk_interior<MODE, EQ, FORCE, ADE><<<grid, 128, 0, d->stream>>>(
+        d->buf[0][s], d->buf[0][t], d->buf[1][s], d->buf[1][t], d->g, p, row_begin, d->npairs, d->d_aos[0], d->d_aos[1]);
+    d->launches++;
+  }
+  if (do_boundary && d->nb > 0)
+  {
+    BoundaryTable bt;
+    bt.n = d->nb;
+    bt.x = d->d_bx;
+    bt.y = d->d_by;
+    bt.ent = d->d_ent;
+    if (MODE == MODE_PULL_ONLY)
+    {
+      bt.mom_cur = nullptr;
+      bt.mom_prev = d->d_mom[d->mom_cur];
+    }
+    else
+    {
+      bt.mom_cur = d->d_mom[d->mom_cur ^ 1];
+      bt.mom_prev = d->d_mom[d->mom_cur];
+    }
+    k_bgk_boundary<MODE, EQ, FORCE, ADE><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(
+        d->buf[0][s], d->buf[0][t], d->buf[1][s], d->buf[1][t], d->g, p, bt, d->d_aos[0], d->d_aos[1]);
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+template <int MODE>
+static int dispatch_bgk(lbm_domain* d, int rb, int re, bool di, bool db)
+{
+  const bool ade = d->cfg.model == LBM_MODEL_BGK_ADE;
+  const int eq = d->cfg.equilibrium, fo = d->cfg.force;
+  if (ade) return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, rb, re, di, db);
+#define LBM_CASE(E, F) \
+  if (eq == E && fo == F) return launch_bgk<MODE, E, F, false>(d, rb, re, di, db);
+  LBM_CASE(EQ_COMP, FORCE_NONE)
+  LBM_CASE(EQ_COMP, FORCE_UNIFORM)
+  LBM_CASE(EQ_COMP, FORCE_IBM)
+  LBM_CASE(EQ_INCOMP, FORCE_NONE)
+  LBM_CASE(EQ_INCOMP, FORCE_UNIFORM)
+  LBM_CASE(EQ_INCOMP, FORCE_IBM)
+#undef LBM_CASE
+  set_error("unsupported equilibrium/force combination (%d, %d)", eq, fo);
+  return LBM_ERR_INVALID;
+}
+
+static int run_fixups(lbm_domain* d)
+{
+  const int t = d->cur ^ 1;  // freshly written buffers
+  for (auto& grp : d->fix)
+  {
+    if (grp.n == 0) continue;
+    if (d->cfg.equilibrium == EQ_INCOMP)
+      k_bgk_fixup<EQ_INCOMP><<<cdiv(grp.n, 128), 128, 0, d->stream>>>(d->buf[0][t], d->buf[1][t], d->g, grp.d_entries, grp.n,
+                                                                     d->d_mom[d->mom_cur ^ 1]);
+    else
+      k_bgk_fixup<EQ_COMP><<<cdiv(grp.n, 128), 128, 0, d->stream>>>(d->buf[0][t], d->buf[1][t], d->g, grp.d_entries, grp.n,
+                                                                   d->d_mom[d->mom_cur ^ 1]);
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+// ghost rows of buffer `which` of every lattice: neighbours' boundary rows, or the slab's own
+// opposite rows when it is the whole domain (periodic wrap of solver::advect)
+int exchange_ghost_rows(lbm_domain* d, int which)
+{
+  if (d->comm || d->link_lo || d->link_hi) return comm_exchange(d, which);
+  for (int l = 0; l < d->nlat; l++)
+  {
+    k_wrap_ghost_rows<<<cdiv(d->g.pitch, 128), 128, 0, d->stream>>>(d->buf[l][which], d->g, d->wrap_all_q ? 1 : 0);
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+static int bgk_step_once(lbm_domain* d)
+{
+  const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
+  if (d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM) LBM_TRY(ibm_prepass(d, mode));
+  if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, 0, d->g.Xl, true, true));
+  else LBM_TRY(dispatch_bgk<MODE_PULL>(d, 0, d->g.Xl, true, true));
+  LBM_TRY(run_fixups(d));
+  LBM_TRY(exchange_ghost_rows(d, d->cur ^ 1));
+  d->cur ^= 1;
+  d->mom_cur ^= 1;
+  d->post_stream = false;
+  return LBM_OK;
+}
+
+int ensure_aos_scratch(lbm_domain* d)
+{
+  const size_t bytes = (size_t)d->g.Xl * d->g.Y * 9 * sizeof(double);
+  for (int l = 0; l < d->nlat; l++)
+    if (!d->d_aos[l]) LBM_CUDA(cudaMalloc(&d->d_aos[l], bytes));
+  return LBM_OK;
+}
+
+// post-stream populations of every lattice into d_aos[] (device, reference layout)
+static int export_post_stream(lbm_domain* d)
+{
+  LBM_TRY(ensure_aos_scratch(d));
+  if (d->tp) return tp_export(d);
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (d->post_stream)
+  {
+    for (int l = 0; l < d->nlat; l++)
+    {
+      k_export_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[l][d->cur], d->d_aos[l], d->g);
+      d->launches++;
+    }
+    LBM_CUDA(cudaGetLastError());
+    return LBM_OK;
+  }
+  return dispatch_bgk<MODE_PULL_ONLY>(d, 0, d->g.Xl, true, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary compiler
+// ------------------------------------------------------------------------------------------------
+static void resolve_slice(int b, int e, int n, int& lo, int& hi)
+{
+  // torch::indexing::Slice semantics for step 1
+  long long bb = b, ee = (e == LBM_END) ? n : e;
+  if (bb < 0) bb += n;
+  if (ee < 0) ee += n;
+  bb = std::max(0LL, std::min<long long>(bb, n));
+  ee = std::max(0LL, std::min<long long>(ee, n));
+  lo = (int)bb;
+  hi = (int)std::max(bb, ee);
+}
+
+static int resolve_index(int v, int n) { return v < 0 ? v + n : v; }
+
+struct SrcNode
+{
+  int gx, y;
+  bool ok;
+};
+
+static SrcNode src_of(const lbm_bc_op& op, int gx, int y, int X, int Y)
+{
+  SrcNode s{gx, y, true};
+  switch (op.src_mode)
+  {
+    case LBM_SRC_SAME_NODE: break;
+    case LBM_SRC_SHIFT: s.gx = gx + op.src_a; s.y = y + op.src_b; break;
+    case LBM_SRC_ROW: s.gx = resolve_index(op.src_a, X); break;
+    case LBM_SRC_COL: s.y = resolve_index(op.src_a, Y); break;
+    default: s.ok = false;
+  }
+  if (s.y < 0 || s.y >= Y || s.gx < 0 || s.gx >= X) s.ok = false;
+  return s;
+}
+
+// global row -> local storage row (ghost rows -1 and Xl included); INT_MIN if not reachable
+static int local_row(const lbm_domain* d, int gx)
+{
+  const int X = d->cfg.X, x0 = d->cfg.x0, x1 = d->cfg.x1;
+  if (gx >= x0 - 1 && gx <= x1) return gx - x0;
+  if (x0 == 0 && gx == X - 1) return -1;          // periodic image below row 0
+  if (x1 == X && gx == 0) return x1 - x0;         // periodic image above the last row
+  return INT_MIN;
+}
+
+static void release_compiled(lbm_domain* d)
+{
+  cudaFree(d->d_bx); cudaFree(d->d_by); cudaFree(d->d_ent); cudaFree(d->d_mom[0]); cudaFree(d->d_mom[1]);
+  d->d_bx = d->d_by = nullptr; d->d_ent = nullptr; d->d_mom[0] = d->d_mom[1] = nullptr;
+  for (auto& grp : d->fix) cudaFree(grp.d_entries);
+  d->fix.clear();
+  d->nb = 0;
+  d->committed = false;
+}
+
+static bool is_post_stream(int kind)
+{
+  return kind == LBM_BC_LINEAR || kind == LBM_BC_ABB_FIXED || kind == LBM_BC_ABB_EXTRAPOLATED || kind == LBM_BC_ADE_INLET;
+}
+
+static int commit_single_phase(lbm_domain* d)
+{
+  const int X = d->cfg.X, Y = d->cfg.Y, x0 = d->cfg.x0, Xl = d->g.Xl;
+  const SlabGeom& g = d->g;
+  const int y_int_end = 2 + 2 * d->npairs;  // first column past the interior pairs
+
+  // ---- pass 1: which nodes need a table entry
+  std::map<long long, int> index;  // local node id -> boundary index
+  auto touch = [&](int lx, int y) {
+    if (lx < 0 || lx >= Xl) return;
+    index.emplace((long long)lx * Y + y, 0);
+  };
+  for (int lx = 0; lx < Xl; lx++)
+    for (int y = 0; y < Y; y++)
+      if (y < 2 || y >= y_int_end) touch(lx, y);
+  d->wrap_all_q = false;
+  for (const auto& so : d->ops)
+  {
+    const lbm_bc_op& op = so.op;
+    int xl, xh, yl, yh;
+    resolve_slice(op.x_begin, op.x_end, X, xl, xh);
+    resolve_slice(op.y_begin, op.y_end, Y, yl, yh);
+    for (int gx = xl; gx < xh; gx++)
+      for (int y = yl; y < yh; y++)
+      {
+        if (is_post_stream(op.kind)) touch(gx - x0, y);
+        if (op.kind == LBM_BC_ABB_EXTRAPOLATED)
+        {
+          touch(gx - x0, Y - 1);
+          touch(gx - x0, Y - 2);
+        }
+        if (op.kind == LBM_BC_PRESSURE_PERIODIC)
+        {
+          SrcNode s = src_of(op, gx, y, X, Y);
+          if (s.ok) touch(s.gx - x0, s.y);
+        }
+        if (op.kind == LBM_BC_LINEAR && op.src_mode != LBM_SRC_SAME_NODE)
+        {
+          SrcNode s = src_of(op, gx, y, X, Y);
+          if (s.ok && std::abs(s.gx - gx) > 1) d->wrap_all_q = true;  // reads across the periodic wrap
+        }
+      }
+  }
+  int nb = 0;
+  for (auto& kv : index) kv.second = nb++;
+
+  // ---- pass 2: default entries = periodic pull (solver::advect)
+  std::vector<int> bx(nb), by(nb);
+  std::vector<BcEntry> ent((size_t)d->nlat * 9 * nb);
+  for (auto& kv : index)
+  {
+    const int i = kv.second, lx = (int)(kv.first / Y), y = (int)(kv.first % Y);
+    bx[i] = lx;
+    by[i] = y;
+    for (int l = 0; l < d->nlat; l++)
+      for (int q = 0; q < 9; q++)
+      {
+        int sy = y - CY(q);
+        if (sy < 0) sy += Y;
+        if (sy >= Y) sy -= Y;
+        const int sx = lx - CX(q);  // ghost rows carry the wrap / the neighbour slab
+        BcEntry e;
+        e.src = (long long)q * g.plane + (long long)(sx + 1) * g.pitch + sy;
+        e.coef = 1.0; e.cst = 0.0; e.kind = OP_LINEAR; e.sq = q; e.aux0 = e.aux1 = 0;
+        ent[((size_t)l * 9 + q) * nb + i] = e;
+      }
+  }
+  for (int l = 0; l < 2; l++) d->mask[l].assign(l < d->nlat ? (size_t)Xl * Y * 9 : 0, 0);
+
+  // ---- pass 3: ops in order (later ops win, like the reference's successive assignments)
+  std::vector<std::vector<FixEntry>> groups;
+  for (size_t k = 0; k < d->ops.size(); k++)
+  {
+    const lbm_bc_op& op = d->ops[k].op;
+    int xl, xh, yl, yh;
+    resolve_slice(op.x_begin, op.x_end, X, xl, xh);
+    resolve_slice(op.y_begin, op.y_end, Y, yl, yh);
+    const int lat_lo = op.lattice < 0 ? 0 : op.lattice, lat_hi = op.lattice < 0 ? d->nlat - 1 : op.lattice;
+    if (lat_hi >= d->nlat) { set_error("bc op %zu: lattice %d does not exist in this model", k, op.lattice); return LBM_ERR_INVALID; }
+    if (op.kind == LBM_BC_PRESSURE_PERIODIC || op.kind == LBM_BC_COPY_PRE)
+    {
+      std::vector<FixEntry> grp;
+      for (int gx = xl; gx < xh; gx++)
+      {
+        if (gx < x0 || gx >= d->cfg.x1) continue;
+        for (int y = yl; y < yh; y++)
+        {
+          SrcNode s = src_of(op, gx, y, X, Y);
+          if (!s.ok) { set_error("bc op %zu: source node outside the grid", k); return LBM_ERR_INVALID; }
+          if (s.gx < x0 || s.gx >= d->cfg.x1)
+          {
+            set_error("bc op %zu: pre-stream source row %d is owned by another slab (not supported across ranks)", k, s.gx);
+            return LBM_ERR_UNSUPPORTED;
+          }
+          for (int l = lat_lo; l <= lat_hi; l++)
+          {
+            FixEntry e;
+            e.dst = (long long)(gx - x0 + 1) * g.pitch + y;
+            e.src = (long long)(s.gx - x0 + 1) * g.pitch + s.y;
+            e.rho_bc = op.rho_bc;
+            e.kind = op.kind == LBM_BC_COPY_PRE ? FIX_COPY : FIX_PRESSURE;
+            e.lattice = l;
+            e.j = 0;
+            e.pad = 0;
+            if (e.kind == FIX_PRESSURE) e.j = index.at((long long)(s.gx - x0) * Y + s.y);
+            grp.push_back(e);
+          }
+        }
+      }
+      groups.push_back(std::move(grp));
+      continue;
+    }
+    if (!is_post_stream(op.kind)) { set_error("bc op %zu: unknown kind %d", k, op.kind); return LBM_ERR_INVALID; }
+    if (op.kind == LBM_BC_ADE_INLET && (d->cfg.model != LBM_MODEL_BGK_ADE || op.lattice != 1))
+    { set_error("bc op %zu: LBM_BC_ADE_INLET applies to lattice 1 of LBM_MODEL_BGK_ADE", k); return LBM_ERR_INVALID; }
+    for (int gx = xl; gx < xh; gx++)
+    {
+      if (gx < x0 || gx >= d->cfg.x1) continue;
+      const int lx = gx - x0;
+      for (int y = yl; y < yh; y++)
+      {
+        const int i = index.at((long long)lx * Y + y);
+        // population loop: LINEAR with dst_q = -1 copies all nine; ABB-type rules with src_q = -1 cover the 8 moving ones
+        const bool abb_like = op.kind != LBM_BC_LINEAR;
+        const int q_lo = abb_like ? (op.src_q < 0 ? 1 : op.src_q) : (op.dst_q < 0 ? 0 : op.dst_q);
+        const int q_hi = abb_like ? (op.src_q < 0 ? 8 : op.src_q) : (op.dst_q < 0 ? 8 : op.dst_q);
+        for (int qq = q_lo; qq <= q_hi; qq++)
+        {
+          int dq, sq;
+          if (abb_like) { sq = qq; dq = OPP(qq); }
+          else { dq = qq; sq = op.dst_q < 0 ? qq : op.src_q; }
+          if (dq < 0 || dq > 8 || sq < 0 || sq > 8) { set_error("bc op %zu: population index out of range", k); return LBM_ERR_INVALID; }
+          SrcNode s = src_of(op, gx, y, X, Y);
+          if (!s.ok) { set_error("bc op %zu: source node outside the grid", k); return LBM_ERR_INVALID; }
+          const int slx = local_row(d, s.gx);
+          if (slx == INT_MIN)
+          {
+            set_error("bc op %zu: source row %d is not reachable from slab rows [%d,%d)", k, s.gx, x0, d->cfg.x1);
+            return LBM_ERR_UNSUPPORTED;
+          }
+          for (int l = lat_lo; l <= lat_hi; l++)
+          {
+            BcEntry e;
+            e.src = (long long)sq * g.plane + (long long)(slx + 1) * g.pitch + s.y;
+            e.sq = sq; e.aux0 = e.aux1 = 0;
+            switch (op.kind)
+            {
+              case LBM_BC_LINEAR: e.kind = OP_LINEAR; e.coef = op.coef; e.cst = op.cst; break;
+              case LBM_BC_ABB_FIXED: e.kind = OP_LINEAR; e.coef = -1.0; e.cst = abb_term(sq, op.uw[0], op.uw[1]); break;
+              case LBM_BC_ABB_EXTRAPOLATED:
+                e.kind = OP_ABB_EXTRAP; e.coef = -1.0; e.cst = 0.0;
+                e.aux0 = index.at((long long)lx * Y + (Y - 1));
+                e.aux1 = index.at((long long)lx * Y + (Y - 2));
+                break;
+              case LBM_BC_ADE_INLET: e.kind = OP_ADE_INLET; e.coef = -1.0; e.cst = d->ops[k].per_row[gx]; break;
+            }
+            ent[((size_t)l * 9 + dq) * nb + i] = e;
+            d->mask[l][((size_t)lx * Y + y) * 9 + dq] = (int32_t)(k + 1);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- upload
+  d->nb = nb;
+  if (nb > 0)
+  {
+    LBM_CUDA(cudaMalloc(&d->d_bx, sizeof(int) * nb));
+    LBM_CUDA(cudaMalloc(&d->d_by, sizeof(int) * nb));
+    LBM_CUDA(cudaMalloc(&d->d_ent, sizeof(BcEntry) * ent.size()));
+    LBM_CUDA(cudaMalloc(&d->d_mom[0], sizeof(double) * 4 * nb));
+    LBM_CUDA(cudaMalloc(&d->d_mom[1], sizeof(double) * 4 * nb));
+    LBM_CUDA(cudaMemcpy(d->d_bx, bx.data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
+    LBM_CUDA(cudaMemcpy(d->d_by, by.data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
+    LBM_CUDA(cudaMemcpy(d->d_ent, ent.data(), sizeof(BcEntry) * ent.size(), cudaMemcpyHostToDevice));
+    LBM_CUDA(cudaMemset(d->d_mom[0], 0, sizeof(double) * 4 * nb));
+    LBM_CUDA(cudaMemset(d->d_mom[1], 0, sizeof(double) * 4 * nb));
+  }
+  for (auto& grp : groups)
+  {
+    FixGroup fg;
+    fg.n = (int)grp.size();
+    if (fg.n > 0)
+    {
+      LBM_CUDA(cudaMalloc(&fg.d_entries, sizeof(FixEntry) * fg.n));
+      LBM_CUDA(cudaMemcpy(fg.d_entries, grp.data(), sizeof(FixEntry) * fg.n, cudaMemcpyHostToDevice));
+    }
+    d->fix.push_back(fg);
+  }
+  d->committed = true;
+  return LBM_OK;
+}
+
+}  // namespace lbm
+
+using namespace lbm;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C"
+{
+
+const char* lbm_last_error(void) { return g_error.c_str(); }
+const char* lbm_version(void) { return "lbm_b200 0.1 (sm_100a, fp64 SoA, pull)"; }
+
+void lbm_config_default(lbm_config* c)
+{
+  std::memset(c, 0, sizeof(*c));
+  c->model = LBM_MODEL_BGK;
+  c->equilibrium = LBM_EQ_COMPRESSIBLE;
+  c->force = LBM_FORCE_NONE;
+  c->omega = 1.0;
+  c->omega_g = 1.0;
+  c->delta = 0.1;
+  c->sigma = 0.1;
+}
+
+void lbm_bc_op_default(lbm_bc_op* op)
+{
+  std::memset(op, 0, sizeof(*op));
+  op->kind = LBM_BC_LINEAR;
+  op->x_end = LBM_END;
+  op->y_end = LBM_END;
+  op->coef = 1.0;
+  op->src_mode = LBM_SRC_SAME_NODE;
+}
+
+int lbm_create(const lbm_config* cfg, lbm_domain** out)
+{
+  if (!cfg || !out) { set_error("lbm_create: null argument"); return LBM_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->X < 3 || cfg->Y < 3) { set_error("lbm_create: grid %dx%d too small (need >= 3x3)", cfg->X, cfg->Y); return LBM_ERR_INVALID; }
+  if (cfg->x0 < 0 || cfg->x1 > cfg->X || cfg->x1 <= cfg->x0) { set_error("lbm_create: bad slab rows [%d,%d) of %d", cfg->x0, cfg->x1, cfg->X); return LBM_ERR_INVALID; }
+  if (cfg->model < LBM_MODEL_BGK || cfg->model > LBM_MODEL_RK) { set_error("lbm_create: unknown model %d", cfg->model); return LBM_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+  {
+    set_error("lbm_create: no CUDA device (this library has no CPU fallback)");
+    return LBM_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_error("lbm_create: device %d of %d", cfg->device, ndev); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(cfg->device));
+  lbm_domain* d = new lbm_domain();
+  d->cfg = *cfg;
+  d->g.Xl = cfg->x1 - cfg->x0;
+  d->g.Y = cfg->Y;
+  d->g.pitch = ((cfg->Y + 15) / 16) * 16;
+  d->g.xg0 = cfg->x0;
+  d->g.plane = (long long)(d->g.Xl + 2) * d->g.pitch;
+  d->nlat = cfg->model == LBM_MODEL_BGK ? 1 : 2;
+  d->npairs = cfg->Y >= 5 ? (cfg->Y - 3) / 2 : 0;
+  const size_t bytes = (size_t)9 * d->g.plane * sizeof(double);
+  for (int l = 0; l < d->nlat; l++)
+    for (int b = 0; b < 2; b++)
+    {
+      cudaError_t e = cudaMalloc(&d->buf[l][b], bytes);
+      if (e != cudaSuccess)
+      {
+        set_error("lbm_create: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        lbm_destroy(d);
+        return LBM_ERR_CUDA;
+      }
+      cudaMemset(d->buf[l][b], 0, bytes);
+    }
+  LBM_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  LBM_CUDA(cudaEventCreate(&d->ev_begin));
+  LBM_CUDA(cudaEventCreate(&d->ev_end));
+  if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK)
+  {
+    int s = tp_create(d);
+    if (s != LBM_OK) { lbm_destroy(d); return s; }
+  }
+  *out = d;
+  return LBM_OK;
+}
+
+int lbm_destroy(lbm_domain* d)
+{
+  if (!d) return LBM_OK;
+  cudaSetDevice(d->cfg.device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  release_compiled(d);
+  ibm_release(d);
+  tp_destroy(d);
+  comm_release(d);
+  for (int l = 0; l < 2; l++)
+  {
+    for (int b = 0; b < 2; b++) cudaFree(d->buf[l][b]);
+    cudaFree(d->d_aos[l]);
+  }
+  for (int k = 0; k < 2; k++)
+    if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
+  if (d->ev_begin) cudaEventDestroy(d->ev_begin);
+  if (d->ev_end) cudaEventDestroy(d->ev_end);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+  return LBM_OK;
+}
+
+// ---------------------------------------------------------------- boundary description
+int lbm_bc_clear(lbm_domain* d)
+{
+  if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
+  d->ops.clear();
+  cudaSetDevice(d->cfg.device);
+  release_compiled(d);
+  return LBM_OK;
+}
+
+int lbm_bc_add(lbm_domain* d, const lbm_bc_op* op)
+{
+  if (!d || !op) { set_error("lbm_bc_add: null argument"); return LBM_ERR_INVALID; }
+  if (op->kind < LBM_BC_LINEAR || op->kind > LBM_BC_COPY_PRE) { set_error("lbm_bc_add: unknown kind %d", op->kind); return LBM_ERR_INVALID; }
+  if (op->lattice < -1 || op->lattice > 1) { set_error("lbm_bc_add: lattice %d", op->lattice); return LBM_ERR_INVALID; }
+  StoredOp so;
+  so.op = *op;
+  if (op->kind == LBM_BC_ADE_INLET)
+  {
+    if (!op->per_row) { set_error("lbm_bc_add: LBM_BC_ADE_INLET needs per_row (C_w[X])"); return LBM_ERR_INVALID; }
+    so.per_row.assign(op->per_row, op->per_row + d->cfg.X);
+  }
+  so.op.per_row = nullptr;
+  d->ops.push_back(std::move(so));
+  d->committed = false;
+  return LBM_OK;
+}
+
+int lbm_bc_commit(lbm_domain* d)
+{
+  if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  release_compiled(d);
+  if (d->tp) return tp_commit(d);
+  return commit_single_phase(d);
+}
+
+int lbm_bc_get_mask(lbm_domain* d, int lattice, int32_t* mask)
+{
+  if (!d || !mask || lattice < 0 || lattice >= d->nlat) { set_error("lbm_bc_get_mask: bad argument"); return LBM_ERR_INVALID; }
+  if (!d->committed) { set_error("lbm_bc_get_mask: call lbm_bc_commit first"); return LBM_ERR_INVALID; }
+  std::memcpy(mask, d->mask[lattice].data(), d->mask[lattice].size() * sizeof(int32_t));
+  return LBM_OK;
+}
+
+// ---------------------------------------------------------------- state
+static int upload(lbm_domain* d, const double* host, size_t n, double** dev_out)
+{
+  double* p = nullptr;
+  LBM_CUDA(cudaMalloc(&p, n * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, d->stream);
+  if (e != cudaSuccess) { cudaFree(p); set_error("cudaMemcpyAsync H2D failed: %s", cudaGetErrorString(e)); return LBM_ERR_CUDA; }
+  *dev_out = p;
+  return LBM_OK;
+}
+
+int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos)
+{
+  if (!d || !f_aos || lattice < 0 || lattice >= d->nlat) { set_error("lbm_set_f: bad argument"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (!d->post_stream && d->have_state)
+  {
+    // the other lattice (if any) is stored post-collision: bring the whole state back to post-stream first
+    if (d->nlat > 1)
+    {
+      LBM_TRY(export_post_stream(d));
+      for (int l = 0; l < d->nlat; l++)
+      {
+        k_import_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->d_aos[l], d->buf[l][d->cur], d->g);
+        d->launches++;
+      }
+    }
+    d->post_stream = true;
+  }
+  LBM_TRY(ensure_aos_scratch(d));
+  LBM_CUDA(cudaMemcpyAsync(d->d_aos[lattice], f_aos, N * 9 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  k_import_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->d_aos[lattice], d->buf[lattice][d->cur], d->g);
+  d->launches++;
+  LBM_CUDA(cudaGetLastError());
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  d->post_stream = true;
+  d->have_state = true;
+  return LBM_OK;
+}
+
+int lbm_get_f(lbm_domain* d, int lattice, double* f_aos)
+{
+  if (!d || !f_aos || lattice < 0 || lattice >= d->nlat) { set_error("lbm_get_f: bad argument"); return LBM_ERR_INVALID; }
+  if (!d->have_state) { set_error("lbm_get_f: no state (call lbm_set_f / lbm_init_* first)"); return LBM_ERR_INVALID; }
+  if (!d->committed) { set_error("lbm_get_f: call lbm_bc_commit first"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_TRY(export_post_stream(d));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  LBM_CUDA(cudaMemcpyAsync(f_aos, d->d_aos[lattice], N * 9 * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  return LBM_OK;
+}
+
+int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u)
+{
+  if (!d || lattice < 0 || lattice >= d->nlat) { set_error("lbm_get_moments: bad argument"); return LBM_ERR_INVALID; }
+  if (!d->have_state || !d->committed) { set_error("lbm_get_moments: no state or boundary rules not committed"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_TRY(export_post_stream(d));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  double *d_rho = nullptr, *d_u = nullptr;
+  LBM_CUDA(cudaMalloc(&d_rho, N * sizeof(double)));
+  LBM_CUDA(cudaMalloc(&d_u, 2 * N * sizeof(double)));
+  int incompressible = 0;
+  double sx = 0.0, sy = 0.0;
+  if (d->cfg.model == LBM_MODEL_BGK)
+  {
+    incompressible = d->cfg.equilibrium == LBM_EQ_INCOMPRESSIBLE;
+    if (d->cfg.force == LBM_FORCE_UNIFORM) { sx = d->cfg.Fg[0]; sy = d->cfg.Fg[1]; }
+  }
+  k_moments_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->d_aos[lattice], N, incompressible, sx, sy, d_rho, d_u);
+  d->launches++;
+  if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d_rho, N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  if (u) LBM_CUDA(cudaMemcpyAsync(u, d_u, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  cudaFree(d_rho);
+  cudaFree(d_u);
+  return LBM_OK;
+}
+
+int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* rho, const double* u)
+{
+  if (!d || !rho || !u || lattice < 0 || lattice >= d->nlat) { set_error("lbm_init_equilibrium: bad argument"); return LBM_ERR_INVALID; }
+  if (d->tp) { set_error("lbm_init_equilibrium: use lbm_init_two_phase for two-phase models"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  double *d_rho = nullptr, *d_u = nullptr;
+  LBM_TRY(upload(d, rho, N, &d_rho));
+  LBM_TRY(upload(d, u, 2 * N, &d_u));
+  k_init_equilibrium<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[lattice][d->cur], d->g, eq_kind == LBM_EQ_INCOMPRESSIBLE, d_rho, d_u);
+  d->launches++;
+  LBM_CUDA(cudaGetLastError());
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  cudaFree(d_rho);
+  cudaFree(d_u);
+  d->post_stream = true;
+  d->have_state = true;
+  return LBM_OK;
+}
+
+// ---------------------------------------------------------------- stepping
+int lbm_step(lbm_domain* d, int n_steps)
+{
+  if (!d || n_steps < 0) { set_error("lbm_step: bad argument"); return LBM_ERR_INVALID; }
+  if (!d->have_state) { set_error("lbm_step: no state (call lbm_set_f / lbm_init_* first)"); return LBM_ERR_INVALID; }
+  if (!d->committed) { set_error("lbm_step: call lbm_bc_commit first"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaEventRecord(d->ev_begin, d->stream));
+  for (int s = 0; s < n_steps; s++)
+  {
+    if (d->tp) LBM_TRY(tp_step(d));
+    else LBM_TRY(bgk_step_once(d));
+  }
+  LBM_CUDA(cudaEventRecord(d->ev_end, d->stream));
+  return LBM_OK;
+}
+
+int lbm_synchronize(lbm_domain* d)
+{
+  if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  return LBM_OK;
+}
+
+int lbm_last_step_ms(lbm_domain* d, float* ms)
+{
+  if (!d || !ms) { set_error("lbm_last_step_ms: bad argument"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaEventSynchronize(d->ev_end));
+  LBM_CUDA(cudaEventElapsedTime(ms, d->ev_begin, d->ev_end));
+  return LBM_OK;
+}
+
+int lbm_kernel_launches(lbm_domain* d, long long* n)
+{
+  if (!d || !n) { set_error("lbm_kernel_launches: bad argument"); return LBM_ERR_INVALID; }
+  *n = d->launches;
+  return LBM_OK;
+}
+
+int lbm_get_stream(lbm_domain* d, void** stream)
+{
+  if (!d || !stream) { set_error("lbm_get_stream: bad argument"); return LBM_ERR_INVALID; }
+  *stream = (void*)d->stream;
+  return LBM_OK;
+}
+
+int lbm_use_graph(lbm_domain* d, int enable)
+{
+  if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
+  d->use_graph = enable != 0;
+  return LBM_OK;
+}
+
+int lbm_decompose_rows(int X, int n_ranks, int rank, int* x0, int* x1)
+{
+  if (X <= 0 || n_ranks <= 0 || rank < 0 || rank >= n_ranks || !x0 || !x1) { set_error("lbm_decompose_rows: bad argument"); return LBM_ERR_INVALID; }
+  // contiguous slabs along axis 0; the first X % n_ranks slabs get one extra row
+  const int base = X / n_ranks, rem = X % n_ranks;
+  *x0 = rank * base + std::min(rank, rem);
+  *x1 = *x0 + base + (rank < rem ? 1 : 0);
+  return LBM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// lbm_internal.hpp — host-side state of one slab (the opaque lbm_domain of include/lbm_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "lbm_bgk_kernels.cuh"
+
+namespace lbm
+{
+
+void set_error(const char* fmt, ...);
+
+#define LBM_CUDA(call)                                                                         \
+  do                                                                                           \
+  {                                                                                            \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+    {                                                                                          \
+      lbm::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return LBM_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define LBM_TRY(call)              \
+  do                               \
+  {                                \
+    int s__ = (call);              \
+    if (s__ != LBM_OK) return s__; \
+  } while (0)
+
+struct StoredOp
+{
+  lbm_bc_op op;
+  std::vector<double> per_row;
+};
+
+struct FixGroup
+{
+  int n = 0;
+  FixEntry* d_entries = nullptr;
+};
+
+struct IbmState
+{
+  bool enabled = false;
+  int n_markers = 0, m_max = 5;
+  long r0 = 0, r1 = 0, c0 = 0, c1 = 0;  // global ROI [r0,r1) x [c0,c1)
+  // markers
+  int* d_mrow = nullptr;   // box start row / col in ROI coordinates
+  int* d_mcol = nullptr;
+  double* d_phi = nullptr; // [n][16]
+  double* d_fj = nullptr;  // [n][2]
+  // node -> covering (marker, weight) lists in marker order
+  int* d_ptr = nullptr;    // [roi_nodes + 1]
+  int* d_ent_marker = nullptr;
+  double* d_ent_phi = nullptr;
+  // ROI fields
+  double* d_u = nullptr;   // [roi][2]
+  double* d_rho = nullptr; // [roi]
+  double* d_Fx = nullptr;  // [roi]
+  double* d_Fy = nullptr;
+};
+
+struct TwoPhaseState;  // lbm_two_phase.cu
+struct CommState;      // lbm_comm.cu
+
+}  // namespace lbm
+
+struct lbm_domain
+{
+  lbm_config cfg;
+  lbm::SlabGeom g;
+  int nlat = 1;
+  double* buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [lattice][buffer]
+  int cur = 0;              // buffer holding the current state
+  bool post_stream = true;  // true: buf[cur] = f_adve (just imported); false: buf[cur] = f_coll
+  bool have_state = false;
+  int npairs = 0;           // interior column pairs per row
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  float last_ms = 0.f;
+  long long launches = 0;
+
+  // boundary description and its compiled form
+  std::vector<lbm::StoredOp> ops;
+  bool committed = false;
+  int nb = 0;
+  int *d_bx = nullptr, *d_by = nullptr;
+  lbm::BcEntry* d_ent = nullptr;
+  double* d_mom[2] = {nullptr, nullptr};
+  int mom_cur = 0;
+  std::vector<lbm::FixGroup> fix;
+  std::vector<int32_t> mask[2];
+  bool wrap_all_q = false;  // some rule reads a whole row across the periodic wrap
+
+  // scratch for export
+  double* d_aos[2] = {nullptr, nullptr};
+
+  lbm::IbmState ibm;
+  lbm::TwoPhaseState* tp = nullptr;
+  lbm::CommState* comm = nullptr;
+  lbm_domain *link_lo = nullptr, *link_hi = nullptr;
+
+  // CUDA graph of one steady-state step pair
+  bool use_graph = false;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+};
+
+namespace lbm
+{
+// lbm_domain.cu
+int ensure_aos_scratch(lbm_domain* d);
+int exchange_ghost_rows(lbm_domain* d, int which);
+// lbm_ibm.cu
+int ibm_release(lbm_domain* d);
+int ibm_prepass(lbm_domain* d, int mode);
+// lbm_two_phase.cu
+int tp_create(lbm_domain* d);
+int tp_destroy(lbm_domain* d);
+int tp_step(lbm_domain* d);
+int tp_commit(lbm_domain* d);
+int tp_export(lbm_domain* d);
+// lbm_comm.cu
+int comm_release(lbm_domain* d);
+int comm_exchange(lbm_domain* d, int which);
+}  // namespace lbm

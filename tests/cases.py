@@ -1,0 +1,70 @@
+"""Builders that configure an lbm_b200.Domain like each reference driver does (test helpers)."""
+import os
+
+import numpy as np
+
+import lbm_b200 as L
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def channel_constants(H, W, u_max):
+    """test/horizontal_poiseuille_test.cpp:50-66"""
+    tau = np.sqrt(3.0 / 16.0) + 0.5
+    omega = 1.0 / tau
+    nu = (2.0 * tau - 1.0) / 6.0
+    p_grad = 8.0 * nu * u_max / (W * W)
+    rho_out = 1.0
+    rho_in = 3.0 * (H - 1) * p_grad + rho_out
+    return omega, rho_in, rho_out
+
+
+def poiseuille(H=21, W=21, u_max=1.030985714e-1, **slab):
+    omega, rho_in, rho_out = channel_constants(H, W, u_max)
+    d = L.Domain(L.default_config(model=L.MODEL_BGK, X=H, Y=W, omega=omega, equilibrium=L.EQ_INCOMPRESSIBLE, **slab))
+    d.preset_poiseuille(rho_in, rho_out)
+    return d, (omega, rho_in, rho_out)
+
+
+def specular(H=51, W=51, u_max=0.1):
+    omega, rho_in, rho_out = channel_constants(H, W, u_max)
+    d = L.Domain(L.default_config(model=L.MODEL_BGK, X=H, Y=W, omega=omega, equilibrium=L.EQ_COMPRESSIBLE))
+    d.preset_specular_channel(rho_in, rho_out)
+    return d, (omega, rho_in, rho_out)
+
+
+def gravity(H=21, W=21, Fg=(-0.0003, 0.0)):
+    omega, _, _ = channel_constants(H, W, 0.1)
+    d = L.Domain(L.default_config(model=L.MODEL_BGK, X=H, Y=W, omega=omega, equilibrium=L.EQ_INCOMPRESSIBLE,
+                                  force=L.FORCE_UNIFORM, Fg=Fg))
+    d.preset_poiseuille(1.0, 1.0)
+    return d, omega
+
+
+def free_stream(X, Y, omega, uwx):
+    d = L.Domain(L.default_config(model=L.MODEL_BGK, X=X, Y=Y, omega=omega, equilibrium=L.EQ_INCOMPRESSIBLE))
+    d.preset_free_stream(uwx, 0.0)
+    return d
+
+
+def cylinder(X, Y, omega, u_lb, xs, ys):
+    d = L.Domain(L.default_config(model=L.MODEL_BGK, X=X, Y=Y, omega=omega, equilibrium=L.EQ_COMPRESSIBLE,
+                                  force=L.FORCE_IBM))
+    d.preset_free_stream(u_lb, 0.0)
+    d.ibm_set_markers(xs, ys)
+    return d
+
+
+def sedimentation(X, Y, omega, u_lb, w_s, C_w, walls):
+    d = L.Domain(L.default_config(model=L.MODEL_BGK_ADE, X=X, Y=Y, omega=omega, omega_g=omega / 1.0,
+                                  equilibrium=L.EQ_COMPRESSIBLE, w_s=w_s))
+    d.preset_sedimentation(u_lb, C_w, int(walls[0]), int(walls[1]), int(walls[2]))
+    return d
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))

@@ -285,8 +285,9 @@ def case_cylinder():
     print(f"  oracle vs reference driver over {NS - 1} steps ({X}x{Y}): worst abs err {worst:.3e}")
     assert worst < 1e-13
     ORC.ibm_destroy(ib)
-    save("cylinder_99x77", ux=np.moveaxis(ux, -1, 0), uy=np.moveaxis(uy, -1, 0), ps=np.moveaxis(ps, -1, 0),
-         Fs=np.moveaxis(Fs, -1, 0), F=np.moveaxis(FF, -1, 0), omega=omega, u_lb=u_lb, X=X, Y=Y, f0=f0,
+    K = 16  # snapshots kept in the fixture (the comparison above covers all of them)
+    save("cylinder_99x77", ux=np.moveaxis(ux, -1, 0)[:K], uy=np.moveaxis(uy, -1, 0)[:K], ps=np.moveaxis(ps, -1, 0)[:K],
+         Fs=np.moveaxis(Fs, -1, 0)[:K], F=np.moveaxis(FF, -1, 0)[:K], omega=omega, u_lb=u_lb, X=X, Y=Y, f0=f0,
          marker_x=xs, marker_y=ys, roi=np.array(roi), ibm_u=ut, ibm_rho=rt, ibm_F=F_r,
          toml=open(toml).read())
 
@@ -447,7 +448,7 @@ def case_rk():
                     float(np.abs(st["relax"] - ref["rparams"][..., t]).max()))
     print(f"  oracle vs reference driver over {NS} steps (101x101): worst abs err {worst:.3e}")
     assert worst < 1e-12
-    keep = [0, 1, 2, 10, 100, NS - 1]
+    keep = [0, 1, 10, NS - 1]
     save("rk_droplet_101", steps=np.array(keep), **{k: np.stack([v[..., t] for t in keep]) for k, v in ref.items()})
 
 
