@@ -233,6 +233,21 @@ int lbm_kernel_launches(lbm_domain* d, long long* n);
 int lbm_get_stream(lbm_domain* d, void** stream);
 /* capture one step into a CUDA graph and replay it in lbm_step (launch-bound small grids) */
 int lbm_use_graph(lbm_domain* d, int enable);
+/* per-kernel-class device timing with CUDA events on the domain's stream (the reference has no
+ * timers at all).  enable != 0 starts a fresh recording; lbm_profile_read synchronises
+ * and returns the summed duration and the launch count of one class since then. */
+typedef enum
+{
+  LBM_PROF_INTERIOR = 0, /* fused collide+stream over the interior nodes (the dominant kernel) */
+  LBM_PROF_BOUNDARY = 1, /* table-driven boundary-node kernel */
+  LBM_PROF_FIXUP = 2,    /* pre-stream rules */
+  LBM_PROF_GHOST = 3,    /* ghost-row wrap / exchange */
+  LBM_PROF_IBM = 4,      /* immersed-boundary pre-pass */
+  LBM_PROF_MOMENTS = 5,  /* two-phase models: stream + moments kernel */
+  LBM_PROF_CLASSES = 6
+} lbm_prof_class;
+int lbm_profile_enable(lbm_domain* d, int enable);
+int lbm_profile_read(lbm_domain* d, int prof_class, double* total_ms, long long* launches);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU slabs (test/decompose_domain.cpp:181-187 generalised to P slabs along axis 0)

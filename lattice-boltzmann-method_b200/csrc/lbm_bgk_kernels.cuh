@@ -438,4 +438,15 @@ static __global__ void k_import_aos(const double* __restrict__ aos, double* __re
   for (int q = 0; q < 9; q++) f[q * g.plane + o] = aos[n * 9 + q];
 }
 
+// SoA planes -> AoS {Xl,Y,9}
+static __global__ void k_export_soa_to_aos(const double* __restrict__ f, double* __restrict__ aos, const SlabGeom g)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++) aos[n * 9 + q] = f[q * g.plane + o];
+}
+
 }  // namespace lbm

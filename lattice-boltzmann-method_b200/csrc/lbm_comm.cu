@@ -4,6 +4,7 @@ namespace lbm
 {
 int comm_release(lbm_domain*) { return LBM_OK; }
 int comm_exchange(lbm_domain*, int) { return LBM_ERR_UNSUPPORTED; }
+int comm_exchange_moments(lbm_domain*) { return LBM_OK; }
 }
 extern "C" {
 int lbm_comm_unique_id(char*) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }

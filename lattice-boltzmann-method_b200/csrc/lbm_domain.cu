@@ -25,19 +25,30 @@ void set_error(const char* fmt, ...)
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
+ProfScope::ProfScope(lbm_domain* dom, int cls) : d(dom)
+{
+  if (!d->profiling) return;
+  if (d->prof_used == d->prof.size())
+  {
+    if (d->prof.size() >= 65536) return;  // stop recording rather than grow without bound
+    ProfRec rec;
+    rec.cls = cls;
+    if (cudaEventCreate(&rec.a) != cudaSuccess || cudaEventCreate(&rec.b) != cudaSuccess) return;
+    d->prof.push_back(rec);
+  }
+  idx = (long)d->prof_used++;
+  d->prof[idx].cls = cls;
+  cudaEventRecord(d->prof[idx].a, d->stream);
+}
+
+ProfScope::~ProfScope()
+{
+  if (idx >= 0) cudaEventRecord(d->prof[idx].b, d->stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // small kernels used only by the import / export paths
 // ------------------------------------------------------------------------------------------------
-__global__ void k_export_aos(const double* __restrict__ f, double* __restrict__ aos, const SlabGeom g)
-{
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= (long long)g.Xl * g.Y) return;
-  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
-  const long long o = node_off(g, x, y);
-#pragma unroll
-  for (int q = 0; q < 9; q++) aos[n * 9 + q] = f[q * g.plane + o];
-}
-
 // moments of an AoS post-stream state, with the conventions of the model's driver
 __global__ void k_moments_aos(const double* __restrict__ aos, long long n_nodes, int incompressible, double sx,
                               double sy, double* __restrict__ rho_out, double* __restrict__ u_out)
@@ -91,6 +102,7 @@ static int launch_bgk(lbm_domain* d, int row_begin, int row_end, bool do_interio
   p.Fy = d->ibm.d_Fy;
   if (do_interior && d->npairs > 0 && row_end > row_begin)
   {
+    ProfScope ps(d, LBM_PROF_INTERIOR);
     dim3 grid(cdiv(d->npairs, 128), row_end - row_begin);
     k_bgk_interior<MODE, EQ, FORCE, ADE><<<grid, 128, 0, d->stream>>>(
         d->buf[0][s], d->buf[0][t], d->buf[1][s], d->buf[1][t], d->g, p, row_begin, d->npairs, d->d_aos[0], d->d_aos[1]);
@@ -98,6 +110,7 @@ static int launch_bgk(lbm_domain* d, int row_begin, int row_end, bool do_interio
   }
   if (do_boundary && d->nb > 0)
   {
+    ProfScope ps(d, LBM_PROF_BOUNDARY);
     BoundaryTable bt;
     bt.n = d->nb;
     bt.x = d->d_bx;
@@ -143,6 +156,7 @@ static int dispatch_bgk(lbm_domain* d, int rb, int re, bool di, bool db)
 static int run_fixups(lbm_domain* d)
 {
   const int t = d->cur ^ 1;  // freshly written buffers
+  ProfScope ps(d, LBM_PROF_FIXUP);
   for (auto& grp : d->fix)
   {
     if (grp.n == 0) continue;
@@ -162,6 +176,7 @@ static int run_fixups(lbm_domain* d)
 // opposite rows when it is the whole domain (periodic wrap of solver::advect)
 int exchange_ghost_rows(lbm_domain* d, int which)
 {
+  ProfScope ps(d, LBM_PROF_GHOST);
   if (d->comm || d->link_lo || d->link_hi) return comm_exchange(d, which);
   for (int l = 0; l < d->nlat; l++)
   {
@@ -175,7 +190,11 @@ int exchange_ghost_rows(lbm_domain* d, int which)
 static int bgk_step_once(lbm_domain* d)
 {
   const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
-  if (d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM) LBM_TRY(ibm_prepass(d, mode));
+  if (d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM)
+  {
+    ProfScope ps(d, LBM_PROF_IBM);
+    LBM_TRY(ibm_prepass(d, mode));
+  }
   if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, 0, d->g.Xl, true, true));
   else LBM_TRY(dispatch_bgk<MODE_PULL>(d, 0, d->g.Xl, true, true));
   LBM_TRY(run_fixups(d));
@@ -204,7 +223,7 @@ static int export_post_stream(lbm_domain* d)
   {
     for (int l = 0; l < d->nlat; l++)
     {
-      k_export_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[l][d->cur], d->d_aos[l], d->g);
+      k_export_soa_to_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[l][d->cur], d->d_aos[l], d->g);
       d->launches++;
     }
     LBM_CUDA(cudaGetLastError());
@@ -276,11 +295,11 @@ static bool is_post_stream(int kind)
   return kind == LBM_BC_LINEAR || kind == LBM_BC_ABB_FIXED || kind == LBM_BC_ABB_EXTRAPOLATED || kind == LBM_BC_ADE_INLET;
 }
 
-static int commit_single_phase(lbm_domain* d)
+int commit_boundary_tables(lbm_domain* d)
 {
   const int X = d->cfg.X, Y = d->cfg.Y, x0 = d->cfg.x0, Xl = d->g.Xl;
   const SlabGeom& g = d->g;
-  const int y_int_end = 2 + 2 * d->npairs;  // first column past the interior pairs
+  const int y_int_begin = d->y_int_begin, y_int_end = d->y_int_end;  // columns owned by the interior kernel
 
   // ---- pass 1: which nodes need a table entry
   std::map<long long, int> index;  // local node id -> boundary index
@@ -290,7 +309,7 @@ static int commit_single_phase(lbm_domain* d)
   };
   for (int lx = 0; lx < Xl; lx++)
     for (int y = 0; y < Y; y++)
-      if (y < 2 || y >= y_int_end) touch(lx, y);
+      if (y < y_int_begin || y >= y_int_end) touch(lx, y);
   d->wrap_all_q = false;
   for (const auto& so : d->ops)
   {
@@ -528,7 +547,20 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
   d->g.xg0 = cfg->x0;
   d->g.plane = (long long)(d->g.Xl + 2) * d->g.pitch;
   d->nlat = cfg->model == LBM_MODEL_BGK ? 1 : 2;
-  d->npairs = cfg->Y >= 5 ? (cfg->Y - 3) / 2 : 0;
+  if (d->nlat == 1 || cfg->model == LBM_MODEL_BGK_ADE)
+  {
+    // two nodes per thread: pairs (y, y+1), y even, 2 <= y and y + 2 <= Y - 1
+    d->npairs = cfg->Y >= 5 ? (cfg->Y - 3) / 2 : 0;
+    d->y_int_begin = 2;
+    d->y_int_end = 2 + 2 * d->npairs;
+  }
+  else
+  {
+    // one node per thread: columns 1 .. Y-2
+    d->npairs = 0;
+    d->y_int_begin = 1;
+    d->y_int_end = cfg->Y - 1;
+  }
   const size_t bytes = (size_t)9 * d->g.plane * sizeof(double);
   for (int l = 0; l < d->nlat; l++)
     for (int b = 0; b < 2; b++)
@@ -570,6 +602,11 @@ int lbm_destroy(lbm_domain* d)
   }
   for (int k = 0; k < 2; k++)
     if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
+  for (auto& r : d->prof)
+  {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
   if (d->ev_begin) cudaEventDestroy(d->ev_begin);
   if (d->ev_end) cudaEventDestroy(d->ev_end);
   if (d->stream) cudaStreamDestroy(d->stream);
@@ -612,7 +649,7 @@ int lbm_bc_commit(lbm_domain* d)
   LBM_CUDA(cudaStreamSynchronize(d->stream));
   release_compiled(d);
   if (d->tp) return tp_commit(d);
-  return commit_single_phase(d);
+  return commit_boundary_tables(d);
 }
 
 int lbm_bc_get_mask(lbm_domain* d, int lattice, int32_t* mask)
@@ -658,9 +695,10 @@ int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos)
   k_import_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->d_aos[lattice], d->buf[lattice][d->cur], d->g);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
-  LBM_CUDA(cudaStreamSynchronize(d->stream));
   d->post_stream = true;
   d->have_state = true;
+  if (d->tp) LBM_TRY(tp_refresh_moments(d));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
   return LBM_OK;
 }
 
@@ -682,6 +720,7 @@ int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u)
   if (!d || lattice < 0 || lattice >= d->nlat) { set_error("lbm_get_moments: bad argument"); return LBM_ERR_INVALID; }
   if (!d->have_state || !d->committed) { set_error("lbm_get_moments: no state or boundary rules not committed"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
+  if (d->tp) return tp_read_moments(d, rho, u, nullptr, nullptr, nullptr);
   LBM_TRY(export_post_stream(d));
   const long long N = (long long)d->g.Xl * d->g.Y;
   double *d_rho = nullptr, *d_u = nullptr;
@@ -776,6 +815,36 @@ int lbm_use_graph(lbm_domain* d, int enable)
 {
   if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
   d->use_graph = enable != 0;
+  return LBM_OK;
+}
+
+int lbm_profile_enable(lbm_domain* d, int enable)
+{
+  if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  d->profiling = enable != 0;
+  d->prof_used = 0;
+  return LBM_OK;
+}
+
+int lbm_profile_read(lbm_domain* d, int cls, double* total_ms, long long* launches)
+{
+  if (!d || !total_ms || !launches || cls < 0 || cls >= LBM_PROF_CLASSES) { set_error("lbm_profile_read: bad argument"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  double sum = 0.0;
+  long long n = 0;
+  for (size_t i = 0; i < d->prof_used; i++)
+  {
+    if (d->prof[i].cls != cls) continue;
+    float ms = 0.f;
+    LBM_CUDA(cudaEventElapsedTime(&ms, d->prof[i].a, d->prof[i].b));
+    sum += ms;
+    n++;
+  }
+  *total_ms = sum;
+  *launches = n;
   return LBM_OK;
 }
 

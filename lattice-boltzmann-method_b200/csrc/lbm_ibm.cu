@@ -183,8 +183,8 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   ib.r0 = r_min; ib.r1 = r_max + 1; ib.c0 = c_min; ib.c1 = c_max + 1;
   ib.n_markers = n;
   ib.m_max = m_max;
-  const int y_int_end = 2 + 2 * d->npairs;
-  if (ib.r0 < d->cfg.x0 || ib.r1 > d->cfg.x1 || ib.c0 < 2 || ib.c1 > y_int_end)
+  const int y_int_end = d->y_int_end;
+  if (ib.r0 < d->cfg.x0 || ib.r1 > d->cfg.x1 || ib.c0 < d->y_int_begin || ib.c1 > y_int_end)
   {
     set_error("lbm_ibm_set_markers: ROI rows [%ld,%ld) cols [%ld,%ld) must lie inside this slab's rows [%d,%d) and interior columns [2,%d)",
               ib.r0, ib.r1, ib.c0, ib.c1, d->cfg.x0, d->cfg.x1, y_int_end);

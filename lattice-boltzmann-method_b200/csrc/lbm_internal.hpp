@@ -66,6 +66,12 @@ struct IbmState
   double* d_Fy = nullptr;
 };
 
+struct ProfRec
+{
+  cudaEvent_t a, b;
+  int cls;
+};
+
 struct TwoPhaseState;  // lbm_two_phase.cu
 struct CommState;      // lbm_comm.cu
 
@@ -80,7 +86,9 @@ struct lbm_domain
   int cur = 0;              // buffer holding the current state
   bool post_stream = true;  // true: buf[cur] = f_adve (just imported); false: buf[cur] = f_coll
   bool have_state = false;
-  int npairs = 0;           // interior column pairs per row
+  int npairs = 0;           // interior column pairs per row (single-phase kernels)
+  int y_int_begin = 2;      // columns [y_int_begin, y_int_end) belong to the interior kernel,
+  int y_int_end = 2;        // every other column is a listed (table-driven) node
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   float last_ms = 0.f;
@@ -106,6 +114,11 @@ struct lbm_domain
   lbm::CommState* comm = nullptr;
   lbm_domain *link_lo = nullptr, *link_hi = nullptr;
 
+  // optional per-kernel-class timing
+  bool profiling = false;
+  std::vector<lbm::ProfRec> prof;
+  size_t prof_used = 0;
+
   // CUDA graph of one steady-state step pair
   bool use_graph = false;
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
@@ -115,7 +128,16 @@ namespace lbm
 {
 // lbm_domain.cu
 int ensure_aos_scratch(lbm_domain* d);
+// brackets a group of launches of one class with events when profiling is on
+struct ProfScope
+{
+  lbm_domain* d;
+  long idx = -1;
+  ProfScope(lbm_domain* dom, int cls);
+  ~ProfScope();
+};
 int exchange_ghost_rows(lbm_domain* d, int which);
+int commit_boundary_tables(lbm_domain* d);
 // lbm_ibm.cu
 int ibm_release(lbm_domain* d);
 int ibm_prepass(lbm_domain* d, int mode);
@@ -125,7 +147,10 @@ int tp_destroy(lbm_domain* d);
 int tp_step(lbm_domain* d);
 int tp_commit(lbm_domain* d);
 int tp_export(lbm_domain* d);
+int tp_read_moments(lbm_domain* d, double* rho, double* u, double* ph, double* rr, double* rb);
+int tp_refresh_moments(lbm_domain* d);
 // lbm_comm.cu
 int comm_release(lbm_domain* d);
 int comm_exchange(lbm_domain* d, int which);
+int comm_exchange_moments(lbm_domain* d);  // two-phase: 2 ghost rows of the moment planes at slab cuts
 }  // namespace lbm

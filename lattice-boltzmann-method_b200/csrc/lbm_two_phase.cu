@@ -1,15 +1,731 @@
-// temporary: two-phase entry points not built yet
+// lbm_two_phase.cu — kernels and step sequencing of the colour-gradient models
+// (LBM_MODEL_MRTCG, LBM_MODEL_RK).  Arithmetic: lbm_two_phase.cuh.
+//
+// One time step = two passes over the grid:
+//   collide  : pull both lattices (post-collision buffers + boundary table) -> f_adve in registers,
+//              read the node's moments and the 5x5 (3x3 for RK) neighbourhood of the moment planes
+//              from a shared-memory tile with a 2-cell halo, collide, write f_coll (both colours).
+//   moments  : pull the fresh f_coll again, write rho_r, rho_b, u, phase of the NEW post-stream
+//              state for the next step's stencils (the drivers' end-of-iteration block,
+//              mrtcg_rayleigh_taylor.cpp:472-477).
+// Algorithmic traffic per node: 144 R + 40 R + 144 W (collide) + 144 R + 40 W (moments) = 512 B,
+// against SURVEY §8(d)'s 352 B model (which assumes the second population read is avoided).
+#include <cmath>
+#include <cstring>
+
 #include "lbm_internal.hpp"
+#include "lbm_two_phase.cuh"
+
 namespace lbm
 {
-int tp_create(lbm_domain*) { set_error("two-phase models are not built yet"); return LBM_ERR_UNSUPPORTED; }
-int tp_destroy(lbm_domain*) { return LBM_OK; }
-int tp_step(lbm_domain*) { return LBM_ERR_UNSUPPORTED; }
-int tp_commit(lbm_domain*) { return LBM_ERR_UNSUPPORTED; }
-int tp_export(lbm_domain*) { return LBM_ERR_UNSUPPORTED; }
+
+struct TwoPhaseState
+{
+  MomGeom mg;
+  double* mom = nullptr;  // M_COUNT planes
+  TpParams p;
+  int model = TP_MRTCG;
+};
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+constexpr int TILE_X = 8, TILE_Y = 32, HALO = 2;
+constexpr int SM_X = TILE_X + 2 * HALO, SM_Y = TILE_Y + 2 * HALO;
+
+// ------------------------------------------------------------------------------------------------
+// loaders
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void tp_load_interior(const double* __restrict__ src, const SlabGeom& g, int x, int y, double (&f)[9])
+{
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    if constexpr (MODE == MODE_LOCAL) f[q] = src[q * g.plane + node_off(g, x, y)];
+    else f[q] = src[q * g.plane + node_off(g, x - CX(q), y - CY(q))];
+  }
 }
-extern "C" {
-int lbm_get_phase(lbm_domain*, double*, double*, double*) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }
-int lbm_set_u(lbm_domain*, const double*) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }
-int lbm_init_two_phase(lbm_domain*, const double*, const double*, const double*) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }
+
+template <int MODE>
+__device__ __forceinline__ void tp_load_listed(const double* __restrict__ src, const SlabGeom& g, const BoundaryTable& t,
+                                               int lattice, int i, int x, int y, double (&f)[9])
+{
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    if constexpr (MODE == MODE_LOCAL) f[q] = src[q * g.plane + node_off(g, x, y)];
+    else
+    {
+      const BcEntry e = t.ent[(long long)(lattice * 9 + q) * t.n + i];
+      f[q] = e.coef * src[e.src] + e.cst;
+    }
+  }
 }
+
+// finite differences straight from the padded global planes (listed nodes, few of them)
+template <int MODEL>
+__device__ __forceinline__ void tp_stencil_global(const TpParams& p, const double* __restrict__ mom, const MomGeom& mg,
+                                                  int x, int y, TpStencil& st)
+{
+  const long long o = mom_off(mg, x, y);
+  const double* ph = mom + M_PH * mg.mplane;
+  st.gx = st.gy = st.rDxQx = st.rDyQy = st.bDxQx = st.bDyQy = 0.0;
+  if constexpr (MODEL == TP_RK)
+  {
+    // rk_static_droplet_test.cpp:52-62: "x" kernel differentiates along axis 1, "y" kernel along axis 0
+#pragma unroll
+    for (int a = -1; a <= 1; a++)
+#pragma unroll
+      for (int b = -1; b <= 1; b++)
+      {
+        const double v = ph[o + (long long)a * mg.pm + b];
+        const double wa = a == 0 ? 1.0 / 9.0 : 1.0 / 36.0, wb = b == 0 ? 1.0 / 9.0 : 1.0 / 36.0;
+        if (b != 0) st.gx += (3.0 * (wa * (double)b)) * v;
+        if (a != 0) st.gy += (3.0 * (wb * (double)a)) * v;
+      }
+  }
+  else
+  {
+    const double* RR = mom + M_RR * mg.mplane;
+    const double* RB = mom + M_RB * mg.mplane;
+    const double* UX = mom + M_UX * mg.mplane;
+    const double* UY = mom + M_UY * mg.mplane;
+#pragma unroll
+    for (int a = -2; a <= 2; a++)
+#pragma unroll
+      for (int b = -2; b <= 2; b++)
+      {
+        if (a == 0 && b == 0) continue;
+        const long long k = o + (long long)a * mg.pm + b;
+        const double w = XI5(a, b);
+        const double rr = RR[k], rb = RB[k], ux = UX[k], uy = UY[k], phv = ph[k];
+        if (a != 0)
+        {
+          st.gx += (w * (double)a) * phv;
+          st.rDxQx += (w * (double)a) * ((p.cr * rr) * ux);
+          st.bDxQx += (w * (double)a) * ((p.cb * rb) * ux);
+        }
+        if (b != 0)
+        {
+          st.gy += (w * (double)b) * phv;
+          st.rDyQy += (w * (double)b) * ((p.cr * rr) * uy);
+          st.bDyQy += (w * (double)b) * ((p.cb * rb) * uy);
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// collide, interior: block (TILE_Y, TILE_X) threads, one node per thread, columns 1 .. Y-2
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int MODE>
+__global__ void __launch_bounds__(TILE_X* TILE_Y)
+k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
+                      double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom,
+                      const TpParams p, int row_begin, int row_end)
+{
+  constexpr int NF = MODEL == TP_MRTCG ? 5 : 1;
+  __shared__ double sm[NF][SM_X][SM_Y + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x_t = row_begin + blockIdx.y * TILE_X, y_t = 1 + blockIdx.x * TILE_Y;  // tile origin
+  // stage phase (and the four momentum fields Q_k = (1.8 alpha_k - 0.8) rho_k u) with the halo
+  for (int n = ty * TILE_Y + tx; n < SM_X * SM_Y; n += TILE_X * TILE_Y)
+  {
+    const int i = n / SM_Y, j = n % SM_Y;
+    int xs = x_t - HALO + i, ys = y_t - HALO + j;
+    xs = min(xs, g.Xl + 1);
+    ys = min(ys, g.Y + 1);
+    const long long k = mom_off(mg, xs, ys);
+    sm[0][i][j] = mom[M_PH * mg.mplane + k];
+    if constexpr (MODEL == TP_MRTCG)
+    {
+      const double rr = mom[M_RR * mg.mplane + k], rb = mom[M_RB * mg.mplane + k];
+      const double ux = mom[M_UX * mg.mplane + k], uy = mom[M_UY * mg.mplane + k];
+      sm[1][i][j] = (p.cr * rr) * ux;
+      sm[2][i][j] = (p.cr * rr) * uy;
+      sm[3][i][j] = (p.cb * rb) * ux;
+      sm[4][i][j] = (p.cb * rb) * uy;
+    }
+  }
+  __syncthreads();
+  const int x = x_t + ty, y = y_t + tx;
+  if (x >= row_end || y > g.Y - 2) return;
+
+  TpStencil st;
+  st.gx = st.gy = st.rDxQx = st.rDyQy = st.bDxQx = st.bDyQy = 0.0;
+  const int ci = ty + HALO, cj = tx + HALO;
+  if constexpr (MODEL == TP_RK)
+  {
+#pragma unroll
+    for (int a = -1; a <= 1; a++)
+#pragma unroll
+      for (int b = -1; b <= 1; b++)
+      {
+        const double v = sm[0][ci + a][cj + b];
+        const double wa = a == 0 ? 1.0 / 9.0 : 1.0 / 36.0, wb = b == 0 ? 1.0 / 9.0 : 1.0 / 36.0;
+        if (b != 0) st.gx += (3.0 * (wa * (double)b)) * v;
+        if (a != 0) st.gy += (3.0 * (wb * (double)a)) * v;
+      }
+  }
+  else
+  {
+#pragma unroll
+    for (int a = -2; a <= 2; a++)
+#pragma unroll
+      for (int b = -2; b <= 2; b++)
+      {
+        if (a == 0 && b == 0) continue;
+        const double w = XI5(a, b);
+        if (a != 0)
+        {
+          st.gx += (w * (double)a) * sm[0][ci + a][cj + b];
+          st.rDxQx += (w * (double)a) * sm[1][ci + a][cj + b];
+          st.bDxQx += (w * (double)a) * sm[3][ci + a][cj + b];
+        }
+        if (b != 0)
+        {
+          st.gy += (w * (double)b) * sm[0][ci + a][cj + b];
+          st.rDyQy += (w * (double)b) * sm[2][ci + a][cj + b];
+          st.bDyQy += (w * (double)b) * sm[4][ci + a][cj + b];
+        }
+      }
+  }
+  const long long km = mom_off(mg, x, y);
+  const double rr = mom[M_RR * mg.mplane + km], rb = mom[M_RB * mg.mplane + km];
+  const double ux = mom[M_UX * mg.mplane + km], uy = mom[M_UY * mg.mplane + km];
+  const double ph = sm[0][ci][cj];
+
+  double fr[9], fb[9];
+  tp_load_interior<MODE>(rsrc, g, x, y, fr);
+  tp_load_interior<MODE>(bsrc, g, x, y, fb);
+  tp_collide<MODEL>(p, fr, fb, rr, rb, ux, uy, ph, st);
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    rdst[q * g.plane + o] = fr[q];
+    bdst[q * g.plane + o] = fb[q];
+  }
+}
+
+template <int MODEL, int MODE>
+__global__ void __launch_bounds__(128)
+k_tp_collide_listed(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
+                    double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom,
+                    const TpParams p, const BoundaryTable t)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n) return;
+  const int x = t.x[i], y = t.y[i];
+  TpStencil st;
+  tp_stencil_global<MODEL>(p, mom, mg, x, y, st);
+  const long long km = mom_off(mg, x, y);
+  const double rr = mom[M_RR * mg.mplane + km], rb = mom[M_RB * mg.mplane + km];
+  const double ux = mom[M_UX * mg.mplane + km], uy = mom[M_UY * mg.mplane + km], ph = mom[M_PH * mg.mplane + km];
+  double fr[9], fb[9];
+  tp_load_listed<MODE>(rsrc, g, t, 0, i, x, y, fr);
+  tp_load_listed<MODE>(bsrc, g, t, 1, i, x, y, fb);
+  tp_collide<MODEL>(p, fr, fb, rr, rb, ux, uy, ph, st);
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    rdst[q * g.plane + o] = fr[q];
+    bdst[q * g.plane + o] = fb[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// moments of the new post-stream state (and, with out_* set, its export in AoS)
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int MODE>
+__global__ void __launch_bounds__(256)
+k_tp_moments_interior(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                      double* __restrict__ mom, const TpParams p, double* __restrict__ out_r, double* __restrict__ out_b)
+{
+  const int y = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (y > g.Y - 2) return;
+  double fr[9], fb[9];
+  tp_load_interior<MODE>(rsrc, g, x, y, fr);
+  tp_load_interior<MODE>(bsrc, g, x, y, fb);
+  if (out_r)
+  {
+    double* a = out_r + ((long long)x * g.Y + y) * 9;
+    double* b = out_b + ((long long)x * g.Y + y) * 9;
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+    {
+      a[q] = fr[q];
+      b[q] = fb[q];
+    }
+    return;
+  }
+  double rr, rb, ux, uy, ph;
+  tp_moments<MODEL>(p, fr, fb, rr, rb, ux, uy, ph);
+  const long long k = mom_off(mg, x, y);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
+template <int MODEL, int MODE>
+__global__ void __launch_bounds__(128)
+k_tp_moments_listed(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                    double* __restrict__ mom, const TpParams p, const BoundaryTable t, double* __restrict__ out_r,
+                    double* __restrict__ out_b)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n) return;
+  const int x = t.x[i], y = t.y[i];
+  double fr[9], fb[9];
+  tp_load_listed<MODE>(rsrc, g, t, 0, i, x, y, fr);
+  tp_load_listed<MODE>(bsrc, g, t, 1, i, x, y, fb);
+  if (out_r)
+  {
+    double* a = out_r + ((long long)x * g.Y + y) * 9;
+    double* b = out_b + ((long long)x * g.Y + y) * 9;
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+    {
+      a[q] = fr[q];
+      b[q] = fb[q];
+    }
+    return;
+  }
+  double rr, rb, ux, uy, ph;
+  tp_moments<MODEL>(p, fr, fb, rr, rb, ux, uy, ph);
+  const long long k = mom_off(mg, x, y);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
+// replicate padding of the moment planes: columns first (all owned rows), then rows (whole padded width)
+__global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const MomGeom mg)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= g.Xl) return;
+#pragma unroll
+  for (int f = 0; f < M_COUNT; f++)
+  {
+    double* pl = mom + f * mg.mplane;
+    const double lo = pl[mom_off(mg, x, 0)], hi = pl[mom_off(mg, x, g.Y - 1)];
+    pl[mom_off(mg, x, -1)] = lo;
+    pl[mom_off(mg, x, -2)] = lo;
+    pl[mom_off(mg, x, g.Y)] = hi;
+    pl[mom_off(mg, x, g.Y + 1)] = hi;
+  }
+}
+
+// lo_global / hi_global: this slab holds the global first / last row, where the padding replicates;
+// elsewhere the two ghost rows come from the neighbouring slab (lbm_comm.cu)
+__global__ void k_tp_pad_rows(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int lo_global, int hi_global)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // padded column index 0 .. Y+3
+  if (j >= g.Y + 4) return;
+  const int y = j - 2;
+#pragma unroll
+  for (int f = 0; f < M_COUNT; f++)
+  {
+    double* pl = mom + f * mg.mplane;
+    if (lo_global)
+    {
+      const double v = pl[mom_off(mg, 0, y)];
+      pl[mom_off(mg, -1, y)] = v;
+      pl[mom_off(mg, -2, y)] = v;
+    }
+    if (hi_global)
+    {
+      const double v = pl[mom_off(mg, g.Xl - 1, y)];
+      pl[mom_off(mg, g.Xl, y)] = v;
+      pl[mom_off(mg, g.Xl + 1, y)] = v;
+    }
+  }
+}
+
+// initial state: adv_f = eq(rho_k, u) (mrtcg_rayleigh_taylor.cpp:409-410 ; rk_static_droplet_test.cpp:509-515)
+template <int MODEL>
+__global__ void k_tp_init(double* __restrict__ rbuf, double* __restrict__ bbuf, const SlabGeom g, const MomGeom mg,
+                          double* __restrict__ mom, const TpParams p, const double* __restrict__ rho_r,
+                          const double* __restrict__ rho_b, const double* __restrict__ u)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  double rr = rho_r[n], rb = rho_b[n];
+  const double ux = u[2 * n], uy = u[2 * n + 1];
+  const double uu = ux * ux + uy * uy;
+  double fr[9], fb[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    fr[q] = tp_feq<MODEL>(q, rr, p.r_phi, p.r_eta, ux, uy, uu);
+    fb[q] = tp_feq<MODEL>(q, rb, p.b_phi, p.b_eta, ux, uy, uu);
+  }
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    rbuf[q * g.plane + o] = fr[q];
+    bbuf[q * g.plane + o] = fb[q];
+  }
+  if constexpr (MODEL == TP_RK)
+  {
+    // the RK driver re-reads the densities from the populations (rk_static_droplet_test.cpp:513-514)
+    double jx, jy;
+    moments(fr, rr, jx, jy);
+    moments(fb, rb, jx, jy);
+  }
+  const long long k = mom_off(mg, x, y);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = phase_of(p, rr, rb);
+}
+
+// moments from imported populations (lbm_set_f on a two-phase domain)
+template <int MODEL>
+__global__ void k_tp_moments_local(const double* __restrict__ rbuf, const double* __restrict__ bbuf, const SlabGeom g,
+                                   const MomGeom mg, double* __restrict__ mom, const TpParams p)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  double fr[9], fb[9];
+  tp_load_interior<MODE_LOCAL>(rbuf, g, x, y, fr);
+  tp_load_interior<MODE_LOCAL>(bbuf, g, x, y, fb);
+  double rr, rb, ux, uy, ph;
+  tp_moments<MODEL>(p, fr, fb, rr, rb, ux, uy, ph);
+  const long long k = mom_off(mg, x, y);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
+__global__ void k_tp_read_moments(const double* __restrict__ mom, const SlabGeom g, const MomGeom mg, double* __restrict__ rho,
+                                  double* __restrict__ u, double* __restrict__ ph, double* __restrict__ rr_out,
+                                  double* __restrict__ rb_out)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const long long k = mom_off(mg, x, y);
+  const double rr = mom[M_RR * mg.mplane + k], rb = mom[M_RB * mg.mplane + k];
+  if (rho) rho[n] = rr + rb;
+  if (u)
+  {
+    u[2 * n] = mom[M_UX * mg.mplane + k];
+    u[2 * n + 1] = mom[M_UY * mg.mplane + k];
+  }
+  if (ph) ph[n] = mom[M_PH * mg.mplane + k];
+  if (rr_out) rr_out[n] = rr;
+  if (rb_out) rb_out[n] = rb;
+}
+
+__global__ void k_tp_write_u(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, const double* __restrict__ u)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const long long k = mom_off(mg, x, y);
+  mom[M_UX * mg.mplane + k] = u[2 * n];
+  mom[M_UY * mg.mplane + k] = u[2 * n + 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static void fill_colour(const lbm_colour_desc& c, double (&phi)[3], double (&eta)[3], double& cs2)
+{
+  cs2 = 3.0 * (1.0 - c.alpha) / 5.0;  // src/colour.cpp:37
+  phi[0] = c.alpha;
+  phi[1] = 0.2 * (1.0 - c.alpha);
+  phi[2] = 0.05 * (1.0 - c.alpha);
+  for (int k = 0; k < 3; k++) eta[k] = 1.0 + 0.5 * (3.0 * cs2 - 1.0) * (3.0 * (double)k - 4.0);
+}
+
+int tp_create(lbm_domain* d)
+{
+  TwoPhaseState* tp = new TwoPhaseState();
+  d->tp = tp;
+  tp->model = d->cfg.model == LBM_MODEL_MRTCG ? TP_MRTCG : TP_RK;
+  tp->mg.pm = ((d->g.Y + 4 + 15) / 16) * 16;
+  tp->mg.mplane = (long long)(d->g.Xl + 4) * tp->mg.pm;
+  const size_t bytes = sizeof(double) * M_COUNT * tp->mg.mplane;
+  LBM_CUDA(cudaMalloc(&tp->mom, bytes));
+  LBM_CUDA(cudaMemset(tp->mom, 0, bytes));
+  TpParams& p = tp->p;
+  const lbm_config& c = d->cfg;
+  if (!(c.red.rho_0 > 0.0) || !(c.blue.rho_0 > 0.0) || !(c.delta > 0.0))
+  {
+    set_error("two-phase model: red/blue initial_density and delta must be positive");
+    return LBM_ERR_INVALID;
+  }
+  double r_cs2, b_cs2;
+  fill_colour(c.red, p.r_phi, p.r_eta, r_cs2);
+  fill_colour(c.blue, p.b_phi, p.b_eta, b_cs2);
+  p.r_rho0 = c.red.rho_0; p.b_rho0 = c.blue.rho_0;
+  p.r_beta = c.red.beta; p.b_beta = c.blue.beta;
+  p.r_A = c.red.A; p.b_A = c.blue.A;
+  p.cr = 1.8 * c.red.alpha - 0.8;
+  p.cb = 1.8 * c.blue.alpha - 0.8;
+  p.sigma = c.sigma;
+  p.Fg0 = c.Fg[0]; p.Fg1 = c.Fg[1];
+  p.add_force = c.add_force;
+  p.delta = c.delta;
+  if (tp->model == TP_MRTCG)
+  {
+    // relaxation_function{r, b, delta}: omegas from nu and the colour's own cs2 (mrtcg_rayleigh_taylor.cpp:57-66)
+    p.r_val = 1.0 / (0.5 + c.red.nu / r_cs2);
+    p.b_val = 1.0 / (0.5 + c.blue.nu / b_cs2);
+  }
+  else
+  {
+    // colour::init_omega with cs2 = 1/3, blended in tau space (rk_static_droplet_test.cpp:264-265,320-323)
+    const double cs2 = 1.0 / 3.0;
+    const double r_om = 1.0 / (0.5 + c.red.nu / cs2), b_om = 1.0 / (0.5 + c.blue.nu / cs2);
+    p.r_val = 1.0 / r_om;
+    p.b_val = 1.0 / b_om;
+  }
+  p.s1 = 2.0 * p.r_val * p.b_val / (p.r_val + p.b_val);
+  p.s2 = 2.0 * (p.r_val - p.s1) / p.delta;
+  p.s3 = -p.s2 / (2.0 * p.delta);
+  p.t2 = 2.0 * (p.s1 - p.b_val) / p.delta;
+  p.t3 = p.t2 / (2.0 * p.delta);
+  return LBM_OK;
+}
+
+int tp_destroy(lbm_domain* d)
+{
+  if (!d->tp) return LBM_OK;
+  cudaFree(d->tp->mom);
+  delete d->tp;
+  d->tp = nullptr;
+  return LBM_OK;
+}
+
+static BoundaryTable table_of(lbm_domain* d)
+{
+  BoundaryTable bt;
+  bt.n = d->nb;
+  bt.x = d->d_bx;
+  bt.y = d->d_by;
+  bt.ent = d->d_ent;
+  bt.mom_cur = nullptr;
+  bt.mom_prev = nullptr;
+  return bt;
+}
+
+int tp_pad(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg);
+  const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
+  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi);
+  d->launches += 2;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+template <int MODEL, int MODE>
+static int tp_launch_collide(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  const int s = d->cur, t = d->cur ^ 1;
+  const int Yi = d->g.Y - 2;
+  if (Yi > 0)
+  {
+    ProfScope ps(d, LBM_PROF_INTERIOR);
+    dim3 grid(cdiv(Yi, TILE_Y), cdiv(d->g.Xl, TILE_X)), block(TILE_Y, TILE_X);
+    k_tp_collide_interior<MODEL, MODE><<<grid, block, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g,
+                                                                     tp->mg, tp->mom, tp->p, 0, d->g.Xl);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    ProfScope ps(d, LBM_PROF_BOUNDARY);
+    k_tp_collide_listed<MODEL, MODE><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t],
+                                                                             d->g, tp->mg, tp->mom, tp->p, table_of(d));
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+// moments (out == nullptr) or AoS export (out set) of the post-stream state pulled from buffer `which`
+template <int MODEL>
+static int tp_launch_moments(lbm_domain* d, int which, double* out_r, double* out_b)
+{
+  TwoPhaseState* tp = d->tp;
+  const int Yi = d->g.Y - 2;
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  if (Yi > 0)
+  {
+    dim3 grid(cdiv(Yi, 256), d->g.Xl);
+    k_tp_moments_interior<MODEL, MODE_PULL><<<grid, 256, 0, d->stream>>>(d->buf[0][which], d->buf[1][which], d->g, tp->mg, tp->mom,
+                                                                        tp->p, out_r, out_b);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    k_tp_moments_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][which], d->buf[1][which], d->g, tp->mg,
+                                                                                  tp->mom, tp->p, table_of(d), out_r, out_b);
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+int tp_step(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  const bool local = d->post_stream;
+  if (tp->model == TP_MRTCG)
+  {
+    if (local) LBM_TRY((tp_launch_collide<TP_MRTCG, MODE_LOCAL>(d)));
+    else LBM_TRY((tp_launch_collide<TP_MRTCG, MODE_PULL>(d)));
+  }
+  else
+  {
+    if (local) LBM_TRY((tp_launch_collide<TP_RK, MODE_LOCAL>(d)));
+    else LBM_TRY((tp_launch_collide<TP_RK, MODE_PULL>(d)));
+  }
+  LBM_TRY(exchange_ghost_rows(d, d->cur ^ 1));
+  d->cur ^= 1;
+  d->post_stream = false;
+  if (tp->model == TP_MRTCG) LBM_TRY(tp_launch_moments<TP_MRTCG>(d, d->cur, nullptr, nullptr));
+  else LBM_TRY(tp_launch_moments<TP_RK>(d, d->cur, nullptr, nullptr));
+  {
+    ProfScope ps(d, LBM_PROF_GHOST);
+    LBM_TRY(tp_pad(d));
+    LBM_TRY(comm_exchange_moments(d));
+  }
+  return LBM_OK;
+}
+
+int tp_commit(lbm_domain* d)
+{
+  for (const auto& so : d->ops)
+    if (so.op.kind != LBM_BC_LINEAR)
+    {
+      set_error("two-phase models take LBM_BC_LINEAR rules only");
+      return LBM_ERR_UNSUPPORTED;
+    }
+  return commit_boundary_tables(d);
+}
+
+// post-stream populations of both colours into d_aos[] (device, reference layout)
+int tp_export(lbm_domain* d)
+{
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (d->post_stream)
+  {
+    for (int l = 0; l < 2; l++)
+    {
+      k_export_soa_to_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[l][d->cur], d->d_aos[l], d->g);
+      d->launches++;
+    }
+    LBM_CUDA(cudaGetLastError());
+    return LBM_OK;
+  }
+  if (d->tp->model == TP_MRTCG) return tp_launch_moments<TP_MRTCG>(d, d->cur, d->d_aos[0], d->d_aos[1]);
+  return tp_launch_moments<TP_RK>(d, d->cur, d->d_aos[0], d->d_aos[1]);
+}
+
+int tp_read_moments(lbm_domain* d, double* rho, double* u, double* ph, double* rr, double* rb)
+{
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  double* tmp = nullptr;
+  LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 6 * N));
+  double *d_rho = tmp, *d_u = tmp + N, *d_ph = tmp + 3 * N, *d_rr = tmp + 4 * N, *d_rb = tmp + 5 * N;
+  k_tp_read_moments<<<cdiv(N, 256), 256, 0, d->stream>>>(d->tp->mom, d->g, d->tp->mg, d_rho, d_u, d_ph, d_rr, d_rb);
+  d->launches++;
+  if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d_rho, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  if (u) LBM_CUDA(cudaMemcpyAsync(u, d_u, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, d->stream));
+  if (ph) LBM_CUDA(cudaMemcpyAsync(ph, d_ph, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  if (rr) LBM_CUDA(cudaMemcpyAsync(rr, d_rr, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  if (rb) LBM_CUDA(cudaMemcpyAsync(rb, d_rb, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  cudaFree(tmp);
+  return LBM_OK;
+}
+
+// after lbm_set_f on a two-phase domain: rebuild the moment planes from the imported populations
+int tp_refresh_moments(lbm_domain* d)
+{
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (d->tp->model == TP_MRTCG)
+    k_tp_moments_local<TP_MRTCG><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p);
+  else
+    k_tp_moments_local<TP_RK><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p);
+  d->launches++;
+  LBM_TRY(tp_pad(d));
+  return comm_exchange_moments(d);
+}
+
+}  // namespace lbm
+
+using namespace lbm;
+
+extern "C"
+{
+
+int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b)
+{
+  if (!d || !d->tp) { set_error("lbm_get_phase: not a two-phase domain"); return LBM_ERR_INVALID; }
+  if (!d->have_state) { set_error("lbm_get_phase: no state"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  return tp_read_moments(d, nullptr, nullptr, phase, rho_r, rho_b);
+}
+
+int lbm_set_u(lbm_domain* d, const double* u_aos)
+{
+  if (!d || !d->tp || !u_aos) { set_error("lbm_set_u: not a two-phase domain / null argument"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  double* tmp = nullptr;
+  LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 2 * N));
+  LBM_CUDA(cudaMemcpyAsync(tmp, u_aos, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, d->stream));
+  k_tp_write_u<<<cdiv(N, 256), 256, 0, d->stream>>>(d->tp->mom, d->g, d->tp->mg, tmp);
+  d->launches++;
+  int s = tp_pad(d);
+  if (s == LBM_OK) s = comm_exchange_moments(d);
+  cudaStreamSynchronize(d->stream);
+  cudaFree(tmp);
+  return s;
+}
+
+int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, const double* u)
+{
+  if (!d || !d->tp || !rho_r || !rho_b || !u) { set_error("lbm_init_two_phase: not a two-phase domain / null argument"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  double* tmp = nullptr;
+  LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 4 * N));
+  LBM_CUDA(cudaMemcpyAsync(tmp, rho_r, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
+  LBM_CUDA(cudaMemcpyAsync(tmp + N, rho_b, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
+  LBM_CUDA(cudaMemcpyAsync(tmp + 2 * N, u, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, d->stream));
+  if (d->tp->model == TP_MRTCG)
+    k_tp_init<TP_MRTCG><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p, tmp, tmp + N, tmp + 2 * N);
+  else
+    k_tp_init<TP_RK><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p, tmp, tmp + N, tmp + 2 * N);
+  d->launches++;
+  int s = tp_pad(d);
+  if (s == LBM_OK) s = comm_exchange_moments(d);
+  cudaStreamSynchronize(d->stream);
+  cudaFree(tmp);
+  if (s != LBM_OK) return s;
+  d->post_stream = true;
+  d->have_state = true;
+  return LBM_OK;
+}
+
+}  // extern "C"

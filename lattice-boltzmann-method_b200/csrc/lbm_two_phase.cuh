@@ -1,0 +1,243 @@
+// lbm_two_phase.cuh — per-node arithmetic of the two colour-gradient models.
+//
+//   MODEL_MRTCG : test/mrtcg_rayleigh_taylor.cpp:431-464 (and mrtcg_static_droplet.cpp, same operators)
+//   MODEL_RK    : test/rk_static_droplet_test.cpp:157-262,544-609
+//
+// Two lattices (red = 0, blue = 1) in the same SoA layout as the single-phase family, plus five
+// scalar moment planes (rho_r, rho_b, u_x, u_y, phase) padded by two replicated cells on every
+// side — the padding of the reference's replicate-mode Conv2d (src/differential.cpp:8-9) — so the
+// 5x5 / 3x3 finite differences never clamp an index.
+#pragma once
+#include "lbm_device.cuh"
+
+namespace lbm
+{
+
+enum TpModel { TP_MRTCG = 0, TP_RK = 1 };
+
+struct TpParams
+{
+  double r_rho0, b_rho0, r_beta, b_beta, r_A, b_A;
+  double r_phi[3], b_phi[3];  // by |c|^2 class: q = 0, q = 1..4, q = 5..8  (src/colour.cpp:56-64)
+  double r_eta[3], b_eta[3];  // src/colour.cpp:49-54
+  double cr, cb;              // (1.8 alpha_k - 0.8)   (mrtcg_rayleigh_taylor.cpp:328-329)
+  double sigma, Fg0, Fg1;
+  int add_force;
+  // relaxation blend (mrtcg_rayleigh_taylor.cpp:34-100 in omega; rk_static_droplet_test.cpp:287-359 in tau)
+  double delta, r_val, b_val, s1, s2, s3, t2, t3;
+};
+
+struct MomGeom
+{
+  int pm;            // pitch of a moment plane (>= Y + 4, multiple of 16)
+  long long mplane;  // (Xl + 4) * pm
+};
+
+enum MomPlane { M_RR = 0, M_RB = 1, M_UX = 2, M_UY = 3, M_PH = 4, M_COUNT = 5 };
+
+__device__ __forceinline__ long long mom_off(const MomGeom& m, int x, int y) { return (long long)(x + 2) * m.pm + (y + 2); }
+
+__host__ __device__ __forceinline__ constexpr int QCLASS(int q) { return q == 0 ? 0 : (q < 5 ? 1 : 2); }
+
+// B of the perturbation operator (mrtcg_rayleigh_taylor.cpp:158-163)
+__host__ __device__ __forceinline__ constexpr double BQ(int q) { return q == 0 ? -4.0 / 27.0 : (q < 5 ? 2.0 / 27.0 : 5.0 / 108.0); }
+
+// 5x5 isotropic weights xi[|a|][|b|] / 5040 (src/differential.hpp:9-18)
+__host__ __device__ __forceinline__ constexpr double XI5(int a, int b)
+{
+  const int aa = a < 0 ? -a : a, bb = b < 0 ? -b : b;
+  return (aa == 0 ? (bb == 0 ? 0.0 : (bb == 1 ? 960.0 : 84.0))
+                  : (aa == 1 ? (bb == 0 ? 960.0 : (bb == 1 ? 448.0 : 32.0)) : (bb == 0 ? 84.0 : (bb == 1 ? 32.0 : 1.0)))) *
+         (1.0 / 5040.0);
+}
+
+// M (Lallemand-Luo ordering rho,e,eps,jx,qx,jy,qy,pxx,pxy) and 36 M^-1 (mrtcg_rayleigh_taylor.cpp:130-156)
+__host__ __device__ __forceinline__ constexpr double MM(int a, int q)
+{
+  switch (a)
+  {
+    case 0: return 1.0;
+    case 1: return q == 0 ? -4.0 : (q < 5 ? -1.0 : 2.0);
+    case 2: return q == 0 ? 4.0 : (q < 5 ? -2.0 : 1.0);
+    case 3: return (double)CX(q);
+    case 4: return q < 5 ? -2.0 * (double)CX(q) : (double)CX(q);
+    case 5: return (double)CY(q);
+    case 6: return q < 5 ? -2.0 * (double)CY(q) : (double)CY(q);
+    case 7: return (q == 1 || q == 3) ? 1.0 : ((q == 2 || q == 4) ? -1.0 : 0.0);
+    default: return (q == 5 || q == 7) ? 1.0 : ((q == 6 || q == 8) ? -1.0 : 0.0);
+  }
+}
+__host__ __device__ __forceinline__ constexpr double MI36(int q, int a)
+{
+  switch (a)
+  {
+    case 0: return 4.0;
+    case 1: return q == 0 ? -4.0 : (q < 5 ? -1.0 : 2.0);
+    case 2: return q == 0 ? 4.0 : (q < 5 ? -2.0 : 1.0);
+    case 3: return 6.0 * (double)CX(q);
+    case 4: return q < 5 ? -6.0 * (double)CX(q) : 3.0 * (double)CX(q);
+    case 5: return 6.0 * (double)CY(q);
+    case 6: return q < 5 ? -6.0 * (double)CY(q) : 3.0 * (double)CY(q);
+    case 7: return (q == 1 || q == 3) ? 9.0 : ((q == 2 || q == 4) ? -9.0 : 0.0);
+    default: return (q == 5 || q == 7) ? 9.0 : ((q == 6 || q == 8) ? -9.0 : 0.0);
+  }
+}
+
+// relaxation_function::eval; a NaN phase matches no branch (the reference then keeps the previous
+// value, zero on the first step)
+__device__ __forceinline__ double relax_eval(const TpParams& p, double psi)
+{
+  double s = 0.0;
+  if (psi > p.delta) s = p.r_val;
+  if (p.delta >= psi && psi > 0.0) s = p.s1 + p.s2 * psi + p.s3 * psi * psi;
+  if (0.0 >= psi && psi >= -p.delta) s = p.s1 + p.t2 * psi + p.t3 * psi * psi;
+  if (psi < -p.delta) s = p.b_val;
+  return s;
+}
+
+// eval_phase_field (mrtcg_rayleigh_taylor.cpp:212-225)
+__device__ __forceinline__ double phase_of(const TpParams& p, double rr, double rb)
+{
+  return (rr / p.r_rho0 - rb / p.b_rho0) / (rr / p.r_rho0 + rb / p.b_rho0);
+}
+
+// Moments of a freshly streamed node: what the drivers compute at the END of an iteration
+// (mrtcg_rayleigh_taylor.cpp:472-477 ; rk_static_droplet_test.cpp:602-609).
+template <int MODEL>
+__device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)[9], const double (&fb)[9], double& rr,
+                                           double& rb, double& ux, double& uy, double& ph)
+{
+  double jx, jy, dummy;
+  moments(fr, rr, jx, jy);
+  moments(fb, rb, jx, jy);
+  const double rho = rr + rb;
+  double t[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) t[q] = fr[q] + fb[q];
+  moments(t, dummy, jx, jy);
+  ux = jx / rho;
+  uy = jy / rho;
+  if constexpr (MODEL == TP_MRTCG)
+  {
+    ux = ux + 0.5 * p.Fg0 / rho;
+    uy = uy + 0.5 * p.Fg1 / rho;
+  }
+  ph = phase_of(p, rr, rb);
+}
+
+// eval_equilibrium of one colour
+template <int MODEL>
+__device__ __forceinline__ double tp_feq(int q, double rho_k, const double (&phi)[3], const double (&eta)[3], double ux,
+                                         double uy, double uu)
+{
+  const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
+  if constexpr (MODEL == TP_MRTCG)  // mrtcg_rayleigh_taylor.cpp:233-247 (note 9 and 3, not 4.5 and 1.5)
+    return rho_k * (phi[QCLASS(q)] + W(q) * ((3.0 * ue) * eta[QCLASS(q)] + 9.0 * (ue * ue) - 3.0 * uu));
+  else  // rk_static_droplet_test.cpp:183-199
+    return rho_k * (phi[QCLASS(q)] + ((3.0 * ue + 4.5 * (ue * ue)) - 1.5 * uu) * W(q));
+}
+
+// Stencil results a collision needs
+struct TpStencil
+{
+  double gx, gy;               // grad(phase): MRTCG axis-0 / axis-1 derivatives; RK the driver's swapped pair
+  double rDxQx, rDyQy, bDxQx, bDyQy;  // MRTCG only
+};
+
+// One two-colour collision in registers: fr/fb in = post-stream, out = post-collision.
+template <int MODEL>
+__device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], double (&fb)[9], double rr, double rb,
+                                           double ux, double uy, double ph, const TpStencil& st)
+{
+  const double uu = ux * ux + uy * uy;
+  const double gn = sqrt(st.gx * st.gx + st.gy * st.gy);
+  if constexpr (MODEL == TP_RK)
+  {
+    // relax = 1/tau(phase) (:587-588); omega1 = relax (feq - f) (:255-262); omega2 Reis (:239-245); col = f + (w1 + w2)
+    const double relax = 1.0 / relax_eval(p, ph);
+    const double gn2 = gn * gn;
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+    {
+      const double fe = st.gx * (double)CX(q) + st.gy * (double)CY(q);
+      const double core = ((fe * fe) / (1e-20 + gn2)) * W(q) - BQ(q);
+      const double o1r = relax * (tp_feq<TP_RK>(q, rr, p.r_phi, p.r_eta, ux, uy, uu) - fr[q]);
+      const double o1b = relax * (tp_feq<TP_RK>(q, rb, p.b_phi, p.b_eta, ux, uy, uu) - fb[q]);
+      fr[q] = fr[q] + (o1r + ((0.5 * p.r_A) * gn) * core);
+      fb[q] = fb[q] + (o1b + ((0.5 * p.b_A) * gn) * core);
+    }
+  }
+  else
+  {
+    const double rho = rr + rb;
+    const double s_nu = relax_eval(p, ph);
+    // S = diag(0, 1.25, 1.14, 0, 1.6, 0, 1.6, s_nu, s_nu) (:384-387, update_S)
+    const double S[9] = {0.0, 1.25, 1.14, 0.0, 1.6, 0.0, 1.6, s_nu, s_nu};
+    double o1r[9], o1b[9];
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+    {
+      const double rk = k == 0 ? rr : rb;
+      double d[9], m[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+        d[q] = (k == 0 ? tp_feq<TP_MRTCG>(q, rk, p.r_phi, p.r_eta, ux, uy, uu) - fr[q]
+                       : tp_feq<TP_MRTCG>(q, rk, p.b_phi, p.b_eta, ux, uy, uu) - fb[q]);
+      const double DxQx = k == 0 ? st.rDxQx : st.bDxQx, DyQy = k == 0 ? st.rDyQy : st.bDyQy;
+#pragma unroll
+      for (int a = 0; a < 9; a++)
+      {
+        double s = 0.0;
+        if (a != 0 && a != 3 && a != 5)  // conserved moments: S = 0 and C = 0 there
+        {
+#pragma unroll
+          for (int q = 0; q < 9; q++)
+            if (MM(a, q) != 0.0) s += MM(a, q) * d[q];
+        }
+        double c = 0.0;
+        if (a == 1) c = 3.0 * (1.0 - 0.5 * 1.25) * (DxQx + DyQy);  // update_C (:320-336)
+        if (a == 7) c = (1.0 - 0.5 * s_nu) * (DxQx - DyQy);
+        m[a] = S[a] * s + c;
+      }
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+      {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 1; a < 9; a++)
+          if (a != 3 && a != 5 && MI36(q, a) != 0.0) s += ((1.0 / 36.0) * MI36(q, a)) * m[a];
+        if (k == 0) o1r[q] = s;
+        else o1b[q] = s;
+      }
+    }
+    const double A = 4.5 * p.sigma * s_nu;
+    const double inv = 1e-20 + gn;
+    const double uF = ux * p.Fg0 + uy * p.Fg1;
+    constexpr double SQ2 = 1.4142135623730951;
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+    {
+      const double ge = st.gx * (double)CX(q) + st.gy * (double)CY(q);
+      const double t = ge / inv;
+      const double o2 = A * ((0.5 * gn) * (W(q) * (t * t) - BQ(q)));  // eval_xi, eval_per_operator
+      const double nrm = q < 5 ? 1.0 : SQ2;
+      const double gue = st.gx * ((double)CX(q) / nrm) + st.gy * ((double)CY(q) / nrm);
+      const double kap = (((rr * rb) * gue) * (rr * p.r_phi[QCLASS(q)] + rb * p.b_phi[QCLASS(q)])) / ((rho * rho) * inv);  // eval_kappa
+      const double total = ((((fr[q] + o1r[q]) + o2) + fb[q]) + o1b[q]) + o2;  // :455
+      double nr = rr * total / rho + p.r_beta * kap;                           // eval_rec_operator
+      double nb = rb * total / rho + p.b_beta * kap;
+      if (p.add_force)  // :460-464 (ics2 = 3, ics4 = 9)
+      {
+        const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
+        const double Fe = (double)CX(q) * p.Fg0 + (double)CY(q) * p.Fg1;
+        const double src = ((1.0 - 0.5 * s_nu) * ((3.0 + 9.0 * ue) * Fe - 3.0 * uF)) * W(q);
+        nr += src;
+        nb += src;
+      }
+      fr[q] = nr;
+      fb[q] = nb;
+    }
+  }
+}
+
+}  // namespace lbm

@@ -97,7 +97,9 @@ EXPORTS = [
     "lbm_differential3", "lbm_params_from_toml", "lbm_colour_from_toml", "lbm_two_phase_from_toml",
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
+    "lbm_profile_enable", "lbm_profile_read",
 ]
+PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
 _lib = None
 
@@ -135,6 +137,8 @@ def load():
         _lib.lbm_kernel_launches.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         _lib.lbm_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         _lib.lbm_use_graph.argtypes = [C.c_void_p, C.c_int]
+        _lib.lbm_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        _lib.lbm_profile_read.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_longlong)]
         _lib.lbm_comm_unique_id.argtypes = [C.c_char_p]
         _lib.lbm_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.lbm_link_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -346,6 +350,14 @@ class Domain:
         s = C.c_void_p()
         _chk(self.lib.lbm_get_stream(self.h, C.byref(s)))
         return s.value
+
+    def profile_enable(self, enable=True):
+        _chk(self.lib.lbm_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self, prof_class):
+        ms = C.c_double(); n = C.c_longlong()
+        _chk(self.lib.lbm_profile_read(self.h, prof_class, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def use_graph(self, enable=True):
         _chk(self.lib.lbm_use_graph(self.h, 1 if enable else 0))

@@ -9,6 +9,7 @@
 #include <torch/torch.h>
 #include <toml++/toml.hpp>
 
+#include <chrono>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -221,6 +222,69 @@ int ref_ibm_force(const char* toml_path, const char* name, const double* u, cons
     auto F = ib.eulerian_force_density(tu, tr);
     copy_out(F, F_out);
   }
+  REF_CATCH
+}
+
+// Times the loop body of test/cylinder_test.cpp:100-163 (the statements below are that loop,
+// calling the reference's own solver:: / ibm functions; snapshots and prompts left out) on a
+// {X,Y} grid: `warmup` untimed + `steps` timed iterations.  Used by bench.py as the CPU baseline
+// ("kind": "reference").  markers_toml holds `[cylinder-a] x=[..] y=[..]`.
+int ref_cylinder_loop(int X, int Y, double omega, double u_lb, const char* markers_toml, int warmup, int steps,
+                      double* seconds_per_step, double* checksum)
+{
+  REF_TRY
+  using torch::Tensor;
+  using torch::indexing::Slice;
+  using torch::indexing::Ellipsis;
+  using solver::E;
+  using solver::c;
+  toml::table tbl_boundary = toml::parse_file(markers_toml);
+  const torch::Device dev = torch::kCPU;
+  Tensor f_equi = torch::zeros({X, Y, 9}, dev);
+  Tensor f_coll = torch::zeros_like(f_equi, dev);
+  Tensor f_adve = torch::zeros_like(f_equi, dev);
+  Tensor u = torch::zeros({X, Y, 2}, dev);
+  Tensor rho = torch::ones({X, Y, 1}, dev);
+  ibm ib{tbl_boundary, "cylinder-a", dev};
+  Tensor F, S;
+  const double ics2 = 1.0 / 3.0, ics4 = 1.0 / 9.0;
+  Tensor equi_populations = torch::zeros_like(f_equi);
+  Tensor u_w = torch::zeros({Y, 2}, dev);
+  u_w.index({Slice(), 0}) = u_lb;
+  u.index({Ellipsis, 0}) = u_lb;
+  Tensor abb_bc = torch::zeros({Y, 1}, dev);
+  solver::incomp_equilibrium(f_adve, u, rho);
+  std::chrono::steady_clock::time_point t0;
+  for (int t = 0; t < warmup + steps; t++)
+  {
+    if (t == warmup) t0 = std::chrono::steady_clock::now();
+    solver::calc_rho(rho, f_adve);
+    solver::calc_u(u, f_adve, rho);
+    solver::equilibrium(f_equi, u, rho);
+    equi_populations.copy_(-omega * (f_adve - f_equi));
+    F = ib.eulerian_force_density(u, rho);
+    auto u_roi = u.index({ib.rows, ib.cols, Slice()});
+    S = ((1 - 0.5 * omega) * ((ics2 + ics4 * u_roi.matmul(c)) * F.matmul(c) - ics2 * (u_roi * F).sum(2).unsqueeze(2)) * E).clone().detach();
+    f_coll.copy_(f_adve + equi_populations);
+    f_coll.index({ib.rows, ib.cols, Slice()}) += S;
+    solver::advect(f_adve, f_coll);
+    const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    for (int row : {0, -1})
+    {
+      abb_bc = ((2.0 + 9.0 * torch::pow(u_w.matmul(c), 2.0) - 3.0 * u_w.mul(u_w).sum(1).unsqueeze(1)) * E).squeeze(0).clone().detach();
+      for (int q : {1, 2, 3, 4, 5, 6, 7, 8})
+        f_adve.index({row, Slice(), opp[q]}) = (-f_coll.index({row, Slice(), q}) + abb_bc.index({Slice(), q})).clone().detach();
+    }
+    f_adve.index({Slice(), -1, 4}) = f_coll.index({Slice(), -1, 2}).clone().detach();
+    f_adve.index({Slice(), -1, 7}) = f_coll.index({Slice(), -1, 6}).clone().detach();
+    f_adve.index({Slice(), -1, 8}) = f_coll.index({Slice(), -1, 5}).clone().detach();
+    f_adve.index({Slice(), 0, 2}) = f_coll.index({Slice(), 0, 4}).clone().detach();
+    f_adve.index({Slice(), 0, 5}) = f_coll.index({Slice(), 0, 8}).clone().detach();
+    f_adve.index({Slice(), 0, 6}) = f_coll.index({Slice(), 0, 7}).clone().detach();
+  }
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *seconds_per_step = dt / steps;
+  *checksum = f_adve.sum().item<double>();
   REF_CATCH
 }
 

@@ -68,3 +68,22 @@ def sedimentation(X, Y, omega, u_lb, w_s, C_w, walls):
 
 def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+RED = dict(rho_0=3.0, alpha=0.7, A=0.5, nu=0.04, beta=0.7)     # configs/mrtcg-rayleigh-taylor-gamma3.toml
+BLUE = dict(rho_0=1.0, alpha=0.1, A=0.5, nu=0.04, beta=-0.7)
+RK_RED = dict(rho_0=1.2, alpha=1.0 / 3.0, A=1e-4, nu=0.16, beta=0.7)   # rk_static_droplet_test.cpp:504-506
+RK_BLUE = dict(rho_0=1.0, alpha=0.2, A=1e-4, nu=0.14, beta=-0.7)
+
+
+def mrtcg(R, C, Fg, add_force, sigma=0.1, **slab):
+    d = L.Domain(L.default_config(model=L.MODEL_MRTCG, X=R, Y=C, red=RED, blue=BLUE, sigma=sigma, delta=0.1,
+                                  Fg=Fg, add_force=add_force, **slab))
+    d.preset_mrtcg()
+    return d
+
+
+def rk(Ln, **slab):
+    d = L.Domain(L.default_config(model=L.MODEL_RK, X=Ln, Y=Ln, red=RK_RED, blue=RK_BLUE, delta=0.98, **slab))
+    d.preset_rk()
+    return d

@@ -331,6 +331,16 @@ class Ref:
         self._chk(self.lib.ref_ibm_force(path.encode(), name.encode(), _p(u), _p(rho), X, Y, roi, _p(F)))
         return (r0, r1, c0, c1), F
 
+    def cylinder_loop(self, X, Y, omega, u_lb, markers_toml, warmup, steps):
+        """seconds per step of the loop body of test/cylinder_test.cpp:100-163 on CPU libtorch"""
+        sec = C.c_double(); chk = C.c_double()
+        self._chk(self.lib.ref_cylinder_loop(X, Y, C.c_double(omega), C.c_double(u_lb), markers_toml.encode(),
+                                             warmup, steps, C.byref(sec), C.byref(chk)))
+        return sec.value, chk.value
+
+    def num_threads(self):
+        return int(self.lib.ref_get_num_threads())
+
     def domain_shapes(self, R, Cc):
         s = (C.c_long * 15)()
         self._chk(self.lib.ref_domain_shapes(R, Cc, s))
