@@ -260,6 +260,8 @@ int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks
 /* single-process alternative: link two domains on the same host process; ghost rows are exchanged with
  * cudaMemcpyPeerAsync (what decompose_domain.cpp's "bind" does between tensors) */
 int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper);
+/* advance a set of linked slabs in lock step (what decompose_domain.cpp's loop does for A and B) */
+int lbm_step_group(lbm_domain* const* domains, int n_domains, int n_steps);
 /* bit-exact decomposition indexing: rows [x0,x1) for `rank` of `n_ranks` over X rows */
 int lbm_decompose_rows(int X, int n_ranks, int rank, int* x0, int* x1);
 

@@ -15,8 +15,8 @@
 //   k_bgk_boundary  : one thread per listed node (edge columns, every node some boundary rule
 //                     touches, probe nodes); table-driven gather.  Runs after the interior kernel
 //                     on the same stream and overwrites what that wrote for listed nodes.
-//   k_bgk_fixup     : pre-stream rules applied to the freshly written f_coll (pressure-periodic
-//                     rows, zero-gradient copies).
+//   k_fix_copy, k_pressure_pack/apply : pre-stream rules applied to the freshly written f_coll
+//                     (zero-gradient copies, pressure-periodic rows).
 #pragma once
 #include "lbm_device.cuh"
 
@@ -53,20 +53,11 @@ struct BoundaryTable
   const double* mom_prev; // [n][4] of the previous collide
 };
 
-enum FixKind : int
-{
-  FIX_COPY = 0,     // f_coll[dst, :] = f_coll[src, :]
-  FIX_PRESSURE = 1  // f_coll[dst, :] = feq(rho_bc, u[src]) + f_coll[src, :] - feq(rho[src], u[src])
-};
-
 struct FixEntry
 {
   long long dst;  // node offsets (no plane offset)
   long long src;
-  double rho_bc;
-  int kind;
   int lattice;
-  int j;  // boundary-node index of src (moments), FIX_PRESSURE
   int pad;
 };
 
@@ -377,33 +368,54 @@ k_bgk_boundary(const double* __restrict__ fsrc, double* __restrict__ fdst, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// pre-stream fix-ups on the freshly written post-collision buffers
+// pre-stream rules applied to the freshly written post-collision buffers
 // ------------------------------------------------------------------------------------------------
-template <int EQ>
-__global__ void __launch_bounds__(128)
-k_bgk_fixup(double* __restrict__ f, double* __restrict__ gl, const SlabGeom g, const FixEntry* __restrict__ fix,
-            int n, const double* __restrict__ mom)
+// zero-gradient copies (test/rectangle_sedimentation_test.cpp:138-141): f_coll[dst, :] = f_coll[src, :]
+static __global__ void __launch_bounds__(128)
+k_fix_copy(double* __restrict__ f, double* __restrict__ gl, const SlabGeom g, const FixEntry* __restrict__ fix, int n)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const FixEntry e = fix[i];
   double* b = e.lattice == 0 ? f : gl;
-  if (e.kind == FIX_COPY)
-  {
 #pragma unroll
-    for (int q = 0; q < 9; q++) b[q * g.plane + e.dst] = b[q * g.plane + e.src];
-  }
-  else
-  {
-    // test/horizontal_poiseuille_test.cpp:39-44 ; (temp_equi + f_coll[src]) - f_equi[src]
-    const double rho = mom[4 * e.j + 0], ux = mom[4 * e.j + 1], uy = mom[4 * e.j + 2];
-    const double uu = ux * ux + uy * uy;
+  for (int q = 0; q < 9; q++) b[q * g.plane + e.dst] = b[q * g.plane + e.src];
+}
+
+// Pressure-periodic rows (test/horizontal_poiseuille_test.cpp:25-45) in two halves, so that the source
+// row may live on another slab (test/decompose_domain.cpp:50-73):
+//   pack  (owner of the source row): packet[q][y] = f_coll[src_row, y, q], packet[9..11][y] = rho, ux, uy
+//   apply (owner of the written row): f_coll[dst_row] = (feq(rho_bc, u) + f_coll[src]) - feq(rho, u)
+static __global__ void __launch_bounds__(128)
+k_pressure_pack(const double* __restrict__ f, const SlabGeom g, int src_lx, const int* __restrict__ src_bidx,
+                const double* __restrict__ mom, double* __restrict__ packet, int y_lo, int y_hi)
+{
+  const int y = y_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= y_hi) return;
+  const long long o = node_off(g, src_lx, y);
 #pragma unroll
-    for (int q = 0; q < 9; q++)
-    {
-      const double t = feq_any<EQ>(q, e.rho_bc * 1.0, ux, uy, uu);
-      b[q * g.plane + e.dst] = (t + b[q * g.plane + e.src]) - feq_any<EQ>(q, rho, ux, uy, uu);
-    }
+  for (int q = 0; q < 9; q++) packet[q * g.Y + y] = f[q * g.plane + o];
+  const int j = src_bidx[y];
+  packet[9 * g.Y + y] = mom[4 * j + 0];
+  packet[10 * g.Y + y] = mom[4 * j + 1];
+  packet[11 * g.Y + y] = mom[4 * j + 2];
+}
+
+template <int EQ>
+static __global__ void __launch_bounds__(128)
+k_pressure_apply(double* __restrict__ f, const SlabGeom g, int dst_lx, const double* __restrict__ packet, double rho_bc,
+                 int y_lo, int y_hi)
+{
+  const int y = y_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= y_hi) return;
+  const long long o = node_off(g, dst_lx, y);
+  const double rho = packet[9 * g.Y + y], ux = packet[10 * g.Y + y], uy = packet[11 * g.Y + y];
+  const double uu = ux * ux + uy * uy;
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    const double t = feq_any<EQ>(q, rho_bc * 1.0, ux, uy, uu);
+    f[q * g.plane + o] = (t + packet[q * g.Y + y]) - feq_any<EQ>(q, rho, ux, uy, uu);
   }
 }
 

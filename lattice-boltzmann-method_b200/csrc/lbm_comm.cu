@@ -1,13 +1,412 @@
-// temporary: multi-GPU entry points not built yet
+// lbm_comm.cu — slabs along axis 0 on several GPUs (test/decompose_domain.cpp:181-187).
+//
+// What crosses a cut, per lattice and per step: the three populations of the boundary row that head
+// for the neighbour — c_x = +1 {1,5,8} upwards, c_x = -1 {3,6,7} downwards — copied into the
+// neighbour's ghost row, where the pull then finds them with the +-1 column shift of the diagonal
+// directions exactly as the reference's "bind" block writes them.  The slabs form a ring, which is
+// the periodic wrap of solver::advect.  Two-phase models also exchange two rows of the five moment
+// planes for the 5x5 differences (no wrap: the global edge replicates).  Pressure-periodic rows whose
+// source row lives on another slab travel as a 12 x Y packet (lbm_bgk_kernels.cuh).
+//
+// Two transports:
+//   NCCL   one process per GPU (torchrun): ncclSend/ncclRecv grouped per step on the slab's side
+//          stream, overlapping the interior rows.  libnccl is dlopen'ed so that single-GPU use has
+//          no NCCL dependency.
+//   link   several slabs inside one process (same or different devices): cudaMemcpyPeerAsync between
+//          the slabs' streams, driven by lbm_step_group.  This is also how the decomposition is
+//          tested on a single GPU.
+#include <dlfcn.h>
+
+#include <cstring>
+
 #include "lbm_internal.hpp"
+
 namespace lbm
 {
-int comm_release(lbm_domain*) { return LBM_OK; }
-int comm_exchange(lbm_domain*, int) { return LBM_ERR_UNSUPPORTED; }
-int comm_exchange_moments(lbm_domain*) { return LBM_OK; }
+
+// ---- the few NCCL declarations used (ABI-stable since NCCL 2.7)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+
+struct NcclApi
+{
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+  if (g_nccl.handle) return LBM_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+  {
+    h = dlopen(n, RTLD_NOW | RTLD_NOLOAD);  // the copy the host process (e.g. torch) already loaded
+    if (h) break;
+  }
+  for (const char* n : names)
+  {
+    if (h) break;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+  }
+  if (!h)
+  {
+    set_error("cannot load libnccl.so.2: %s", dlerror());
+    return LBM_ERR_COMM;
+  }
+  NcclApi a;
+  a.handle = h;
+#define LBM_SYM(field, name)                                                  \
+  a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name));              \
+  if (!a.field) { set_error("libnccl lacks %s", name); return LBM_ERR_COMM; }
+  LBM_SYM(GetUniqueId, "ncclGetUniqueId")
+  LBM_SYM(CommInitRank, "ncclCommInitRank")
+  LBM_SYM(CommDestroy, "ncclCommDestroy")
+  LBM_SYM(Send, "ncclSend")
+  LBM_SYM(Recv, "ncclRecv")
+  LBM_SYM(GroupStart, "ncclGroupStart")
+  LBM_SYM(GroupEnd, "ncclGroupEnd")
+  LBM_SYM(GetErrorString, "ncclGetErrorString")
+#undef LBM_SYM
+  g_nccl = a;
+  return LBM_OK;
 }
-extern "C" {
-int lbm_comm_unique_id(char*) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }
-int lbm_comm_init(lbm_domain*, const char*, int, int) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }
-int lbm_link_neighbours(lbm_domain*, lbm_domain*, lbm_domain*) { lbm::set_error("not built yet"); return LBM_ERR_UNSUPPORTED; }
+
+#define LBM_NCCL(call)                                                                         \
+  do                                                                                           \
+  {                                                                                            \
+    ncclResult_t r__ = (call);                                                                 \
+    if (r__ != 0)                                                                              \
+    {                                                                                          \
+      set_error("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+      return LBM_ERR_COMM;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+struct CommState
+{
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+};
+
+bool comm_active(const lbm_domain* d) { return d->comm != nullptr && d->comm->n_ranks > 1; }
+
+int comm_release(lbm_domain* d)
+{
+  if (!d->comm) return LBM_OK;
+  if (d->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm->comm);
+  delete d->comm;
+  d->comm = nullptr;
+  return LBM_OK;
 }
+
+// rank that owns global row gx under lbm_decompose_rows
+static int owner_of(int X, int n_ranks, int gx)
+{
+  const int base = X / n_ranks, rem = X % n_ranks;
+  const int split = rem * (base + 1);
+  if (gx < split) return gx / (base + 1);
+  return rem + (gx - split) / base;
+}
+
+// population ghost rows of buffer `which` of every lattice, on stream st
+int comm_exchange(lbm_domain* d, int which, cudaStream_t st)
+{
+  CommState* c = d->comm;
+  const int up = (c->rank + 1) % c->n_ranks, dn = (c->rank + c->n_ranks - 1) % c->n_ranks;
+  const SlabGeom& g = d->g;
+  const size_t n = (size_t)g.pitch;
+  LBM_NCCL(g_nccl.GroupStart());
+  for (int l = 0; l < d->nlat; l++)
+  {
+    double* f = d->buf[l][which];
+    for (int q = 0; q < 9; q++)
+    {
+      double* plane = f + (long long)q * g.plane;
+      double* ghost_lo = plane;                                   // storage row 0      = row -1
+      double* first = plane + (long long)g.pitch;                 // storage row 1      = row 0
+      double* last = plane + (long long)g.Xl * g.pitch;           // storage row Xl     = row Xl-1
+      double* ghost_hi = plane + (long long)(g.Xl + 1) * g.pitch; // storage row Xl + 1 = row Xl
+      if (d->wrap_all_q || CX(q) == 1)
+      {
+        LBM_NCCL(g_nccl.Send(last, n, ncclFloat64, up, c->comm, st));
+        LBM_NCCL(g_nccl.Recv(ghost_lo, n, ncclFloat64, dn, c->comm, st));
+      }
+      if (d->wrap_all_q || CX(q) == -1)
+      {
+        LBM_NCCL(g_nccl.Send(first, n, ncclFloat64, dn, c->comm, st));
+        LBM_NCCL(g_nccl.Recv(ghost_hi, n, ncclFloat64, up, c->comm, st));
+      }
+    }
+  }
+  LBM_NCCL(g_nccl.GroupEnd());
+  d->launches++;
+  return LBM_OK;
+}
+
+// two ghost rows of the moment planes across every INTERNAL cut (the global edge replicates)
+int comm_exchange_moments(lbm_domain* d)
+{
+  if (!d->tp || !comm_active(d)) return LBM_OK;
+  CommState* c = d->comm;
+  int pm = 0;
+  long long mplane = 0;
+  double* mom = tp_moment_planes(d, &pm, &mplane);
+  const int Xl = d->g.Xl;
+  const size_t n = (size_t)2 * pm;
+  const bool has_dn = d->cfg.x0 > 0, has_up = d->cfg.x1 < d->cfg.X;
+  LBM_NCCL(g_nccl.GroupStart());
+  for (int f = 0; f < 5; f++)
+  {
+    double* pl = mom + (long long)f * mplane;
+    // storage row r holds slab row r - 2
+    if (has_up)
+    {
+      LBM_NCCL(g_nccl.Send(pl + (long long)Xl * pm, n, ncclFloat64, c->rank + 1, c->comm, d->stream));        // rows Xl-2, Xl-1
+      LBM_NCCL(g_nccl.Recv(pl + (long long)(Xl + 2) * pm, n, ncclFloat64, c->rank + 1, c->comm, d->stream));  // rows Xl, Xl+1
+    }
+    if (has_dn)
+    {
+      LBM_NCCL(g_nccl.Send(pl + (long long)2 * pm, n, ncclFloat64, c->rank - 1, c->comm, d->stream));  // rows 0, 1
+      LBM_NCCL(g_nccl.Recv(pl, n, ncclFloat64, c->rank - 1, c->comm, d->stream));                      // rows -2, -1
+    }
+  }
+  LBM_NCCL(g_nccl.GroupEnd());
+  d->launches++;
+  return LBM_OK;
+}
+
+// pressure packet of stage k: from the rank that owns the source row to the rank that owns the written row
+int comm_stage_transfer(lbm_domain* d, size_t k)
+{
+  Stage& sg = d->stages[k];
+  if (sg.kind != 1) return LBM_OK;
+  CommState* c = d->comm;
+  const int src_rank = owner_of(d->cfg.X, c->n_ranks, sg.src_gx), dst_rank = owner_of(d->cfg.X, c->n_ranks, sg.dst_gx);
+  if (src_rank == dst_rank) return LBM_OK;
+  const size_t n = (size_t)12 * d->g.Y;
+  if (c->rank == src_rank) LBM_NCCL(g_nccl.Send(sg.d_packet, n, ncclFloat64, dst_rank, c->comm, d->stream));
+  if (c->rank == dst_rank) LBM_NCCL(g_nccl.Recv(sg.d_packet, n, ncclFloat64, src_rank, c->comm, d->stream));
+  if (c->rank == src_rank || c->rank == dst_rank) d->launches++;
+  return LBM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// link transport: slabs of one process
+// ------------------------------------------------------------------------------------------------
+static int copy_rows(lbm_domain* dst, double* dptr, lbm_domain* src, const double* sptr, size_t count)
+{
+  if (dst->cfg.device == src->cfg.device)
+    LBM_CUDA(cudaMemcpyAsync(dptr, sptr, count * sizeof(double), cudaMemcpyDeviceToDevice, dst->stream));
+  else
+    LBM_CUDA(cudaMemcpyPeerAsync(dptr, dst->cfg.device, sptr, src->cfg.device, count * sizeof(double), dst->stream));
+  dst->launches++;
+  return LBM_OK;
+}
+
+// ghost rows of buffer `which` of slab d from its linked neighbours (on d's stream, after the
+// neighbours' ev_ready)
+static int link_exchange(lbm_domain* d, int which)
+{
+  const SlabGeom& g = d->g;
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  if (d->link_lo) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->link_lo->ev_ready, 0));
+  if (d->link_hi) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->link_hi->ev_ready, 0));
+  for (int l = 0; l < d->nlat; l++)
+    for (int q = 0; q < 9; q++)
+    {
+      double* plane = d->buf[l][which] + (long long)q * g.plane;
+      if (d->link_lo && (d->wrap_all_q || CX(q) == 1))
+      {
+        lbm_domain* s = d->link_lo;
+        const double* last = s->buf[l][s->cur] + (long long)q * s->g.plane + (long long)s->g.Xl * s->g.pitch;
+        LBM_TRY(copy_rows(d, plane, s, last, g.pitch));
+      }
+      if (d->link_hi && (d->wrap_all_q || CX(q) == -1))
+      {
+        lbm_domain* s = d->link_hi;
+        const double* first = s->buf[l][s->cur] + (long long)q * s->g.plane + (long long)s->g.pitch;
+        LBM_TRY(copy_rows(d, plane + (long long)(g.Xl + 1) * g.pitch, s, first, g.pitch));
+      }
+    }
+  return LBM_OK;
+}
+
+int comm_link_refresh(lbm_domain* d)
+{
+  for (lbm_domain* o : {d->link_lo, d->link_hi})
+  {
+    if (!o) continue;
+    LBM_CUDA(cudaSetDevice(o->cfg.device));
+    LBM_CUDA(cudaEventRecord(o->ev_ready, o->stream));
+  }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  return link_exchange(d, d->cur);
+}
+
+}  // namespace lbm
+
+using namespace lbm;
+
+extern "C"
+{
+
+int lbm_comm_unique_id(char id[LBM_UNIQUE_ID_BYTES])
+{
+  if (!id) { set_error("lbm_comm_unique_id: null argument"); return LBM_ERR_INVALID; }
+  LBM_TRY(load_nccl());
+  ncclUniqueId u;
+  LBM_NCCL(g_nccl.GetUniqueId(&u));
+  static_assert(sizeof(u) == LBM_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+  std::memcpy(id, &u, sizeof(u));
+  return LBM_OK;
+}
+
+int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank)
+{
+  if (!d || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) { set_error("lbm_comm_init: bad argument"); return LBM_ERR_INVALID; }
+  int x0 = 0, x1 = 0;
+  LBM_TRY(lbm_decompose_rows(d->cfg.X, n_ranks, rank, &x0, &x1));
+  if (x0 != d->cfg.x0 || x1 != d->cfg.x1)
+  {
+    set_error("lbm_comm_init: rank %d of %d must own rows [%d,%d) (lbm_decompose_rows), the domain has [%d,%d)", rank, n_ranks,
+              x0, x1, d->cfg.x0, d->cfg.x1);
+    return LBM_ERR_INVALID;
+  }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  comm_release(d);
+  LBM_TRY(load_nccl());
+  CommState* c = new CommState();
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, u, rank);
+  if (r != 0)
+  {
+    set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    delete c;
+    return LBM_ERR_COMM;
+  }
+  d->comm = c;
+  d->ghost_valid = false;
+  return LBM_OK;
+}
+
+int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper)
+{
+  if (!d) { set_error("lbm_link_neighbours: null domain"); return LBM_ERR_INVALID; }
+  for (lbm_domain* o : {lower, upper})
+  {
+    if (!o) continue;
+    if (o->cfg.Y != d->cfg.Y || o->cfg.X != d->cfg.X || o->nlat != d->nlat)
+    {
+      set_error("lbm_link_neighbours: slabs of different grids / models");
+      return LBM_ERR_INVALID;
+    }
+    if (o->cfg.device != d->cfg.device)
+    {
+      int can = 0;
+      LBM_CUDA(cudaDeviceCanAccessPeer(&can, d->cfg.device, o->cfg.device));
+      if (can)
+      {
+        LBM_CUDA(cudaSetDevice(d->cfg.device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(o->cfg.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) LBM_CUDA(e);
+        cudaGetLastError();
+      }
+    }
+  }
+  d->link_lo = lower;
+  d->link_hi = upper;
+  d->ghost_valid = false;
+  return LBM_OK;
+}
+
+// Advance a set of linked slabs in lock step.  Per step: every slab publishes "previous step done",
+// pulls its ghost rows from its neighbours, computes; then the pre-stream stages run slab by slab
+// with the pressure packets copied between owners.
+int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
+{
+  if (!ds || n < 1 || n_steps < 0) { set_error("lbm_step_group: bad argument"); return LBM_ERR_INVALID; }
+  for (int i = 0; i < n; i++)
+  {
+    if (!ds[i] || !ds[i]->have_state || !ds[i]->committed) { set_error("lbm_step_group: slab %d has no state / uncommitted rules", i); return LBM_ERR_INVALID; }
+    if (ds[i]->tp) { set_error("lbm_step_group: two-phase slabs are stepped over NCCL (lbm_comm_init), not linked"); return LBM_ERR_UNSUPPORTED; }
+    if (ds[i]->stages.size() != ds[0]->stages.size()) { set_error("lbm_step_group: slabs carry different rule lists"); return LBM_ERR_INVALID; }
+  }
+  for (int i = 0; i < n; i++)
+  {
+    LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_begin, ds[i]->stream));
+  }
+  for (int s = 0; s < n_steps; s++)
+  {
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_ready, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      lbm_domain* d = ds[i];
+      if (!d->post_stream)
+      {
+        ProfScope ps(d, LBM_PROF_GHOST);
+        if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur));
+        else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
+      }
+      d->ghost_valid = true;
+      d->ghost_pending = false;
+    }
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+      LBM_TRY(step_compute(ds[i]));
+    }
+    for (size_t k = 0; k < ds[0]->stages.size(); k++)
+    {
+      lbm_domain *src = nullptr, *dst = nullptr;
+      for (int i = 0; i < n; i++)
+      {
+        LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+        LBM_TRY(stage_pack(ds[i], k));
+        if (ds[i]->stages[k].kind == 1 && ds[i]->stages[k].own_src) src = ds[i];
+        if (ds[i]->stages[k].kind == 1 && ds[i]->stages[k].own_dst) dst = ds[i];
+      }
+      if (src && dst && src != dst)
+      {
+        LBM_CUDA(cudaSetDevice(src->cfg.device));
+        LBM_CUDA(cudaEventRecord(src->ev_packet, src->stream));
+        LBM_CUDA(cudaSetDevice(dst->cfg.device));
+        LBM_CUDA(cudaStreamWaitEvent(dst->stream, src->ev_packet, 0));
+        LBM_TRY(copy_rows(dst, dst->stages[k].d_packet, src, src->stages[k].d_packet, (size_t)12 * dst->g.Y));
+      }
+      for (int i = 0; i < n; i++)
+      {
+        LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+        LBM_TRY(stage_apply(ds[i], k));
+      }
+    }
+    for (int i = 0; i < n; i++) LBM_TRY(step_finish(ds[i]));
+  }
+  for (int i = 0; i < n; i++)
+  {
+    LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_end, ds[i]->stream));
+  }
+  return LBM_OK;
+}
+
+}  // extern "C"

@@ -153,56 +153,160 @@ static int dispatch_bgk(lbm_domain* d, int rb, int re, bool di, bool db)
   return LBM_ERR_INVALID;
 }
 
-static int run_fixups(lbm_domain* d)
+int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st)
 {
-  const int t = d->cur ^ 1;  // freshly written buffers
-  ProfScope ps(d, LBM_PROF_FIXUP);
-  for (auto& grp : d->fix)
+  for (int l = 0; l < d->nlat; l++)
   {
-    if (grp.n == 0) continue;
-    if (d->cfg.equilibrium == EQ_INCOMP)
-      k_bgk_fixup<EQ_INCOMP><<<cdiv(grp.n, 128), 128, 0, d->stream>>>(d->buf[0][t], d->buf[1][t], d->g, grp.d_entries, grp.n,
-                                                                     d->d_mom[d->mom_cur ^ 1]);
-    else
-      k_bgk_fixup<EQ_COMP><<<cdiv(grp.n, 128), 128, 0, d->stream>>>(d->buf[0][t], d->buf[1][t], d->g, grp.d_entries, grp.n,
-                                                                   d->d_mom[d->mom_cur ^ 1]);
+    k_wrap_ghost_rows<<<cdiv(d->g.pitch, 128), 128, 0, st>>>(d->buf[l][which], d->g, d->wrap_all_q ? 1 : 0);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
 }
 
-// ghost rows of buffer `which` of every lattice: neighbours' boundary rows, or the slab's own
-// opposite rows when it is the whole domain (periodic wrap of solver::advect)
-int exchange_ghost_rows(lbm_domain* d, int which)
+// Ghost rows of the SOURCE buffer: the neighbour slabs' boundary rows (NCCL), or the slab's own
+// opposite rows when it is the whole domain (periodic wrap of solver::advect along axis 0).
+// Issued on the side stream so that it overlaps the interior rows, which do not read ghost rows.
+int step_prepare(lbm_domain* d)
 {
-  ProfScope ps(d, LBM_PROF_GHOST);
-  if (d->comm || d->link_lo || d->link_hi) return comm_exchange(d, which);
-  for (int l = 0; l < d->nlat; l++)
+  if (d->ghost_valid || d->post_stream) return LBM_OK;  // a post-stream (just imported) state is read locally
+  if (d->link_lo || d->link_hi)                         // linked slabs outside lbm_step_group (export, solo stepping)
   {
-    k_wrap_ghost_rows<<<cdiv(d->g.pitch, 128), 128, 0, d->stream>>>(d->buf[l][which], d->g, d->wrap_all_q ? 1 : 0);
+    LBM_TRY(comm_link_refresh(d));
+    d->ghost_valid = true;
+    d->ghost_pending = false;
+    return LBM_OK;
+  }
+  LBM_CUDA(cudaEventRecord(d->ev_ready, d->stream));
+  LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
+  {
+    ProfScope ps(d, LBM_PROF_GHOST);
+    if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->side));
+    else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->side));
+  }
+  LBM_CUDA(cudaEventRecord(d->ev_ghost, d->side));
+  d->ghost_valid = true;
+  d->ghost_pending = true;
+  return LBM_OK;
+}
+
+// IBM pre-pass on the side stream + the fused collide/stream kernels on the main stream.  Row
+// ranges that need neither ghost rows nor the ROI force field are launched first.
+int step_compute(lbm_domain* d)
+{
+  const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
+  const int Xl = d->g.Xl;
+  const bool ibm = d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM;
+  if (ibm)
+  {
+    LBM_CUDA(cudaEventRecord(d->ev_ready, d->stream));
+    LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
+    cudaStream_t main_stream = d->stream;
+    d->stream = d->side;  // the pre-pass kernels launch on d->stream
+    int st;
+    {
+      ProfScope ps(d, LBM_PROF_IBM);
+      st = ibm_prepass(d, mode);
+    }
+    d->stream = main_stream;
+    LBM_TRY(st);
+    LBM_CUDA(cudaEventRecord(d->ev_ibm, d->side));
+  }
+  // split [0, Xl) at the rows that need the ghost rows (0 and Xl-1 when pulling) and at the ROI rows
+  int cuts[6] = {0, Xl, Xl, Xl, Xl, Xl};
+  int nc = 1;
+  auto add_cut = [&](int c) { if (c > 0 && c < Xl) cuts[nc++] = c; };
+  const bool need_ghost = mode == MODE_PULL && d->ghost_pending;
+  if (need_ghost) { add_cut(1); add_cut(Xl - 1); }
+  const int r0 = (int)d->ibm.r0 - d->cfg.x0, r1 = (int)d->ibm.r1 - d->cfg.x0;
+  if (ibm) { add_cut(r0); add_cut(r1); }
+  std::sort(cuts, cuts + nc);
+  cuts[nc] = Xl;
+  auto flags = [&](int lo, int hi) {
+    int f = 0;
+    if (need_ghost && (lo == 0 || hi == Xl)) f |= 1;
+    if (ibm && lo < r1 && hi > r0) f |= 2;
+    return f;
+  };
+  bool waited_ghost = false, waited_ibm = false;
+  for (int pass = 0; pass < 4; pass++)  // flags 0, then 1 (ghost), then 2 (ibm), then 3 (both)
+  {
+    for (int k = 0; k < nc; k++)
+    {
+      const int lo = cuts[k], hi = cuts[k + 1];
+      if (hi <= lo || flags(lo, hi) != pass) continue;
+      if ((pass & 1) && !waited_ghost) { LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ghost, 0)); waited_ghost = true; }
+      if ((pass & 2) && !waited_ibm) { LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ibm, 0)); waited_ibm = true; }
+      if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, lo, hi, true, false));
+      else LBM_TRY(dispatch_bgk<MODE_PULL>(d, lo, hi, true, false));
+    }
+  }
+  if (need_ghost && !waited_ghost) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ghost, 0));
+  if (ibm && !waited_ibm) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ibm, 0));
+  d->ghost_pending = false;
+  if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, 0, 0, false, true));
+  else LBM_TRY(dispatch_bgk<MODE_PULL>(d, 0, 0, false, true));
+  return LBM_OK;
+}
+
+int stage_pack(lbm_domain* d, size_t k)
+{
+  Stage& sg = d->stages[k];
+  if (sg.kind != 1 || !sg.own_src || sg.y_hi <= sg.y_lo) return LBM_OK;
+  ProfScope ps(d, LBM_PROF_FIXUP);
+  const int t = d->cur ^ 1;
+  k_pressure_pack<<<cdiv(sg.y_hi - sg.y_lo, 128), 128, 0, d->stream>>>(d->buf[0][t], d->g, sg.src_gx - d->cfg.x0, sg.d_src_bidx,
+                                                                      d->d_mom[d->mom_cur ^ 1], sg.d_packet, sg.y_lo, sg.y_hi);
+  d->launches++;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+int stage_apply(lbm_domain* d, size_t k)
+{
+  Stage& sg = d->stages[k];
+  const int t = d->cur ^ 1;
+  ProfScope ps(d, LBM_PROF_FIXUP);
+  if (sg.kind == 0)
+  {
+    if (sg.n == 0) return LBM_OK;
+    k_fix_copy<<<cdiv(sg.n, 128), 128, 0, d->stream>>>(d->buf[0][t], d->buf[1][t], d->g, sg.d_entries, sg.n);
+    d->launches++;
+  }
+  else
+  {
+    if (!sg.own_dst || sg.y_hi <= sg.y_lo) return LBM_OK;
+    const int lx = sg.dst_gx - d->cfg.x0, nblk = cdiv(sg.y_hi - sg.y_lo, 128);
+    if (d->cfg.equilibrium == EQ_INCOMP)
+      k_pressure_apply<EQ_INCOMP><<<nblk, 128, 0, d->stream>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+    else
+      k_pressure_apply<EQ_COMP><<<nblk, 128, 0, d->stream>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+int step_finish(lbm_domain* d)
+{
+  d->cur ^= 1;
+  d->mom_cur ^= 1;
+  d->post_stream = false;
+  d->ghost_valid = false;
   return LBM_OK;
 }
 
 static int bgk_step_once(lbm_domain* d)
 {
-  const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
-  if (d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM)
+  LBM_TRY(step_prepare(d));
+  LBM_TRY(step_compute(d));
+  for (size_t k = 0; k < d->stages.size(); k++)
   {
-    ProfScope ps(d, LBM_PROF_IBM);
-    LBM_TRY(ibm_prepass(d, mode));
+    LBM_TRY(stage_pack(d, k));
+    if (comm_active(d)) LBM_TRY(comm_stage_transfer(d, k));
+    LBM_TRY(stage_apply(d, k));
   }
-  if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, 0, d->g.Xl, true, true));
-  else LBM_TRY(dispatch_bgk<MODE_PULL>(d, 0, d->g.Xl, true, true));
-  LBM_TRY(run_fixups(d));
-  LBM_TRY(exchange_ghost_rows(d, d->cur ^ 1));
-  d->cur ^= 1;
-  d->mom_cur ^= 1;
-  d->post_stream = false;
-  return LBM_OK;
+  return step_finish(d);
 }
 
 int ensure_aos_scratch(lbm_domain* d)
@@ -228,6 +332,13 @@ static int export_post_stream(lbm_domain* d)
     }
     LBM_CUDA(cudaGetLastError());
     return LBM_OK;
+  }
+  // pull-only pass: ghost rows first (they are refreshed lazily, at the start of a step)
+  LBM_TRY(step_prepare(d));
+  if (d->ghost_pending)
+  {
+    LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ghost, 0));
+    d->ghost_pending = false;
   }
   return dispatch_bgk<MODE_PULL_ONLY>(d, 0, d->g.Xl, true, true);
 }
@@ -284,8 +395,13 @@ static void release_compiled(lbm_domain* d)
 {
   cudaFree(d->d_bx); cudaFree(d->d_by); cudaFree(d->d_ent); cudaFree(d->d_mom[0]); cudaFree(d->d_mom[1]);
   d->d_bx = d->d_by = nullptr; d->d_ent = nullptr; d->d_mom[0] = d->d_mom[1] = nullptr;
-  for (auto& grp : d->fix) cudaFree(grp.d_entries);
-  d->fix.clear();
+  for (auto& sg : d->stages)
+  {
+    cudaFree(sg.d_entries);
+    cudaFree(sg.d_src_bidx);
+    cudaFree(sg.d_packet);
+  }
+  d->stages.clear();
   d->nb = 0;
   d->committed = false;
 }
@@ -365,7 +481,15 @@ int commit_boundary_tables(lbm_domain* d)
   for (int l = 0; l < 2; l++) d->mask[l].assign(l < d->nlat ? (size_t)Xl * Y * 9 : 0, 0);
 
   // ---- pass 3: ops in order (later ops win, like the reference's successive assignments)
-  std::vector<std::vector<FixEntry>> groups;
+  struct HostStage
+  {
+    int kind = 0, dst_gx = 0, src_gx = 0, y_lo = 0, y_hi = 0;
+    double rho_bc = 1.0;
+    bool own_src = false, own_dst = false;
+    std::vector<FixEntry> entries;
+    std::vector<int> src_bidx;
+  };
+  std::vector<HostStage> host_stages;
   for (size_t k = 0; k < d->ops.size(); k++)
   {
     const lbm_bc_op& op = d->ops[k].op;
@@ -374,9 +498,10 @@ int commit_boundary_tables(lbm_domain* d)
     resolve_slice(op.y_begin, op.y_end, Y, yl, yh);
     const int lat_lo = op.lattice < 0 ? 0 : op.lattice, lat_hi = op.lattice < 0 ? d->nlat - 1 : op.lattice;
     if (lat_hi >= d->nlat) { set_error("bc op %zu: lattice %d does not exist in this model", k, op.lattice); return LBM_ERR_INVALID; }
-    if (op.kind == LBM_BC_PRESSURE_PERIODIC || op.kind == LBM_BC_COPY_PRE)
+    if (op.kind == LBM_BC_COPY_PRE)
     {
-      std::vector<FixEntry> grp;
+      HostStage hs;
+      hs.kind = 0;
       for (int gx = xl; gx < xh; gx++)
       {
         if (gx < x0 || gx >= d->cfg.x1) continue;
@@ -386,7 +511,7 @@ int commit_boundary_tables(lbm_domain* d)
           if (!s.ok) { set_error("bc op %zu: source node outside the grid", k); return LBM_ERR_INVALID; }
           if (s.gx < x0 || s.gx >= d->cfg.x1)
           {
-            set_error("bc op %zu: pre-stream source row %d is owned by another slab (not supported across ranks)", k, s.gx);
+            set_error("bc op %zu: copy source row %d is owned by another slab (not supported across slabs)", k, s.gx);
             return LBM_ERR_UNSUPPORTED;
           }
           for (int l = lat_lo; l <= lat_hi; l++)
@@ -394,17 +519,36 @@ int commit_boundary_tables(lbm_domain* d)
             FixEntry e;
             e.dst = (long long)(gx - x0 + 1) * g.pitch + y;
             e.src = (long long)(s.gx - x0 + 1) * g.pitch + s.y;
-            e.rho_bc = op.rho_bc;
-            e.kind = op.kind == LBM_BC_COPY_PRE ? FIX_COPY : FIX_PRESSURE;
             e.lattice = l;
-            e.j = 0;
             e.pad = 0;
-            if (e.kind == FIX_PRESSURE) e.j = index.at((long long)(s.gx - x0) * Y + s.y);
-            grp.push_back(e);
+            hs.entries.push_back(e);
           }
         }
       }
-      groups.push_back(std::move(grp));
+      host_stages.push_back(std::move(hs));
+      continue;
+    }
+    if (op.kind == LBM_BC_PRESSURE_PERIODIC)
+    {
+      if (xh - xl != 1 || op.src_mode != LBM_SRC_ROW)
+      {
+        set_error("bc op %zu: LBM_BC_PRESSURE_PERIODIC writes one row from one source row (LBM_SRC_ROW)", k);
+        return LBM_ERR_INVALID;
+      }
+      HostStage hs;
+      hs.kind = 1;
+      hs.dst_gx = xl;
+      hs.src_gx = resolve_index(op.src_a, X);
+      if (hs.src_gx < 0 || hs.src_gx >= X) { set_error("bc op %zu: source row outside the grid", k); return LBM_ERR_INVALID; }
+      hs.y_lo = yl; hs.y_hi = yh; hs.rho_bc = op.rho_bc;
+      hs.own_dst = hs.dst_gx >= x0 && hs.dst_gx < d->cfg.x1;
+      hs.own_src = hs.src_gx >= x0 && hs.src_gx < d->cfg.x1;
+      if (hs.own_src)
+      {
+        hs.src_bidx.assign(Y, 0);
+        for (int y = yl; y < yh; y++) hs.src_bidx[y] = index.at((long long)(hs.src_gx - x0) * Y + y);
+      }
+      host_stages.push_back(std::move(hs));
       continue;
     }
     if (!is_post_stream(op.kind)) { set_error("bc op %zu: unknown kind %d", k, op.kind); return LBM_ERR_INVALID; }
@@ -474,16 +618,29 @@ int commit_boundary_tables(lbm_domain* d)
     LBM_CUDA(cudaMemset(d->d_mom[0], 0, sizeof(double) * 4 * nb));
     LBM_CUDA(cudaMemset(d->d_mom[1], 0, sizeof(double) * 4 * nb));
   }
-  for (auto& grp : groups)
+  for (auto& hs : host_stages)
   {
-    FixGroup fg;
-    fg.n = (int)grp.size();
-    if (fg.n > 0)
+    Stage sg;
+    sg.kind = hs.kind;
+    sg.n = (int)hs.entries.size();
+    sg.dst_gx = hs.dst_gx; sg.src_gx = hs.src_gx; sg.y_lo = hs.y_lo; sg.y_hi = hs.y_hi; sg.rho_bc = hs.rho_bc;
+    sg.own_src = hs.own_src; sg.own_dst = hs.own_dst;
+    if (sg.n > 0)
     {
-      LBM_CUDA(cudaMalloc(&fg.d_entries, sizeof(FixEntry) * fg.n));
-      LBM_CUDA(cudaMemcpy(fg.d_entries, grp.data(), sizeof(FixEntry) * fg.n, cudaMemcpyHostToDevice));
+      LBM_CUDA(cudaMalloc(&sg.d_entries, sizeof(FixEntry) * sg.n));
+      LBM_CUDA(cudaMemcpy(sg.d_entries, hs.entries.data(), sizeof(FixEntry) * sg.n, cudaMemcpyHostToDevice));
     }
-    d->fix.push_back(fg);
+    if (hs.kind == 1 && (hs.own_src || hs.own_dst))
+    {
+      LBM_CUDA(cudaMalloc(&sg.d_packet, sizeof(double) * 12 * Y));
+      LBM_CUDA(cudaMemset(sg.d_packet, 0, sizeof(double) * 12 * Y));
+      if (hs.own_src)
+      {
+        LBM_CUDA(cudaMalloc(&sg.d_src_bidx, sizeof(int) * Y));
+        LBM_CUDA(cudaMemcpy(sg.d_src_bidx, hs.src_bidx.data(), sizeof(int) * Y, cudaMemcpyHostToDevice));
+      }
+    }
+    d->stages.push_back(sg);
   }
   d->committed = true;
   return LBM_OK;
@@ -575,8 +732,13 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
       cudaMemset(d->buf[l][b], 0, bytes);
     }
   LBM_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  LBM_CUDA(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
   LBM_CUDA(cudaEventCreate(&d->ev_begin));
   LBM_CUDA(cudaEventCreate(&d->ev_end));
+  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_ready, cudaEventDisableTiming));
+  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_ibm, cudaEventDisableTiming));
+  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_ghost, cudaEventDisableTiming));
+  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_packet, cudaEventDisableTiming));
   if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK)
   {
     int s = tp_create(d);
@@ -591,6 +753,7 @@ int lbm_destroy(lbm_domain* d)
   if (!d) return LBM_OK;
   cudaSetDevice(d->cfg.device);
   if (d->stream) cudaStreamSynchronize(d->stream);
+  if (d->side) cudaStreamSynchronize(d->side);
   release_compiled(d);
   ibm_release(d);
   tp_destroy(d);
@@ -609,6 +772,11 @@ int lbm_destroy(lbm_domain* d)
   }
   if (d->ev_begin) cudaEventDestroy(d->ev_begin);
   if (d->ev_end) cudaEventDestroy(d->ev_end);
+  if (d->ev_ready) cudaEventDestroy(d->ev_ready);
+  if (d->ev_ibm) cudaEventDestroy(d->ev_ibm);
+  if (d->ev_ghost) cudaEventDestroy(d->ev_ghost);
+  if (d->ev_packet) cudaEventDestroy(d->ev_packet);
+  if (d->side) cudaStreamDestroy(d->side);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
   return LBM_OK;
@@ -697,6 +865,7 @@ int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos)
   LBM_CUDA(cudaGetLastError());
   d->post_stream = true;
   d->have_state = true;
+  d->ghost_valid = false;
   if (d->tp) LBM_TRY(tp_refresh_moments(d));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
   return LBM_OK;

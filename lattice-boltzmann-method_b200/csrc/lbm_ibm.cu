@@ -30,12 +30,15 @@ static double peskin(double r_)
 }
 
 // moments of the ROI nodes from the stored populations (ROI nodes are interior: plain pull)
+// Only the nodes some marker's 4x4 box covers are ever read (gather) or changed (spread), so the
+// pre-pass runs over that short "active" list, not over the whole ROI rectangle.
 template <int MODE, int EQ>
-__global__ void k_ibm_roi_moments(const double* __restrict__ f, const SlabGeom g, int r0, int c0, int RR, int RC,
-                                  double* __restrict__ u, double* __restrict__ rho)
+__global__ void k_ibm_roi_moments(const double* __restrict__ f, const SlabGeom g, int r0, int c0, int na, int RC,
+                                  const int* __restrict__ active, double* __restrict__ u, double* __restrict__ rho)
 {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= RR * RC) return;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int n = active[a];
   const int i = n / RC, j = n % RC;
   const int x = r0 + i - g.xg0, y = c0 + j;
   double v[9];
@@ -74,14 +77,16 @@ __global__ void k_ibm_gather(int nm, const int* __restrict__ mrow, const int* __
 }
 
 // src/ibm.cpp:180-186
-__global__ void k_ibm_spread(int nn, const int* __restrict__ ptr, const int* __restrict__ em,
-                             const double* __restrict__ ephi, const double* __restrict__ fj, double* __restrict__ u,
-                             const double* __restrict__ rho, double* __restrict__ Fx, double* __restrict__ Fy, int first)
+__global__ void k_ibm_spread(int na, const int* __restrict__ active, const int* __restrict__ ptr,
+                             const int* __restrict__ em, const double* __restrict__ ephi, const double* __restrict__ fj,
+                             double* __restrict__ u, const double* __restrict__ rho, double* __restrict__ Fx,
+                             double* __restrict__ Fy, int first)
 {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nn) return;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int n = active[a];
   double fx = 0.0, fy = 0.0;
-  for (int e = ptr[n]; e < ptr[n + 1]; e++)
+  for (int e = ptr[a]; e < ptr[a + 1]; e++)
   {
     fx += ephi[e] * fj[2 * em[e]];
     fy += ephi[e] * fj[2 * em[e] + 1];
@@ -115,7 +120,7 @@ __global__ void k_ibm_pack_force(int nn, const double* __restrict__ Fx, const do
 int ibm_release(lbm_domain* d)
 {
   IbmState& ib = d->ibm;
-  cudaFree(ib.d_mrow); cudaFree(ib.d_mcol); cudaFree(ib.d_phi); cudaFree(ib.d_fj); cudaFree(ib.d_ptr);
+  cudaFree(ib.d_active); cudaFree(ib.d_mrow); cudaFree(ib.d_mcol); cudaFree(ib.d_phi); cudaFree(ib.d_fj); cudaFree(ib.d_ptr);
   cudaFree(ib.d_ent_marker); cudaFree(ib.d_ent_phi); cudaFree(ib.d_u); cudaFree(ib.d_rho); cudaFree(ib.d_Fx); cudaFree(ib.d_Fy);
   ib = IbmState();
   return LBM_OK;
@@ -125,7 +130,7 @@ int ibm_release(lbm_domain* d)
 static int ibm_iterate(lbm_domain* d)
 {
   IbmState& ib = d->ibm;
-  const int RR = (int)(ib.r1 - ib.r0), RC = (int)(ib.c1 - ib.c0), nn = RR * RC;
+  const int RC = (int)(ib.c1 - ib.c0), nn = (int)(ib.r1 - ib.r0) * RC;
   if (ib.m_max <= 1)
   {
     LBM_CUDA(cudaMemsetAsync(ib.d_Fx, 0, sizeof(double) * nn, d->stream));
@@ -135,8 +140,8 @@ static int ibm_iterate(lbm_domain* d)
   {
     k_ibm_gather<<<cdiv(ib.n_markers, 128), 128, 0, d->stream>>>(ib.n_markers, ib.d_mrow, ib.d_mcol, ib.d_phi, RC, ib.d_u,
                                                                  ib.d_rho, ib.d_fj);
-    k_ibm_spread<<<cdiv(nn, 128), 128, 0, d->stream>>>(nn, ib.d_ptr, ib.d_ent_marker, ib.d_ent_phi, ib.d_fj, ib.d_u, ib.d_rho,
-                                                       ib.d_Fx, ib.d_Fy, n == 1 ? 1 : 0);
+    k_ibm_spread<<<cdiv(ib.n_active, 128), 128, 0, d->stream>>>(ib.n_active, ib.d_active, ib.d_ptr, ib.d_ent_marker, ib.d_ent_phi,
+                                                                ib.d_fj, ib.d_u, ib.d_rho, ib.d_Fx, ib.d_Fy, n == 1 ? 1 : 0);
     d->launches += 2;
   }
   LBM_CUDA(cudaGetLastError());
@@ -146,11 +151,12 @@ static int ibm_iterate(lbm_domain* d)
 int ibm_prepass(lbm_domain* d, int mode)
 {
   IbmState& ib = d->ibm;
-  const int RR = (int)(ib.r1 - ib.r0), RC = (int)(ib.c1 - ib.c0), nn = RR * RC;
+  const int RC = (int)(ib.c1 - ib.c0);
   const double* f = d->buf[0][d->cur];
   const bool comp = d->cfg.equilibrium == LBM_EQ_COMPRESSIBLE;
-#define LBM_ROI(M, E) \
-  k_ibm_roi_moments<M, E><<<cdiv(nn, 128), 128, 0, d->stream>>>(f, d->g, (int)ib.r0, (int)ib.c0, RR, RC, ib.d_u, ib.d_rho)
+#define LBM_ROI(M, E)                                                                                                   \
+  k_ibm_roi_moments<M, E><<<cdiv(ib.n_active, 128), 128, 0, d->stream>>>(f, d->g, (int)ib.r0, (int)ib.c0, ib.n_active, RC, \
+                                                                         ib.d_active, ib.d_u, ib.d_rho)
   if (mode == MODE_LOCAL) { if (comp) LBM_ROI(MODE_LOCAL, EQ_COMP); else LBM_ROI(MODE_LOCAL, EQ_INCOMP); }
   else { if (comp) LBM_ROI(MODE_PULL, EQ_COMP); else LBM_ROI(MODE_PULL, EQ_INCOMP); }
 #undef LBM_ROI
@@ -209,19 +215,24 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
       cover[node].push_back({i, phi[(size_t)i * 16 + k]});  // markers arrive in increasing order
     }
   }
-  std::vector<int> ptr(nn + 1, 0), em;
+  std::vector<int> ptr, em, active;
   std::vector<double> ephi;
   for (int node = 0; node < nn; node++)
   {
-    ptr[node] = (int)em.size();
+    if (cover[node].empty()) continue;
+    active.push_back(node);
+    ptr.push_back((int)em.size());
     for (auto& c : cover[node]) { em.push_back(c.first); ephi.push_back(c.second); }
   }
-  ptr[nn] = (int)em.size();
+  ptr.push_back((int)em.size());
+  ib.n_active = (int)active.size();
   LBM_CUDA(cudaMalloc(&ib.d_mrow, sizeof(int) * n));
   LBM_CUDA(cudaMalloc(&ib.d_mcol, sizeof(int) * n));
   LBM_CUDA(cudaMalloc(&ib.d_phi, sizeof(double) * n * 16));
   LBM_CUDA(cudaMalloc(&ib.d_fj, sizeof(double) * n * 2));
-  LBM_CUDA(cudaMalloc(&ib.d_ptr, sizeof(int) * (nn + 1)));
+  LBM_CUDA(cudaMalloc(&ib.d_ptr, sizeof(int) * ptr.size()));
+  LBM_CUDA(cudaMalloc(&ib.d_active, sizeof(int) * std::max<size_t>(active.size(), 1)));
+  LBM_CUDA(cudaMemcpy(ib.d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMalloc(&ib.d_ent_marker, sizeof(int) * std::max<size_t>(em.size(), 1)));
   LBM_CUDA(cudaMalloc(&ib.d_ent_phi, sizeof(double) * std::max<size_t>(em.size(), 1)));
   LBM_CUDA(cudaMalloc(&ib.d_u, sizeof(double) * nn * 2));
@@ -231,7 +242,7 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   LBM_CUDA(cudaMemcpy(ib.d_mrow, mrow.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_mcol, mcol.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_phi, phi.data(), sizeof(double) * n * 16, cudaMemcpyHostToDevice));
-  LBM_CUDA(cudaMemcpy(ib.d_ptr, ptr.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice));
+  LBM_CUDA(cudaMemcpy(ib.d_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_ent_marker, em.data(), sizeof(int) * em.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_ent_phi, ephi.data(), sizeof(double) * ephi.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemset(ib.d_Fx, 0, sizeof(double) * nn));

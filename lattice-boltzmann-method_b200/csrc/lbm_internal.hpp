@@ -39,10 +39,20 @@ struct StoredOp
   std::vector<double> per_row;
 };
 
-struct FixGroup
+// One pre-stream rule, in the order the rules were added.  Every slab builds the same list (the
+// rules are global), so stage k of one slab pairs with stage k of every other slab.
+struct Stage
 {
+  int kind = 0;  // 0 = copy group (local), 1 = pressure-periodic row
+  // copy group
   int n = 0;
   FixEntry* d_entries = nullptr;
+  // pressure row
+  int dst_gx = 0, src_gx = 0, y_lo = 0, y_hi = 0;
+  double rho_bc = 1.0;
+  bool own_src = false, own_dst = false;
+  int* d_src_bidx = nullptr;  // [Y] boundary-node index of the source-row nodes (owner of the source row)
+  double* d_packet = nullptr; // [12][Y] packed by the source owner; the writer reads it (its own copy when remote)
 };
 
 struct IbmState
@@ -55,8 +65,10 @@ struct IbmState
   int* d_mcol = nullptr;
   double* d_phi = nullptr; // [n][16]
   double* d_fj = nullptr;  // [n][2]
-  // node -> covering (marker, weight) lists in marker order
-  int* d_ptr = nullptr;    // [roi_nodes + 1]
+  // nodes covered by some marker box ("active"), and for each its (marker, weight) list in marker order
+  int n_active = 0;
+  int* d_active = nullptr; // [n_active] ROI-local node ids
+  int* d_ptr = nullptr;    // [n_active + 1]
   int* d_ent_marker = nullptr;
   double* d_ent_phi = nullptr;
   // ROI fields
@@ -90,7 +102,14 @@ struct lbm_domain
   int y_int_begin = 2;      // columns [y_int_begin, y_int_end) belong to the interior kernel,
   int y_int_end = 2;        // every other column is a listed (table-driven) node
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;      // IBM pre-pass / ghost exchange, overlapped with the interior rows
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_ready = nullptr;   // state of the previous step complete (main stream)
+  cudaEvent_t ev_ibm = nullptr;     // ROI force field ready (side stream)
+  cudaEvent_t ev_ghost = nullptr;   // ghost rows of the source buffer valid (side stream)
+  cudaEvent_t ev_packet = nullptr;  // pressure packet packed (main stream), linked slabs
+  bool ghost_valid = false;         // ghost rows of buf[cur] are up to date (or being brought up to date)
+  bool ghost_pending = false;       // ... by work on the side stream that the main stream has not waited for yet
   float last_ms = 0.f;
   long long launches = 0;
 
@@ -102,7 +121,7 @@ struct lbm_domain
   lbm::BcEntry* d_ent = nullptr;
   double* d_mom[2] = {nullptr, nullptr};
   int mom_cur = 0;
-  std::vector<lbm::FixGroup> fix;
+  std::vector<lbm::Stage> stages;
   std::vector<int32_t> mask[2];
   bool wrap_all_q = false;  // some rule reads a whole row across the periodic wrap
 
@@ -136,8 +155,14 @@ struct ProfScope
   ProfScope(lbm_domain* dom, int cls);
   ~ProfScope();
 };
-int exchange_ghost_rows(lbm_domain* d, int which);
 int commit_boundary_tables(lbm_domain* d);
+// step phases (lbm_domain.cu); lbm_comm.cu interleaves them across linked slabs / ranks
+int step_prepare(lbm_domain* d);           // ghost rows of the source buffer (local wrap or neighbours)
+int step_compute(lbm_domain* d);           // IBM pre-pass + interior + listed nodes
+int stage_pack(lbm_domain* d, size_t k);   // source side of stage k
+int stage_apply(lbm_domain* d, size_t k);  // writer side of stage k
+int step_finish(lbm_domain* d);            // buffer swap
+int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st);
 // lbm_ibm.cu
 int ibm_release(lbm_domain* d);
 int ibm_prepass(lbm_domain* d, int mode);
@@ -151,6 +176,10 @@ int tp_read_moments(lbm_domain* d, double* rho, double* u, double* ph, double* r
 int tp_refresh_moments(lbm_domain* d);
 // lbm_comm.cu
 int comm_release(lbm_domain* d);
-int comm_exchange(lbm_domain* d, int which);
+bool comm_active(const lbm_domain* d);
+int comm_exchange(lbm_domain* d, int which, cudaStream_t st);  // population ghost rows over NCCL
 int comm_exchange_moments(lbm_domain* d);  // two-phase: 2 ghost rows of the moment planes at slab cuts
+int comm_stage_transfer(lbm_domain* d, size_t k);
+int comm_link_refresh(lbm_domain* d);                             // linked slabs: ghost rows of buf[cur] outside lbm_step_group               // pressure packet of stage k between ranks
+double* tp_moment_planes(lbm_domain* d, int* pm, long long* mplane);
 }  // namespace lbm

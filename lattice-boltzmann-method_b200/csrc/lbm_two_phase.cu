@@ -503,6 +503,13 @@ int tp_create(lbm_domain* d)
   return LBM_OK;
 }
 
+double* tp_moment_planes(lbm_domain* d, int* pm, long long* mplane)
+{
+  *pm = d->tp->mg.pm;
+  *mplane = d->tp->mg.mplane;
+  return d->tp->mom;
+}
+
 int tp_destroy(lbm_domain* d)
 {
   if (!d->tp) return LBM_OK;
@@ -598,9 +605,15 @@ int tp_step(lbm_domain* d)
     if (local) LBM_TRY((tp_launch_collide<TP_RK, MODE_LOCAL>(d)));
     else LBM_TRY((tp_launch_collide<TP_RK, MODE_PULL>(d)));
   }
-  LBM_TRY(exchange_ghost_rows(d, d->cur ^ 1));
   d->cur ^= 1;
   d->post_stream = false;
+  {
+    // the moments pass pulls from the buffer just written: its ghost rows first
+    ProfScope ps(d, LBM_PROF_GHOST);
+    if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->stream));
+    else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
+  }
+  d->ghost_valid = true;
   if (tp->model == TP_MRTCG) LBM_TRY(tp_launch_moments<TP_MRTCG>(d, d->cur, nullptr, nullptr));
   else LBM_TRY(tp_launch_moments<TP_RK>(d, d->cur, nullptr, nullptr));
   {

@@ -97,7 +97,7 @@ EXPORTS = [
     "lbm_differential3", "lbm_params_from_toml", "lbm_colour_from_toml", "lbm_two_phase_from_toml",
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
-    "lbm_profile_enable", "lbm_profile_read",
+    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -142,6 +142,7 @@ def load():
         _lib.lbm_comm_unique_id.argtypes = [C.c_char_p]
         _lib.lbm_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.lbm_link_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.lbm_step_group.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
         _lib.lbm_decompose_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.lbm_calc_rho.argtypes = [dp, C.c_int, C.c_int, dp]
         _lib.lbm_calc_u.argtypes = [dp, dp, C.c_int, C.c_int, dp]
@@ -368,6 +369,12 @@ class Domain:
 
     def link(self, lower, upper):
         _chk(self.lib.lbm_link_neighbours(self.h, lower.h if lower else None, upper.h if upper else None))
+
+
+def step_group(domains, n_steps=1):
+    """advance linked slabs in lock step"""
+    arr = (C.c_void_p * len(domains))(*[d.h for d in domains])
+    _chk(load().lbm_step_group(arr, len(domains), int(n_steps)))
 
 
 def comm_unique_id():

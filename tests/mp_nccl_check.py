@@ -1,0 +1,97 @@
+"""Multi-process check of the NCCL slab ring (run under torchrun on >= 2 GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tests/mp_nccl_check.py
+
+Every rank owns one slab; the gathered result must equal the monolithic single-GPU run bit for bit
+(single-phase cases) or to 1e-12 (two-phase), and the oracle for the cylinder case."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lattice-boltzmann-method_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+import lbm_b200 as L  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ident = [L.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+
+    def gather(a):
+        out = [None] * world
+        dist.all_gather_object(out, a)
+        return np.concatenate(out, axis=0)
+
+    failures = []
+
+    # ---- Poiseuille: pressure packets cross the ring (row 0 <- row X-2)
+    X, Y = 8 * world + 5, 33
+    omega, rho_in, rho_out = cases.channel_constants(X, Y, 0.1)
+    kw = dict(model=L.MODEL_BGK, X=X, Y=Y, omega=omega, equilibrium=L.EQ_INCOMPRESSIBLE)
+    rng = np.random.default_rng(5)
+    w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+    f0 = w * (1.0 + 0.02 * rng.standard_normal((X, Y, 9)))
+    x0, x1 = L.decompose_rows(X, world, rank)
+    d = L.Domain(L.default_config(x0=x0, x1=x1, device=local, **kw))
+    d.comm_init(ident[0], world, rank)
+    d.preset_poiseuille(rho_in, rho_out)
+    d.set_f(f0[x0:x1])
+    d.step(37)
+    got = gather(d.get_f())
+    if rank == 0:
+        mono = L.Domain(L.default_config(device=local, **kw))
+        mono.preset_poiseuille(rho_in, rho_out)
+        mono.set_f(f0)
+        mono.step(37)
+        ok = np.array_equal(got, mono.get_f())
+        print(f"poiseuille ring of {world}: bit-exact vs monolithic = {ok}")
+        if not ok:
+            failures.append("poiseuille")
+    d.close()
+
+    # ---- MRT colour gradient: population ghost rows + 2-row moment halos
+    from oracle_lib import MrtcgParams, Oracle
+
+    R, C = 16 * world + 6, 40
+    Fg = (6.25e-6, 0.0)
+    orc = Oracle()
+    p = MrtcgParams()
+    p.R, p.C = R, C
+    p.r_rho0, p.r_alpha, p.r_nu, p.r_beta = 3.0, 0.7, 0.04, 0.7
+    p.b_rho0, p.b_alpha, p.b_nu, p.b_beta = 1.0, 0.1, 0.04, -0.7
+    p.sigma, p.delta = 0.1, 0.1
+    p.Fg[0], p.Fg[1] = Fg
+    p.add_force = 1
+    st = orc.mrtcg_init(p, "rt")
+    x0, x1 = L.decompose_rows(R, world, rank)
+    d = cases.mrtcg(R, C, Fg, 1, x0=x0, x1=x1, device=local)
+    d.comm_init(ident[0], world, rank)
+    d.init_two_phase(st["r_rho"][x0:x1], st["b_rho"][x0:x1], st["u"][x0:x1])
+    d.step(12)
+    fr, fb = gather(d.get_f(0)), gather(d.get_f(1))
+    if rank == 0:
+        for _ in range(12):
+            orc.mrtcg_step(p, st)
+        e = max(cases.relerr(fr, st["r_adv"]), cases.relerr(fb, st["b_adv"]))
+        print(f"mrtcg ring of {world}: rel err vs oracle after 12 steps = {e:.2e}")
+        if not e < 1e-12:
+            failures.append("mrtcg")
+    d.close()
+
+    dist.barrier()
+    flag = [len(failures)]
+    dist.broadcast_object_list(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(1 if flag[0] else 0)
+
+
+if __name__ == "__main__":
+    main()
