@@ -147,15 +147,16 @@ __device__ __forceinline__ void load_streamed_pair(const double* __restrict__ ba
   }
 }
 
-// grid: x = ceil(npairs / blockDim.x), y = rows in [row_begin, row_end)
+// grid: x = ceil(npairs / blockDim.x), y = number of rows in `rows` (the launch's row list: the
+// "early" rows whose results feed the ghost exchange / IBM pre-pass of the next step, or the bulk)
 template <int MODE, int EQ, int FORCE, bool ADE>
 __global__ void __launch_bounds__(128)
 k_bgk_interior(const double* __restrict__ fsrc, double* __restrict__ fdst, const double* __restrict__ gsrc,
-               double* __restrict__ gdst, const SlabGeom g, const BgkParams p, int row_begin, int npairs,
+               double* __restrict__ gdst, const SlabGeom g, const BgkParams p, const int* __restrict__ rows, int npairs,
                double* __restrict__ out_f, double* __restrict__ out_g)
 {
   const int pi = blockIdx.x * blockDim.x + threadIdx.x;
-  const int x = row_begin + blockIdx.y;
+  const int x = rows[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const bool active = pi < npairs;
   const bool last_active = (pi == npairs - 1);

@@ -188,7 +188,7 @@ int comm_exchange_moments(lbm_domain* d)
 }
 
 // pressure packet of stage k: from the rank that owns the source row to the rank that owns the written row
-int comm_stage_transfer(lbm_domain* d, size_t k)
+int comm_stage_transfer(lbm_domain* d, size_t k, cudaStream_t st)
 {
   Stage& sg = d->stages[k];
   if (sg.kind != 1) return LBM_OK;
@@ -196,8 +196,8 @@ int comm_stage_transfer(lbm_domain* d, size_t k)
   const int src_rank = owner_of(d->cfg.X, c->n_ranks, sg.src_gx), dst_rank = owner_of(d->cfg.X, c->n_ranks, sg.dst_gx);
   if (src_rank == dst_rank) return LBM_OK;
   const size_t n = (size_t)12 * d->g.Y;
-  if (c->rank == src_rank) LBM_NCCL(g_nccl.Send(sg.d_packet, n, ncclFloat64, dst_rank, c->comm, d->stream));
-  if (c->rank == dst_rank) LBM_NCCL(g_nccl.Recv(sg.d_packet, n, ncclFloat64, src_rank, c->comm, d->stream));
+  if (c->rank == src_rank) LBM_NCCL(g_nccl.Send(sg.d_packet, n, ncclFloat64, dst_rank, c->comm, st));
+  if (c->rank == dst_rank) LBM_NCCL(g_nccl.Recv(sg.d_packet, n, ncclFloat64, src_rank, c->comm, st));
   if (c->rank == src_rank || c->rank == dst_rank) d->launches++;
   return LBM_OK;
 }
@@ -205,24 +205,21 @@ int comm_stage_transfer(lbm_domain* d, size_t k)
 // ------------------------------------------------------------------------------------------------
 // link transport: slabs of one process
 // ------------------------------------------------------------------------------------------------
-static int copy_rows(lbm_domain* dst, double* dptr, lbm_domain* src, const double* sptr, size_t count)
+static int copy_rows(lbm_domain* dst, double* dptr, lbm_domain* src, const double* sptr, size_t count, cudaStream_t st)
 {
   if (dst->cfg.device == src->cfg.device)
-    LBM_CUDA(cudaMemcpyAsync(dptr, sptr, count * sizeof(double), cudaMemcpyDeviceToDevice, dst->stream));
+    LBM_CUDA(cudaMemcpyAsync(dptr, sptr, count * sizeof(double), cudaMemcpyDeviceToDevice, st));
   else
-    LBM_CUDA(cudaMemcpyPeerAsync(dptr, dst->cfg.device, sptr, src->cfg.device, count * sizeof(double), dst->stream));
+    LBM_CUDA(cudaMemcpyPeerAsync(dptr, dst->cfg.device, sptr, src->cfg.device, count * sizeof(double), st));
   dst->launches++;
   return LBM_OK;
 }
 
-// ghost rows of buffer `which` of slab d from its linked neighbours (on d's stream, after the
-// neighbours' ev_ready)
-static int link_exchange(lbm_domain* d, int which)
+// Ghost rows of buffer `which` of slab d from the same buffer index of its linked neighbours, on
+// stream st.  The caller has made st wait for the neighbours' rows to be final.
+int link_exchange(lbm_domain* d, int which, cudaStream_t st)
 {
   const SlabGeom& g = d->g;
-  LBM_CUDA(cudaSetDevice(d->cfg.device));
-  if (d->link_lo) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->link_lo->ev_ready, 0));
-  if (d->link_hi) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->link_hi->ev_ready, 0));
   for (int l = 0; l < d->nlat; l++)
     for (int q = 0; q < 9; q++)
     {
@@ -230,29 +227,47 @@ static int link_exchange(lbm_domain* d, int which)
       if (d->link_lo && (d->wrap_all_q || CX(q) == 1))
       {
         lbm_domain* s = d->link_lo;
-        const double* last = s->buf[l][s->cur] + (long long)q * s->g.plane + (long long)s->g.Xl * s->g.pitch;
-        LBM_TRY(copy_rows(d, plane, s, last, g.pitch));
+        const double* last = s->buf[l][which] + (long long)q * s->g.plane + (long long)s->g.Xl * s->g.pitch;
+        LBM_TRY(copy_rows(d, plane, s, last, g.pitch, st));
       }
       if (d->link_hi && (d->wrap_all_q || CX(q) == -1))
       {
         lbm_domain* s = d->link_hi;
-        const double* first = s->buf[l][s->cur] + (long long)q * s->g.plane + (long long)s->g.pitch;
-        LBM_TRY(copy_rows(d, plane + (long long)(g.Xl + 1) * g.pitch, s, first, g.pitch));
+        const double* first = s->buf[l][which] + (long long)q * s->g.plane + (long long)s->g.pitch;
+        LBM_TRY(copy_rows(d, plane + (long long)(g.Xl + 1) * g.pitch, s, first, g.pitch, st));
       }
     }
   return LBM_OK;
 }
 
+// Linked slab outside lbm_step_group (export right after an import): bring the ghost rows of
+// buf[cur] in from the neighbours' current buffers and signal ev_side.
 int comm_link_refresh(lbm_domain* d)
 {
-  for (lbm_domain* o : {d->link_lo, d->link_hi})
-  {
-    if (!o) continue;
-    LBM_CUDA(cudaSetDevice(o->cfg.device));
-    LBM_CUDA(cudaEventRecord(o->ev_ready, o->stream));
-  }
+  if (d->side_ready) return LBM_OK;
   LBM_CUDA(cudaSetDevice(d->cfg.device));
-  return link_exchange(d, d->cur);
+  LBM_CUDA(cudaEventRecord(d->ev_ready, d->stream));
+  LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
+  if (!d->post_stream)
+  {
+    for (lbm_domain* o : {d->link_lo, d->link_hi})
+    {
+      if (!o || o == d) continue;
+      if (o->cur != d->cur || o->post_stream)
+      {
+        set_error("linked slabs are out of step (advance them together with lbm_step_group)");
+        return LBM_ERR_INVALID;
+      }
+      LBM_CUDA(cudaSetDevice(o->cfg.device));
+      LBM_CUDA(cudaEventRecord(o->ev_ready, o->stream));
+      LBM_CUDA(cudaSetDevice(d->cfg.device));
+      LBM_CUDA(cudaStreamWaitEvent(d->side, o->ev_ready, 0));
+      LBM_CUDA(cudaStreamWaitEvent(d->side, o->ev_side, 0));
+    }
+    LBM_TRY(link_exchange(d, d->cur, d->side));
+  }
+  LBM_TRY(step_prologue(d, false));  // IBM field if any, then ev_side (on the same side stream)
+  return LBM_OK;
 }
 
 }  // namespace lbm
@@ -300,7 +315,7 @@ int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks
     return LBM_ERR_COMM;
   }
   d->comm = c;
-  d->ghost_valid = false;
+  d->side_ready = false;
   return LBM_OK;
 }
 
@@ -330,13 +345,12 @@ int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper)
   }
   d->link_lo = lower;
   d->link_hi = upper;
-  d->ghost_valid = false;
+  d->side_ready = false;
   return LBM_OK;
 }
 
-// Advance a set of linked slabs in lock step.  Per step: every slab publishes "previous step done",
-// pulls its ghost rows from its neighbours, computes; then the pre-stream stages run slab by slab
-// with the pressure packets copied between owners.
+// Advance a set of linked slabs in lock step: the phases of one step (lbm_domain.cu) interleaved
+// across the slabs, with the ghost rows and pressure packets copied between the slabs' side streams.
 int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
 {
   if (!ds || n < 1 || n_steps < 0) { set_error("lbm_step_group: bad argument"); return LBM_ERR_INVALID; }
@@ -345,65 +359,88 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
     if (!ds[i] || !ds[i]->have_state || !ds[i]->committed) { set_error("lbm_step_group: slab %d has no state / uncommitted rules", i); return LBM_ERR_INVALID; }
     if (ds[i]->tp) { set_error("lbm_step_group: two-phase slabs are stepped over NCCL (lbm_comm_init), not linked"); return LBM_ERR_UNSUPPORTED; }
     if (ds[i]->stages.size() != ds[0]->stages.size()) { set_error("lbm_step_group: slabs carry different rule lists"); return LBM_ERR_INVALID; }
+    if (ds[i]->cur != ds[0]->cur || ds[i]->post_stream != ds[0]->post_stream) { set_error("lbm_step_group: slabs are out of step"); return LBM_ERR_INVALID; }
   }
+  auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
   for (int i = 0; i < n; i++)
   {
-    LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+    LBM_CUDA(on(ds[i]));
     LBM_CUDA(cudaEventRecord(ds[i]->ev_begin, ds[i]->stream));
   }
   for (int s = 0; s < n_steps; s++)
   {
-    for (int i = 0; i < n; i++)
+    // ---- state nobody prepared yet (first step): ghost rows from the neighbours + IBM field
+    bool any = false;
+    for (int i = 0; i < n; i++) any = any || !ds[i]->side_ready;
+    if (any)
     {
-      LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
-      LBM_CUDA(cudaEventRecord(ds[i]->ev_ready, ds[i]->stream));
-    }
-    for (int i = 0; i < n; i++)
-    {
-      lbm_domain* d = ds[i];
-      if (!d->post_stream)
+      for (int i = 0; i < n; i++)
       {
-        ProfScope ps(d, LBM_PROF_GHOST);
-        if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur));
-        else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
+        LBM_CUDA(on(ds[i]));
+        LBM_CUDA(cudaEventRecord(ds[i]->ev_ready, ds[i]->stream));
       }
-      d->ghost_valid = true;
-      d->ghost_pending = false;
+      for (int i = 0; i < n; i++)
+      {
+        lbm_domain* d = ds[i];
+        if (d->side_ready) continue;
+        LBM_CUDA(on(d));
+        if (!d->post_stream)
+        {
+          for (lbm_domain* o : {d->link_lo, d->link_hi})
+            if (o) LBM_CUDA(cudaStreamWaitEvent(d->side, o->ev_ready, 0));
+          LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
+          ProfScope ps(d, LBM_PROF_GHOST, d->side);
+          if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur, d->side));
+          else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->side));
+        }
+        LBM_TRY(step_prologue(d, false));
+      }
     }
-    for (int i = 0; i < n; i++)
-    {
-      LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
-      LBM_TRY(step_compute(ds[i]));
-    }
+    // ---- early rows, listed nodes
+    for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_early(ds[i])); }
+    for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_listed(ds[i])); }
+    // ---- pre-stream stages, packets handed from the source owner to the writer
     for (size_t k = 0; k < ds[0]->stages.size(); k++)
     {
       lbm_domain *src = nullptr, *dst = nullptr;
       for (int i = 0; i < n; i++)
       {
-        LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+        LBM_CUDA(on(ds[i]));
         LBM_TRY(stage_pack(ds[i], k));
         if (ds[i]->stages[k].kind == 1 && ds[i]->stages[k].own_src) src = ds[i];
         if (ds[i]->stages[k].kind == 1 && ds[i]->stages[k].own_dst) dst = ds[i];
       }
       if (src && dst && src != dst)
       {
-        LBM_CUDA(cudaSetDevice(src->cfg.device));
-        LBM_CUDA(cudaEventRecord(src->ev_packet, src->stream));
-        LBM_CUDA(cudaSetDevice(dst->cfg.device));
-        LBM_CUDA(cudaStreamWaitEvent(dst->stream, src->ev_packet, 0));
-        LBM_TRY(copy_rows(dst, dst->stages[k].d_packet, src, src->stages[k].d_packet, (size_t)12 * dst->g.Y));
+        LBM_CUDA(on(src));
+        LBM_CUDA(cudaEventRecord(src->ev_packet, src->side));
+        LBM_CUDA(on(dst));
+        LBM_CUDA(cudaStreamWaitEvent(dst->side, src->ev_packet, 0));
+        LBM_TRY(copy_rows(dst, dst->stages[k].d_packet, src, src->stages[k].d_packet, (size_t)12 * dst->g.Y, dst->side));
       }
-      for (int i = 0; i < n; i++)
-      {
-        LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
-        LBM_TRY(stage_apply(ds[i], k));
-      }
+      for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(stage_apply(ds[i], k)); }
     }
-    for (int i = 0; i < n; i++) LBM_TRY(step_finish(ds[i]));
+    for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_CUDA(cudaEventRecord(ds[i]->ev_stage, ds[i]->side)); }
+    // ---- ghost rows of the new buffers, next IBM field
+    for (int i = 0; i < n; i++)
+    {
+      lbm_domain* d = ds[i];
+      LBM_CUDA(on(d));
+      for (lbm_domain* o : {d->link_lo, d->link_hi})
+        if (o && o != d) LBM_CUDA(cudaStreamWaitEvent(d->side, o->ev_stage, 0));
+      {
+        ProfScope ps(d, LBM_PROF_GHOST, d->side);
+        if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur ^ 1, d->side));
+        else LBM_TRY(wrap_ghost_rows_local(d, d->cur ^ 1, d->side));
+      }
+      LBM_TRY(step_side_tail(d, false));
+    }
+    // ---- bulk rows
+    for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_bulk(ds[i])); }
   }
   for (int i = 0; i < n; i++)
   {
-    LBM_CUDA(cudaSetDevice(ds[i]->cfg.device));
+    LBM_CUDA(on(ds[i]));
     LBM_CUDA(cudaEventRecord(ds[i]->ev_end, ds[i]->stream));
   }
   return LBM_OK;

@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...)
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
-ProfScope::ProfScope(lbm_domain* dom, int cls) : d(dom)
+ProfScope::ProfScope(lbm_domain* dom, int cls, cudaStream_t stream) : d(dom), st(stream ? stream : dom->stream)
 {
   if (!d->profiling) return;
   if (d->prof_used == d->prof.size())
@@ -38,12 +38,12 @@ ProfScope::ProfScope(lbm_domain* dom, int cls) : d(dom)
   }
   idx = (long)d->prof_used++;
   d->prof[idx].cls = cls;
-  cudaEventRecord(d->prof[idx].a, d->stream);
+  cudaEventRecord(d->prof[idx].a, st);
 }
 
 ProfScope::~ProfScope()
 {
-  if (idx >= 0) cudaEventRecord(d->prof[idx].b, d->stream);
+  if (idx >= 0) cudaEventRecord(d->prof[idx].b, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -87,10 +87,20 @@ __global__ void k_init_equilibrium(double* __restrict__ f, const SlabGeom g, int
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int EQ, int FORCE, bool ADE>
-static int launch_bgk(lbm_domain* d, int row_begin, int row_end, bool do_interior, bool do_boundary)
+// what one launch of the fused kernels works on
+struct LaunchArgs
 {
-  const int s = d->cur, t = d->cur ^ 1;
+  int s, t;             // source / destination buffer
+  const int* rows;      // row list of the interior kernel (nullptr: no interior launch)
+  int n_rows;
+  bool listed;          // run the listed-node kernel
+  int slot;             // IBM force-field slot to read
+  cudaStream_t stream;
+};
+
+template <int MODE, int EQ, int FORCE, bool ADE>
+static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
+{
   BgkParams p;
   p.omega = d->cfg.omega;
   p.omega_g = d->cfg.omega_g;
@@ -98,36 +108,28 @@ static int launch_bgk(lbm_domain* d, int row_begin, int row_end, bool do_interio
   p.Fg1 = d->cfg.Fg[1];
   p.w_s = d->cfg.w_s;
   p.roi_r0 = (int)d->ibm.r0; p.roi_r1 = (int)d->ibm.r1; p.roi_c0 = (int)d->ibm.c0; p.roi_c1 = (int)d->ibm.c1;
-  p.Fx = d->ibm.d_Fx;
-  p.Fy = d->ibm.d_Fy;
-  if (do_interior && d->npairs > 0 && row_end > row_begin)
+  p.Fx = d->ibm.d_Fx[a.slot];
+  p.Fy = d->ibm.d_Fy[a.slot];
+  if (a.rows && d->npairs > 0 && a.n_rows > 0)
   {
-    ProfScope ps(d, LBM_PROF_INTERIOR);
-    dim3 grid(cdiv(d->npairs, 128), row_end - row_begin);
-    k_bgk_interior<MODE, EQ, FORCE, ADE><<<grid, 128, 0, d->stream>>>(
-        d->buf[0][s], d->buf[0][t], d->buf[1][s], d->buf[1][t], d->g, p, row_begin, d->npairs, d->d_aos[0], d->d_aos[1]);
+    ProfScope ps(d, LBM_PROF_INTERIOR, a.stream);
+    dim3 grid(cdiv(d->npairs, 128), a.n_rows);
+    k_bgk_interior<MODE, EQ, FORCE, ADE><<<grid, 128, 0, a.stream>>>(d->buf[0][a.s], d->buf[0][a.t], d->buf[1][a.s], d->buf[1][a.t],
+                                                                    d->g, p, a.rows, d->npairs, d->d_aos[0], d->d_aos[1]);
     d->launches++;
   }
-  if (do_boundary && d->nb > 0)
+  if (a.listed && d->nb > 0)
   {
-    ProfScope ps(d, LBM_PROF_BOUNDARY);
+    ProfScope ps(d, LBM_PROF_BOUNDARY, a.stream);
     BoundaryTable bt;
     bt.n = d->nb;
     bt.x = d->d_bx;
     bt.y = d->d_by;
     bt.ent = d->d_ent;
-    if (MODE == MODE_PULL_ONLY)
-    {
-      bt.mom_cur = nullptr;
-      bt.mom_prev = d->d_mom[d->mom_cur];
-    }
-    else
-    {
-      bt.mom_cur = d->d_mom[d->mom_cur ^ 1];
-      bt.mom_prev = d->d_mom[d->mom_cur];
-    }
-    k_bgk_boundary<MODE, EQ, FORCE, ADE><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(
-        d->buf[0][s], d->buf[0][t], d->buf[1][s], d->buf[1][t], d->g, p, bt, d->d_aos[0], d->d_aos[1]);
+    bt.mom_prev = d->d_mom[d->mom_cur];
+    bt.mom_cur = MODE == MODE_PULL_ONLY ? nullptr : d->d_mom[d->mom_cur ^ 1];
+    k_bgk_boundary<MODE, EQ, FORCE, ADE><<<cdiv(d->nb, 128), 128, 0, a.stream>>>(d->buf[0][a.s], d->buf[0][a.t], d->buf[1][a.s],
+                                                                                d->buf[1][a.t], d->g, p, bt, d->d_aos[0], d->d_aos[1]);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
@@ -135,13 +137,13 @@ static int launch_bgk(lbm_domain* d, int row_begin, int row_end, bool do_interio
 }
 
 template <int MODE>
-static int dispatch_bgk(lbm_domain* d, int rb, int re, bool di, bool db)
+static int dispatch_bgk(lbm_domain* d, const LaunchArgs& a)
 {
   const bool ade = d->cfg.model == LBM_MODEL_BGK_ADE;
   const int eq = d->cfg.equilibrium, fo = d->cfg.force;
-  if (ade) return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, rb, re, di, db);
+  if (ade) return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, a);
 #define LBM_CASE(E, F) \
-  if (eq == E && fo == F) return launch_bgk<MODE, E, F, false>(d, rb, re, di, db);
+  if (eq == E && fo == F) return launch_bgk<MODE, E, F, false>(d, a);
   LBM_CASE(EQ_COMP, FORCE_NONE)
   LBM_CASE(EQ_COMP, FORCE_UNIFORM)
   LBM_CASE(EQ_COMP, FORCE_IBM)
@@ -151,6 +153,13 @@ static int dispatch_bgk(lbm_domain* d, int rb, int re, bool di, bool db)
 #undef LBM_CASE
   set_error("unsupported equilibrium/force combination (%d, %d)", eq, fo);
   return LBM_ERR_INVALID;
+}
+
+static int dispatch_mode(lbm_domain* d, int mode, const LaunchArgs& a)
+{
+  if (mode == MODE_LOCAL) return dispatch_bgk<MODE_LOCAL>(d, a);
+  if (mode == MODE_PULL) return dispatch_bgk<MODE_PULL>(d, a);
+  return dispatch_bgk<MODE_PULL_ONLY>(d, a);
 }
 
 int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st)
@@ -164,99 +173,105 @@ int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st)
   return LBM_OK;
 }
 
-// Ghost rows of the SOURCE buffer: the neighbour slabs' boundary rows (NCCL), or the slab's own
-// opposite rows when it is the whole domain (periodic wrap of solver::advect along axis 0).
-// Issued on the side stream so that it overlaps the interior rows, which do not read ghost rows.
-int step_prepare(lbm_domain* d)
+// ------------------------------------------------------------------------------------------------
+// One time step of the single-phase family.
+//
+//   main stream : [wait side chain of the previous step]  EARLY rows  ->  ev_early  ->  BULK rows
+//   side stream : [wait ev_early] listed nodes -> pre-stream stages -> ghost rows of the new buffer
+//                 (local wrap / NCCL ring) -> IBM pre-pass for the NEXT step -> ev_side
+//
+// EARLY rows are the few rows whose results something else needs soon: the first and last row
+// (ghost exchange), rows owning a listed node in an interior column or feeding a stage (the listed
+// kernel and the stages overwrite / read them), and the immersed-boundary ROI rows (next pre-pass).
+// Everything small therefore runs concurrently with the BULK launch, which is >95 % of the step.
+// ------------------------------------------------------------------------------------------------
+int step_rows(lbm_domain* d)
 {
-  if (d->ghost_valid || d->post_stream) return LBM_OK;  // a post-stream (just imported) state is read locally
-  if (d->link_lo || d->link_hi)                         // linked slabs outside lbm_step_group (export, solo stepping)
+  if (!d->rows_dirty) return LBM_OK;
+  const int Xl = d->g.Xl;
+  std::vector<char> early(Xl, 0);
+  early[0] = early[Xl - 1] = 1;
+  for (int x = 0; x < Xl && x < (int)d->row_has_listed.size(); x++)
+    if (d->row_has_listed[x]) early[x] = 1;
+  if (d->ibm.enabled)
+    for (long gx = d->ibm.r0 - 1; gx < d->ibm.r1 + 1; gx++)
+    {
+      const long x = gx - d->cfg.x0;
+      if (x >= 0 && x < Xl) early[x] = 1;
+    }
+  std::vector<int> all(Xl), e, b;
+  for (int x = 0; x < Xl; x++)
   {
-    LBM_TRY(comm_link_refresh(d));
-    d->ghost_valid = true;
-    d->ghost_pending = false;
-    return LBM_OK;
+    all[x] = x;
+    (early[x] ? e : b).push_back(x);
   }
-  LBM_CUDA(cudaEventRecord(d->ev_ready, d->stream));
-  LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
-  {
-    ProfScope ps(d, LBM_PROF_GHOST);
-    if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->side));
-    else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->side));
-  }
-  LBM_CUDA(cudaEventRecord(d->ev_ghost, d->side));
-  d->ghost_valid = true;
-  d->ghost_pending = true;
+  cudaFree(d->d_rows_all); cudaFree(d->d_rows_early); cudaFree(d->d_rows_bulk);
+  d->d_rows_all = d->d_rows_early = d->d_rows_bulk = nullptr;
+  LBM_CUDA(cudaMalloc(&d->d_rows_all, sizeof(int) * Xl));
+  LBM_CUDA(cudaMalloc(&d->d_rows_early, sizeof(int) * std::max<size_t>(e.size(), 1)));
+  LBM_CUDA(cudaMalloc(&d->d_rows_bulk, sizeof(int) * std::max<size_t>(b.size(), 1)));
+  LBM_CUDA(cudaMemcpy(d->d_rows_all, all.data(), sizeof(int) * Xl, cudaMemcpyHostToDevice));
+  LBM_CUDA(cudaMemcpy(d->d_rows_early, e.data(), sizeof(int) * e.size(), cudaMemcpyHostToDevice));
+  LBM_CUDA(cudaMemcpy(d->d_rows_bulk, b.data(), sizeof(int) * b.size(), cudaMemcpyHostToDevice));
+  d->n_early = (int)e.size();
+  d->n_bulk = (int)b.size();
+  d->rows_dirty = false;
   return LBM_OK;
 }
 
-// IBM pre-pass on the side stream + the fused collide/stream kernels on the main stream.  Row
-// ranges that need neither ghost rows nor the ROI force field are launched first.
-int step_compute(lbm_domain* d)
+static bool uses_ibm(const lbm_domain* d) { return d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM; }
+
+// Side chain for a state that no step has prepared (first step after an import, or an export):
+// ghost rows of buf[cur] and the IBM field the next step reads.
+int step_prologue(lbm_domain* d, bool exchange_local)
+{
+  if (d->side_ready) return LBM_OK;
+  const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
+  LBM_CUDA(cudaEventRecord(d->ev_ready, d->stream));
+  LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
+  if (mode == MODE_PULL && exchange_local)
+  {
+    ProfScope ps(d, LBM_PROF_GHOST, d->side);
+    if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->side));
+    else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->side));
+  }
+  if (uses_ibm(d))
+  {
+    ProfScope ps(d, LBM_PROF_IBM, d->side);
+    LBM_TRY(ibm_prepass(d, mode, d->cur, d->ibm.next_slot, d->side));
+  }
+  LBM_CUDA(cudaEventRecord(d->ev_side, d->side));
+  d->side_ready = true;
+  return LBM_OK;
+}
+
+int step_early(lbm_domain* d)
+{
+  LBM_TRY(step_rows(d));
+  const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
+  LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+  LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_early, d->n_early, false, d->ibm.next_slot, d->stream};
+  LBM_TRY(dispatch_mode(d, mode, a));
+  LBM_CUDA(cudaEventRecord(d->ev_early, d->stream));
+  return LBM_OK;
+}
+
+int step_listed(lbm_domain* d)
 {
   const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
-  const int Xl = d->g.Xl;
-  const bool ibm = d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM;
-  if (ibm)
-  {
-    LBM_CUDA(cudaEventRecord(d->ev_ready, d->stream));
-    LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_ready, 0));
-    cudaStream_t main_stream = d->stream;
-    d->stream = d->side;  // the pre-pass kernels launch on d->stream
-    int st;
-    {
-      ProfScope ps(d, LBM_PROF_IBM);
-      st = ibm_prepass(d, mode);
-    }
-    d->stream = main_stream;
-    LBM_TRY(st);
-    LBM_CUDA(cudaEventRecord(d->ev_ibm, d->side));
-  }
-  // split [0, Xl) at the rows that need the ghost rows (0 and Xl-1 when pulling) and at the ROI rows
-  int cuts[6] = {0, Xl, Xl, Xl, Xl, Xl};
-  int nc = 1;
-  auto add_cut = [&](int c) { if (c > 0 && c < Xl) cuts[nc++] = c; };
-  const bool need_ghost = mode == MODE_PULL && d->ghost_pending;
-  if (need_ghost) { add_cut(1); add_cut(Xl - 1); }
-  const int r0 = (int)d->ibm.r0 - d->cfg.x0, r1 = (int)d->ibm.r1 - d->cfg.x0;
-  if (ibm) { add_cut(r0); add_cut(r1); }
-  std::sort(cuts, cuts + nc);
-  cuts[nc] = Xl;
-  auto flags = [&](int lo, int hi) {
-    int f = 0;
-    if (need_ghost && (lo == 0 || hi == Xl)) f |= 1;
-    if (ibm && lo < r1 && hi > r0) f |= 2;
-    return f;
-  };
-  bool waited_ghost = false, waited_ibm = false;
-  for (int pass = 0; pass < 4; pass++)  // flags 0, then 1 (ghost), then 2 (ibm), then 3 (both)
-  {
-    for (int k = 0; k < nc; k++)
-    {
-      const int lo = cuts[k], hi = cuts[k + 1];
-      if (hi <= lo || flags(lo, hi) != pass) continue;
-      if ((pass & 1) && !waited_ghost) { LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ghost, 0)); waited_ghost = true; }
-      if ((pass & 2) && !waited_ibm) { LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ibm, 0)); waited_ibm = true; }
-      if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, lo, hi, true, false));
-      else LBM_TRY(dispatch_bgk<MODE_PULL>(d, lo, hi, true, false));
-    }
-  }
-  if (need_ghost && !waited_ghost) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ghost, 0));
-  if (ibm && !waited_ibm) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ibm, 0));
-  d->ghost_pending = false;
-  if (mode == MODE_LOCAL) LBM_TRY(dispatch_bgk<MODE_LOCAL>(d, 0, 0, false, true));
-  else LBM_TRY(dispatch_bgk<MODE_PULL>(d, 0, 0, false, true));
-  return LBM_OK;
+  LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_early, 0));
+  LaunchArgs a{d->cur, d->cur ^ 1, nullptr, 0, true, d->ibm.next_slot, d->side};
+  return dispatch_mode(d, mode, a);
 }
 
 int stage_pack(lbm_domain* d, size_t k)
 {
   Stage& sg = d->stages[k];
   if (sg.kind != 1 || !sg.own_src || sg.y_hi <= sg.y_lo) return LBM_OK;
-  ProfScope ps(d, LBM_PROF_FIXUP);
+  ProfScope ps(d, LBM_PROF_FIXUP, d->side);
   const int t = d->cur ^ 1;
-  k_pressure_pack<<<cdiv(sg.y_hi - sg.y_lo, 128), 128, 0, d->stream>>>(d->buf[0][t], d->g, sg.src_gx - d->cfg.x0, sg.d_src_bidx,
-                                                                      d->d_mom[d->mom_cur ^ 1], sg.d_packet, sg.y_lo, sg.y_hi);
+  k_pressure_pack<<<cdiv(sg.y_hi - sg.y_lo, 128), 128, 0, d->side>>>(d->buf[0][t], d->g, sg.src_gx - d->cfg.x0, sg.d_src_bidx,
+                                                                    d->d_mom[d->mom_cur ^ 1], sg.d_packet, sg.y_lo, sg.y_hi);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
@@ -266,11 +281,11 @@ int stage_apply(lbm_domain* d, size_t k)
 {
   Stage& sg = d->stages[k];
   const int t = d->cur ^ 1;
-  ProfScope ps(d, LBM_PROF_FIXUP);
+  ProfScope ps(d, LBM_PROF_FIXUP, d->side);
   if (sg.kind == 0)
   {
     if (sg.n == 0) return LBM_OK;
-    k_fix_copy<<<cdiv(sg.n, 128), 128, 0, d->stream>>>(d->buf[0][t], d->buf[1][t], d->g, sg.d_entries, sg.n);
+    k_fix_copy<<<cdiv(sg.n, 128), 128, 0, d->side>>>(d->buf[0][t], d->buf[1][t], d->g, sg.d_entries, sg.n);
     d->launches++;
   }
   else
@@ -278,35 +293,66 @@ int stage_apply(lbm_domain* d, size_t k)
     if (!sg.own_dst || sg.y_hi <= sg.y_lo) return LBM_OK;
     const int lx = sg.dst_gx - d->cfg.x0, nblk = cdiv(sg.y_hi - sg.y_lo, 128);
     if (d->cfg.equilibrium == EQ_INCOMP)
-      k_pressure_apply<EQ_INCOMP><<<nblk, 128, 0, d->stream>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+      k_pressure_apply<EQ_INCOMP><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     else
-      k_pressure_apply<EQ_COMP><<<nblk, 128, 0, d->stream>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+      k_pressure_apply<EQ_COMP><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
 }
 
-int step_finish(lbm_domain* d)
+// ghost rows of the NEW buffer and the IBM field of the NEXT step, then ev_side
+int step_side_tail(lbm_domain* d, bool exchange_local)
 {
+  const int t = d->cur ^ 1;
+  if (exchange_local)
+  {
+    ProfScope ps(d, LBM_PROF_GHOST, d->side);
+    if (comm_active(d)) LBM_TRY(comm_exchange(d, t, d->side));
+    else LBM_TRY(wrap_ghost_rows_local(d, t, d->side));
+  }
+  if (uses_ibm(d))
+  {
+    ProfScope ps(d, LBM_PROF_IBM, d->side);
+    LBM_TRY(ibm_prepass(d, MODE_PULL, t, d->ibm.next_slot ^ 1, d->side));
+  }
+  LBM_CUDA(cudaEventRecord(d->ev_side, d->side));
+  return LBM_OK;
+}
+
+int step_bulk(lbm_domain* d)
+{
+  const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
+  LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_bulk, d->n_bulk, false, d->ibm.next_slot, d->stream};
+  LBM_TRY(dispatch_mode(d, mode, a));
   d->cur ^= 1;
   d->mom_cur ^= 1;
   d->post_stream = false;
-  d->ghost_valid = false;
+  d->ibm.used_slot = d->ibm.next_slot;
+  d->ibm.next_slot ^= 1;
+  d->side_ready = true;  // the side chain enqueued during this step prepared the new buffer
   return LBM_OK;
 }
 
 static int bgk_step_once(lbm_domain* d)
 {
-  LBM_TRY(step_prepare(d));
-  LBM_TRY(step_compute(d));
+  if (d->link_lo || d->link_hi)
+  {
+    set_error("lbm_step: this slab is linked to neighbours; advance the set with lbm_step_group");
+    return LBM_ERR_INVALID;
+  }
+  LBM_TRY(step_prologue(d, true));
+  LBM_TRY(step_early(d));
+  LBM_TRY(step_listed(d));
   for (size_t k = 0; k < d->stages.size(); k++)
   {
     LBM_TRY(stage_pack(d, k));
-    if (comm_active(d)) LBM_TRY(comm_stage_transfer(d, k));
+    if (comm_active(d)) LBM_TRY(comm_stage_transfer(d, k, d->side));
     LBM_TRY(stage_apply(d, k));
   }
-  return step_finish(d);
+  LBM_TRY(step_side_tail(d, true));
+  return step_bulk(d);
 }
 
 int ensure_aos_scratch(lbm_domain* d)
@@ -333,14 +379,13 @@ static int export_post_stream(lbm_domain* d)
     LBM_CUDA(cudaGetLastError());
     return LBM_OK;
   }
-  // pull-only pass: ghost rows first (they are refreshed lazily, at the start of a step)
-  LBM_TRY(step_prepare(d));
-  if (d->ghost_pending)
-  {
-    LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ghost, 0));
-    d->ghost_pending = false;
-  }
-  return dispatch_bgk<MODE_PULL_ONLY>(d, 0, d->g.Xl, true, true);
+  // pull-only pass over every row: the ghost rows of buf[cur] must be in place
+  LBM_TRY(step_rows(d));
+  if (d->link_lo || d->link_hi) LBM_TRY(comm_link_refresh(d));
+  else LBM_TRY(step_prologue(d, true));
+  LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+  LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_all, d->g.Xl, true, d->ibm.used_slot, d->stream};
+  return dispatch_bgk<MODE_PULL_ONLY>(d, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -603,6 +648,29 @@ int commit_boundary_tables(lbm_domain* d)
     }
   }
 
+  // rows the interior kernel must finish before the listed-node kernel / the stages touch them
+  d->row_has_listed.assign(Xl, 0);
+  for (auto& kv : index)
+  {
+    const int lx = (int)(kv.first / Y), y = (int)(kv.first % Y);
+    if (y >= y_int_begin && y < y_int_end) d->row_has_listed[lx] = 1;
+  }
+  for (auto& hs : host_stages)
+  {
+    if (hs.kind == 1)
+    {
+      if (hs.own_dst) d->row_has_listed[hs.dst_gx - x0] = 1;
+      if (hs.own_src) d->row_has_listed[hs.src_gx - x0] = 1;
+    }
+    for (auto& e : hs.entries)
+    {
+      d->row_has_listed[(int)(e.dst / g.pitch) - 1] = 1;
+      d->row_has_listed[(int)(e.src / g.pitch) - 1] = 1;
+    }
+  }
+  d->rows_dirty = true;
+  d->side_ready = false;
+
   // ---- upload
   d->nb = nb;
   if (nb > 0)
@@ -732,13 +800,17 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
       cudaMemset(d->buf[l][b], 0, bytes);
     }
   LBM_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-  LBM_CUDA(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
+  {
+    // the side chain is a string of tiny kernels: give it priority so it slips in between the
+    // blocks of the bulk launch instead of queueing behind them
+    int lo = 0, hi = 0;
+    LBM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LBM_CUDA(cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, hi));
+  }
   LBM_CUDA(cudaEventCreate(&d->ev_begin));
   LBM_CUDA(cudaEventCreate(&d->ev_end));
-  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_ready, cudaEventDisableTiming));
-  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_ibm, cudaEventDisableTiming));
-  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_ghost, cudaEventDisableTiming));
-  LBM_CUDA(cudaEventCreateWithFlags(&d->ev_packet, cudaEventDisableTiming));
+  for (cudaEvent_t* e : {&d->ev_ready, &d->ev_early, &d->ev_side, &d->ev_stage, &d->ev_packet})
+    LBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK)
   {
     int s = tp_create(d);
@@ -772,10 +844,9 @@ int lbm_destroy(lbm_domain* d)
   }
   if (d->ev_begin) cudaEventDestroy(d->ev_begin);
   if (d->ev_end) cudaEventDestroy(d->ev_end);
-  if (d->ev_ready) cudaEventDestroy(d->ev_ready);
-  if (d->ev_ibm) cudaEventDestroy(d->ev_ibm);
-  if (d->ev_ghost) cudaEventDestroy(d->ev_ghost);
-  if (d->ev_packet) cudaEventDestroy(d->ev_packet);
+  for (cudaEvent_t e : {d->ev_ready, d->ev_early, d->ev_side, d->ev_stage, d->ev_packet})
+    if (e) cudaEventDestroy(e);
+  cudaFree(d->d_rows_all); cudaFree(d->d_rows_early); cudaFree(d->d_rows_bulk);
   if (d->side) cudaStreamDestroy(d->side);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
@@ -865,7 +936,7 @@ int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos)
   LBM_CUDA(cudaGetLastError());
   d->post_stream = true;
   d->have_state = true;
-  d->ghost_valid = false;
+  d->side_ready = false;
   if (d->tp) LBM_TRY(tp_refresh_moments(d));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
   return LBM_OK;
@@ -929,6 +1000,7 @@ int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* 
   cudaFree(d_u);
   d->post_stream = true;
   d->have_state = true;
+  d->side_ready = false;
   return LBM_OK;
 }
 

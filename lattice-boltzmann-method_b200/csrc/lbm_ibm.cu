@@ -121,47 +121,48 @@ int ibm_release(lbm_domain* d)
 {
   IbmState& ib = d->ibm;
   cudaFree(ib.d_active); cudaFree(ib.d_mrow); cudaFree(ib.d_mcol); cudaFree(ib.d_phi); cudaFree(ib.d_fj); cudaFree(ib.d_ptr);
-  cudaFree(ib.d_ent_marker); cudaFree(ib.d_ent_phi); cudaFree(ib.d_u); cudaFree(ib.d_rho); cudaFree(ib.d_Fx); cudaFree(ib.d_Fy);
+  cudaFree(ib.d_ent_marker); cudaFree(ib.d_ent_phi); cudaFree(ib.d_u); cudaFree(ib.d_rho);
+  for (int k = 0; k < 2; k++) { cudaFree(ib.d_Fx[k]); cudaFree(ib.d_Fy[k]); }
   ib = IbmState();
   return LBM_OK;
 }
 
 // the four forcing iterations n = 1 .. m_max-1 on the ROI copies (src/ibm.cpp:166-187)
-static int ibm_iterate(lbm_domain* d)
+static int ibm_iterate(lbm_domain* d, int slot, cudaStream_t st)
 {
   IbmState& ib = d->ibm;
   const int RC = (int)(ib.c1 - ib.c0), nn = (int)(ib.r1 - ib.r0) * RC;
   if (ib.m_max <= 1)
   {
-    LBM_CUDA(cudaMemsetAsync(ib.d_Fx, 0, sizeof(double) * nn, d->stream));
-    LBM_CUDA(cudaMemsetAsync(ib.d_Fy, 0, sizeof(double) * nn, d->stream));
+    LBM_CUDA(cudaMemsetAsync(ib.d_Fx[slot], 0, sizeof(double) * nn, st));
+    LBM_CUDA(cudaMemsetAsync(ib.d_Fy[slot], 0, sizeof(double) * nn, st));
   }
   for (int n = 1; n < ib.m_max; n++)
   {
-    k_ibm_gather<<<cdiv(ib.n_markers, 128), 128, 0, d->stream>>>(ib.n_markers, ib.d_mrow, ib.d_mcol, ib.d_phi, RC, ib.d_u,
-                                                                 ib.d_rho, ib.d_fj);
-    k_ibm_spread<<<cdiv(ib.n_active, 128), 128, 0, d->stream>>>(ib.n_active, ib.d_active, ib.d_ptr, ib.d_ent_marker, ib.d_ent_phi,
-                                                                ib.d_fj, ib.d_u, ib.d_rho, ib.d_Fx, ib.d_Fy, n == 1 ? 1 : 0);
+    k_ibm_gather<<<cdiv(ib.n_markers, 128), 128, 0, st>>>(ib.n_markers, ib.d_mrow, ib.d_mcol, ib.d_phi, RC, ib.d_u, ib.d_rho, ib.d_fj);
+    k_ibm_spread<<<cdiv(ib.n_active, 128), 128, 0, st>>>(ib.n_active, ib.d_active, ib.d_ptr, ib.d_ent_marker, ib.d_ent_phi, ib.d_fj,
+                                                         ib.d_u, ib.d_rho, ib.d_Fx[slot], ib.d_Fy[slot], n == 1 ? 1 : 0);
     d->launches += 2;
   }
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
 }
 
-int ibm_prepass(lbm_domain* d, int mode)
+// force field for the step that will read buffer `which` (mode: how that buffer is to be read)
+int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st)
 {
   IbmState& ib = d->ibm;
   const int RC = (int)(ib.c1 - ib.c0);
-  const double* f = d->buf[0][d->cur];
+  const double* f = d->buf[0][which];
   const bool comp = d->cfg.equilibrium == LBM_EQ_COMPRESSIBLE;
 #define LBM_ROI(M, E)                                                                                                   \
-  k_ibm_roi_moments<M, E><<<cdiv(ib.n_active, 128), 128, 0, d->stream>>>(f, d->g, (int)ib.r0, (int)ib.c0, ib.n_active, RC, \
-                                                                         ib.d_active, ib.d_u, ib.d_rho)
+  k_ibm_roi_moments<M, E><<<cdiv(ib.n_active, 128), 128, 0, st>>>(f, d->g, (int)ib.r0, (int)ib.c0, ib.n_active, RC, ib.d_active, \
+                                                                  ib.d_u, ib.d_rho)
   if (mode == MODE_LOCAL) { if (comp) LBM_ROI(MODE_LOCAL, EQ_COMP); else LBM_ROI(MODE_LOCAL, EQ_INCOMP); }
   else { if (comp) LBM_ROI(MODE_PULL, EQ_COMP); else LBM_ROI(MODE_PULL, EQ_INCOMP); }
 #undef LBM_ROI
   d->launches++;
-  return ibm_iterate(d);
+  return ibm_iterate(d, slot, st);
 }
 
 }  // namespace lbm
@@ -237,17 +238,22 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   LBM_CUDA(cudaMalloc(&ib.d_ent_phi, sizeof(double) * std::max<size_t>(em.size(), 1)));
   LBM_CUDA(cudaMalloc(&ib.d_u, sizeof(double) * nn * 2));
   LBM_CUDA(cudaMalloc(&ib.d_rho, sizeof(double) * nn));
-  LBM_CUDA(cudaMalloc(&ib.d_Fx, sizeof(double) * nn));
-  LBM_CUDA(cudaMalloc(&ib.d_Fy, sizeof(double) * nn));
+  for (int k = 0; k < 2; k++)
+  {
+    LBM_CUDA(cudaMalloc(&ib.d_Fx[k], sizeof(double) * nn));
+    LBM_CUDA(cudaMalloc(&ib.d_Fy[k], sizeof(double) * nn));
+    LBM_CUDA(cudaMemset(ib.d_Fx[k], 0, sizeof(double) * nn));
+    LBM_CUDA(cudaMemset(ib.d_Fy[k], 0, sizeof(double) * nn));
+  }
   LBM_CUDA(cudaMemcpy(ib.d_mrow, mrow.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_mcol, mcol.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_phi, phi.data(), sizeof(double) * n * 16, cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_ent_marker, em.data(), sizeof(int) * em.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_ent_phi, ephi.data(), sizeof(double) * ephi.size(), cudaMemcpyHostToDevice));
-  LBM_CUDA(cudaMemset(ib.d_Fx, 0, sizeof(double) * nn));
-  LBM_CUDA(cudaMemset(ib.d_Fy, 0, sizeof(double) * nn));
   ib.enabled = true;
+  d->rows_dirty = true;
+  d->side_ready = false;
   return LBM_OK;
 }
 
@@ -258,13 +264,13 @@ int lbm_ibm_get_roi(lbm_domain* d, long* roi)
   return LBM_OK;
 }
 
-static int ibm_download_force(lbm_domain* d, double* F_aos)
+static int ibm_download_force(lbm_domain* d, double* F_aos, int slot)
 {
   IbmState& ib = d->ibm;
   const int nn = (int)((ib.r1 - ib.r0) * (ib.c1 - ib.c0));
   double* tmp = nullptr;
   LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 2 * nn));
-  k_ibm_pack_force<<<cdiv(nn, 128), 128, 0, d->stream>>>(nn, ib.d_Fx, ib.d_Fy, tmp);
+  k_ibm_pack_force<<<cdiv(nn, 128), 128, 0, d->stream>>>(nn, ib.d_Fx[slot], ib.d_Fy[slot], tmp);
   d->launches++;
   LBM_CUDA(cudaMemcpyAsync(F_aos, tmp, sizeof(double) * 2 * nn, cudaMemcpyDeviceToHost, d->stream));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
@@ -276,7 +282,8 @@ int lbm_ibm_get_force(lbm_domain* d, double* F_aos)
 {
   if (!d || !F_aos || !d->ibm.enabled) { set_error("lbm_ibm_get_force: no immersed boundary"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
-  return ibm_download_force(d, F_aos);
+  // the field the last step read; the side stream may already be filling the other slot
+  return ibm_download_force(d, F_aos, d->ibm.used_slot);
 }
 
 int lbm_ibm_force(lbm_domain* d, const double* u_aos, const double* rho_aos, double* F_aos)
@@ -294,8 +301,11 @@ int lbm_ibm_force(lbm_domain* d, const double* u_aos, const double* rho_aos, dou
   LBM_CUDA(cudaMemcpyAsync(dr, rho_aos, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
   k_ibm_load_roi<<<cdiv(nn, 128), 128, 0, d->stream>>>(du, dr, d->cfg.Y, (int)ib.r0, (int)ib.c0, RR, RC, ib.d_u, ib.d_rho);
   d->launches++;
-  LBM_TRY(ibm_iterate(d));
-  int s = ibm_download_force(d, F_aos);
+  // scratch use of the slot no enqueued step reads; the side stream must be idle first
+  LBM_CUDA(cudaStreamSynchronize(d->side));
+  const int slot = d->ibm.next_slot ^ 1;
+  LBM_TRY(ibm_iterate(d, slot, d->stream));
+  int s = ibm_download_force(d, F_aos, slot);
   cudaFree(du);
   cudaFree(dr);
   return s;

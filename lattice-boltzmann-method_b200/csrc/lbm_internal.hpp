@@ -74,8 +74,10 @@ struct IbmState
   // ROI fields
   double* d_u = nullptr;   // [roi][2]
   double* d_rho = nullptr; // [roi]
-  double* d_Fx = nullptr;  // [roi]
-  double* d_Fy = nullptr;
+  double* d_Fx[2] = {nullptr, nullptr};  // [roi], double-buffered: the pre-pass of step t+1 runs while
+  double* d_Fy[2] = {nullptr, nullptr};  // the bulk rows of step t still read the field of step t
+  int next_slot = 0;  // slot the next step reads (filled by the last pre-pass)
+  int used_slot = 0;  // slot the last enqueued step read (lbm_ibm_get_force)
 };
 
 struct ProfRec
@@ -104,12 +106,17 @@ struct lbm_domain
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;      // IBM pre-pass / ghost exchange, overlapped with the interior rows
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  cudaEvent_t ev_ready = nullptr;   // state of the previous step complete (main stream)
-  cudaEvent_t ev_ibm = nullptr;     // ROI force field ready (side stream)
-  cudaEvent_t ev_ghost = nullptr;   // ghost rows of the source buffer valid (side stream)
-  cudaEvent_t ev_packet = nullptr;  // pressure packet packed (main stream), linked slabs
-  bool ghost_valid = false;         // ghost rows of buf[cur] are up to date (or being brought up to date)
-  bool ghost_pending = false;       // ... by work on the side stream that the main stream has not waited for yet
+  cudaEvent_t ev_ready = nullptr;   // everything enqueued so far on the main stream
+  cudaEvent_t ev_early = nullptr;   // early rows of the step written (main stream)
+  cudaEvent_t ev_side = nullptr;    // side chain done: listed nodes, stages, ghost rows, next IBM field
+  cudaEvent_t ev_stage = nullptr;   // listed nodes + stages done (side stream), linked slabs
+  cudaEvent_t ev_packet = nullptr;  // pressure packet packed (side stream), linked slabs
+  bool side_ready = false;          // ghost rows of buf[cur] and the IBM field for the next step are (being) prepared
+  // row lists of the interior kernel
+  bool rows_dirty = true;
+  int n_early = 0, n_bulk = 0;
+  int *d_rows_all = nullptr, *d_rows_early = nullptr, *d_rows_bulk = nullptr;
+  std::vector<char> row_has_listed;  // row owns a listed node in an interior column, or feeds a stage
   float last_ms = 0.f;
   long long launches = 0;
 
@@ -151,21 +158,25 @@ int ensure_aos_scratch(lbm_domain* d);
 struct ProfScope
 {
   lbm_domain* d;
+  cudaStream_t st;
   long idx = -1;
-  ProfScope(lbm_domain* dom, int cls);
+  ProfScope(lbm_domain* dom, int cls, cudaStream_t stream = nullptr);
   ~ProfScope();
 };
 int commit_boundary_tables(lbm_domain* d);
-// step phases (lbm_domain.cu); lbm_comm.cu interleaves them across linked slabs / ranks
-int step_prepare(lbm_domain* d);           // ghost rows of the source buffer (local wrap or neighbours)
-int step_compute(lbm_domain* d);           // IBM pre-pass + interior + listed nodes
-int stage_pack(lbm_domain* d, size_t k);   // source side of stage k
-int stage_apply(lbm_domain* d, size_t k);  // writer side of stage k
-int step_finish(lbm_domain* d);            // buffer swap
+// step phases (lbm_domain.cu); lbm_comm.cu interleaves them across linked slabs
+int step_rows(lbm_domain* d);                            // (re)build the early / bulk row lists
+int step_early(lbm_domain* d);                           // main: wait side chain, early rows, record ev_early
+int step_listed(lbm_domain* d);                          // side: wait ev_early, listed-node kernel
+int stage_pack(lbm_domain* d, size_t k);                 // side: source half of stage k
+int stage_apply(lbm_domain* d, size_t k);                // side: writer half of stage k
+int step_side_tail(lbm_domain* d, bool exchange_local);  // side: ghost rows of the new buffer, next IBM field, ev_side
+int step_bulk(lbm_domain* d);                            // main: bulk rows, then the buffer swap
+int step_prologue(lbm_domain* d, bool exchange_local);   // side chain for a state no step has prepared yet
 int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st);
 // lbm_ibm.cu
 int ibm_release(lbm_domain* d);
-int ibm_prepass(lbm_domain* d, int mode);
+int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st);
 // lbm_two_phase.cu
 int tp_create(lbm_domain* d);
 int tp_destroy(lbm_domain* d);
@@ -177,9 +188,10 @@ int tp_refresh_moments(lbm_domain* d);
 // lbm_comm.cu
 int comm_release(lbm_domain* d);
 bool comm_active(const lbm_domain* d);
+int link_exchange(lbm_domain* d, int which, cudaStream_t st);  // ghost rows from linked neighbours
 int comm_exchange(lbm_domain* d, int which, cudaStream_t st);  // population ghost rows over NCCL
 int comm_exchange_moments(lbm_domain* d);  // two-phase: 2 ghost rows of the moment planes at slab cuts
-int comm_stage_transfer(lbm_domain* d, size_t k);
+int comm_stage_transfer(lbm_domain* d, size_t k, cudaStream_t st);  // pressure packet of stage k between ranks
 int comm_link_refresh(lbm_domain* d);                             // linked slabs: ghost rows of buf[cur] outside lbm_step_group               // pressure packet of stage k between ranks
 double* tp_moment_planes(lbm_domain* d, int* pm, long long* mplane);
 }  // namespace lbm

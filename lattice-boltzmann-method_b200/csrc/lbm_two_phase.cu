@@ -613,7 +613,6 @@ int tp_step(lbm_domain* d)
     if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->stream));
     else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
   }
-  d->ghost_valid = true;
   if (tp->model == TP_MRTCG) LBM_TRY(tp_launch_moments<TP_MRTCG>(d, d->cur, nullptr, nullptr));
   else LBM_TRY(tp_launch_moments<TP_RK>(d, d->cur, nullptr, nullptr));
   {
