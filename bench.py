@@ -3,12 +3,13 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
     python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, rank 0 only)
+    python bench.py --workload mrtcg_rt|rk_droplet|sedimentation|poiseuille   (the other BASELINE.json configs)
 
-A "step" is one lattice-Boltzmann time step of the whole grid.  Workload at every N: configs[1] of
-BASELINE.json — flow past a cylinder, D2Q9 BGK, compressible equilibrium, immersed-boundary cylinder
-(multi-direct forcing), anti-bounce-back inlet/outlet rows, specular side columns
-(test/cylinder_test.cpp of the reference), 8192 x 8192 nodes PER GPU (weak scaling: the global
-grid is (8192 N) x 8192, slab-decomposed along axis 0 like test/decompose_domain.cpp).
+A "step" is one lattice-Boltzmann time step of the whole grid.  Default workload at every N:
+configs[1] of BASELINE.json — flow past a cylinder, D2Q9 BGK, compressible equilibrium,
+immersed-boundary cylinder (multi-direct forcing), anti-bounce-back inlet/outlet rows, specular
+side columns (test/cylinder_test.cpp of the reference), 8192 x 8192 nodes PER GPU (weak scaling:
+the global grid is (8192 N) x 8192, slab-decomposed along axis 0 like test/decompose_domain.cpp).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -26,8 +27,44 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "lattice-boltzmann-method_b200", "python"))
 
-BYTES_PER_NODE = {"bgk": 144.0}  # 9 populations x 8 B x (1 read + 1 write)
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md
+
+W9 = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+CX9 = np.array([0, 1, 0, -1, 0, 1, -1, -1, 1], dtype=np.float64)
+CY9 = np.array([0, 0, 1, 0, -1, 1, 1, -1, -1], dtype=np.float64)
+
+# BASELINE.json configs -> workload; bytes/node = SURVEY §8(d)'s minimal-traffic model (fp64, every population
+# read once and written once; two-phase models add their scalar moment planes)
+WORKLOADS = {
+    # configs[1] — the headline: test/cylinder_test.cpp at 8192 x 8192 per GPU
+    "cylinder": dict(X=8192, Y=8192, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,COMP,IBM>", driver="test/cylinder_test.cpp",
+                     what="cylinder flow, D2Q9 BGK + IBM cylinder, ABB inlet/outlet, specular walls", cpu_sample=1024),
+    # configs[0] at the parameters.toml grid (the 21 x 21 reference case is a parity test)
+    "poiseuille": dict(X=2700, Y=2100, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,INCOMP,NONE>",
+                       driver="test/horizontal_poiseuille_test.cpp",
+                       what="horizontal Poiseuille, D2Q9 BGK incompressible, pressure-periodic rows, bounce-back walls",
+                       cpu_sample=1024),
+    # configs[2]
+    "mrtcg_rt": dict(X=16384, Y=16384, bytes=352.0, nlat=2, kernel="k_tp_step<MRTCG>",
+                     driver="test/mrtcg_rayleigh_taylor.cpp",
+                     what="MRT colour-gradient Rayleigh-Taylor (mrtcg-rayleigh-taylor-gamma3.toml), two lattices",
+                     cpu_sample=512),
+    # configs[3]
+    "rk_droplet": dict(X=4096, Y=4096, bytes=304.0, nlat=2, kernel="k_tp_step<RK>",
+                       driver="test/rk_static_droplet_test.cpp",
+                       what="Rothman-Keller static droplet, R = L/4, two lattices", cpu_sample=512),
+    # configs[4]
+    "sedimentation": dict(X=4096, Y=8192, bytes=288.0, nlat=2, kernel="k_bgk_interior<PULL,COMP,NONE,ADE>",
+                          driver="test/rectangle_sedimentation_test.cpp",
+                          what="rectangle sedimentation: fluid + advection-diffusion lattice, bounce-back rectangle walls",
+                          cpu_sample=1024),
+}
+
+RED = dict(rho_0=3.0, alpha=0.7, A=0.5, nu=0.04, beta=0.7)      # configs/mrtcg-rayleigh-taylor-gamma3.toml
+BLUE = dict(rho_0=1.0, alpha=0.1, A=0.5, nu=0.04, beta=-0.7)
+RK_RED = dict(rho_0=1.2, alpha=1.0 / 3.0, A=1e-4, nu=0.16, beta=0.7)   # rk_static_droplet_test.cpp:504-506
+RK_BLUE = dict(rho_0=1.0, alpha=0.2, A=1e-4, nu=0.14, beta=-0.7)
+RT_FG = (6.25e-6, 0.0)
 
 
 def parse_args():
@@ -36,12 +73,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--X", type=int, default=8192, help="rows per GPU")
-    ap.add_argument("--Y", type=int, default=8192, help="columns")
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="edge of the square grid the CPU baseline is timed on")
+    ap.add_argument("--workload", default="cylinder", choices=sorted(WORKLOADS),
+                    help="cylinder = BASELINE.json configs[1] (the headline); the others are the remaining configs")
+    ap.add_argument("--X", type=int, default=0, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--Y", type=int, default=0, help="columns (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="edge of the square grid the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.X = args.X or wl["X"]
+    args.Y = args.Y or wl["Y"]
+    args.cpu_sample = args.cpu_sample or wl["cpu_sample"]
+    return args
 
 
 # ---------------------------------------------------------------------------------------------
@@ -53,6 +97,14 @@ def lattice_parameters():
 
     p = L.params_from_toml(os.path.join(ROOT, "configs", "parameters.toml"), False)
     return p.omega, p.u
+
+
+def channel_constants(H, W, u_max=0.1030985714):
+    """test/horizontal_poiseuille_test.cpp:50-66"""
+    tau = np.sqrt(3.0 / 16.0) + 0.5
+    nu = (2.0 * tau - 1.0) / 6.0
+    p_grad = 8.0 * nu * u_max / (W * W)
+    return 1.0 / tau, 3.0 * (H - 1) * p_grad + 1.0, 1.0
 
 
 def cylinder_markers(X, Y):
@@ -71,37 +123,112 @@ def write_markers_toml(path, xs, ys):
         fh.write("y = [" + ", ".join(repr(float(v)) for v in ys) + "]\n")
 
 
+def sedimentation_geometry(X, Y):
+    """rectangle_sedimentation_test.cpp:73-75,89-95 scaled from the parameters.toml grid (2700 x 2100)"""
+    R23 = -max(3, int(round(151 * X / 2700)))
+    C28 = max(3, int(round(200 * Y / 2100)))
+    C38 = max(C28 + 2, int(round(250 * Y / 2100)))
+    C_w = np.zeros(X)
+    C_w[X - max(1, int(round(50 * X / 2700))):] = 1e-3
+    return R23, C28, C38, C_w
+
+
+def rt_densities(R, C, r0, r1):
+    """init_rho_cosine (mrtcg_rayleigh_taylor.cpp:182-210) for global rows [r0, r1)"""
+    s = R / 2.0 - 0.1 * C * np.cos(2.0 * 3.141592 * np.arange(C) / C)
+    below = np.arange(r0, r1)[:, None] < s[None, :]
+    return RED["rho_0"] * below.astype(np.float64), BLUE["rho_0"] * (~below).astype(np.float64)
+
+
+def droplet_densities(Ln, radius, r0, r1):
+    """init_rho (rk_static_droplet_test.cpp:363-396) for global rows [r0, r1)"""
+    c = Ln / 2.0
+    s = np.sqrt((np.arange(r0, r1)[:, None] - c) ** 2 + (np.arange(Ln)[None, :] - c) ** 2)
+    sg = 1.0 / (1.0 + np.exp(-2.0 * (s - radius)))
+    return RK_RED["rho_0"] * (1.0 - sg), RK_BLUE["rho_0"] * sg
+
+
+def workload_config(args, n):
+    wl = WORKLOADS[args.workload]
+    gb = args.X * args.Y * 72.0 * wl["nlat"] / 1e9
+    return {
+        "workload": f"{wl['what']}, {args.X}x{args.Y} nodes per GPU",
+        "grid_per_gpu": [args.X, args.Y], "global_grid": [args.X * n, args.Y], "decomposition": f"{n} slab(s) along axis 0",
+        "l2": f"inputs larger than L2 (2 x {gb:.1f} GB of populations per GPU), no flush needed" if gb > 0.5 else
+              f"populations per GPU: 2 x {gb * 1e3:.0f} MB (fits the 126 MB L2 when below that: reported as such)",
+        "reference_driver": wl["driver"],
+    }
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU arms
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_mlups(edge, warmup, steps):
-    """The reference's own CPU implementation of the cylinder loop (oracle/_ref, CPU libtorch, all host
-    threads); falls back to the plain-C oracle port when the reference was not compiled."""
+def cpu_reference_mlups(workload, edge, warmup, steps):
+    """The reference's own CPU implementation (oracle/_ref: unmodified sources on CPU libtorch, all host
+    threads) where the harness exposes the workload's loop (cylinder); the plain-C oracle port otherwise.
+    Returns (MLUPS, seconds per step, kind, cores, sample description)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
 
     omega, u_lb = lattice_parameters()
-    xs, ys = cylinder_markers(edge, edge)
-    if oracle_lib.have_ref():
-        ref = oracle_lib.Ref()
-        with tempfile.TemporaryDirectory() as td:
-            path = os.path.join(td, "boundary.toml")
-            write_markers_toml(path, xs, ys)
-            sec, _ = ref.cylinder_loop(edge, edge, omega, u_lb, path, warmup, steps)
-        return edge * edge / sec / 1e6, sec, "reference", ref.num_threads()
+    port_cores = os.cpu_count() or 1  # the port's loops are OpenMP-parallel (oracle/Makefile: -fopenmp when available)
+
+    def timed(step_fn):
+        for _ in range(warmup):
+            step_fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()
+        return (time.perf_counter() - t0) / max(steps, 1)
+
+    if workload == "cylinder":
+        xs, ys = cylinder_markers(edge, edge)
+        desc = f"{edge}x{edge} crop of the cylinder workload"
+        if oracle_lib.have_ref():
+            ref = oracle_lib.Ref()
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "boundary.toml")
+                write_markers_toml(path, xs, ys)
+                sec, _ = ref.cylinder_loop(edge, edge, omega, u_lb, path, warmup, steps)
+            return edge * edge / sec / 1e6, sec, "reference", ref.num_threads(), desc
+        orc = oracle_lib.Oracle()
+        ib = orc.ibm_create(xs, ys)
+        u = np.zeros((edge, edge, 2)); u[..., 0] = u_lb
+        rho = np.ones((edge, edge, 1))
+        f = orc.incomp_equilibrium(u, rho)
+        sec = timed(lambda: orc.cylinder_step(f, u, rho, omega, u_lb, ib))
+        orc.ibm_destroy(ib)
+        return edge * edge / sec / 1e6, sec, "port", port_cores, desc
+
     orc = oracle_lib.Oracle()
-    ib = orc.ibm_create(xs, ys)
-    u = np.zeros((edge, edge, 2)); u[..., 0] = u_lb
-    rho = np.ones((edge, edge, 1))
-    f = orc.incomp_equilibrium(u, rho)
-    for _ in range(warmup):
-        orc.cylinder_step(f, u, rho, omega, u_lb, ib)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.cylinder_step(f, u, rho, omega, u_lb, ib)
-    sec = (time.perf_counter() - t0) / steps
-    orc.ibm_destroy(ib)
-    return edge * edge / sec / 1e6, sec, "port", os.cpu_count() or 1
+    if workload == "poiseuille":
+        om, rho_in, rho_out = channel_constants(edge, edge)
+        u = np.zeros((edge, edge, 2)); rho = np.ones((edge, edge, 1))
+        f = orc.incomp_equilibrium(u, rho)
+        sec = timed(lambda: orc.poiseuille_step(f, u, rho, om, rho_in, rho_out))
+    elif workload == "sedimentation":
+        R23, C28, C38, C_w = sedimentation_geometry(edge, edge)
+        f, g, u, rho, Cc = orc.sedimentation_init(edge, edge, u_lb, C_w)
+        sec = timed(lambda: orc.sedimentation_step(f, g, u, rho, Cc, omega, u_lb, 3e-3, C_w, R23, C28, C38))
+    elif workload == "mrtcg_rt":
+        p = oracle_lib.MrtcgParams()
+        p.R, p.C = edge, edge
+        p.r_rho0, p.r_alpha, p.r_nu, p.r_beta = RED["rho_0"], RED["alpha"], RED["nu"], RED["beta"]
+        p.b_rho0, p.b_alpha, p.b_nu, p.b_beta = BLUE["rho_0"], BLUE["alpha"], BLUE["nu"], BLUE["beta"]
+        p.sigma, p.delta = 0.1, 0.1
+        p.Fg[0], p.Fg[1] = RT_FG
+        p.add_force = 1
+        st = orc.mrtcg_init(p, "rt")
+        sec = timed(lambda: orc.mrtcg_step(p, st))
+    else:  # rk_droplet
+        p = oracle_lib.RkParams()
+        p.L, p.radius = edge, edge / 4.0
+        p.r_rho0, p.r_alpha, p.r_A, p.r_nu = RK_RED["rho_0"], RK_RED["alpha"], RK_RED["A"], RK_RED["nu"]
+        p.b_rho0, p.b_alpha, p.b_A, p.b_nu = RK_BLUE["rho_0"], RK_BLUE["alpha"], RK_BLUE["A"], RK_BLUE["nu"]
+        p.delta = 0.98
+        st = orc.rk_init(p)
+        sec = timed(lambda: orc.rk_step(p, st))
+    return edge * edge / sec / 1e6, sec, "port", port_cores, f"{edge}x{edge} crop of the {workload} workload"
 
 
 def run_reference_arm(args):
@@ -109,8 +236,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     edge = args.cpu_sample
-    mlups, sec, kind, cores = cpu_reference_mlups(edge, args.warmup, args.steps)
-    sample = f"{edge}x{edge} crop of the cylinder workload, {args.steps} steps after {args.warmup} warm-up"
+    mlups, sec, kind, cores, desc = cpu_reference_mlups(args.workload, edge, args.warmup, args.steps)
+    sample = f"{desc}, {args.steps} steps after {args.warmup} warm-up"
     line = {
         "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -120,15 +247,6 @@ def run_reference_arm(args):
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, n):
-    return {
-        "workload": f"cylinder flow, D2Q9 BGK + IBM cylinder, ABB inlet/outlet, specular walls, {args.X}x{args.Y} nodes per GPU",
-        "grid_per_gpu": [args.X, args.Y], "global_grid": [args.X * n, args.Y], "decomposition": f"{n} slab(s) along axis 0",
-        "l2": "inputs larger than L2 (2 x 4.8 GB of populations per GPU), no flush needed",
-        "reference_driver": "test/cylinder_test.cpp",
-    }
 
 
 # ---------------------------------------------------------------------------------------------
@@ -183,13 +301,121 @@ def measured_hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the interior kernel from the committed ncu capture"""
+def ncu_traffic_per_launch(workload, X, Y):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
+    (profiles/roofline_traffic.json), only when it was taken at this grid size"""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-            return json.load(fh).get("k_bgk_interior_bytes_per_launch_8192x8192")
+            return json.load(fh).get(f"{workload}_{X}x{Y}_bytes_per_launch")
     except Exception:
         return None
+
+
+class Case:
+    """One workload on one slab: builds the domain, holds the pinned host state, imports it."""
+
+    def __init__(self, L, torch, args, rank, world, local):
+        self.L, self.torch, self.args = L, torch, args
+        self.rank, self.world, self.local = rank, world, local
+        self.X, self.Y = args.X, args.Y
+        self.Xg = args.X * world
+        self.x0, self.x1 = rank * args.X, (rank + 1) * args.X
+        self.name = args.workload
+        self.omega, self.u_lb = lattice_parameters()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        slab = dict(X=self.Xg, Y=self.Y, x0=self.x0, x1=self.x1, device=local)
+        if self.name == "cylinder":
+            cfg = L.default_config(model=L.MODEL_BGK, omega=self.omega, equilibrium=L.EQ_COMPRESSIBLE, force=L.FORCE_IBM, **slab)
+        elif self.name == "poiseuille":
+            om, self.rho_in, self.rho_out = channel_constants(self.Xg, self.Y)
+            cfg = L.default_config(model=L.MODEL_BGK, omega=om, equilibrium=L.EQ_INCOMPRESSIBLE, **slab)
+        elif self.name == "sedimentation":
+            cfg = L.default_config(model=L.MODEL_BGK_ADE, omega=self.omega, omega_g=self.omega, equilibrium=L.EQ_COMPRESSIBLE,
+                                   w_s=3e-3, **slab)
+        elif self.name == "mrtcg_rt":
+            cfg = L.default_config(model=L.MODEL_MRTCG, red=RED, blue=BLUE, sigma=0.1, delta=0.1, Fg=RT_FG, add_force=1, **slab)
+        else:
+            cfg = L.default_config(model=L.MODEL_RK, red=RK_RED, blue=RK_BLUE, delta=0.98, **slab)
+        self.d = L.Domain(cfg)
+
+    def comm_init(self, ident):
+        if self.world > 1:
+            self.d.comm_init(ident, self.world, self.rank)
+
+    def pinned(self, shape):
+        t = self.torch.empty(shape, dtype=self.torch.float64, pin_memory=True)
+        return t, t.numpy()
+
+    def setup(self):
+        d, X, Y = self.d, self.X, self.Y
+        if self.name == "cylinder":
+            d.preset_free_stream(self.u_lb, 0.0)
+            xs, ys = cylinder_markers(self.X, Y)  # the body sits in rank 0's slab
+            if self.rank == 0:
+                d.ibm_set_markers(xs, ys)
+            # the drivers' incomp_equilibrium(u=(u_lb,0), rho=1) (cylinder_test.cpp:84-86)
+            self.f_t, self.f = self.pinned((X, Y, 9))
+            self.f[...] = (1.0 + 3.0 * CX9 * self.u_lb) * W9
+        elif self.name == "poiseuille":
+            d.preset_poiseuille(self.rho_in, self.rho_out)
+            self.f_t, self.f = self.pinned((X, Y, 9))
+            self.f[...] = W9  # incomp_equilibrium(u=0, rho=1) (horizontal_poiseuille_test.cpp:91)
+        elif self.name == "sedimentation":
+            R23, C28, C38, C_w = sedimentation_geometry(self.Xg, Y)
+            d.preset_sedimentation(self.u_lb, C_w, R23, C28, C38)
+            # rectangle_sedimentation_test.cpp:84-103: u = (0, u_lb); f = incomp_eq(u, 1); g = eq(u, C), C = C_w on column 0
+            self.f_t, self.f = self.pinned((X, Y, 9))
+            self.g_t, self.g = self.pinned((X, Y, 9))
+            self.f[...] = (1.0 + 3.0 * CY9 * self.u_lb) * W9
+            cu = CY9 * self.u_lb
+            geq = W9 * (1.0 + 3.0 * cu + 4.5 * cu * cu - 1.5 * self.u_lb ** 2)
+            self.g[...] = 0.0
+            self.g[:, 0, :] = C_w[self.x0:self.x1, None] * geq[None, :]
+        else:
+            (d.preset_mrtcg if self.name == "mrtcg_rt" else d.preset_rk)()
+            self.rr_t, self.rr = self.pinned((X, Y))
+            self.rb_t, self.rb = self.pinned((X, Y))
+            self.u_t, self.u = self.pinned((X, Y, 2))
+            self.u[...] = 0.0
+            if self.name == "mrtcg_rt":
+                self.rr[...], self.rb[...] = rt_densities(self.Xg, Y, self.x0, self.x1)
+            else:
+                self.rr[...], self.rb[...] = droplet_densities(self.Xg, self.Xg / 4.0, self.x0, self.x1)
+        self.rho_t, self.rho = self.pinned((X, Y, 1))
+        self.uo_t, self.uo = self.pinned((X, Y, 2))
+
+    def import_state(self):
+        """host -> device through the C ABI; returns the bytes copied"""
+        d = self.d
+        if self.name in ("cylinder", "poiseuille"):
+            d.set_f(self.f)
+            return self.f.nbytes
+        if self.name == "sedimentation":
+            d.set_f(self.f, 0)
+            d.set_f(self.g, 1)
+            return self.f.nbytes + self.g.nbytes
+        d.init_two_phase(self.rr, self.rb, self.u)
+        return self.rr.nbytes + self.rb.nbytes + self.u.nbytes
+
+    def export_moments(self):
+        """device -> host: rho and u of the current state (what every driver snapshots)"""
+        lib = self.L.load()
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = lib.lbm_get_moments(self.d.h, 0, self.rho.ctypes.data_as(dp), self.uo.ctypes.data_as(dp))
+        if rc != 0:
+            raise RuntimeError(lib.lbm_last_error().decode())
+        return self.rho.nbytes + self.uo.nbytes
+
+    def dominant_classes(self):
+        L = self.L
+        return [L.PROF_INTERIOR, L.PROF_MOMENTS] if self.name in ("mrtcg_rt", "rk_droplet") else [L.PROF_INTERIOR]
+
+    def dominant_nodes(self):
+        """nodes per step the dominant kernel owns (the remaining edge columns are listed nodes)"""
+        if self.name in ("mrtcg_rt", "rk_droplet"):
+            return self.X * (self.Y - 2)
+        return self.X * (2 * ((self.Y - 3) // 2))
 
 
 def run_b200_arm(args):
@@ -211,30 +437,14 @@ def run_b200_arm(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    omega, u_lb = lattice_parameters()
-    Xg, Y = args.X * world, args.Y
-    x0, x1 = rank * args.X, (rank + 1) * args.X
-    cfg = L.default_config(model=L.MODEL_BGK, X=Xg, Y=Y, x0=x0, x1=x1, device=local, omega=omega,
-                           equilibrium=L.EQ_COMPRESSIBLE, force=L.FORCE_IBM)
-    d = L.Domain(cfg)
+    wl = WORKLOADS[args.workload]
+    case = Case(L, torch, args, rank, world, local)
+    d = case.d
     if world > 1:
         ident = [L.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
-        d.comm_init(ident[0], world, rank)
-    d.preset_free_stream(u_lb, 0.0)
-    xs, ys = cylinder_markers(args.X, Y)  # the body sits in rank 0's slab
-    if rank == 0:
-        d.ibm_set_markers(xs, ys)
-
-    # initial state from pinned host memory (the drivers' incomp_equilibrium(u=(u_lb,0), rho=1))
-    N = args.X * Y
-    w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
-    cx = np.array([0, 1, 0, -1, 0, 1, -1, -1, 1], dtype=np.float64)
-    f_host_t = torch.empty((args.X, Y, 9), dtype=torch.float64, pin_memory=True)
-    f_host = f_host_t.numpy()
-    f_host[...] = (1.0 + 3.0 * cx * u_lb) * w
-    rho_host_t = torch.empty((args.X, Y, 1), dtype=torch.float64, pin_memory=True)
-    u_host_t = torch.empty((args.X, Y, 2), dtype=torch.float64, pin_memory=True)
+        case.comm_init(ident[0])
+    case.setup()
 
     def barrier():
         d.synchronize()
@@ -249,7 +459,7 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    d.set_f(f_host)
+    case.import_state()
     d.step(args.warmup)
     barrier()
 
@@ -268,28 +478,27 @@ def run_b200_arm(args):
     launches = d.kernel_launches() - launches0
     prof = {name: d.profile_read(cls) for name, cls in
             [("interior", L.PROF_INTERIOR), ("boundary", L.PROF_BOUNDARY), ("fixup", L.PROF_FIXUP),
-             ("ghost", L.PROF_GHOST), ("ibm", L.PROF_IBM)]}
+             ("ghost", L.PROF_GHOST), ("ibm", L.PROF_IBM), ("moments", L.PROF_MOMENTS)]}
+    dom_ms = sum(d.profile_read(c)[0] for c in case.dominant_classes())
+    dom_n = sum(d.profile_read(c)[1] for c in case.dominant_classes())
     d.profile_enable(False)
     ms = max_over_ranks(ms)
-    mlups = (Xg * Y) * args.steps / (ms * 1e-3) / 1e6
+    mlups = (case.Xg * case.Y) * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with host buffers: import f (H2D), K steps, export rho,u (D2H)
+    # ---- end to end through the C ABI with host buffers: import the state (H2D), K steps, export rho,u (D2H)
     e2e = None
     if not args.no_e2e:
         barrier()
         t0 = time.perf_counter()
-        d.set_f(f_host)
+        h2d = case.import_state()
         d.step(args.steps)
-        lib = L.load()
-        dp = ctypes.POINTER(ctypes.c_double)
-        rc = lib.lbm_get_moments(d.h, 0, rho_host_t.numpy().ctypes.data_as(dp), u_host_t.numpy().ctypes.data_as(dp))
-        assert rc == 0, lib.lbm_last_error()
+        d2h = case.export_moments()
         d.synchronize()
         sec = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": (Xg * Y) * args.steps / sec / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": N * 9 * 8 / args.steps, "d2h_bytes_per_step": N * 3 * 8 / args.steps,
-               "what": f"lbm_set_f from pinned host + lbm_step({args.steps}) + lbm_get_moments to pinned host, per rank",
-               "seconds": sec, "rho_mean": float(rho_host_t.mean())}
+        e2e = {"value": (case.Xg * case.Y) * args.steps / sec / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "what": f"state import from pinned host + lbm_step({args.steps}) + lbm_get_moments to pinned host, per rank",
+               "seconds": sec, "rho_mean": float(case.rho_t.mean())}
 
     if rank != 0:
         if dist is not None:
@@ -297,33 +506,32 @@ def run_b200_arm(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_bgk_interior: one launch over the early rows + one over the
-    # bulk rows per step; both timed with CUDA events on the main stream inside the timed region above)
+    # ---- roofline of the dominant kernel, timed with CUDA events on its own stream inside the timed region above
     peak, peak_src = measured_hbm_peak()
-    int_ms, int_n = prof["interior"]
-    nodes_per_step = args.X * (2 * ((Y - 3) // 2))   # nodes the interior kernel owns (edge columns are listed nodes)
-    launches_per_step = int_n / args.steps if args.steps else 0
-    achieved = BYTES_PER_NODE["bgk"] * nodes_per_step * args.steps / (int_ms * 1e-3) / 1e9 if int_ms > 0 else None
-    traffic = ncu_traffic_per_launch()
+    B = wl["bytes"]
+    nodes_per_step = case.dominant_nodes()
+    achieved = B * nodes_per_step * args.steps / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+    per_gpu_mlups = mlups / world
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": traffic,
-                "kernel": "k_bgk_interior<PULL,COMP,IBM>", "bytes_per_node": BYTES_PER_NODE["bgk"],
-                "algorithmic_bytes_per_step": BYTES_PER_NODE["bgk"] * nodes_per_step,
-                "launches_per_step": launches_per_step, "kernel_ms_per_step": int_ms / args.steps,
+                "frac": achieved / peak if achieved else None,
+                "traffic": ncu_traffic_per_launch(args.workload, args.X, args.Y),
+                "kernel": wl["kernel"], "bytes_per_node": B,
+                "algorithmic_bytes_per_step": B * nodes_per_step,
+                "launches_per_step": dom_n / args.steps if args.steps else 0, "kernel_ms_per_step": dom_ms / args.steps,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0 if achieved else None,
-                "whole_step_frac": BYTES_PER_NODE["bgk"] * mlups * 1e6 / 1e9 / peak,
-                "whole_step_frac_of_nominal_8TBs": BYTES_PER_NODE["bgk"] * mlups * 1e6 / 1e9 / 8000.0,
-                "share_of_step": int_ms / ms,
-                "side_stream_spans_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if k != "interior"},
-                "note": "achieved = 144 B x interior nodes per step / summed duration of the step's interior launches; "
-                        "listed nodes, stages, ghost rows and the IBM pre-pass run on a side stream under the bulk launch"}
+                "whole_step_frac_per_gpu": B * per_gpu_mlups * 1e6 / 1e9 / peak,
+                "whole_step_frac_per_gpu_of_nominal_8TBs": B * per_gpu_mlups * 1e6 / 1e9 / 8000.0,
+                "share_of_step": dom_ms / ms,
+                "other_spans_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()
+                                            if v[1] and not (k == "interior" or (k == "moments" and len(case.dominant_classes()) > 1))},
+                "note": f"achieved = {B:.0f} B x nodes the dominant kernel owns per step / summed duration of its launches "
+                        "(rank 0); listed nodes, stages, ghost rows and the IBM pre-pass run on a side stream under the bulk launch"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        c_mlups, c_sec, kind, cores = cpu_reference_mlups(args.cpu_sample, 1, 5)
+        c_mlups, c_sec, kind, cores, desc = cpu_reference_mlups(args.workload, args.cpu_sample, 1, 5)
         cpu_baseline = {"value": c_mlups, "unit": "MLUPS", "cores": cores, "kind": kind,
-                        "sample": f"{args.cpu_sample}x{args.cpu_sample} crop of the cylinder workload, 5 steps after 1 warm-up",
-                        "ms_per_step": c_sec * 1e3}
+                        "sample": f"{desc}, 5 steps after 1 warm-up", "ms_per_step": c_sec * 1e3}
 
     line = {
         "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
