@@ -1,17 +1,28 @@
 // lbm_two_phase.cu — kernels and step sequencing of the colour-gradient models
 // (LBM_MODEL_MRTCG, LBM_MODEL_RK).  Arithmetic: lbm_two_phase.cuh.
 //
-// One time step = two passes over the grid:
-//   collide  : pull both lattices (post-collision buffers + boundary table) -> f_adve in registers,
-//              read the node's moments and the 5x5 (3x3 for RK) neighbourhood of the moment planes
-//              from a shared-memory tile with a 2-cell halo, collide, write f_coll (both colours).
-//   moments  : pull the fresh f_coll again, write rho_r, rho_b, u, phase of the NEW post-stream
-//              state for the next step's stencils (the drivers' end-of-iteration block,
-//              mrtcg_rayleigh_taylor.cpp:472-477).
-// Algorithmic traffic per node: 144 R + 40 R + 144 W (collide) + 144 R + 40 W (moments) = 512 B,
-// against SURVEY §8(d)'s 352 B model (which assumes the second population read is avoided).
+// Steady state (the stored state is post-collision): ONE pass over the grid per time step,
+//   k_tp_fused : a block owns a strip of columns and marches down a band of rows.  Per row it pulls
+//              both lattices of row r+H (H = stencil half-width: 2 for the 5x5 differences of
+//              MRTCG, 1 for the 3x3 ones of RK), computes the moments of that row — what the
+//              drivers compute at the end of an iteration (mrtcg_rayleigh_taylor.cpp:472-477) —
+//              into a shared-memory ring of 2H+2 rows, then collides row r from the ring (stencil
+//              + own moments) and the re-pulled populations (an L1/L2 hit: the same block read them
+//              H iterations earlier), and writes f_coll of both colours.
+//              DRAM traffic per node: 144 R + 144 W + the strip/band halo re-reads (~3-6 %, mostly
+//              L2 hits) — the moment planes never travel, which is below SURVEY §8(d)'s 352 B / 304 B
+//              models (those assume a stored moment field).
+//   The moment planes survive only where something other than the fused kernel needs them: listed
+//   (table-driven) nodes and their 2-neighbourhood, the replicate padding, the two rows exchanged
+//   across a slab cut.  k_tp_moments_nodes fills that thin region (O(X+Y) nodes) before the fused
+//   kernel, which reads plane values there instead of recomputing.
+// First step after an import (the stored state is post-stream and the caller supplied u): the
+// two-pass pair k_tp_collide_interior<MODE_LOCAL> over the full moment planes.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "lbm_internal.hpp"
 #include "lbm_two_phase.cuh"
@@ -25,6 +36,15 @@ struct TwoPhaseState
   double* mom = nullptr;  // M_COUNT planes
   TpParams p;
   int model = TP_MRTCG;
+  // fused step: where the moment planes stay authoritative
+  bool planes_full = false;            // planes hold the moments of every own node of the current state
+  bool region_dirty = true;            // (re)build the lists below
+  unsigned char* d_rowflag = nullptr;  // [Xl] 1 = every node of the row takes its moments from the planes
+  int* d_region = nullptr;             // [n_region] local node ids x * Y + y the region kernel recomputes
+  int n_region = 0;
+  int rows_per_block = 64;
+  bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
+  int rpb_override = 0;
 };
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -44,6 +64,15 @@ __device__ __forceinline__ void tp_load_interior(const double* __restrict__ src,
     if constexpr (MODE == MODE_LOCAL) f[q] = src[q * g.plane + node_off(g, x, y)];
     else f[q] = src[q * g.plane + node_off(g, x - CX(q), y - CY(q))];
   }
+}
+
+// Pull through a per-thread node pointer (src + node_off(g, x, y)) plus WARP-UNIFORM offsets
+// q * plane - c_x * pitch - c_y: two integer instructions per access instead of a 64-bit index
+// rebuilt per thread and per population.
+__device__ __forceinline__ void tp_pull_at(const double* __restrict__ node, const SlabGeom& g, double (&f)[9])
+{
+#pragma unroll
+  for (int q = 0; q < 9; q++) f[q] = __ldg(node + ((long long)q * g.plane - (long long)CX(q) * g.pitch - CY(q)));
 }
 
 template <int MODE>
@@ -206,6 +235,212 @@ k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict_
     rdst[q * g.plane + o] = fr[q];
     bdst[q * g.plane + o] = fb[q];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused step: moments of row r+H into a shared-memory ring, collision of row r out of it
+// ------------------------------------------------------------------------------------------------
+constexpr int TPF_NT = 128;  // threads per block = columns of a strip including the 2H halo columns
+
+template <int MODEL>
+struct TpFused
+{
+  static constexpr int H = MODEL == TP_MRTCG ? 2 : 1;   // stencil half-width
+  static constexpr int NR = 2 * H + 2;                  // ring rows: 2H+1 live + the one being written
+  // ring fields: phase, [Q_rx, Q_ry, Q_bx, Q_by,] rho_r, rho_b, u_x, u_y
+  static constexpr int NF = MODEL == TP_MRTCG ? 9 : 5;
+  static constexpr int F_RR = NF - 4, F_RB = NF - 3, F_UX = NF - 2, F_UY = NF - 1;
+  static constexpr int USEFUL = TPF_NT - 2 * H;         // columns a strip collides
+  static constexpr size_t SMEM = sizeof(double) * NF * NR * TPF_NT;
+};
+
+// stencil of row-slot sc, column t, out of the ring
+template <int MODEL>
+__device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, int sc, int t, TpStencil& st)
+{
+  using C = TpFused<MODEL>;
+  constexpr int NR = C::NR, NT = TPF_NT;
+  auto S = [&](int f, int slot, int col) -> double { return sm[(f * NR + slot) * NT + col]; };
+  st.gx = st.gy = st.rDxQx = st.rDyQy = st.bDxQx = st.bDyQy = 0.0;
+  if constexpr (MODEL == TP_RK)
+  {
+#pragma unroll
+    for (int a = -1; a <= 1; a++)
+    {
+      const int sa = (sc + NR + a) % NR;
+#pragma unroll
+      for (int b = -1; b <= 1; b++)
+      {
+        const double v = S(0, sa, t + b);
+        const double wa = a == 0 ? 1.0 / 9.0 : 1.0 / 36.0, wb = b == 0 ? 1.0 / 9.0 : 1.0 / 36.0;
+        if (b != 0) st.gx += (3.0 * (wa * (double)b)) * v;
+        if (a != 0) st.gy += (3.0 * (wb * (double)a)) * v;
+      }
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int a = -2; a <= 2; a++)
+    {
+      const int sa = (sc + NR + a) % NR;
+#pragma unroll
+      for (int b = -2; b <= 2; b++)
+      {
+        if (a == 0 && b == 0) continue;
+        const double w = XI5(a, b);
+        if (a != 0)
+        {
+          st.gx += (w * (double)a) * S(0, sa, t + b);
+          st.rDxQx += (w * (double)a) * S(1, sa, t + b);
+          st.bDxQx += (w * (double)a) * S(3, sa, t + b);
+        }
+        if (b != 0)
+        {
+          st.gy += (w * (double)b) * S(0, sa, t + b);
+          st.rDyQy += (w * (double)b) * S(2, sa, t + b);
+          st.bDyQy += (w * (double)b) * S(4, sa, t + b);
+        }
+      }
+    }
+  }
+}
+
+// grid: x = strips of USEFUL columns starting at column 1, y = bands of rows_per_block rows.
+// Iteration r of the row loop:   A  issue the pulls of row r (both lattices)
+//                                B  collide row r - LAG out of the ring (rows r-LAG-H .. r-LAG+H)
+//                                C  moments of row r -> ring slot of r ;  __syncthreads
+// PIPE = false: LAG = H and B runs after C and the barrier (collision of row r-H sees row r);
+// PIPE = true : LAG = H + 1 and B runs between A and C, so the DRAM latency of A hides under the fp64
+//               work of B (software pipelining, 36 more live registers).
+// Resident blocks per SM the register allocation aims at.  Measured on B200 at 8192^2 (MRTCG, pipelined):
+// 2 blocks (208 regs) 12.1 GLUPS, 3 blocks (168 regs, no spills) 12.9 GLUPS, 4 blocks (128 regs, spills) 8.0 GLUPS.
+#ifndef LBM_TPF_MINB
+#define LBM_TPF_MINB 3
+#endif
+template <int MODEL, bool PIPE>
+__global__ void __launch_bounds__(TPF_NT, MODEL == TP_MRTCG ? LBM_TPF_MINB : 3)
+k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
+           double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const TpParams p,
+           const unsigned char* __restrict__ rowflag, int rows_per_block)
+{
+  using C = TpFused<MODEL>;
+  constexpr int H = C::H, NR = C::NR, NT = TPF_NT, LAG = PIPE ? H + 1 : H;
+  extern __shared__ double sm[];  // [NF][NR][NT]
+  auto S = [&](int f, int slot, int col) -> double& { return sm[(f * NR + slot) * NT + col]; };
+
+  const int t = threadIdx.x;
+  const int y = 1 + blockIdx.x * C::USEFUL - H + t;
+  const int xb = blockIdx.y * rows_per_block;
+  const int xe = min(xb + rows_per_block, g.Xl);
+  const bool col_ok = y >= -2 && y <= g.Y + 1;           // inside the padded planes
+  const bool col_plane = y < 1 || y > g.Y - 2;           // edge columns (listed nodes) and the padding
+  const bool collider = t >= H && t < NT - H && y >= 1 && y <= g.Y - 2;
+
+  // node pointers of (r, y) in both source lattices, advanced row by row
+  const long long o0 = node_off(g, xb - H, y);
+  const double* pr = rsrc + o0;
+  const double* pb = bsrc + o0;
+  const long long back = (long long)LAG * g.pitch;
+
+  auto collide_row = [&](int sc) {
+    TpStencil st;
+    tp_ring_stencil<MODEL>(sm, sc, t, st);
+    const double rr = S(C::F_RR, sc, t), rb = S(C::F_RB, sc, t);
+    const double ux = S(C::F_UX, sc, t), uy = S(C::F_UY, sc, t), ph = S(0, sc, t);
+    double fr[9], fb[9];
+    tp_pull_at(pr - back, g, fr);
+    tp_pull_at(pb - back, g, fb);
+    tp_collide<MODEL>(p, fr, fb, rr, rb, ux, uy, ph, st);
+    double* wr = rdst + ((pr - back) - rsrc);
+    double* wb = bdst + ((pr - back) - rsrc);
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+    {
+      wr[(long long)q * g.plane] = fr[q];
+      wb[(long long)q * g.plane] = fb[q];
+    }
+  };
+
+  int slot = 0;
+  const int r_end = xe + LAG;
+  for (int r = xb - H; r < r_end; r++, pr += g.pitch, pb += g.pitch)
+  {
+    const bool want = col_ok && r < xe + H;                                            // row r enters the ring
+    const bool plane = col_plane || r < 0 || r >= g.Xl || (want && rowflag[min(max(r, 0), g.Xl - 1)]);
+    double fr[9], fb[9];
+    double rr, rb, ux, uy, ph;
+    // ---- A: moments of node (r, y) of the post-stream state: from the planes, or pulled
+    if (want)
+    {
+      if (plane)
+      {
+        const long long k = mom_off(mg, r, y);
+        rr = mom[M_RR * mg.mplane + k];
+        rb = mom[M_RB * mg.mplane + k];
+        ux = mom[M_UX * mg.mplane + k];
+        uy = mom[M_UY * mg.mplane + k];
+        ph = mom[M_PH * mg.mplane + k];
+      }
+      else
+      {
+        tp_pull_at(pr, g, fr);
+        tp_pull_at(pb, g, fb);
+      }
+    }
+    // ---- B (pipelined): collision of row r - LAG
+    if constexpr (PIPE)
+    {
+      if (r - LAG >= xb && collider) collide_row((slot + NR - LAG) % NR);
+    }
+    // ---- C: finish the moments, publish them
+    if (want)
+    {
+      if (!plane) tp_moments<MODEL>(p, fr, fb, rr, rb, ux, uy, ph);
+      S(0, slot, t) = ph;
+      if constexpr (MODEL == TP_MRTCG)
+      {
+        S(1, slot, t) = (p.cr * rr) * ux;
+        S(2, slot, t) = (p.cr * rr) * uy;
+        S(3, slot, t) = (p.cb * rb) * ux;
+        S(4, slot, t) = (p.cb * rb) * uy;
+      }
+      S(C::F_RR, slot, t) = rr;
+      S(C::F_RB, slot, t) = rb;
+      S(C::F_UX, slot, t) = ux;
+      S(C::F_UY, slot, t) = uy;
+    }
+    __syncthreads();
+    // ---- B (plain): collision of row r - H, whose stencil rows are the last 2H+1 ring slots
+    if constexpr (!PIPE)
+    {
+      if (r - LAG >= xb && collider) collide_row((slot + NR - LAG) % NR);
+    }
+    slot = slot + 1 == NR ? 0 : slot + 1;
+  }
+}
+
+// moments of a short list of nodes (plain pull) into the planes: the region around listed nodes,
+// the global edge rows and the rows next to a slab cut
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+k_tp_moments_nodes(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                   double* __restrict__ mom, const TpParams p, const int* __restrict__ nodes, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = nodes[i] / g.Y, y = nodes[i] % g.Y;
+  double fr[9], fb[9];
+  tp_load_interior<MODE_PULL>(rsrc, g, x, y, fr);
+  tp_load_interior<MODE_PULL>(bsrc, g, x, y, fb);
+  double rr, rb, ux, uy, ph;
+  tp_moments<MODEL>(p, fr, fb, rr, rb, ux, uy, ph);
+  const long long k = mom_off(mg, x, y);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
 }
 
 template <int MODEL, int MODE>
@@ -473,6 +708,7 @@ int tp_create(lbm_domain* d)
   fill_colour(c.red, p.r_phi, p.r_eta, r_cs2);
   fill_colour(c.blue, p.b_phi, p.b_eta, b_cs2);
   p.r_rho0 = c.red.rho_0; p.b_rho0 = c.blue.rho_0;
+  p.r_irho0 = 1.0 / c.red.rho_0; p.b_irho0 = 1.0 / c.blue.rho_0;
   p.r_beta = c.red.beta; p.b_beta = c.blue.beta;
   p.r_A = c.red.A; p.b_A = c.blue.A;
   p.cr = 1.8 * c.red.alpha - 0.8;
@@ -500,6 +736,12 @@ int tp_create(lbm_domain* d)
   p.s3 = -p.s2 / (2.0 * p.delta);
   p.t2 = 2.0 * (p.s1 - p.b_val) / p.delta;
   p.t3 = p.t2 / (2.0 * p.delta);
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));
+  if (const char* e = getenv("LBM_TP_PIPE")) tp->pipe = atoi(e) != 0;
+  if (const char* e = getenv("LBM_TP_RPB")) tp->rpb_override = atoi(e);
   return LBM_OK;
 }
 
@@ -514,6 +756,8 @@ int tp_destroy(lbm_domain* d)
 {
   if (!d->tp) return LBM_OK;
   cudaFree(d->tp->mom);
+  cudaFree(d->tp->d_rowflag);
+  cudaFree(d->tp->d_region);
   delete d->tp;
   d->tp = nullptr;
   return LBM_OK;
@@ -591,35 +835,143 @@ static int tp_launch_moments(lbm_domain* d, int which, double* out_r, double* ou
   return LBM_OK;
 }
 
+// rows whose moments stay in the planes, and the node list the region kernel recomputes every step
+static int tp_build_region(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  if (!tp->region_dirty) return LBM_OK;
+  const int Xl = d->g.Xl, Y = d->g.Y;
+  std::vector<unsigned char> flag(Xl, 0);
+  auto mark = [&](int x) { if (x >= 0 && x < Xl) flag[x] = 1; };
+  // global edge rows feed the replicate padding, the rows next to a cut travel to the neighbour
+  for (int x : {0, 1, Xl - 2, Xl - 1}) mark(x);
+  // listed nodes read their 5x5 neighbourhood from the planes
+  for (int x = 0; x < Xl && x < (int)d->row_has_listed.size(); x++)
+    if (d->row_has_listed[x])
+      for (int k = -2; k <= 2; k++) mark(x + k);
+  std::vector<int> nodes;
+  for (int x = 0; x < Xl; x++)
+  {
+    if (flag[x])
+    {
+      for (int y = 1; y <= Y - 2; y++) nodes.push_back(x * Y + y);
+      continue;
+    }
+    int last = 0;
+    for (int y : {1, 2, Y - 3, Y - 2})
+      if (y >= 1 && y <= Y - 2 && y > last)
+      {
+        nodes.push_back(x * Y + y);
+        last = y;
+      }
+  }
+  cudaFree(tp->d_rowflag);
+  cudaFree(tp->d_region);
+  tp->d_rowflag = nullptr;
+  tp->d_region = nullptr;
+  LBM_CUDA(cudaMalloc(&tp->d_rowflag, Xl));
+  LBM_CUDA(cudaMemcpy(tp->d_rowflag, flag.data(), Xl, cudaMemcpyHostToDevice));
+  tp->n_region = (int)nodes.size();
+  if (tp->n_region > 0)
+  {
+    LBM_CUDA(cudaMalloc(&tp->d_region, sizeof(int) * nodes.size()));
+    LBM_CUDA(cudaMemcpy(tp->d_region, nodes.data(), sizeof(int) * nodes.size(), cudaMemcpyHostToDevice));
+  }
+  // enough blocks for several waves over 148 SMs, bands as tall as that allows (the 2H warm-up rows
+  // of a band are recomputed by the band above)
+  const int useful = tp->model == TP_MRTCG ? TpFused<TP_MRTCG>::USEFUL : TpFused<TP_RK>::USEFUL;
+  const int strips = cdiv(std::max(Y - 2, 1), useful);
+  const int bands = std::max(1, cdiv(148 * 3 * 6, strips));
+  tp->rows_per_block = std::min(128, std::max(16, cdiv(Xl, bands)));
+  if (tp->rpb_override > 0) tp->rows_per_block = tp->rpb_override;
+  tp->region_dirty = false;
+  return LBM_OK;
+}
+
+template <int MODEL>
+static int tp_launch_fused(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  using C = TpFused<MODEL>;
+  const int s = d->cur, t = d->cur ^ 1;
+  {
+    // moments of the thin region the planes stay authoritative for, its padding and the cut rows
+    ProfScope ps(d, LBM_PROF_MOMENTS);
+    if (tp->n_region > 0)
+    {
+      k_tp_moments_nodes<MODEL><<<cdiv(tp->n_region, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom,
+                                                                                tp->p, tp->d_region, tp->n_region);
+      d->launches++;
+    }
+    if (d->nb > 0)
+    {
+      k_tp_moments_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom,
+                                                                                    tp->p, table_of(d), nullptr, nullptr);
+      d->launches++;
+    }
+    LBM_TRY(tp_pad(d));
+    LBM_TRY(comm_exchange_moments(d));
+  }
+  const int Yi = d->g.Y - 2;
+  if (Yi > 0)
+  {
+    ProfScope ps(d, LBM_PROF_INTERIOR);
+    dim3 grid(cdiv(Yi, C::USEFUL), cdiv(d->g.Xl, tp->rows_per_block));
+    if (tp->pipe)
+      k_tp_fused<MODEL, true><<<grid, TPF_NT, C::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                    tp->mom, tp->p, tp->d_rowflag, tp->rows_per_block);
+    else
+      k_tp_fused<MODEL, false><<<grid, TPF_NT, C::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                     tp->mom, tp->p, tp->d_rowflag, tp->rows_per_block);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    ProfScope ps(d, LBM_PROF_BOUNDARY);
+    k_tp_collide_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t],
+                                                                                  d->buf[1][t], d->g, tp->mg, tp->mom, tp->p, table_of(d));
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
 int tp_step(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
-  const bool local = d->post_stream;
-  if (tp->model == TP_MRTCG)
+  LBM_TRY(tp_build_region(d));
+  if (d->post_stream)
   {
-    if (local) LBM_TRY((tp_launch_collide<TP_MRTCG, MODE_LOCAL>(d)));
-    else LBM_TRY((tp_launch_collide<TP_MRTCG, MODE_PULL>(d)));
+    // first step after an import: the caller's u lives in the (full) moment planes
+    if (tp->model == TP_MRTCG) LBM_TRY((tp_launch_collide<TP_MRTCG, MODE_LOCAL>(d)));
+    else LBM_TRY((tp_launch_collide<TP_RK, MODE_LOCAL>(d)));
   }
   else
   {
-    if (local) LBM_TRY((tp_launch_collide<TP_RK, MODE_LOCAL>(d)));
-    else LBM_TRY((tp_launch_collide<TP_RK, MODE_PULL>(d)));
+    if (tp->model == TP_MRTCG) LBM_TRY(tp_launch_fused<TP_MRTCG>(d));
+    else LBM_TRY(tp_launch_fused<TP_RK>(d));
   }
   d->cur ^= 1;
   d->post_stream = false;
+  tp->planes_full = false;
   {
-    // the moments pass pulls from the buffer just written: its ghost rows first
+    // the next step pulls from the buffer just written: its ghost rows
     ProfScope ps(d, LBM_PROF_GHOST);
     if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->stream));
     else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
   }
+  return LBM_OK;
+}
+
+// moments of every own node of the current state into the planes (diagnostics: lbm_get_moments /
+// lbm_get_phase after fused steps).  No exchange: the halo cells are rebuilt by the next step.
+static int tp_fill_planes(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  if (tp->planes_full || d->post_stream) return LBM_OK;
   if (tp->model == TP_MRTCG) LBM_TRY(tp_launch_moments<TP_MRTCG>(d, d->cur, nullptr, nullptr));
   else LBM_TRY(tp_launch_moments<TP_RK>(d, d->cur, nullptr, nullptr));
-  {
-    ProfScope ps(d, LBM_PROF_GHOST);
-    LBM_TRY(tp_pad(d));
-    LBM_TRY(comm_exchange_moments(d));
-  }
+  tp->planes_full = true;
   return LBM_OK;
 }
 
@@ -631,6 +983,7 @@ int tp_commit(lbm_domain* d)
       set_error("two-phase models take LBM_BC_LINEAR rules only");
       return LBM_ERR_UNSUPPORTED;
     }
+  d->tp->region_dirty = true;
   return commit_boundary_tables(d);
 }
 
@@ -655,6 +1008,7 @@ int tp_export(lbm_domain* d)
 int tp_read_moments(lbm_domain* d, double* rho, double* u, double* ph, double* rr, double* rb)
 {
   const long long N = (long long)d->g.Xl * d->g.Y;
+  LBM_TRY(tp_fill_planes(d));
   double* tmp = nullptr;
   LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 6 * N));
   double *d_rho = tmp, *d_u = tmp + N, *d_ph = tmp + 3 * N, *d_rr = tmp + 4 * N, *d_rb = tmp + 5 * N;
@@ -679,6 +1033,7 @@ int tp_refresh_moments(lbm_domain* d)
   else
     k_tp_moments_local<TP_RK><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p);
   d->launches++;
+  d->tp->planes_full = true;
   LBM_TRY(tp_pad(d));
   return comm_exchange_moments(d);
 }
@@ -737,6 +1092,7 @@ int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, 
   if (s != LBM_OK) return s;
   d->post_stream = true;
   d->have_state = true;
+  d->tp->planes_full = true;
   return LBM_OK;
 }
 

@@ -18,6 +18,7 @@ enum TpModel { TP_MRTCG = 0, TP_RK = 1 };
 struct TpParams
 {
   double r_rho0, b_rho0, r_beta, b_beta, r_A, b_A;
+  double r_irho0, b_irho0;    // 1 / rho0_k
   double r_phi[3], b_phi[3];  // by |c|^2 class: q = 0, q = 1..4, q = 5..8  (src/colour.cpp:56-64)
   double r_eta[3], b_eta[3];  // src/colour.cpp:49-54
   double cr, cb;              // (1.8 alpha_k - 0.8)   (mrtcg_rayleigh_taylor.cpp:328-329)
@@ -95,10 +96,16 @@ __device__ __forceinline__ double relax_eval(const TpParams& p, double psi)
   return s;
 }
 
+// Divisions: fp64 division costs ~12 issue slots on the fp64 pipe, and the reference's formulas hold
+// ~45 of them per node.  Every quotient by a per-node scalar (rho, |grad|, rho0_k) is therefore taken as
+// a product with ONE reciprocal of that scalar; the result differs from the reference's quotient by
+// <= 1 ulp per operation, far inside the parity tolerance (1e-12 relative after one step).
+
 // eval_phase_field (mrtcg_rayleigh_taylor.cpp:212-225)
 __device__ __forceinline__ double phase_of(const TpParams& p, double rr, double rb)
 {
-  return (rr / p.r_rho0 - rb / p.b_rho0) / (rr / p.r_rho0 + rb / p.b_rho0);
+  const double a = rr * p.r_irho0, b = rb * p.b_irho0;
+  return (a - b) / (a + b);
 }
 
 // Moments of a freshly streamed node: what the drivers compute at the END of an iteration
@@ -115,12 +122,13 @@ __device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)
 #pragma unroll
   for (int q = 0; q < 9; q++) t[q] = fr[q] + fb[q];
   moments(t, dummy, jx, jy);
-  ux = jx / rho;
-  uy = jy / rho;
+  const double inv_rho = 1.0 / rho;
+  ux = jx * inv_rho;
+  uy = jy * inv_rho;
   if constexpr (MODEL == TP_MRTCG)
   {
-    ux = ux + 0.5 * p.Fg0 / rho;
-    uy = uy + 0.5 * p.Fg1 / rho;
+    ux = ux + (0.5 * p.Fg0) * inv_rho;
+    uy = uy + (0.5 * p.Fg1) * inv_rho;
   }
   ph = phase_of(p, rr, rb);
 }
@@ -156,11 +164,12 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
     // relax = 1/tau(phase) (:587-588); omega1 = relax (feq - f) (:255-262); omega2 Reis (:239-245); col = f + (w1 + w2)
     const double relax = 1.0 / relax_eval(p, ph);
     const double gn2 = gn * gn;
+    const double ign2 = 1.0 / (1e-20 + gn2);
 #pragma unroll
     for (int q = 0; q < 9; q++)
     {
       const double fe = st.gx * (double)CX(q) + st.gy * (double)CY(q);
-      const double core = ((fe * fe) / (1e-20 + gn2)) * W(q) - BQ(q);
+      const double core = ((fe * fe) * ign2) * W(q) - BQ(q);
       const double o1r = relax * (tp_feq<TP_RK>(q, rr, p.r_phi, p.r_eta, ux, uy, uu) - fr[q]);
       const double o1b = relax * (tp_feq<TP_RK>(q, rb, p.b_phi, p.b_eta, ux, uy, uu) - fb[q]);
       fr[q] = fr[q] + (o1r + ((0.5 * p.r_A) * gn) * core);
@@ -169,68 +178,73 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
   }
   else
   {
+    // mrtcg_rayleigh_taylor.cpp:431-464.  Only the SUM of the two colours' MRT operators enters the
+    // update (total = sum_k (f_k + omega1_k + omega2_k), :455, then recoloured, :456-457), and
+    // M^-1 S M is linear, so the transform runs once on d = (feq_r + feq_b) - (f_r + f_b) with
+    // C = C_r + C_b instead of once per colour.
     const double rho = rr + rb;
     const double s_nu = relax_eval(p, ph);
-    // S = diag(0, 1.25, 1.14, 0, 1.6, 0, 1.6, s_nu, s_nu) (:384-387, update_S)
-    const double S[9] = {0.0, 1.25, 1.14, 0.0, 1.6, 0.0, 1.6, s_nu, s_nu};
-    double o1r[9], o1b[9];
+    const double mix[3] = {rr * p.r_phi[0] + rb * p.b_phi[0], rr * p.r_phi[1] + rb * p.b_phi[1], rr * p.r_phi[2] + rb * p.b_phi[2]};
+    const double emix[3] = {rr * p.r_eta[0] + rb * p.b_eta[0], rr * p.r_eta[1] + rb * p.b_eta[1], rr * p.r_eta[2] + rb * p.b_eta[2]};
+    double fs[9], d[9], m[9], o1[9];
 #pragma unroll
-    for (int k = 0; k < 2; k++)
+    for (int q = 0; q < 9; q++)
     {
-      const double rk = k == 0 ? rr : rb;
-      double d[9], m[9];
-#pragma unroll
-      for (int q = 0; q < 9; q++)
-        d[q] = (k == 0 ? tp_feq<TP_MRTCG>(q, rk, p.r_phi, p.r_eta, ux, uy, uu) - fr[q]
-                       : tp_feq<TP_MRTCG>(q, rk, p.b_phi, p.b_eta, ux, uy, uu) - fb[q]);
-      const double DxQx = k == 0 ? st.rDxQx : st.bDxQx, DyQy = k == 0 ? st.rDyQy : st.bDyQy;
-#pragma unroll
-      for (int a = 0; a < 9; a++)
-      {
-        double s = 0.0;
-        if (a != 0 && a != 3 && a != 5)  // conserved moments: S = 0 and C = 0 there
-        {
-#pragma unroll
-          for (int q = 0; q < 9; q++)
-            if (MM(a, q) != 0.0) s += MM(a, q) * d[q];
-        }
-        double c = 0.0;
-        if (a == 1) c = 3.0 * (1.0 - 0.5 * 1.25) * (DxQx + DyQy);  // update_C (:320-336)
-        if (a == 7) c = (1.0 - 0.5 * s_nu) * (DxQx - DyQy);
-        m[a] = S[a] * s + c;
-      }
-#pragma unroll
-      for (int q = 0; q < 9; q++)
-      {
-        double s = 0.0;
-#pragma unroll
-        for (int a = 1; a < 9; a++)
-          if (a != 3 && a != 5 && MI36(q, a) != 0.0) s += ((1.0 / 36.0) * MI36(q, a)) * m[a];
-        if (k == 0) o1r[q] = s;
-        else o1b[q] = s;
-      }
+      // eval_equilibrium summed over the colours: rho_k (phi_k + w (3 ue eta_k + 9 ue^2 - 3 uu)), note 9 and 3 (:244)
+      const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
+      fs[q] = fr[q] + fb[q];
+      d[q] = (mix[QCLASS(q)] + W(q) * ((3.0 * ue) * emix[QCLASS(q)] + rho * (9.0 * (ue * ue) - 3.0 * uu))) - fs[q];
     }
-    const double A = 4.5 * p.sigma * s_nu;
-    const double inv = 1e-20 + gn;
+    // S = diag(0, 1.25, 1.14, 0, 1.6, 0, 1.6, s_nu, s_nu) (:384-387, update_S); conserved moments: S = 0 and C = 0
+    const double S[9] = {0.0, 1.25, 1.14, 0.0, 1.6, 0.0, 1.6, s_nu, s_nu};
+    const double DQ1 = (st.rDxQx + st.rDyQy) + (st.bDxQx + st.bDyQy);  // update_C (:320-336), both colours
+    const double DQ7 = (st.rDxQx - st.rDyQy) + (st.bDxQx - st.bDyQy);
+#pragma unroll
+    for (int a = 1; a < 9; a++)
+    {
+      if (a == 3 || a == 5) continue;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+        if (MM(a, q) != 0.0) s += MM(a, q) * d[q];
+      double c = 0.0;
+      if (a == 1) c = (3.0 * (1.0 - 0.5 * 1.25)) * DQ1;
+      if (a == 7) c = (1.0 - 0.5 * s_nu) * DQ7;
+      m[a] = S[a] * s + c;
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 1; a < 9; a++)
+        if (a != 3 && a != 5 && MI36(q, a) != 0.0) s += ((1.0 / 36.0) * MI36(q, a)) * m[a];
+      o1[q] = s;
+    }
+    const double rinv = 1.0 / (1e-20 + gn);
+    const double inv_rho = 1.0 / rho;
+    const double wr = rr * inv_rho, wb = rb * inv_rho;  // rho_k / rho
+    const double k0 = (wr * wb) * rinv;                 // rho_r rho_b / (rho^2 (1e-20 + |grad|))
+    const double A2 = (4.5 * p.sigma * s_nu) * (0.5 * gn) * 2.0;  // both colours' perturbation: A = 4.5 sigma s_nu, xi = 0.5 |grad| (..)
     const double uF = ux * p.Fg0 + uy * p.Fg1;
-    constexpr double SQ2 = 1.4142135623730951;
+    const double pref = 1.0 - 0.5 * s_nu;
+    constexpr double ISQ2 = 0.7071067811865476;
 #pragma unroll
     for (int q = 0; q < 9; q++)
     {
       const double ge = st.gx * (double)CX(q) + st.gy * (double)CY(q);
-      const double t = ge / inv;
-      const double o2 = A * ((0.5 * gn) * (W(q) * (t * t) - BQ(q)));  // eval_xi, eval_per_operator
-      const double nrm = q < 5 ? 1.0 : SQ2;
-      const double gue = st.gx * ((double)CX(q) / nrm) + st.gy * ((double)CY(q) / nrm);
-      const double kap = (((rr * rb) * gue) * (rr * p.r_phi[QCLASS(q)] + rb * p.b_phi[QCLASS(q)])) / ((rho * rho) * inv);  // eval_kappa
-      const double total = ((((fr[q] + o1r[q]) + o2) + fb[q]) + o1b[q]) + o2;  // :455
-      double nr = rr * total / rho + p.r_beta * kap;                           // eval_rec_operator
-      double nb = rb * total / rho + p.b_beta * kap;
+      const double t = ge * rinv;
+      const double o2x2 = A2 * (W(q) * (t * t) - BQ(q));  // eval_xi, eval_per_operator (omega2_r + omega2_b)
+      const double gue = q < 5 ? ge : ge * ISQ2;          // grad . c / |c|
+      const double kap = (k0 * gue) * mix[QCLASS(q)];      // eval_kappa
+      const double total = (fs[q] + o1[q]) + o2x2;         // :455
+      double nr = wr * total + p.r_beta * kap;             // eval_rec_operator
+      double nb = wb * total + p.b_beta * kap;
       if (p.add_force)  // :460-464 (ics2 = 3, ics4 = 9)
       {
         const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
         const double Fe = (double)CX(q) * p.Fg0 + (double)CY(q) * p.Fg1;
-        const double src = ((1.0 - 0.5 * s_nu) * ((3.0 + 9.0 * ue) * Fe - 3.0 * uF)) * W(q);
+        const double src = (pref * ((3.0 + 9.0 * ue) * Fe - 3.0 * uF)) * W(q);
         nr += src;
         nb += src;
       }

@@ -170,3 +170,40 @@ def test_rk_long_run_stays_on_the_oracle(orc):
     assert np.abs(rho[..., 0] - st["rho"]).max() < 1e-9 and np.abs(u - st["u"]).max() < 1e-9
     # oracle's phase lags one step (it is the phase used by the last collision); compare densities instead
     assert np.abs(rr - st["r_rho"]).max() < 1e-9 and np.abs(rb - st["b_rho"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("R,C", [(300, 400), (131, 253), (40, 127)])
+def test_mrtcg_fused_kernel_many_strips_and_bands(orc, R, C):
+    """sizes that give the fused kernel several column strips (124 useful columns each) and row bands"""
+    Fg = (6.25e-6, 0.0)
+    p = mrtcg_params(R, C, Fg, 1)
+    st = orc.mrtcg_init(p, "rt")
+    d = cases.mrtcg(R, C, Fg, 1)
+    d.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+    for _ in range(6):
+        orc.mrtcg_step(p, st)
+    d.step(6)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
+    rho, u = d.get_moments()
+    assert np.abs(rho - st["rho"]).max() < 1e-12 and np.abs(u - st["u"]).max() < 1e-12
+    # diagnostics in the middle of a run must not disturb it
+    d.step(3)
+    for _ in range(3):
+        orc.mrtcg_step(p, st)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
+
+
+@pytest.mark.parametrize("Ln", [260, 127])
+def test_rk_fused_kernel_many_strips_and_bands(orc, Ln):
+    p = rk_params(Ln)
+    p.radius = Ln / 4.0
+    st = orc.rk_init(p)
+    d = cases.rk(Ln)
+    d.set_f(st["r_adv"], 0)
+    d.set_f(st["b_adv"], 1)
+    for _ in range(8):
+        orc.rk_step(p, st)
+    d.step(8)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
+    rho, u = d.get_moments()
+    assert np.abs(rho[..., 0] - st["rho"]).max() < 1e-12 and np.abs(u - st["u"]).max() < 1e-12
