@@ -354,13 +354,18 @@ class Case:
             xs, ys = cylinder_markers(self.X, Y)  # the body sits in rank 0's slab
             if self.rank == 0:
                 d.ibm_set_markers(xs, ys)
-            # the drivers' incomp_equilibrium(u=(u_lb,0), rho=1) (cylinder_test.cpp:84-86)
-            self.f_t, self.f = self.pinned((X, Y, 9))
-            self.f[...] = (1.0 + 3.0 * CX9 * self.u_lb) * W9
+            # the drivers' f = incomp_equilibrium(u=(u_lb,0), rho=1) (cylinder_test.cpp:84-86): u and rho are the inputs
+            self.ri_t, self.ri = self.pinned((X, Y, 1))
+            self.ui_t, self.ui = self.pinned((X, Y, 2))
+            self.ri[...] = 1.0
+            self.ui[..., 0] = self.u_lb
+            self.ui[..., 1] = 0.0
         elif self.name == "poiseuille":
             d.preset_poiseuille(self.rho_in, self.rho_out)
-            self.f_t, self.f = self.pinned((X, Y, 9))
-            self.f[...] = W9  # incomp_equilibrium(u=0, rho=1) (horizontal_poiseuille_test.cpp:91)
+            self.ri_t, self.ri = self.pinned((X, Y, 1))  # incomp_equilibrium(u=0, rho=1) (horizontal_poiseuille_test.cpp:91)
+            self.ui_t, self.ui = self.pinned((X, Y, 2))
+            self.ri[...] = 1.0
+            self.ui[...] = 0.0
         elif self.name == "sedimentation":
             R23, C28, C38, C_w = sedimentation_geometry(self.Xg, Y)
             d.preset_sedimentation(self.u_lb, C_w, R23, C28, C38)
@@ -389,8 +394,8 @@ class Case:
         """host -> device through the C ABI; returns the bytes copied"""
         d = self.d
         if self.name in ("cylinder", "poiseuille"):
-            d.set_f(self.f)
-            return self.f.nbytes
+            d.init_equilibrium(self.ri, self.ui, self.L.EQ_INCOMPRESSIBLE)
+            return self.ri.nbytes + self.ui.nbytes
         if self.name == "sedimentation":
             d.set_f(self.f, 0)
             d.set_f(self.g, 1)
@@ -499,7 +504,8 @@ def run_b200_arm(args):
         sec = max_over_ranks(t2 - t0)
         e2e = {"value": (case.Xg * case.Y) * args.steps / sec / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-               "what": f"state import from pinned host + lbm_step({args.steps}) + lbm_get_moments to pinned host, per rank",
+               "what": f"initial fields from pinned host (the drivers' u, rho -> equilibrium; populations for the ADE / two-phase "
+                       f"imports) + lbm_step({args.steps}) + lbm_get_moments to pinned host, per rank",
                "seconds": sec, "import_seconds": t1 - t0, "steps_and_export_seconds": t2 - t1,
                "rho_mean": float(case.rho_t.mean())}
 

@@ -346,6 +346,7 @@ int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper)
   d->link_lo = lower;
   d->link_hi = upper;
   d->side_ready = false;
+  drop_graphs(d);
   return LBM_OK;
 }
 

@@ -249,7 +249,8 @@ int step_early(lbm_domain* d)
 {
   LBM_TRY(step_rows(d));
   const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
-  LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+  if (!d->skip_side_wait) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+  d->skip_side_wait = false;
   LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_early, d->n_early, false, d->ibm.next_slot, d->stream};
   LBM_TRY(dispatch_mode(d, mode, a));
   LBM_CUDA(cudaEventRecord(d->ev_early, d->stream));
@@ -436,8 +437,19 @@ static int local_row(const lbm_domain* d, int gx)
   return INT_MIN;
 }
 
+void drop_graphs(lbm_domain* d)
+{
+  for (int k = 0; k < 2; k++)
+    if (d->graph_exec[k])
+    {
+      cudaGraphExecDestroy(d->graph_exec[k]);
+      d->graph_exec[k] = nullptr;
+    }
+}
+
 static void release_compiled(lbm_domain* d)
 {
+  drop_graphs(d);
   cudaFree(d->d_bx); cudaFree(d->d_by); cudaFree(d->d_ent); cudaFree(d->d_mom[0]); cudaFree(d->d_mom[1]);
   d->d_bx = d->d_by = nullptr; d->d_ent = nullptr; d->d_mom[0] = d->d_mom[1] = nullptr;
   for (auto& sg : d->stages)
@@ -835,6 +847,7 @@ int lbm_destroy(lbm_domain* d)
     for (int b = 0; b < 2; b++) cudaFree(d->buf[l][b]);
     cudaFree(d->d_aos[l]);
   }
+  cudaFree(d->d_mom_out);
   for (int k = 0; k < 2; k++)
     if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
   for (auto& r : d->prof)
@@ -963,9 +976,8 @@ int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u)
   if (d->tp) return tp_read_moments(d, rho, u, nullptr, nullptr, nullptr);
   LBM_TRY(export_post_stream(d));
   const long long N = (long long)d->g.Xl * d->g.Y;
-  double *d_rho = nullptr, *d_u = nullptr;
-  LBM_CUDA(cudaMalloc(&d_rho, N * sizeof(double)));
-  LBM_CUDA(cudaMalloc(&d_u, 2 * N * sizeof(double)));
+  if (!d->d_mom_out) LBM_CUDA(cudaMalloc(&d->d_mom_out, 3 * N * sizeof(double)));  // kept: snapshots recur
+  double *d_rho = d->d_mom_out, *d_u = d->d_mom_out + N;
   int incompressible = 0;
   double sx = 0.0, sy = 0.0;
   if (d->cfg.model == LBM_MODEL_BGK)
@@ -978,8 +990,6 @@ int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u)
   if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d_rho, N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
   if (u) LBM_CUDA(cudaMemcpyAsync(u, d_u, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
-  cudaFree(d_rho);
-  cudaFree(d_u);
   return LBM_OK;
 }
 
@@ -1005,6 +1015,48 @@ int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* 
 }
 
 // ---------------------------------------------------------------- stepping
+static int step_once(lbm_domain* d) { return d->tp ? tp_step(d) : bgk_step_once(d); }
+
+// One steady-state step PAIR captured into a CUDA graph (a pair returns every A/B toggle — buffers,
+// listed-node moments, IBM force slots — to where it started, so the graph replays as is).  For the
+// launch-bound small grids: ~12 launches on two streams per step become one graph launch per two steps.
+static int capture_pair(lbm_domain* d)
+{
+  const int k = d->cur;
+  if (d->graph_exec[k]) return LBM_OK;
+  const long long launches0 = d->launches;
+  cudaGraph_t graph = nullptr;
+  LBM_CUDA(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+  int s = LBM_OK;
+  for (int i = 0; i < 2 && s == LBM_OK; i++)
+  {
+    d->skip_side_wait = (i == 0) && !d->tp;  // the side chain of the step before the pair is joined outside the graph
+    s = step_once(d);
+  }
+  d->skip_side_wait = false;
+  // join the side stream (captured through ev_early) back into the origin stream
+  if (s == LBM_OK && !d->tp && cudaStreamWaitEvent(d->stream, d->ev_side, 0) != cudaSuccess) s = LBM_ERR_CUDA;
+  cudaError_t e = cudaStreamEndCapture(d->stream, &graph);
+  if (s != LBM_OK || e != cudaSuccess)
+  {
+    if (graph) cudaGraphDestroy(graph);
+    if (s == LBM_OK) set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return s != LBM_OK ? s : LBM_ERR_CUDA;
+  }
+  e = cudaGraphInstantiate(&d->graph_exec[k], graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return LBM_ERR_CUDA; }
+  d->graph_launches[k] = d->launches - launches0;
+  d->launches = launches0;  // nothing ran yet
+  return LBM_OK;
+}
+
+static bool graph_eligible(const lbm_domain* d)
+{
+  return d->use_graph && !d->profiling && !comm_active(d) && !d->link_lo && !d->link_hi;
+}
+
 int lbm_step(lbm_domain* d, int n_steps)
 {
   if (!d || n_steps < 0) { set_error("lbm_step: bad argument"); return LBM_ERR_INVALID; }
@@ -1012,11 +1064,31 @@ int lbm_step(lbm_domain* d, int n_steps)
   if (!d->committed) { set_error("lbm_step: call lbm_bc_commit first"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   LBM_CUDA(cudaEventRecord(d->ev_begin, d->stream));
-  for (int s = 0; s < n_steps; s++)
+  int s = 0;
+  if (graph_eligible(d) && n_steps >= 4)
   {
-    if (d->tp) LBM_TRY(tp_step(d));
-    else LBM_TRY(bgk_step_once(d));
+    // reach the steady state (post-collision storage, side chain prepared, row lists built) with plain steps
+    while (s < n_steps && (d->post_stream || (!d->tp && !d->side_ready))) { LBM_TRY(step_once(d)); s++; }
+    if (n_steps - s >= 2)
+    {
+      if (!d->tp)
+      {
+        // everything the side stream still owes the current buffer, joined outside the graph
+        LBM_CUDA(cudaEventRecord(d->ev_ready, d->side));
+        LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_ready, 0));
+      }
+      LBM_TRY(capture_pair(d));
+      const int k = d->cur;
+      for (; n_steps - s >= 2; s += 2)
+      {
+        LBM_CUDA(cudaGraphLaunch(d->graph_exec[k], d->stream));
+        d->launches += d->graph_launches[k];
+      }
+      // events last recorded inside the capture must not be waited on by plain steps: re-record them here
+      if (!d->tp) LBM_CUDA(cudaEventRecord(d->ev_side, d->stream));
+    }
   }
+  for (; s < n_steps; s++) LBM_TRY(step_once(d));
   LBM_CUDA(cudaEventRecord(d->ev_end, d->stream));
   return LBM_OK;
 }
@@ -1056,6 +1128,12 @@ int lbm_use_graph(lbm_domain* d, int enable)
 {
   if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
   d->use_graph = enable != 0;
+  if (!d->use_graph)
+  {
+    cudaSetDevice(d->cfg.device);
+    cudaStreamSynchronize(d->stream);
+    drop_graphs(d);
+  }
   return LBM_OK;
 }
 

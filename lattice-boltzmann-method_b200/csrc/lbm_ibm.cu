@@ -254,6 +254,7 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   ib.enabled = true;
   d->rows_dirty = true;
   d->side_ready = false;
+  drop_graphs(d);
   return LBM_OK;
 }
 

@@ -134,6 +134,7 @@ struct lbm_domain
 
   // scratch for export
   double* d_aos[2] = {nullptr, nullptr};
+  double* d_mom_out = nullptr;  // [3][Xl*Y] rho, u for lbm_get_moments
 
   lbm::IbmState ibm;
   lbm::TwoPhaseState* tp = nullptr;
@@ -147,13 +148,16 @@ struct lbm_domain
 
   // CUDA graph of one steady-state step pair
   bool use_graph = false;
-  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};  // keyed by the buffer the pair starts from
+  long long graph_launches[2] = {0, 0};                // kernels one replay launches
+  bool skip_side_wait = false;                         // first step of a captured pair
 };
 
 namespace lbm
 {
 // lbm_domain.cu
 int ensure_aos_scratch(lbm_domain* d);
+void drop_graphs(lbm_domain* d);  // captured step pairs hold device pointers: drop them when tables / markers change
 // brackets a group of launches of one class with events when profiling is on
 struct ProfScope
 {

@@ -318,8 +318,11 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
 #ifndef LBM_TPF_MINB
 #define LBM_TPF_MINB 3
 #endif
+#ifndef LBM_TPF_MINB_RK
+#define LBM_TPF_MINB_RK 3
+#endif
 template <int MODEL, bool PIPE>
-__global__ void __launch_bounds__(TPF_NT, MODEL == TP_MRTCG ? LBM_TPF_MINB : 3)
+__global__ void __launch_bounds__(TPF_NT, MODEL == TP_MRTCG ? LBM_TPF_MINB : LBM_TPF_MINB_RK)
 k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
            double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const TpParams p,
            const unsigned char* __restrict__ rowflag, int rows_per_block)
