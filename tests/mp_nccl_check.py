@@ -22,8 +22,11 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ident = [L.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ident, src=0)
+    def fresh_id():
+        """one NCCL unique id per communicator: rank 0 creates it, everyone receives it"""
+        ident = [L.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        return ident[0]
 
     def gather(a):
         out = [None] * world
@@ -41,7 +44,7 @@ def main():
     f0 = w * (1.0 + 0.02 * rng.standard_normal((X, Y, 9)))
     x0, x1 = L.decompose_rows(X, world, rank)
     d = L.Domain(L.default_config(x0=x0, x1=x1, device=local, **kw))
-    d.comm_init(ident[0], world, rank)
+    d.comm_init(fresh_id(), world, rank)
     d.preset_poiseuille(rho_in, rho_out)
     d.set_f(f0[x0:x1])
     d.step(37)
@@ -73,7 +76,7 @@ def main():
     st = orc.mrtcg_init(p, "rt")
     x0, x1 = L.decompose_rows(R, world, rank)
     d = cases.mrtcg(R, C, Fg, 1, x0=x0, x1=x1, device=local)
-    d.comm_init(ident[0], world, rank)
+    d.comm_init(fresh_id(), world, rank)
     d.init_two_phase(st["r_rho"][x0:x1], st["b_rho"][x0:x1], st["u"][x0:x1])
     d.step(12)
     fr, fb = gather(d.get_f(0)), gather(d.get_f(1))
@@ -84,6 +87,60 @@ def main():
         print(f"mrtcg ring of {world}: rel err vs oracle after 12 steps = {e:.2e}")
         if not e < 1e-12:
             failures.append("mrtcg")
+    d.close()
+
+    # ---- Rothman-Keller droplet: 1-row moment halo of the 3x3 differences, all-9 wrap rules
+    from oracle_lib import RkParams
+
+    Ln = 24 * world + 6
+    rp = RkParams()
+    rp.L, rp.radius = Ln, Ln / 4.0
+    rp.r_rho0, rp.r_alpha, rp.r_A, rp.r_nu = 1.2, 1.0 / 3.0, 1e-4, 0.16
+    rp.b_rho0, rp.b_alpha, rp.b_A, rp.b_nu = 1.0, 0.2, 1e-4, 0.14
+    rp.delta = 0.98
+    rst = orc.rk_init(rp)
+    x0, x1 = L.decompose_rows(Ln, world, rank)
+    d = cases.rk(Ln, x0=x0, x1=x1, device=local)
+    d.comm_init(fresh_id(), world, rank)
+    d.set_f(rst["r_adv"][x0:x1], 0)
+    d.set_f(rst["b_adv"][x0:x1], 1)
+    d.step(15)
+    fr, fb = gather(d.get_f(0)), gather(d.get_f(1))
+    if rank == 0:
+        for _ in range(15):
+            orc.rk_step(rp, rst)
+        e = max(cases.relerr(fr, rst["r_adv"]), cases.relerr(fb, rst["b_adv"]))
+        print(f"rk ring of {world}: rel err vs oracle after 15 steps = {e:.2e}")
+        if not e < 1e-12:
+            failures.append("rk")
+    d.close()
+
+    # ---- cylinder: IBM body in rank 0's slab, ABB rows at the two global ends, specular columns
+    g = cases.golden("cylinder_99x77")
+    X, Y = int(g["X"]), int(g["Y"])
+    omega, u_lb = float(g["omega"]), float(g["u_lb"])
+    xs = 14.3 + (g["marker_x"] - g["marker_x"].mean()) * 0.3
+    ys = 38.6 + (g["marker_y"] - g["marker_y"].mean()) * 0.3
+    kw = dict(model=L.MODEL_BGK, X=X, Y=Y, omega=omega, equilibrium=L.EQ_COMPRESSIBLE, force=L.FORCE_IBM)
+    x0, x1 = L.decompose_rows(X, world, rank)
+    d = L.Domain(L.default_config(x0=x0, x1=x1, device=local, **kw))
+    d.comm_init(fresh_id(), world, rank)
+    d.preset_free_stream(u_lb, 0.0)
+    if rank == 0:
+        d.ibm_set_markers(xs, ys)
+    d.set_f(g["f0"][x0:x1])
+    d.step(40)
+    got = gather(d.get_f())
+    if rank == 0:
+        mono = L.Domain(L.default_config(device=local, **kw))
+        mono.preset_free_stream(u_lb, 0.0)
+        mono.ibm_set_markers(xs, ys)
+        mono.set_f(g["f0"])
+        mono.step(40)
+        ok = np.array_equal(got, mono.get_f())
+        print(f"cylinder ring of {world}: bit-exact vs monolithic = {ok}")
+        if not ok:
+            failures.append("cylinder")
     d.close()
 
     dist.barrier()

@@ -1,0 +1,27 @@
+"""GPU (>= 2 devices): one process per GPU over NCCL — tests/mp_nccl_check.py under torchrun.  Poiseuille
+(pressure packets across the ring) and cylinder (IBM) must equal the monolithic run bit for bit; MRTCG and
+RK (moment-plane halos) must stay on the oracle to 1e-12."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_devices():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("n_devices() < 2")
+def test_nccl_slab_ring_two_ranks():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join("tests", "mp_nccl_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for case in ("poiseuille", "mrtcg", "rk", "cylinder"):
+        assert f"{case} ring of 2" in r.stdout
