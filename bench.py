@@ -253,16 +253,19 @@ def run_reference_arm(args):
 # clocks sampler
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polled every 20 ms from before the warm-up; the reported clocks are those of the samples whose
+    timestamps fall inside the timed region (mark_begin / mark_end)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -270,24 +273,44 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        import datetime
+
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = time.time()
+            self.rows.append([ts] + c[1:])
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        isnum = lambda v: v.replace(".", "").isdigit()
+        rows = [r for r in self.rows if len(r) > 2 and isnum(r[1])]
+        t0, t1 = self.t0 or 0.0, self.t1 or 1e30
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        if not inside and rows:  # region shorter than the polling period: the sample nearest to it
+            mid = 0.5 * (t0 + t1)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+        sm = [float(r[1]) for r in inside]
+        mx = [float(r[2]) for r in inside if isnum(r[2])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in inside)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_total": len(rows)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -464,21 +487,23 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     case.import_state()
     d.step(args.warmup)
     barrier()
 
     # ---- device-resident timed region: exactly K steps, CUDA events on the domain's stream
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = d.kernel_launches()
     d.profile_enable(True)
     barrier()
+    sampler.mark_begin()
     d.step(args.steps)
     d.synchronize()
     ms = d.last_step_ms()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = d.kernel_launches() - launches0
     prof = {name: d.profile_read(cls) for name, cls in

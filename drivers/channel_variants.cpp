@@ -37,7 +37,7 @@ int main(int argc, char* argv[])
     DRV_CHECK(lbm_step(d, 1));
   }
   const std::string pre = grav ? "gt-" : "sbt-";
-  ux.save(pre + "ux.npy"); uy.save(pre + "uy.npy"); fs.save(pre + "fs.npy"); ps.save(pre + "ps.npy");
+  ux.save(pre + "ux.pt"); uy.save(pre + "uy.pt"); fs.save(pre + "fs.pt"); ps.save(pre + "ps.pt");
   lbm_destroy(d);
   return 0;
 }

@@ -1,8 +1,9 @@
 // common.hpp — shared helpers of the host drivers.  The drivers mirror the reference's test/*.cpp
 // (one main() per case: parse TOML -> allocate -> time loop -> save snapshots) but call the C ABI of
 // include/lbm_b200.h instead of libtorch.  Snapshots are written as NumPy .npy files with the same
-// shapes the reference gives its torch::save'd tensors ({X,Y,T}, {X,Y,9,T}); the .pt writer is a
-// later row of SURVEY §8(f).
+// shapes the reference gives its torch::save'd tensors ({X,Y,T}, {X,Y,9,T}) and in the reference's own
+// on-disk format (lbm_save_pt: the TorchScript archive torch::save writes), under the reference's file
+// names; LBM_SNAPSHOT_FORMAT=npy writes NumPy .npy files instead.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -47,6 +48,19 @@ inline void save_npy(const std::string& path, const std::vector<double>& data, c
   out.write(reinterpret_cast<const char*>(data.data()), data.size() * sizeof(double));
 }
 
+// torch::save(tensor, path) of the reference drivers; path ends in ".pt"
+inline void save_array(const std::string& path, const std::vector<double>& data, const std::vector<long>& shape)
+{
+  const char* fmt = std::getenv("LBM_SNAPSHOT_FORMAT");
+  if (fmt && std::string(fmt) == "npy")
+  {
+    save_npy(path.substr(0, path.size() - 3) + ".npy", data, shape);
+    return;
+  }
+  std::vector<long long> sh(shape.begin(), shape.end());
+  check(lbm_save_pt(path.c_str(), data.data(), sh.data(), (int)sh.size()), "lbm_save_pt");
+}
+
 // {X,Y,T} stack the reference fills with `ux.index({Ellipsis,i}) = ...`
 struct Series
 {
@@ -62,8 +76,8 @@ struct Series
   }
   void save(const std::string& path) const
   {
-    if (C > 1) save_npy(path, a, {X, Y, C, T});
-    else save_npy(path, a, {X, Y, T});
+    if (C > 1) save_array(path, a, {X, Y, C, T});
+    else save_array(path, a, {X, Y, T});
   }
 };
 

@@ -83,11 +83,11 @@ int main(int argc, char* argv[])
   DRV_CHECK(lbm_synchronize(d));
   std::cout << "\nSaving results" << std::endl;
   const std::string pre = std::string(p.file_prefix) + (free_stream ? "fst-" : "ct-");
-  ux.save(pre + "ux.npy"); uy.save(pre + "uy.npy"); ps.save(pre + "ps.npy");
+  ux.save(pre + "ux.pt"); uy.save(pre + "uy.pt"); ps.save(pre + "ps.pt");
   if (!free_stream)
   {
-    drv::save_npy(pre + "Fs.npy", Fs_series, {2, (long)p.total_snapshots});
-    forces.save(pre + "F.npy");
+    drv::save_array(pre + "Fs.pt", Fs_series, {2, (long)p.total_snapshots});
+    forces.save(pre + "F.pt");
   }
   lbm_destroy(d);
   return 0;

@@ -32,7 +32,7 @@ int main()
     DRV_CHECK(lbm_get_f(dom[1], 0, f.data())); fsB.put(t, f, 9, 0);
     DRV_CHECK(lbm_step_group(dom, 2, 1));
   }
-  fsA.save("A-domain-decomp-hpt-fs.npy"); fsB.save("B-domain-decomp-hpt-fs.npy");
+  fsA.save("A-domain-decomp-hpt-fs.pt"); fsB.save("B-domain-decomp-hpt-fs.pt");
   lbm_destroy(dom[0]); lbm_destroy(dom[1]);
   return 0;
 }

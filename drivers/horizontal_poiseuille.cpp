@@ -59,7 +59,7 @@ int main()
   }
   DRV_CHECK(lbm_synchronize(d));
   std::cout << "saving results into files" << std::endl;
-  ux.save("hpt-ux.npy"); uy.save("hpt-uy.npy"); fs.save("hpt-fs.npy"); ps.save("hpt-ps.npy");
+  ux.save("hpt-ux.pt"); uy.save("hpt-uy.pt"); fs.save("hpt-fs.pt"); ps.save("hpt-ps.pt");
 
   // :163-175
   double den = 0.0;

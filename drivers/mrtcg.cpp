@@ -77,7 +77,7 @@ int main(int argc, char* argv[])
   DRV_CHECK(lbm_synchronize(d));
   std::cout << "save snapshots" << std::endl;
   const std::string pre = rt ? std::string(tp.name) + "-mrtcg-rayleigh-taylor-" : std::string("mrtcg-static-droplet-");
-  rhos.save(pre + "rhos.npy"); uxs.save(pre + "uxs.npy"); uys.save(pre + "uys.npy"); phases.save(pre + "phases.npy");
+  rhos.save(pre + "rhos.pt"); uxs.save(pre + "uxs.pt"); uys.save(pre + "uys.pt"); phases.save(pre + "phases.pt");
   lbm_destroy(d);
   return 0;
 }

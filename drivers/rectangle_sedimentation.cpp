@@ -55,7 +55,7 @@ int main(int argc, char* argv[])
   DRV_CHECK(lbm_synchronize(d));
   std::cout << "\nSaving results" << std::endl;
   const std::string pre = p.file_prefix;
-  ux.save(pre + "-ux.npy"); uy.save(pre + "-uy.npy"); ps.save(pre + "-ps.npy"); cs.save(pre + "-cs.npy");
+  ux.save(pre + "-ux.pt"); uy.save(pre + "-uy.pt"); ps.save(pre + "-ps.pt"); cs.save(pre + "-cs.pt");
   lbm_destroy(d);
   return 0;
 }

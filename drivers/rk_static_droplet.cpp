@@ -44,8 +44,8 @@ int main(int argc, char* argv[])
     uxs.put(t, u, 2, 0); uys.put(t, u, 2, 1); rhos.put(t, rho, 1, 0);
   }
   std::cout << "saving results" << std::endl;
-  uxs.save("rk-static-droplet-ux.npy"); uys.save("rk-static-droplet-uy.npy");
-  rhos.save("rk-static-droplet-rho.npy"); rhons.save("rk-static-droplet-rhon.npy");
+  uxs.save("rk-static-droplet-ux.pt"); uys.save("rk-static-droplet-uy.pt");
+  rhos.save("rk-static-droplet-rho.pt"); rhons.save("rk-static-droplet-rhon.pt");
   // Laplace law
   DRV_CHECK(lbm_get_phase(d, ph.data(), rr.data(), rb.data()));
   auto pressure = [&](int r, int c) {

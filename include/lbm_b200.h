@@ -197,6 +197,14 @@ int lbm_get_f(lbm_domain* d, int lattice, double* f_aos);
  * compute them: rho {X,Y,1} (solver::calc_rho), u {X,Y,2} (calc_u / calc_incomp_u, plus the
  * model's force shift).  Either pointer may be NULL.  BGK_ADE: lattice 1 gives C in rho.          */
 int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u);
+/* Snapshot without stalling the time loop (the reference copies CUDA->CPU tensors
+ * synchronously, e.g. test/cylinder_test.cpp:94-98): the fields of the CURRENT state are staged on the
+ * domain's stream and copied to the caller's buffers on a separate copy stream while later lbm_step calls
+ * run.  rho {X,Y,1}, u {X,Y,2}, phase {X,Y} (two-phase models only); any may be NULL.  Pinned host memory
+ * gives a true overlap.  The buffers are valid after lbm_snapshot_wait; a second snapshot (or lbm_get_*)
+ * issued earlier waits for the first copy on the device, not on the host.                          */
+int lbm_snapshot_async(lbm_domain* d, int lattice, double* rho, double* u, double* phase);
+int lbm_snapshot_wait(lbm_domain* d);
 /* two-phase fields of the current state: phase {X,Y} (eval_phase_field), rho_r, rho_b {X,Y}     */
 int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b);
 /* two-phase models carry u between steps (mrtcg_rayleigh_taylor.cpp:476-477); initial value.      */
@@ -320,6 +328,15 @@ int lbm_two_phase_from_toml(const char* path, int require_general, lbm_two_phase
 
 /* boundary file `[name] x=[..] y=[..]` (src/ibm.cpp:78-102).  Call with xs=ys=NULL to get the count. */
 int lbm_markers_from_toml(const char* path, const char* name, double* xs, double* ys, int* n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Snapshot output in the reference's on-disk format
+ * ---------------------------------------------------------------------------------------------- */
+/* replaces `torch::save(tensor, path)` of a contiguous CPU fp64 tensor (test/horizontal_poiseuille_test.cpp:157-160,
+ * test/cylinder_test.cpp:168-172, test/mrtcg_rayleigh_taylor.cpp:481-485): writes the same TorchScript archive
+ * (ZIP of stored entries, one parameter "0"), readable by torch.jit.load / torch.load / torch::load.
+ * shape[ndim] row-major; ZIP64 when the storage exceeds 4 GiB.  Host-only, needs no CUDA device.           */
+int lbm_save_pt(const char* path, const double* data, const long long* shape, int ndim);
 
 #ifdef __cplusplus
 }

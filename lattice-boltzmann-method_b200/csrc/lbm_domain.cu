@@ -726,6 +726,34 @@ int commit_boundary_tables(lbm_domain* d)
   return LBM_OK;
 }
 
+// rho, u (and for two-phase models phase, rho_r, rho_b) of the current state into the staging buffer,
+// on the domain's stream.  A copy still draining the buffer (lbm_snapshot_async) is waited for first.
+int stage_fields(lbm_domain* d, int lattice)
+{
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (!d->d_mom_out) LBM_CUDA(cudaMalloc(&d->d_mom_out, 6 * N * sizeof(double)));
+  if (!d->copy)
+  {
+    LBM_CUDA(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
+    LBM_CUDA(cudaEventCreateWithFlags(&d->ev_staged, cudaEventDisableTiming));
+    LBM_CUDA(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
+  }
+  if (d->copy_pending) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copied, 0));
+  if (d->tp) return tp_stage_moments(d, d->d_mom_out);
+  LBM_TRY(export_post_stream(d));
+  int incompressible = 0;
+  double sx = 0.0, sy = 0.0;
+  if (d->cfg.model == LBM_MODEL_BGK)
+  {
+    incompressible = d->cfg.equilibrium == LBM_EQ_INCOMPRESSIBLE;
+    if (d->cfg.force == LBM_FORCE_UNIFORM) { sx = d->cfg.Fg[0]; sy = d->cfg.Fg[1]; }
+  }
+  k_moments_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->d_aos[lattice], N, incompressible, sx, sy, d->d_mom_out, d->d_mom_out + N);
+  d->launches++;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
 }  // namespace lbm
 
 using namespace lbm;
@@ -848,6 +876,13 @@ int lbm_destroy(lbm_domain* d)
     cudaFree(d->d_aos[l]);
   }
   cudaFree(d->d_mom_out);
+  if (d->copy)
+  {
+    cudaStreamSynchronize(d->copy);
+    cudaEventDestroy(d->ev_staged);
+    cudaEventDestroy(d->ev_copied);
+    cudaStreamDestroy(d->copy);
+  }
   for (int k = 0; k < 2; k++)
     if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
   for (auto& r : d->prof)
@@ -973,23 +1008,40 @@ int lbm_get_moments(lbm_domain* d, int lattice, double* rho, double* u)
   if (!d || lattice < 0 || lattice >= d->nlat) { set_error("lbm_get_moments: bad argument"); return LBM_ERR_INVALID; }
   if (!d->have_state || !d->committed) { set_error("lbm_get_moments: no state or boundary rules not committed"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
-  if (d->tp) return tp_read_moments(d, rho, u, nullptr, nullptr, nullptr);
-  LBM_TRY(export_post_stream(d));
+  LBM_TRY(stage_fields(d, lattice));
   const long long N = (long long)d->g.Xl * d->g.Y;
-  if (!d->d_mom_out) LBM_CUDA(cudaMalloc(&d->d_mom_out, 3 * N * sizeof(double)));  // kept: snapshots recur
-  double *d_rho = d->d_mom_out, *d_u = d->d_mom_out + N;
-  int incompressible = 0;
-  double sx = 0.0, sy = 0.0;
-  if (d->cfg.model == LBM_MODEL_BGK)
-  {
-    incompressible = d->cfg.equilibrium == LBM_EQ_INCOMPRESSIBLE;
-    if (d->cfg.force == LBM_FORCE_UNIFORM) { sx = d->cfg.Fg[0]; sy = d->cfg.Fg[1]; }
-  }
-  k_moments_aos<<<cdiv(N, 256), 256, 0, d->stream>>>(d->d_aos[lattice], N, incompressible, sx, sy, d_rho, d_u);
-  d->launches++;
-  if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d_rho, N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
-  if (u) LBM_CUDA(cudaMemcpyAsync(u, d_u, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d->d_mom_out, N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  if (u) LBM_CUDA(cudaMemcpyAsync(u, d->d_mom_out + N, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
+  return LBM_OK;
+}
+
+// Snapshot without stalling the time loop: the fields are staged on the domain's stream, the
+// device->host copies run on a separate copy stream under the following steps.
+int lbm_snapshot_async(lbm_domain* d, int lattice, double* rho, double* u, double* phase)
+{
+  if (!d || lattice < 0 || lattice >= d->nlat) { set_error("lbm_snapshot_async: bad argument"); return LBM_ERR_INVALID; }
+  if (!d->have_state || !d->committed) { set_error("lbm_snapshot_async: no state or boundary rules not committed"); return LBM_ERR_INVALID; }
+  if (phase && !d->tp) { set_error("lbm_snapshot_async: phase is a two-phase field"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_TRY(stage_fields(d, lattice));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  LBM_CUDA(cudaEventRecord(d->ev_staged, d->stream));
+  LBM_CUDA(cudaStreamWaitEvent(d->copy, d->ev_staged, 0));
+  if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d->d_mom_out, N * sizeof(double), cudaMemcpyDeviceToHost, d->copy));
+  if (u) LBM_CUDA(cudaMemcpyAsync(u, d->d_mom_out + N, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, d->copy));
+  if (phase) LBM_CUDA(cudaMemcpyAsync(phase, d->d_mom_out + 3 * N, N * sizeof(double), cudaMemcpyDeviceToHost, d->copy));
+  LBM_CUDA(cudaEventRecord(d->ev_copied, d->copy));
+  d->copy_pending = true;
+  return LBM_OK;
+}
+
+int lbm_snapshot_wait(lbm_domain* d)
+{
+  if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  if (d->copy_pending) LBM_CUDA(cudaEventSynchronize(d->ev_copied));
+  d->copy_pending = false;
   return LBM_OK;
 }
 

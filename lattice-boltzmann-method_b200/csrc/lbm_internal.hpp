@@ -134,7 +134,12 @@ struct lbm_domain
 
   // scratch for export
   double* d_aos[2] = {nullptr, nullptr};
-  double* d_mom_out = nullptr;  // [3][Xl*Y] rho, u for lbm_get_moments
+  // snapshot staging: [6][Xl*Y] rho, u (2), phase, rho_r, rho_b — filled on `stream`, drained either on `stream`
+  // (lbm_get_moments / lbm_get_phase) or on `copy` while later steps run (lbm_snapshot_async)
+  double* d_mom_out = nullptr;
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
+  bool copy_pending = false;
 
   lbm::IbmState ibm;
   lbm::TwoPhaseState* tp = nullptr;
@@ -187,7 +192,8 @@ int tp_destroy(lbm_domain* d);
 int tp_step(lbm_domain* d);
 int tp_commit(lbm_domain* d);
 int tp_export(lbm_domain* d);
-int tp_read_moments(lbm_domain* d, double* rho, double* u, double* ph, double* rr, double* rb);
+int tp_stage_moments(lbm_domain* d, double* stage);  // planes -> [6][N] staging (rho, u, phase, rho_r, rho_b)
+int stage_fields(lbm_domain* d, int lattice);        // lbm_domain.cu: fills d->d_mom_out on d->stream
 int tp_refresh_moments(lbm_domain* d);
 // lbm_comm.cu
 int comm_release(lbm_domain* d);

@@ -1028,22 +1028,14 @@ int tp_export(lbm_domain* d)
   return tp_launch_moments<TP_RK>(d, d->cur, d->d_aos[0], d->d_aos[1]);
 }
 
-int tp_read_moments(lbm_domain* d, double* rho, double* u, double* ph, double* rr, double* rb)
+int tp_stage_moments(lbm_domain* d, double* stage)
 {
   const long long N = (long long)d->g.Xl * d->g.Y;
   LBM_TRY(tp_fill_planes(d));
-  double* tmp = nullptr;
-  LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 6 * N));
-  double *d_rho = tmp, *d_u = tmp + N, *d_ph = tmp + 3 * N, *d_rr = tmp + 4 * N, *d_rb = tmp + 5 * N;
-  k_tp_read_moments<<<cdiv(N, 256), 256, 0, d->stream>>>(d->tp->mom, d->g, d->tp->mg, d_rho, d_u, d_ph, d_rr, d_rb);
+  k_tp_read_moments<<<cdiv(N, 256), 256, 0, d->stream>>>(d->tp->mom, d->g, d->tp->mg, stage, stage + N, stage + 3 * N, stage + 4 * N,
+                                                         stage + 5 * N);
   d->launches++;
-  if (rho) LBM_CUDA(cudaMemcpyAsync(rho, d_rho, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
-  if (u) LBM_CUDA(cudaMemcpyAsync(u, d_u, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, d->stream));
-  if (ph) LBM_CUDA(cudaMemcpyAsync(ph, d_ph, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
-  if (rr) LBM_CUDA(cudaMemcpyAsync(rr, d_rr, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
-  if (rb) LBM_CUDA(cudaMemcpyAsync(rb, d_rb, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
-  LBM_CUDA(cudaStreamSynchronize(d->stream));
-  cudaFree(tmp);
+  LBM_CUDA(cudaGetLastError());
   return LBM_OK;
 }
 
@@ -1073,7 +1065,14 @@ int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b)
   if (!d || !d->tp) { set_error("lbm_get_phase: not a two-phase domain"); return LBM_ERR_INVALID; }
   if (!d->have_state) { set_error("lbm_get_phase: no state"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
-  return tp_read_moments(d, nullptr, nullptr, phase, rho_r, rho_b);
+  LBM_TRY(stage_fields(d, 0));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  const double* st = d->d_mom_out;
+  if (phase) LBM_CUDA(cudaMemcpyAsync(phase, st + 3 * N, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  if (rho_r) LBM_CUDA(cudaMemcpyAsync(rho_r, st + 4 * N, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  if (rho_b) LBM_CUDA(cudaMemcpyAsync(rho_b, st + 5 * N, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  return LBM_OK;
 }
 
 int lbm_set_u(lbm_domain* d, const double* u_aos)

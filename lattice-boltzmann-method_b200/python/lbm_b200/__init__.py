@@ -97,7 +97,7 @@ EXPORTS = [
     "lbm_differential3", "lbm_params_from_toml", "lbm_colour_from_toml", "lbm_two_phase_from_toml",
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
-    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group",
+    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -125,6 +125,9 @@ def load():
         _lib.lbm_get_f.argtypes = [C.c_void_p, C.c_int, dp]
         _lib.lbm_get_moments.argtypes = [C.c_void_p, C.c_int, dp, dp]
         _lib.lbm_get_phase.argtypes = [C.c_void_p, dp, dp, dp]
+        _lib.lbm_snapshot_async.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+        _lib.lbm_snapshot_wait.argtypes = [C.c_void_p]
+        _lib.lbm_save_pt.argtypes = [C.c_char_p, dp, C.POINTER(C.c_longlong), C.c_int]
         _lib.lbm_set_u.argtypes = [C.c_void_p, dp]
         _lib.lbm_init_equilibrium.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
         _lib.lbm_init_two_phase.argtypes = [C.c_void_p, dp, dp, dp]
@@ -290,6 +293,16 @@ class Domain:
         _chk(self.lib.lbm_get_moments(self.h, lattice, rho.ctypes.data_as(dp), u.ctypes.data_as(dp)))
         return rho, u
 
+    def snapshot_async(self, rho=None, u=None, phase=None, lattice=0):
+        """rho/u/phase: preallocated (ideally pinned) float64 arrays the copy stream fills; valid after snapshot_wait()"""
+        ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
+        for a in (rho, u, phase):
+            assert a is None or (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"])
+        _chk(self.lib.lbm_snapshot_async(self.h, lattice, ptr(rho), ptr(u), ptr(phase)))
+
+    def snapshot_wait(self):
+        _chk(self.lib.lbm_snapshot_wait(self.h))
+
     def get_phase(self):
         ph = np.empty((self.Xl, self.Y)); rr = np.empty((self.Xl, self.Y)); rb = np.empty((self.Xl, self.Y))
         _chk(self.lib.lbm_get_phase(self.h, ph.ctypes.data_as(dp), rr.ctypes.data_as(dp), rb.ctypes.data_as(dp)))
@@ -443,6 +456,13 @@ def differential3(psi):
 
 
 # ---- parameters.toml surface
+def save_pt(path, array):
+    """torch::save(tensor, path) of the reference drivers: a TorchScript archive holding one fp64 tensor"""
+    a = np.ascontiguousarray(array, dtype=np.float64)
+    shape = (C.c_longlong * max(a.ndim, 1))(*a.shape)
+    _chk(load().lbm_save_pt(os.fsencode(path), a.ctypes.data_as(dp), shape, a.ndim))
+
+
 def params_from_toml(path, require_simulation=True):
     p = Params()
     _chk(load().lbm_params_from_toml(path.encode(), 1 if require_simulation else 0, C.byref(p)))
