@@ -367,13 +367,14 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
   const long long back = (long long)LAG * g.pitch;
 
   auto collide_row = [&](int sc) {
+    // the second pull of this row (an L2 hit) first, so that its latency hides under the stencil arithmetic
+    double fr[9], fb[9];
+    tp_pull_at<true>(pr - back, g, fr);
+    tp_pull_at<true>(pb - back, g, fb);
     TpStencil st;
     tp_ring_stencil<MODEL>(sm, sc, t, st);
     const double rr = S(C::F_RR, sc, t), rb = S(C::F_RB, sc, t);
     const double ux = S(C::F_UX, sc, t), uy = S(C::F_UY, sc, t), ph = S(0, sc, t);
-    double fr[9], fb[9];
-    tp_pull_at<true>(pr - back, g, fr);
-    tp_pull_at<true>(pb - back, g, fb);
     tp_collide<MODEL>(p, fr, fb, rr, rb, ux, uy, ph, st);
     double* wr = rdst + ((pr - back) - rsrc);
     double* wb = bdst + ((pr - back) - rsrc);

@@ -178,78 +178,102 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
   }
   else
   {
-    // mrtcg_rayleigh_taylor.cpp:431-464.  Only the SUM of the two colours' MRT operators enters the
-    // update (total = sum_k (f_k + omega1_k + omega2_k), :455, then recoloured, :456-457), and
-    // M^-1 S M is linear, so the transform runs once on d = (feq_r + feq_b) - (f_r + f_b) with
-    // C = C_r + C_b instead of once per colour.
+    // mrtcg_rayleigh_taylor.cpp:431-464.  Two restructurings, both exact up to rounding:
+    //  (1) only the SUM of the two colours' MRT operators enters the update (total = sum_k (f_k + omega1_k
+    //      + omega2_k), :455, then recoloured, :456-457) and M^-1 S M is linear, so the transform runs once on
+    //      d = (feq_r + feq_b) - (f_r + f_b) with C = C_r + C_b instead of once per colour;
+    //  (2) D2Q9 directions come in opposite pairs (1,3) (2,4) (5,7) (6,8): every per-direction term is
+    //      even (u.c)^2-like or odd (u.c)-like in c, so each pair shares one even and one odd part, and the
+    //      M / M^-1 rows act on pair sums and differences.
     const double rho = rr + rb;
     const double s_nu = relax_eval(p, ph);
     const double mix[3] = {rr * p.r_phi[0] + rb * p.b_phi[0], rr * p.r_phi[1] + rb * p.b_phi[1], rr * p.r_phi[2] + rb * p.b_phi[2]};
-    const double emix[3] = {rr * p.r_eta[0] + rb * p.b_eta[0], rr * p.r_eta[1] + rb * p.b_eta[1], rr * p.r_eta[2] + rb * p.b_eta[2]};
-    double fs[9], d[9], m[9], o1[9];
-#pragma unroll
-    for (int q = 0; q < 9; q++)
-    {
-      // eval_equilibrium summed over the colours: rho_k (phi_k + w (3 ue eta_k + 9 ue^2 - 3 uu)), note 9 and 3 (:244)
-      const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
-      fs[q] = fr[q] + fb[q];
-      d[q] = (mix[QCLASS(q)] + W(q) * ((3.0 * ue) * emix[QCLASS(q)] + rho * (9.0 * (ue * ue) - 3.0 * uu))) - fs[q];
-    }
-    // S = diag(0, 1.25, 1.14, 0, 1.6, 0, 1.6, s_nu, s_nu) (:384-387, update_S); conserved moments: S = 0 and C = 0
-    const double S[9] = {0.0, 1.25, 1.14, 0.0, 1.6, 0.0, 1.6, s_nu, s_nu};
-    const double DQ1 = (st.rDxQx + st.rDyQy) + (st.bDxQx + st.bDyQy);  // update_C (:320-336), both colours
-    const double DQ7 = (st.rDxQx - st.rDyQy) + (st.bDxQx - st.bDyQy);
-#pragma unroll
-    for (int a = 1; a < 9; a++)
-    {
-      if (a == 3 || a == 5) continue;
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < 9; q++)
-        if (MM(a, q) != 0.0) s += MM(a, q) * d[q];
-      double c = 0.0;
-      if (a == 1) c = (3.0 * (1.0 - 0.5 * 1.25)) * DQ1;
-      if (a == 7) c = (1.0 - 0.5 * s_nu) * DQ7;
-      m[a] = S[a] * s + c;
-    }
-#pragma unroll
-    for (int q = 0; q < 9; q++)
-    {
-      double s = 0.0;
-#pragma unroll
-      for (int a = 1; a < 9; a++)
-        if (a != 3 && a != 5 && MI36(q, a) != 0.0) s += ((1.0 / 36.0) * MI36(q, a)) * m[a];
-      o1[q] = s;
-    }
+    const double emix1 = rr * p.r_eta[1] + rb * p.b_eta[1], emix2 = rr * p.r_eta[2] + rb * p.b_eta[2];
     const double rinv = 1.0 / (1e-20 + gn);
     const double inv_rho = 1.0 / rho;
-    const double wr = rr * inv_rho, wb = rb * inv_rho;  // rho_k / rho
-    const double k0 = (wr * wb) * rinv;                 // rho_r rho_b / (rho^2 (1e-20 + |grad|))
-    const double A2 = (4.5 * p.sigma * s_nu) * (0.5 * gn) * 2.0;  // both colours' perturbation: A = 4.5 sigma s_nu, xi = 0.5 |grad| (..)
+    const double wr = rr * inv_rho, wb = rb * inv_rho;            // rho_k / rho
+    const double k0 = (wr * wb) * rinv;                           // rho_r rho_b / (rho^2 (1e-20 + |grad|))
+    const double A2 = (4.5 * p.sigma * s_nu) * (0.5 * gn) * 2.0;  // both colours: A = 4.5 sigma s_nu, xi = 0.5 |grad| (..)
     const double uF = ux * p.Fg0 + uy * p.Fg1;
     const double pref = 1.0 - 0.5 * s_nu;
     constexpr double ISQ2 = 0.7071067811865476;
+    constexpr double W1 = 1.0 / 9.0, W2 = 1.0 / 36.0;
+    // c_q . v for the pair representatives q = 1, 2, 5, 6 (the opposite direction has the opposite sign)
+    const double ue[4] = {ux, uy, ux + uy, uy - ux};
+    const double ge[4] = {st.gx, st.gy, st.gx + st.gy, st.gy - st.gx};
+    const double Fe[4] = {p.Fg0, p.Fg1, p.Fg0 + p.Fg1, p.Fg1 - p.Fg0};
+    constexpr int QA[4] = {1, 2, 5, 6}, QB[4] = {3, 4, 7, 8};
+
+    // ---- d = feq_sum - f_sum, as pair sums s and differences a  (eval_equilibrium :233-247, note 9 and 3)
+    const double fs0 = fr[0] + fb[0];
+    const double d0 = (mix[0] + (4.0 / 9.0) * (rho * (-3.0 * uu))) - fs0;
+    double fsA[4], fsB[4], s[4], a[4];
 #pragma unroll
-    for (int q = 0; q < 9; q++)
+    for (int k = 0; k < 4; k++)
     {
-      const double ge = st.gx * (double)CX(q) + st.gy * (double)CY(q);
-      const double t = ge * rinv;
-      const double o2x2 = A2 * (W(q) * (t * t) - BQ(q));  // eval_xi, eval_per_operator (omega2_r + omega2_b)
-      const double gue = q < 5 ? ge : ge * ISQ2;          // grad . c / |c|
-      const double kap = (k0 * gue) * mix[QCLASS(q)];      // eval_kappa
-      const double total = (fs[q] + o1[q]) + o2x2;         // :455
-      double nr = wr * total + p.r_beta * kap;             // eval_rec_operator
-      double nb = wb * total + p.b_beta * kap;
-      if (p.add_force)  // :460-464 (ics2 = 3, ics4 = 9)
+      const double Wc = k < 2 ? W1 : W2, mx = k < 2 ? mix[1] : mix[2], em = k < 2 ? emix1 : emix2;
+      const double even = mx + Wc * (rho * (9.0 * (ue[k] * ue[k]) - 3.0 * uu));
+      const double odd = Wc * ((3.0 * ue[k]) * em);
+      fsA[k] = fr[QA[k]] + fb[QA[k]];
+      fsB[k] = fr[QB[k]] + fb[QB[k]];
+      const double dA = (even + odd) - fsA[k], dB = (even - odd) - fsB[k];
+      s[k] = dA + dB;
+      a[k] = dA - dB;
+    }
+    // ---- m = S M d + C on the six non-conserved moments (M :130-142; S = diag(0,1.25,1.14,0,1.6,0,1.6,s_nu,s_nu)
+    //      :384-387 + update_S; C: update_C :320-336, both colours)
+    const double SA = s[0] + s[1], SD = s[2] + s[3];
+    const double DQ1 = (st.rDxQx + st.rDyQy) + (st.bDxQx + st.bDyQy);
+    const double DQ7 = (st.rDxQx - st.rDyQy) + (st.bDxQx - st.bDyQy);
+    const double m_e = 1.25 * ((2.0 * SD - SA) - 4.0 * d0) + (3.0 * (1.0 - 0.5 * 1.25)) * DQ1;
+    const double m_eps = 1.14 * ((SD - 2.0 * SA) + 4.0 * d0);
+    const double m_qx = 1.6 * ((a[2] - a[3]) - 2.0 * a[0]);
+    const double m_qy = 1.6 * ((a[2] + a[3]) - 2.0 * a[1]);
+    const double m_pxx = s_nu * (s[0] - s[1]) + pref * DQ7;
+    const double m_pxy = s_nu * (s[2] - s[3]);
+    // ---- omega1 = M^-1 m (36 M^-1 :144-156): even and odd part per pair
+    const double o1_0 = (1.0 / 9.0) * (m_eps - m_e);
+    const double E_ax = (-1.0 / 36.0) * (m_e + 2.0 * m_eps), E_dg = (1.0 / 36.0) * (2.0 * m_e + m_eps);
+    const double o1E[4] = {E_ax + 0.25 * m_pxx, E_ax - 0.25 * m_pxx, E_dg + 0.25 * m_pxy, E_dg - 0.25 * m_pxy};
+    const double o1O[4] = {(-1.0 / 6.0) * m_qx, (-1.0 / 6.0) * m_qy, (1.0 / 12.0) * (m_qx + m_qy), (1.0 / 12.0) * (m_qy - m_qx)};
+
+    // ---- perturbation, recolouring, force (eval_xi / eval_per_operator / eval_kappa / eval_rec_operator, :455-464)
+    {
+      const double total = (fs0 + o1_0) + A2 * (4.0 / 27.0);  // q = 0: grad . c = 0, B_0 = -4/27
+      double nr = wr * total, nb = wb * total;
+      if (p.add_force)
       {
-        const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
-        const double Fe = (double)CX(q) * p.Fg0 + (double)CY(q) * p.Fg1;
-        const double src = (pref * ((3.0 + 9.0 * ue) * Fe - 3.0 * uF)) * W(q);
+        const double src = (pref * (-3.0 * uF)) * (4.0 / 9.0);
         nr += src;
         nb += src;
       }
-      fr[q] = nr;
-      fb[q] = nb;
+      fr[0] = nr;
+      fb[0] = nb;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+      const double Wc = k < 2 ? W1 : W2, Bc = k < 2 ? 2.0 / 27.0 : 5.0 / 108.0, mx = k < 2 ? mix[1] : mix[2];
+      const double t = ge[k] * rinv;
+      const double o2x2 = A2 * (Wc * (t * t) - Bc);                   // even in c
+      const double kap = (k0 * (k < 2 ? ge[k] : ge[k] * ISQ2)) * mx;  // odd in c
+      const double totA = (fsA[k] + (o1E[k] + o1O[k])) + o2x2;
+      const double totB = (fsB[k] + (o1E[k] - o1O[k])) + o2x2;
+      const double kr = p.r_beta * kap, kb = p.b_beta * kap;
+      double nrA = wr * totA + kr, nbA = wb * totA + kb;
+      double nrB = wr * totB - kr, nbB = wb * totB - kb;
+      if (p.add_force)  // (1 - s_nu/2) ((3 + 9 u.c) F.c - 3 u.F) w   (ics2 = 3, ics4 = 9)
+      {
+        const double ev = (pref * Wc) * (9.0 * (ue[k] * Fe[k]) - 3.0 * uF), od = (pref * Wc) * (3.0 * Fe[k]);
+        nrA += ev + od;
+        nbA += ev + od;
+        nrB += ev - od;
+        nbB += ev - od;
+      }
+      fr[QA[k]] = nrA;
+      fb[QA[k]] = nbA;
+      fr[QB[k]] = nrB;
+      fb[QB[k]] = nbB;
     }
   }
 }
