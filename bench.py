@@ -58,6 +58,10 @@ WORKLOADS = {
                           driver="test/rectangle_sedimentation_test.cpp",
                           what="rectangle sedimentation: fluid + advection-diffusion lattice, bounce-back rectangle walls",
                           cpu_sample=1024),
+    # not a BASELINE.json config: the SURVEY §8(f) rank-3 collision (ulbm::d2q9::kbc), fully periodic double shear layer
+    "kbc_shear": dict(X=8192, Y=8192, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,KBC>",
+                      driver="test/ulbm_double_shear_flow.cpp",
+                      what="double shear layer, D2Q9 entropic central-moment (KBC) collision, fully periodic", cpu_sample=512),
 }
 
 RED = dict(rho_0=3.0, alpha=0.7, A=0.5, nu=0.04, beta=0.7)      # configs/mrtcg-rayleigh-taylor-gamma3.toml
@@ -220,6 +224,16 @@ def cpu_reference_mlups(workload, edge, warmup, steps):
         p.add_force = 1
         st = orc.mrtcg_init(p, "rt")
         sec = timed(lambda: orc.mrtcg_step(p, st))
+    elif workload == "kbc_shear":
+        r = np.arange(edge)[:, None] + 0.0 * np.arange(edge)[None, :]
+        c = np.arange(edge)[None, :] + 0.0 * np.arange(edge)[:, None]
+        u = np.zeros((edge, edge, 2))
+        u[..., 0] = 0.02 * np.tanh(80.0 * (0.25 * edge - np.abs(c - 0.5 * edge)))
+        u[..., 1] = 0.02 * 0.05 * np.sin(6.2832 * (r + 0.25 * edge) / edge)
+        m0 = np.ones((edge, edge))
+        f = orc.kbc_equilibrium(m0, u)
+        s2 = 1.0 / (0.5 + 3.0 * 1.70766666e-4)
+        sec = timed(lambda: orc.kbc_step(f, m0, u, s2))
     else:  # rk_droplet
         p = oracle_lib.RkParams()
         p.L, p.radius = edge, edge / 4.0
@@ -353,6 +367,8 @@ class Case:
         elif self.name == "poiseuille":
             om, self.rho_in, self.rho_out = channel_constants(self.Xg, self.Y)
             cfg = L.default_config(model=L.MODEL_BGK, omega=om, equilibrium=L.EQ_INCOMPRESSIBLE, **slab)
+        elif self.name == "kbc_shear":
+            cfg = L.default_config(model=L.MODEL_KBC, omega=1.0 / (0.5 + 3.0 * 1.70766666e-4), **slab)
         elif self.name == "sedimentation":
             cfg = L.default_config(model=L.MODEL_BGK_ADE, omega=self.omega, omega_g=self.omega, equilibrium=L.EQ_COMPRESSIBLE,
                                    w_s=3e-3, **slab)
@@ -389,6 +405,14 @@ class Case:
             self.ui_t, self.ui = self.pinned((X, Y, 2))
             self.ri[...] = 1.0
             self.ui[...] = 0.0
+        elif self.name == "kbc_shear":
+            d.preset_periodic()
+            self.ri_t, self.ri = self.pinned((X, Y, 1))
+            self.ui_t, self.ui = self.pinned((X, Y, 2))
+            self.ri[...] = 1.0   # set_initial_conditions (ulbm_double_shear_flow.cpp:44-67) on global rows [x0, x1)
+            r = np.arange(self.x0, self.x1)[:, None]; c = np.arange(Y)[None, :]
+            self.ui[..., 0] = 0.02 * np.tanh(80.0 * (0.25 * self.Xg - np.abs(c - 0.5 * self.Xg))) + 0.0 * r
+            self.ui[..., 1] = 0.02 * 0.05 * np.sin(6.2832 * (r + 0.25 * self.Xg) / self.Xg) + 0.0 * c
         elif self.name == "sedimentation":
             R23, C28, C38, C_w = sedimentation_geometry(self.Xg, Y)
             d.preset_sedimentation(self.u_lb, C_w, R23, C28, C38)
@@ -419,6 +443,10 @@ class Case:
         if self.name in ("cylinder", "poiseuille"):
             d.init_equilibrium(self.ri, self.ui, self.L.EQ_INCOMPRESSIBLE)
             return self.ri.nbytes + self.ui.nbytes
+        if self.name == "kbc_shear":
+            d.init_equilibrium(self.ri, self.ui, self.L.EQ_KBC_FRESH)
+            d.set_moments(self.ri, self.ui)
+            return 2 * (self.ri.nbytes + self.ui.nbytes)
         if self.name == "sedimentation":
             d.set_f(self.f, 0)
             d.set_f(self.g, 1)

@@ -55,13 +55,19 @@ typedef enum
                             free_stream_test.cpp, specular_boundary_test.cpp, gravity_test.cpp) */
   LBM_MODEL_BGK_ADE = 1, /* fluid + advection-diffusion lattice: test/rectangle_sedimentation_test.cpp */
   LBM_MODEL_MRTCG = 2,   /* MRT colour gradient: test/mrtcg_rayleigh_taylor.cpp, test/mrtcg_static_droplet.cpp */
-  LBM_MODEL_RK = 3       /* Rothman-Keller droplet: test/rk_static_droplet_test.cpp */
+  LBM_MODEL_RK = 3,      /* Rothman-Keller droplet: test/rk_static_droplet_test.cpp */
+  LBM_MODEL_KBC = 4      /* entropic central-moment collision ulbm::d2q9::kbc (src/ulbm.hpp:11-90, src/ulbm.cpp):
+                            test/ulbm_double_shear_flow.cpp, test/ulbm_poiseuille.cpp; omega = the class's s2 */
 } lbm_model;
 
 typedef enum
 {
   LBM_EQ_COMPRESSIBLE = 0,  /* solver::equilibrium        src/solver.cpp:51-62 */
-  LBM_EQ_INCOMPRESSIBLE = 1 /* solver::incomp_equilibrium src/solver.cpp:39-49 */
+  LBM_EQ_INCOMPRESSIBLE = 1, /* solver::incomp_equilibrium src/solver.cpp:39-49 */
+  /* lbm_init_equilibrium only: kbc::eval_equilibrium (src/ulbm.cpp:246-262) */
+  LBM_EQ_KBC = 2,            /* with ux2 = ux^2, uy2 = uy^2 */
+  LBM_EQ_KBC_FRESH = 3       /* as called on a fresh object (test/ulbm_double_shear_flow.cpp:97): the members ux2, uy2,
+                                which only collide() refreshes, are still zero */
 } lbm_equilibrium_kind;
 
 typedef enum
@@ -209,6 +215,10 @@ int lbm_snapshot_wait(lbm_domain* d);
 int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b);
 /* two-phase models carry u between steps (mrtcg_rayleigh_taylor.cpp:476-477); initial value.      */
 int lbm_set_u(lbm_domain* d, const double* u_aos);
+/* LBM_MODEL_KBC: the class keeps m0 / m1 as members that its first collide() reads before they are recomputed
+ * from the populations (test/ulbm_poiseuille.cpp:93 starts from adve_f = 0, m0 = 1, m1 = 0).  After an import,
+ * the FIRST step takes rho {X,Y,1}, u {X,Y,2} from here instead of the moments of the imported populations.  */
+int lbm_set_moments(lbm_domain* d, const double* rho, const double* u);
 /* initial condition helpers that mirror the drivers' own initialisation:
  *   BGK       f = incomp_equilibrium(u0, rho0)              (cylinder_test.cpp:86)
  *   two-phase adv_f = eq(rho_r, rho_b, u)                   (mrtcg_rayleigh_taylor.cpp:407-410)     */

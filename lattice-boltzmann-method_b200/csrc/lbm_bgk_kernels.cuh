@@ -221,8 +221,19 @@ k_bgk_interior(const double* __restrict__ fsrc, double* __restrict__ fdst, const
         }
       }
     }
-    bgk_collide<EQ, FORCE>(fa, p, roi_a, Fxa, Fya, rho_a, ux_a, uy_a);
-    bgk_collide<EQ, FORCE>(fb, p, roi_b, Fxb, Fyb, rho_b, ux_b, uy_b);
+    bool given = false;
+    if constexpr (EQ == EQ_KBC && MODE == MODE_LOCAL)
+    {
+      if (p.mom_in_rho != nullptr && active)  // the caller's m0, u for the first step (lbm_set_moments)
+      {
+        const long long n = (long long)x * p.Y + y;
+        given = true;
+        rho_a = p.mom_in_rho[n]; ux_a = p.mom_in_u[2 * n]; uy_a = p.mom_in_u[2 * n + 1];
+        rho_b = p.mom_in_rho[n + 1]; ux_b = p.mom_in_u[2 * n + 2]; uy_b = p.mom_in_u[2 * n + 3];
+      }
+    }
+    bgk_collide<EQ, FORCE>(fa, p, roi_a, Fxa, Fya, rho_a, ux_a, uy_a, given);
+    bgk_collide<EQ, FORCE>(fb, p, roi_b, Fxb, Fyb, rho_b, ux_b, uy_b, given);
     if (active)
     {
 #pragma unroll
@@ -311,7 +322,17 @@ k_bgk_boundary(const double* __restrict__ fsrc, double* __restrict__ fdst, const
     double fpost[9];
 #pragma unroll
     for (int q = 0; q < 9; q++) fpost[q] = f[q];
-    bgk_collide<EQ, FORCE>(fpost, p, in_roi, Fx, Fy, rho, ux, uy);
+    bool given = false;
+    if constexpr (EQ == EQ_KBC && MODE == MODE_LOCAL)
+    {
+      if (p.mom_in_rho != nullptr)
+      {
+        const long long n = (long long)x * p.Y + y;
+        given = true;
+        rho = p.mom_in_rho[n]; ux = p.mom_in_u[2 * n]; uy = p.mom_in_u[2 * n + 1];
+      }
+    }
+    bgk_collide<EQ, FORCE>(fpost, p, in_roi, Fx, Fy, rho, ux, uy, given);
 #pragma unroll
     for (int q = 0; q < 9; q++) fdst[q * g.plane + o] = fpost[q];
   }
@@ -415,7 +436,9 @@ k_pressure_apply(double* __restrict__ f, const SlabGeom g, int dst_lx, const dou
 #pragma unroll
   for (int q = 0; q < 9; q++)
   {
-    const double t = feq_any<EQ>(q, rho_bc * 1.0, ux, uy, uu);
+    // the imposed-density term: the model's own equilibrium, except for the KBC driver, which takes
+    // solver::incomp_equilibrium there and kbc.iequi_f^-1 for the subtracted one (test/ulbm_poiseuille.cpp:52-57,117)
+    const double t = feq_any<EQ == EQ_KBC ? EQ_INCOMP : EQ>(q, rho_bc * 1.0, ux, uy, uu);
     f[q * g.plane + o] = (t + packet[q * g.Y + y]) - feq_any<EQ>(q, rho, ux, uy, uu);
   }
 }

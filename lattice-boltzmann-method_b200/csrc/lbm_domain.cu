@@ -70,7 +70,8 @@ __global__ void k_moments_aos(const double* __restrict__ aos, long long n_nodes,
   }
 }
 
-__global__ void k_init_equilibrium(double* __restrict__ f, const SlabGeom g, int incompressible,
+// kind: lbm_equilibrium_kind
+__global__ void k_init_equilibrium(double* __restrict__ f, const SlabGeom g, int kind,
                                    const double* __restrict__ rho, const double* __restrict__ u)
 {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,9 +80,19 @@ __global__ void k_init_equilibrium(double* __restrict__ f, const SlabGeom g, int
   const long long o = node_off(g, x, y);
   const double r = rho[n], ux = u[2 * n], uy = u[2 * n + 1];
   const double uu = ux * ux + uy * uy;
+  if (kind == LBM_EQ_KBC || kind == LBM_EQ_KBC_FRESH)
+  {
+    // kbc::eval_equilibrium (src/ulbm.cpp:246-262); FRESH: its members ux2, uy2 are still zero, as when
+    // test/ulbm_double_shear_flow.cpp:97 builds the initial state
+    double e[9];
+    kbc_eq_coef(ux, uy, kind == LBM_EQ_KBC ? ux * ux : 0.0, kind == LBM_EQ_KBC ? uy * uy : 0.0, e);
+#pragma unroll
+    for (int q = 0; q < 9; q++) f[q * g.plane + o] = e[q] * r;
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 9; q++)
-    f[q * g.plane + o] = incompressible ? feq_incomp(q, r, ux, uy) : feq_comp(q, r, ux, uy, uu);
+    f[q * g.plane + o] = kind == LBM_EQ_INCOMPRESSIBLE ? feq_incomp(q, r, ux, uy) : feq_comp(q, r, ux, uy, uu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -110,6 +121,9 @@ static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
   p.roi_r0 = (int)d->ibm.r0; p.roi_r1 = (int)d->ibm.r1; p.roi_c0 = (int)d->ibm.c0; p.roi_c1 = (int)d->ibm.c1;
   p.Fx = d->ibm.d_Fx[a.slot];
   p.Fy = d->ibm.d_Fy[a.slot];
+  p.mom_in_rho = (MODE == MODE_LOCAL && d->mom_in_valid) ? d->d_mom_in : nullptr;
+  p.mom_in_u = p.mom_in_rho ? d->d_mom_in + (long long)d->g.Xl * d->g.Y : nullptr;
+  p.Y = d->g.Y;
   if (a.rows && d->npairs > 0 && a.n_rows > 0)
   {
     ProfScope ps(d, LBM_PROF_INTERIOR, a.stream);
@@ -142,6 +156,7 @@ static int dispatch_bgk(lbm_domain* d, const LaunchArgs& a)
   const bool ade = d->cfg.model == LBM_MODEL_BGK_ADE;
   const int eq = d->cfg.equilibrium, fo = d->cfg.force;
   if (ade) return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, a);
+  if (d->cfg.model == LBM_MODEL_KBC) return launch_bgk<MODE, EQ_KBC, FORCE_NONE, false>(d, a);
 #define LBM_CASE(E, F) \
   if (eq == E && fo == F) return launch_bgk<MODE, E, F, false>(d, a);
   LBM_CASE(EQ_COMP, FORCE_NONE)
@@ -293,7 +308,9 @@ int stage_apply(lbm_domain* d, size_t k)
   {
     if (!sg.own_dst || sg.y_hi <= sg.y_lo) return LBM_OK;
     const int lx = sg.dst_gx - d->cfg.x0, nblk = cdiv(sg.y_hi - sg.y_lo, 128);
-    if (d->cfg.equilibrium == EQ_INCOMP)
+    if (d->cfg.model == LBM_MODEL_KBC)
+      k_pressure_apply<EQ_KBC><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+    else if (d->cfg.equilibrium == EQ_INCOMP)
       k_pressure_apply<EQ_INCOMP><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     else
       k_pressure_apply<EQ_COMP><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
@@ -330,6 +347,7 @@ int step_bulk(lbm_domain* d)
   d->cur ^= 1;
   d->mom_cur ^= 1;
   d->post_stream = false;
+  d->mom_in_valid = false;
   d->ibm.used_slot = d->ibm.next_slot;
   d->ibm.next_slot ^= 1;
   d->side_ready = true;  // the side chain enqueued during this step prepared the new buffer
@@ -795,7 +813,7 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
   *out = nullptr;
   if (cfg->X < 3 || cfg->Y < 3) { set_error("lbm_create: grid %dx%d too small (need >= 3x3)", cfg->X, cfg->Y); return LBM_ERR_INVALID; }
   if (cfg->x0 < 0 || cfg->x1 > cfg->X || cfg->x1 <= cfg->x0) { set_error("lbm_create: bad slab rows [%d,%d) of %d", cfg->x0, cfg->x1, cfg->X); return LBM_ERR_INVALID; }
-  if (cfg->model < LBM_MODEL_BGK || cfg->model > LBM_MODEL_RK) { set_error("lbm_create: unknown model %d", cfg->model); return LBM_ERR_INVALID; }
+  if (cfg->model < LBM_MODEL_BGK || cfg->model > LBM_MODEL_KBC) { set_error("lbm_create: unknown model %d", cfg->model); return LBM_ERR_INVALID; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
   {
@@ -811,7 +829,7 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
   d->g.pitch = ((cfg->Y + 15) / 16) * 16;
   d->g.xg0 = cfg->x0;
   d->g.plane = (long long)(d->g.Xl + 2) * d->g.pitch;
-  d->nlat = cfg->model == LBM_MODEL_BGK ? 1 : 2;
+  d->nlat = (cfg->model == LBM_MODEL_BGK || cfg->model == LBM_MODEL_KBC) ? 1 : 2;
   if (d->nlat == 1 || cfg->model == LBM_MODEL_BGK_ADE)
   {
     // two nodes per thread: pairs (y, y+1), y even, 2 <= y and y + 2 <= Y - 1
@@ -876,6 +894,7 @@ int lbm_destroy(lbm_domain* d)
     cudaFree(d->d_aos[l]);
   }
   cudaFree(d->d_mom_out);
+  cudaFree(d->d_mom_in);
   if (d->copy)
   {
     cudaStreamSynchronize(d->copy);
@@ -985,6 +1004,7 @@ int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos)
   d->post_stream = true;
   d->have_state = true;
   d->side_ready = false;
+  d->mom_in_valid = false;
   if (d->tp) LBM_TRY(tp_refresh_moments(d));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
   return LBM_OK;
@@ -1054,7 +1074,8 @@ int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* 
   double *d_rho = nullptr, *d_u = nullptr;
   LBM_TRY(upload(d, rho, N, &d_rho));
   LBM_TRY(upload(d, u, 2 * N, &d_u));
-  k_init_equilibrium<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[lattice][d->cur], d->g, eq_kind == LBM_EQ_INCOMPRESSIBLE, d_rho, d_u);
+  if (eq_kind < LBM_EQ_COMPRESSIBLE || eq_kind > LBM_EQ_KBC_FRESH) { cudaFree(d_rho); cudaFree(d_u); set_error("lbm_init_equilibrium: unknown equilibrium kind %d", eq_kind); return LBM_ERR_INVALID; }
+  k_init_equilibrium<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[lattice][d->cur], d->g, eq_kind, d_rho, d_u);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
   LBM_CUDA(cudaStreamSynchronize(d->stream));
@@ -1063,6 +1084,25 @@ int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* 
   d->post_stream = true;
   d->have_state = true;
   d->side_ready = false;
+  d->mom_in_valid = false;
+  return LBM_OK;
+}
+
+// ulbm drivers keep m0 / m1 as members that the first collide() reads before they are recomputed from the
+// populations (test/ulbm_poiseuille.cpp:93: adve_f = 0, m0 = 1, m1 = 0): the first step after an import
+// takes these fields instead of the moments of the imported populations.
+int lbm_set_moments(lbm_domain* d, const double* rho, const double* u)
+{
+  if (!d || !rho || !u) { set_error("lbm_set_moments: null argument"); return LBM_ERR_INVALID; }
+  if (d->cfg.model != LBM_MODEL_KBC) { set_error("lbm_set_moments: only LBM_MODEL_KBC carries m0 / m1 into its first collision"); return LBM_ERR_UNSUPPORTED; }
+  if (!d->have_state || !d->post_stream) { set_error("lbm_set_moments: import the populations first (lbm_set_f / lbm_init_equilibrium)"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (!d->d_mom_in) LBM_CUDA(cudaMalloc(&d->d_mom_in, 3 * N * sizeof(double)));
+  LBM_CUDA(cudaMemcpyAsync(d->d_mom_in, rho, N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  LBM_CUDA(cudaMemcpyAsync(d->d_mom_in + N, u, 2 * N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  d->mom_in_valid = true;
   return LBM_OK;
 }
 

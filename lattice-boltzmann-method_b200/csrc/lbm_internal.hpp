@@ -134,6 +134,8 @@ struct lbm_domain
 
   // scratch for export
   double* d_aos[2] = {nullptr, nullptr};
+  double* d_mom_in = nullptr;   // LBM_MODEL_KBC: caller's rho {Xl,Y}, u {Xl,Y,2} for the first step (lbm_set_moments)
+  bool mom_in_valid = false;
   // snapshot staging: [6][Xl*Y] rho, u (2), phase, rho_r, rho_b — filled on `stream`, drained either on `stream`
   // (lbm_get_moments / lbm_get_phase) or on `copy` while later steps run (lbm_snapshot_async)
   double* d_mom_out = nullptr;

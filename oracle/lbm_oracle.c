@@ -1160,3 +1160,180 @@ void orc_rk_step(const orc_rk_params* p, double* r_adv, double* b_adv, double* r
   }
   free(gx); free(gy); free(r_col); free(b_col);
 }
+
+/* ------------------------------------------------------------------ ulbm::d2q9::kbc */
+
+/* the nine polynomial factors of kbc::eval_equilibrium / eval_iequilibrium (src/ulbm.cpp:230-240, 250-258) */
+static void kbc_eq_coef(double ux, double uy, double ux2, double uy2, double* e)
+{
+  const double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0;
+  e[0] = 2.0 * cs2 * (0.5 * ux2 + 0.5 * uy2 - 1.0) + cs4 + ux2 * uy2 - ux2 - uy2 + 1.0;
+  e[1] = 0.5 * (-cs2 * (ux2 + uy2 + ux - 1.0) - cs4 - ux2 * uy2 + ux2 - uy2 * ux + ux);
+  e[2] = 0.5 * (-cs2 * (ux2 + uy2 + uy - 1.0) - cs4 - ux2 * uy2 - ux2 * uy + uy2 + uy);
+  e[3] = 0.5 * (-cs2 * (ux2 + uy2 - ux - 1.0) - cs4 - ux2 * uy2 + ux2 + uy2 * ux - ux);
+  e[4] = 0.5 * (-cs2 * (ux2 + uy2 - uy - 1.0) - cs4 - ux2 * uy2 + ux2 * uy + uy2 - uy);
+  e[5] = 0.25 * (cs2 * (ux2 + uy2 + ux + uy) + cs4 + ux2 * uy2 + ux2 * uy + uy2 * ux + ux * uy);
+  e[6] = 0.25 * (cs2 * (ux2 + uy2 - ux + uy) + cs4 + ux2 * uy2 + ux2 * uy - uy2 * ux - ux * uy);
+  e[7] = 0.25 * (cs2 * (ux2 + uy2 - ux - uy) + cs4 + ux2 * uy2 - ux2 * uy - uy2 * ux + ux * uy);
+  e[8] = 0.25 * (cs2 * (ux2 + uy2 + ux - uy) + cs4 + ux2 * uy2 - ux2 * uy + uy2 * ux - ux * uy);
+}
+
+/* kbc::eval_equilibrium reads the members ux2, uy2, which only collide() refreshes (eval_m1_components,
+ * src/ulbm.cpp:150-155): called on a fresh object, as test/ulbm_double_shear_flow.cpp:97 does for its initial
+ * state, it sees ux2 = uy2 = 0.  fresh_object != 0 reproduces that; 0 uses ux2 = ux^2, uy2 = uy^2. */
+void orc_kbc_equilibrium(const double* m0, const double* m1, int X, int Y, int fresh_object, double* feq)
+{
+#pragma omp parallel for
+  for (long n = 0; n < (long)X * Y; n++)
+  {
+    double e[9];
+    const double ux = m1[2 * n], uy = m1[2 * n + 1];
+    kbc_eq_coef(ux, uy, fresh_object ? 0.0 : ux * ux, fresh_object ? 0.0 : uy * uy, e);
+    for (int q = 0; q < 9; q++) feq[n * 9 + q] = e[q] * m0[n];
+  }
+}
+
+/* kbc::collide() of one node (src/ulbm.cpp:91-126 with eval_central_momenta :264-320, eval_s_matrix :128-136,
+ * eval_gamma :138-148, eval_delta_s :157-189, eval_delta_h :191-224 incl. its `ux2+uy` terms, eval_iequilibrium
+ * :226-244).  f = adve_f, out: coll = coll_f, iequi = iequi_f. */
+static void kbc_collide_node(const double* f, double m0, double ux, double uy, double s2, double* coll, double* iequi)
+{
+  const double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0, is2 = 1.0 / s2;
+  double cmx[9], cmy[9], cmx2[9], cmy2[9], cT[9];
+  for (int q = 0; q < 9; q++)
+  {
+    cmx[q] = CXI[q] == 0 ? -ux : (CXI[q] > 0 ? 1.0 - ux : -1.0 - ux);
+    cmy[q] = CYI[q] == 0 ? -uy : (CYI[q] > 0 ? 1.0 - uy : -1.0 - uy);
+    cmx2[q] = cmx[q] * cmx[q];
+    cmy2[q] = cmy[q] * cmy[q];
+  }
+  for (int k = 0; k < 9; k++) cT[k] = 0.0;
+  for (int q = 0; q < 9; q++)
+  {
+    cT[0] += f[q];
+    cT[1] += f[q] * cmx[q];
+    cT[2] += f[q] * cmy[q];
+    cT[3] += f[q] * (cmx2[q] + cmy2[q]);
+    cT[4] += f[q] * (cmx2[q] - cmy2[q]);
+    cT[5] += f[q] * cmx[q] * cmy[q];
+    cT[6] += f[q] * cmx2[q] * cmy[q];
+    cT[7] += f[q] * cmx[q] * cmy2[q];
+    cT[8] += f[q] * cmx2[q] * cmy2[q];
+  }
+  /* eval_gamma */
+  const double ux2 = ux * ux, uy2 = uy * uy;
+  const double C3 = cT[3], C4 = cT[4], C5 = cT[5], C6 = cT[6], C7 = cT[7], C8 = cT[8];
+  double ds[9], dh[9], e[9];
+  ds[0] = -0.5 * C4 * (ux2 - uy2) + 4.0 * C5 * ux * uy - cs4 * m0 - m0 * (ux2 * uy2 - ux2 - uy2 + 1) + (C3 - 2.0 * cs2 * m0) * (0.5 * ux2 + 0.5 * uy2 - 1.0);
+  ds[1] = 0.25 * C4 * (ux2 - uy2 + ux + 1) - C5 * uy * (2.0 * ux + 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 + uy2 * ux - ux) - 0.25 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 + ux - 1.0);
+  ds[2] = -0.25 * C4 * (-ux2 + uy2 + uy + 1) - C5 * ux * (2.0 * uy + 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - uy2 + ux2 * uy - uy) - 0.25 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 + uy - 1.0);
+  ds[3] = 0.25 * C4 * (ux2 - uy2 - ux + 1) - C5 * uy * (2.0 * ux - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 - uy2 * ux + ux) - 0.25 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 - ux - 1.0);
+  ds[4] = 0.25 * C4 * (ux2 - uy2 + uy - 1) - C5 * ux * (2.0 * uy - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - uy2 - ux2 * uy + uy) - 0.25 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 - uy - 1.0);
+  ds[5] = -0.125 * C4 * (ux2 - uy2 + ux - uy) + C5 * (ux * uy + 0.5 * ux + 0.5 * uy + 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 * uy + uy2 * ux + ux * uy) + 0.125 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 + ux + uy);
+  ds[6] = 0.125 * C4 * (-ux2 + uy2 + ux + uy) + C5 * (ux * uy + 0.5 * ux - 0.5 * uy - 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 * uy - uy2 * ux - ux * uy) + 0.125 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 - ux + uy);
+  ds[7] = -0.125 * C4 * (ux2 - uy2 - ux + uy) + C5 * (ux * uy - 0.5 * ux - 0.5 * uy + 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 * uy - uy2 * ux + ux * uy) + 0.125 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 - ux - uy);
+  ds[8] = -0.125 * C4 * (ux2 - uy2 + ux + uy) + C5 * (ux * uy - 0.5 * ux + 0.5 * uy - 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 * uy + uy2 * ux - ux * uy) + 0.125 * (C3 - 2.0 * cs2 * m0) * (ux2 + uy2 + ux - uy);
+  dh[0] = 2.0 * C6 * uy + 2.0 * C7 * ux + C8 - 2.0 * cs2 * m0 * (0.5 * ux2 + 0.5 * uy2 - 1.0) - cs4 * m0 - m0 * (ux2 * uy2 - ux2 - uy2 + 1.0);
+  dh[1] = -C6 * uy - C7 * (ux + 0.5) - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 + ux - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 + uy2 * ux - ux);
+  dh[2] = -C6 * (uy + 0.5) - C7 * ux - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 + uy - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 + ux2 * uy - uy2 - uy);
+  dh[3] = -C6 * uy - C7 * (ux - 0.5) - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 - ux - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 - uy2 * ux + ux);
+  dh[4] = -C6 * (uy - 0.5) - C7 * ux - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 - uy - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 * uy - uy2 + uy);
+  /* :211-223 as written: `ux2+uy`, not `ux2*uy` */
+  dh[5] = C6 * (0.5 * uy + 0.25) + C7 * (0.5 * ux + 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 + ux + uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 + uy + uy2 * ux + ux * uy);
+  dh[6] = C6 * (0.5 * uy + 0.25) + C7 * (0.5 * ux - 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 - ux + uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 + uy - uy2 * ux - ux * uy);
+  dh[7] = C6 * (0.5 * uy - 0.25) + C7 * (0.5 * ux - 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 - ux - uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 + uy - uy2 * ux + ux * uy);
+  dh[8] = C6 * (0.5 * uy - 0.25) + C7 * (0.5 * ux + 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 + ux - uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 + uy + uy2 * ux - ux * uy);
+  kbc_eq_coef(ux, uy, ux2, uy2, e);
+  double num = 0.0, den = 0.0;
+  for (int q = 0; q < 9; q++)
+  {
+    iequi[q] = 1.0 / (e[q] * m0);
+    num += ds[q] * dh[q] * iequi[q];
+    den += dh[q] * dh[q] * iequi[q];
+  }
+  const double gamma = is2 - (1.0 - is2) * num / den;
+  const double S[9] = {1.0, 1.0, 1.0, s2, s2, s2, gamma * s2, gamma * s2, gamma * s2};
+  /* collide() steps 1-5 */
+  cT[0] += -m0;
+  cT[3] += -2.0 * cs2 * m0;
+  cT[8] += -cs4 * m0;
+  for (int k = 0; k < 9; k++) cT[k] *= S[k];
+  double g[9];
+  g[0] = cT[0];
+  g[1] = cT[0] * ux + cT[1];
+  g[2] = cT[0] * uy + cT[2];
+  g[3] = cT[0] * (ux2 + uy2) + 2.0 * cT[1] * ux + 2.0 * cT[2] * uy + cT[3];
+  g[4] = cT[0] * (ux2 - uy2) + 2.0 * cT[1] * ux - 2.0 * cT[2] * uy + cT[4];
+  g[5] = cT[0] * ux * uy + cT[1] * uy + cT[2] * ux + cT[5];
+  g[6] = cT[0] * ux2 * uy + 2.0 * cT[1] * ux * uy + cT[2] * ux2 + 0.5 * cT[3] * uy + 0.5 * cT[4] * uy + 2.0 * cT[5] * ux + cT[6];
+  g[7] = cT[0] * ux * uy2 + cT[1] * uy2 + 2.0 * cT[2] * ux * uy + 0.5 * cT[3] * ux - 0.5 * cT[4] * ux + 2.0 * cT[5] * uy + cT[7];
+  g[8] = cT[0] * ux2 * uy2 + 2.0 * cT[1] * ux * uy2 + 2.0 * cT[2] * ux2 * uy + 0.5 * cT[3] * (ux2 + uy2) - 0.5 * cT[4] * (ux2 - uy2) + 4.0 * cT[5] * ux * uy + 2.0 * cT[6] * uy + 2.0 * cT[7] * ux + cT[8];
+  double c[9];
+  c[0] = g[0] - g[3] + g[8];
+  c[1] = 0.5 * g[1] + 0.25 * g[3] + 0.25 * g[4] - 0.5 * g[7] - 0.5 * g[8];
+  c[2] = 0.5 * g[2] + 0.25 * g[3] - 0.25 * g[4] - 0.5 * g[6] - 0.5 * g[8];
+  c[3] = -0.5 * g[1] + 0.25 * g[3] + 0.25 * g[4] + 0.5 * g[7] - 0.5 * g[8];
+  c[4] = -0.5 * g[2] + 0.25 * g[3] - 0.25 * g[4] + 0.5 * g[6] - 0.5 * g[8];
+  c[5] = 0.25 * (g[5] + g[6] + g[7] + g[8]);
+  c[6] = 0.25 * (-g[5] + g[6] - g[7] + g[8]);
+  c[7] = 0.25 * (g[5] - g[6] - g[7] + g[8]);
+  c[8] = 0.25 * (-g[5] - g[6] + g[7] + g[8]);
+  for (int q = 0; q < 9; q++) coll[q] = c[q] * -1.0 + f[q];
+}
+
+void orc_kbc_step(double* f, double* m0, double* m1, int X, int Y, double s2, int bc, double rho_in, double rho_out)
+{
+  size_t N = (size_t)X * Y;
+  double* fcoll = dalloc(N * 9);
+  double* iequi = dalloc(N * 9);
+#pragma omp parallel for
+  for (long n = 0; n < (long)N; n++) kbc_collide_node(f + n * 9, m0[n], m1[2 * n], m1[2 * n + 1], s2, fcoll + n * 9, iequi + n * 9);
+  if (bc == 1)
+  {
+    /* periodic_boundary_condition(coll_f, iequi_f.pow(-1), m1, m0, rho_inlet, rho_outlet) (ulbm_poiseuille.cpp:39-60,117):
+     * virtual inlet row 0 from row -2, virtual outlet row -1 from row 1, with solver::incomp_equilibrium */
+    for (int side = 0; side < 2; side++)
+    {
+      const int dst = side == 0 ? 0 : X - 1, src = side == 0 ? X - 2 : 1;
+      const double rbc = side == 0 ? rho_in : rho_out;
+      for (int y = 0; y < Y; y++)
+      {
+        const double ux = m1[2 * N2(src, y)], uy = m1[2 * N2(src, y) + 1];
+        for (int q = 0; q < 9; q++)
+        {
+          const double te = (rbc * 1.0 + 3.0 * (ux * CXD[q] + uy * CYD[q])) * W9[q];
+          fcoll[IDX(dst, y, q)] = (te + fcoll[IDX(src, y, q)]) - 1.0 / iequi[IDX(src, y, q)];
+        }
+      }
+    }
+  }
+  orc_advect(fcoll, X, Y, f);
+  if (bc == 1)
+  {
+    for (int x = 0; x < X; x++)
+    {
+      f[IDX(x, Y - 1, 4)] = fcoll[IDX(x, Y - 1, 2)];
+      f[IDX(x, Y - 1, 7)] = fcoll[IDX(x, Y - 1, 5)];
+      f[IDX(x, Y - 1, 8)] = fcoll[IDX(x, Y - 1, 6)];
+      f[IDX(x, 0, 2)] = fcoll[IDX(x, 0, 4)];
+      f[IDX(x, 0, 5)] = fcoll[IDX(x, 0, 7)];
+      f[IDX(x, 0, 6)] = fcoll[IDX(x, 0, 8)];
+    }
+  }
+#pragma omp parallel for
+  for (long n = 0; n < (long)N; n++)
+  {
+    double s = 0.0, jx = 0.0, jy = 0.0;
+    for (int q = 0; q < 9; q++)
+    {
+      s += f[n * 9 + q];
+      jx += f[n * 9 + q] * CXD[q];
+      jy += f[n * 9 + q] * CYD[q];
+    }
+    m0[n] = s;
+    m1[2 * n] = jx / s;
+    m1[2 * n + 1] = jy / s;
+  }
+  free(fcoll);
+  free(iequi);
+}

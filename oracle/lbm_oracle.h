@@ -119,6 +119,18 @@ void orc_rk_init(const orc_rk_params* p, const double* u0, double* r_adv, double
 void orc_rk_step(const orc_rk_params* p, double* r_adv, double* b_adv, double* r_rho, double* b_rho,
                  double* rho_mix, double* u, double* phase, double* relax, double* grad);
 
+/* ---- ulbm::d2q9::kbc (src/ulbm.hpp:11-90, src/ulbm.cpp) and its two drivers -- SURVEY 8(f) rank 3.
+ * Pinned against the compiled reference: ref_kbc_run / ref_kbc_equilibrium of oracle/ref_harness.cpp
+ * (tests/test_oracle_vs_reference.py) and the snapshots of test/ulbm_double_shear_flow.cpp
+ * (tests/golden/kbc_double_shear_128.npz). */
+/* kbc::eval_equilibrium (src/ulbm.cpp:246-262): m0 {X,Y}, m1 {X,Y,2} -> feq {X,Y,9}.  fresh_object != 0: the members
+ * ux2, uy2 are still zero, as in the driver's initialisation (test/ulbm_double_shear_flow.cpp:97) */
+void orc_kbc_equilibrium(const double* m0, const double* m1, int X, int Y, int fresh_object, double* feq);
+/* one loop iteration: collide(); [bc = 1: pressure rows on coll_f]; advect(); [bc = 1: bounce-back columns];
+ * m0 = sum f, m1 = f c / m0.  bc = 0: test/ulbm_double_shear_flow.cpp:115-142 (fully periodic),
+ * bc = 1: test/ulbm_poiseuille.cpp:116-143.  f = adve_f {X,Y,9}, m0 {X,Y}, m1 {X,Y,2} in/out. */
+void orc_kbc_step(double* f, double* m0, double* m1, int X, int Y, double s2, int bc, double rho_in, double rho_out);
+
 #ifdef __cplusplus
 }
 #endif

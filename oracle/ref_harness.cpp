@@ -20,6 +20,7 @@
 #include "src/ibm.hpp"
 #include "src/params.hpp"
 #include "src/solver.hpp"
+#include "src/ulbm.hpp"
 
 namespace
 {
@@ -296,6 +297,68 @@ int ref_domain_shapes(int R, int C, long* shapes15)
   const torch::Tensor* ts[5] = {&d.adve_f, &d.equi_f, &d.coll_f, &d.m_0, &d.m_1};
   for (int i = 0; i < 5; i++)
     for (int j = 0; j < 3; j++) shapes15[3 * i + j] = ts[i]->size(j);
+  REF_CATCH
+}
+
+// ulbm::d2q9::kbc (src/ulbm.hpp:11-90) stepped like its two drivers do.
+//   bc = 0  test/ulbm_double_shear_flow.cpp:118-142  fully periodic (the "bind to self" assignments repeat advect's wrap)
+//   bc = 1  test/ulbm_poiseuille.cpp:116-143         pressure-periodic rows on coll_f, bounce-back columns
+// m0 {R,C}, m1 {R,C,2}, adve {R,C,9} in/out.  The few tensor expressions of the drivers' loop bodies
+// (moments, the pressure rule) are repeated here verbatim; collide() and advect() are the reference's.
+int ref_kbc_run(int R, int C, double s2, double* m0, double* m1, double* adve, int steps, int bc, double rho_in, double rho_out)
+{
+  REF_TRY
+  using torch::indexing::Ellipsis;
+  using torch::indexing::None;
+  using torch::indexing::Slice;
+  ulbm::d2q9::kbc kbc{R, C, s2};
+  kbc.m0 = wrap(m0, {R, C});
+  kbc.m1 = wrap(m1, {R, C, 2});
+  kbc.adve_f = wrap(adve, {R, C, 9});
+  const torch::Tensor c = solver::c;
+  for (int t = 0; t < steps; t++)
+  {
+    kbc.collide();
+    if (bc == 1)
+    {
+      // periodic_boundary_condition(kbc.coll_f, kbc.iequi_f.pow(-1), kbc.m1, kbc.m0, rho_inlet, rho_outlet)  (ulbm_poiseuille.cpp:39-60,117)
+      torch::Tensor f_equi = kbc.iequi_f.pow(-1);
+      torch::Tensor temp_equi = torch::zeros({1, C, 9});
+      torch::Tensor temp_rho = torch::ones({1, C, 1});
+      solver::incomp_equilibrium(temp_equi, kbc.m1.index({-2, Ellipsis}).unsqueeze(0), rho_in * temp_rho);
+      kbc.coll_f.index({0, Ellipsis}) = (temp_equi + kbc.coll_f.index({-2, Ellipsis}) - f_equi.index({-2, Ellipsis})).squeeze(0).clone().detach();
+      solver::incomp_equilibrium(temp_equi, kbc.m1.index({1, Ellipsis}).unsqueeze(0), rho_out * temp_rho);
+      kbc.coll_f.index({-1, Ellipsis}) = (temp_equi + kbc.coll_f.index({1, Ellipsis}) - f_equi.index({1, Ellipsis})).squeeze(0).clone().detach();
+    }
+    kbc.advect();
+    if (bc == 1)
+    {
+      kbc.adve_f.index({Slice(), -1, 4}) = kbc.coll_f.index({Slice(), -1, 2}).clone().detach();
+      kbc.adve_f.index({Slice(), -1, 7}) = kbc.coll_f.index({Slice(), -1, 5}).clone().detach();
+      kbc.adve_f.index({Slice(), -1, 8}) = kbc.coll_f.index({Slice(), -1, 6}).clone().detach();
+      kbc.adve_f.index({Slice(), 0, 2}) = kbc.coll_f.index({Slice(), 0, 4}).clone().detach();
+      kbc.adve_f.index({Slice(), 0, 5}) = kbc.coll_f.index({Slice(), 0, 7}).clone().detach();
+      kbc.adve_f.index({Slice(), 0, 6}) = kbc.coll_f.index({Slice(), 0, 8}).clone().detach();
+    }
+    kbc.m0 = kbc.adve_f.sum(-1).detach().clone();
+    kbc.m1 = (torch::matmul(kbc.adve_f, c.transpose(0, 1)) / kbc.m0.unsqueeze(-1)).detach().clone();
+  }
+  copy_out(kbc.m0, m0);
+  copy_out(kbc.m1, m1);
+  copy_out(kbc.adve_f, adve);
+  REF_CATCH
+}
+
+// kbc::eval_equilibrium(adve_f) from m0 {R,C}, m1 {R,C,2} (src/ulbm.cpp:246-262; the drivers' initial state)
+int ref_kbc_equilibrium(int R, int C, const double* m0, const double* m1, double* feq)
+{
+  REF_TRY
+  ulbm::d2q9::kbc kbc{R, C, 1.0};
+  kbc.m0 = wrap(m0, {R, C});
+  kbc.m1 = wrap(m1, {R, C, 2});
+  torch::Tensor out = torch::zeros({R, C, 9});
+  kbc.eval_equilibrium(out);
+  copy_out(out, feq);
   REF_CATCH
 }
 

@@ -87,3 +87,24 @@ def rk(Ln, **slab):
     d = L.Domain(L.default_config(model=L.MODEL_RK, X=Ln, Y=Ln, red=RK_RED, blue=RK_BLUE, delta=0.98, **slab))
     d.preset_rk()
     return d
+
+
+def kbc(X, Y, s2, poiseuille=None, **slab):
+    """ulbm::d2q9::kbc: fully periodic (test/ulbm_double_shear_flow.cpp) or, with poiseuille = (rho_in, rho_out),
+    pressure rows + bounce-back columns (test/ulbm_poiseuille.cpp)"""
+    d = L.Domain(L.default_config(model=L.MODEL_KBC, X=X, Y=Y, omega=s2, **slab))
+    if poiseuille is None:
+        d.preset_periodic()
+    else:
+        d.preset_poiseuille(*poiseuille)
+    return d
+
+
+def double_shear_fields(R, C, u_max=0.02, alpha=80.0, delta=0.05):
+    """set_initial_conditions of test/ulbm_double_shear_flow.cpp:44-67"""
+    r = np.arange(R)[:, None] + 0.0 * np.arange(C)[None, :]
+    c = np.arange(C)[None, :] + 0.0 * np.arange(R)[:, None]
+    u = np.zeros((R, C, 2))
+    u[..., 0] = u_max * np.tanh(alpha * (0.25 * R - np.abs(c - 0.5 * R)))
+    u[..., 1] = u_max * delta * np.sin(6.2832 * (r + 0.25 * R) / R)
+    return np.ones((R, C)), u

@@ -452,7 +452,47 @@ def case_rk():
     save("rk_droplet_101", steps=np.array(keep), **{k: np.stack([v[..., t] for t in keep]) for k, v in ref.items()})
 
 
-CASES = dict(poiseuille=case_poiseuille, specular=case_specular, gravity=case_gravity, decompose=case_decompose,
+# ------------------------------------------------------------------ driver 26 (ulbm::d2q9::kbc)
+def case_kbc_double_shear():
+    """test/ulbm_double_shear_flow.cpp as shipped: 128 x 128, 10^4 steps, snapshots of m1, m0 every 10 steps.
+    Entry ts of the saved stacks holds the fields at the START of iteration 10 ts.  The flow (Re ~ 15000 shear
+    layers) amplifies rounding differences, so every stored snapshot carries the tolerance the C oracle itself
+    meets against the driver (x10 margin): that is the tolerance the CUDA path is held to."""
+    d = workdir("kbc_dsf")
+    if not os.path.exists(os.path.join(d, "ulbm-double-shear-flow-rho.pt")):
+        r = run_ref_driver("ulbm_double_shear_flow", [], d, timeout=7200)
+        assert r.returncode == 0, r.stderr
+    ux = load_pt(os.path.join(d, "ulbm-double-shear-flow-ux.pt"))
+    uy = load_pt(os.path.join(d, "ulbm-double-shear-flow-uy.pt"))
+    rho = load_pt(os.path.join(d, "ulbm-double-shear-flow-rho.pt"))
+    R, Cc, Ts = ux.shape
+    nu = 1.70766666e-4
+    s2 = 1.0 / (0.5 + 3.0 * nu)
+    r_ = np.arange(R)[:, None] + 0.0 * np.arange(Cc)[None, :]
+    c_ = np.arange(Cc)[None, :] + 0.0 * np.arange(R)[:, None]
+    u = np.zeros((R, Cc, 2))
+    u[..., 0] = 0.02 * np.tanh(80.0 * (0.25 * R - np.abs(c_ - 0.5 * R)))
+    u[..., 1] = 0.02 * 0.05 * np.sin(6.2832 * (r_ + 0.25 * R) / R)
+    m0 = np.ones((R, Cc))
+    assert np.array_equal(ux[..., 0], u[..., 0]) and np.array_equal(uy[..., 0], u[..., 1])
+    f = ORC.kbc_equilibrium(m0, u, fresh_object=True)
+    keep = [10, 100, 1000, 9990]
+    st = 2  # every second row and column is stored (fixture size)
+    out = dict(steps=[], ux=[], uy=[], rho=[], tol=[])
+    for t in range(1, keep[-1] + 1):
+        ORC.kbc_step(f, m0, u, s2)
+        if t in keep:
+            ts = t // 10
+            e = max(np.abs(u[..., 0] - ux[..., ts]).max(), np.abs(u[..., 1] - uy[..., ts]).max(), np.abs(m0 - rho[..., ts]).max())
+            print(f"  step {t}: oracle vs driver max abs err {e:.2e}")
+            out["steps"].append(t); out["ux"].append(ux[::st, ::st, ts]); out["uy"].append(uy[::st, ::st, ts]); out["rho"].append(rho[::st, ::st, ts])
+            out["tol"].append(max(1e-12, 10.0 * e))
+    assert out["tol"][0] <= 1e-12 and out["tol"][1] <= 1e-11, out["tol"]
+    save("kbc_double_shear_128", steps=np.array(out["steps"]), ux=np.array(out["ux"]), uy=np.array(out["uy"]),
+         rho=np.array(out["rho"]), tol=np.array(out["tol"]), s2=s2, stride=st)
+
+
+CASES = dict(kbc_double_shear=case_kbc_double_shear, poiseuille=case_poiseuille, specular=case_specular, gravity=case_gravity, decompose=case_decompose,
              free_stream=case_free_stream, cylinder=case_cylinder, sedimentation=case_sedimentation,
              mrtcg_rt=case_mrtcg_rt, mrtcg_droplet=case_mrtcg_droplet, rk=case_rk)
 

@@ -221,6 +221,18 @@ class Oracle:
         self.lib.orc_mrtcg_step(C.byref(p), _p(st["r_adv"]), _p(st["b_adv"]), _p(st["r_rho"]), _p(st["b_rho"]),
                                 _p(st["rho"]), _p(st["u"]), _p(st["phase"]), _p(st["s_nu"]), _p(st["grad"]))
 
+    # ---- ulbm::d2q9::kbc
+    def kbc_equilibrium(self, m0, m1, fresh_object=True):
+        """fresh_object: kbc::eval_equilibrium as the driver calls it for its initial state (ux2 = uy2 = 0 still)"""
+        X, Y = m0.shape
+        out = np.zeros((X, Y, 9))
+        self.lib.orc_kbc_equilibrium(_p(m0), _p(m1), X, Y, 1 if fresh_object else 0, _p(out))
+        return out
+
+    def kbc_step(self, f, m0, m1, s2, bc=0, rho_in=1.0, rho_out=1.0):
+        X, Y, _ = f.shape
+        self.lib.orc_kbc_step(_p(f), _p(m0), _p(m1), X, Y, C.c_double(s2), int(bc), C.c_double(rho_in), C.c_double(rho_out))
+
     # ---- RK droplet
     def rk_init(self, p, u0=None):
         L = p.L
@@ -337,6 +349,18 @@ class Ref:
         self._chk(self.lib.ref_cylinder_loop(X, Y, C.c_double(omega), C.c_double(u_lb), markers_toml.encode(),
                                              warmup, steps, C.byref(sec), C.byref(chk)))
         return sec.value, chk.value
+
+    def kbc_run(self, f, m0, m1, s2, steps, bc=0, rho_in=1.0, rho_out=1.0):
+        """ulbm::d2q9::kbc stepped like its drivers (in place on f = adve_f, m0, m1)"""
+        X, Y, _ = f.shape
+        self._chk(self.lib.ref_kbc_run(X, Y, C.c_double(s2), _p(m0), _p(m1), _p(f), int(steps), int(bc),
+                                       C.c_double(rho_in), C.c_double(rho_out)))
+
+    def kbc_equilibrium(self, m0, m1):
+        X, Y = m0.shape
+        out = np.zeros((X, Y, 9))
+        self._chk(self.lib.ref_kbc_equilibrium(X, Y, _p(m0), _p(m1), _p(out)))
+        return out
 
     def num_threads(self):
         return int(self.lib.ref_get_num_threads())

@@ -106,3 +106,29 @@ def test_ibm_force(libs, tmp_path):
     assert o.ibm_roi(ib) == roi
     assert cases.relerr(o.ibm_force(ib, u, rho), F) < 1e-14
     o.ibm_destroy(ib)
+
+
+def test_kbc_class_and_driver_loops(libs):
+    """ulbm::d2q9::kbc (src/ulbm.cpp) through ref_kbc_run: both drivers' loop bodies, warm and cold starts"""
+    o, r = libs
+    R, Cc = 28, 36
+    m0, u = cases.double_shear_fields(R, Cc)
+    s2 = 1.0 / (0.5 + 3.0 * 1.70766666e-4)
+    f_fresh = o.kbc_equilibrium(m0, u, fresh_object=True)
+    assert np.array_equal(f_fresh, r.kbc_equilibrium(m0, u))  # the driver's initial state, stale ux2 / uy2 included
+    for bc, pr in ((0, (1.0, 1.0)), (1, (1.0004, 1.0))):
+        fo, ao, bo = f_fresh.copy(), m0.copy(), u.copy()
+        fr, ar, br = f_fresh.copy(), m0.copy(), u.copy()
+        for n in (1, 1, 10, 150):
+            for _ in range(n):
+                o.kbc_step(fo, ao, bo, s2, bc, *pr)
+            r.kbc_run(fr, ar, br, s2, n, bc, *pr)
+            assert cases.relerr(fo, fr) < 1e-12 and np.abs(bo - br).max() < 1e-13 and np.abs(ao - ar).max() < 1e-13, (bc, n)
+    # test/ulbm_poiseuille.cpp starts from adve_f = 0 with m0 = 1, m1 = 0
+    fo = np.zeros((R, Cc, 9)); ao = np.ones((R, Cc)); bo = np.zeros((R, Cc, 2))
+    fr, ar, br = fo.copy(), ao.copy(), bo.copy()
+    for n in (1, 4, 60):
+        for _ in range(n):
+            o.kbc_step(fo, ao, bo, s2, 1, 1.0004, 1.0)
+        r.kbc_run(fr, ar, br, s2, n, 1, 1.0004, 1.0)
+        assert np.abs(fo - fr).max() < 1e-12, n
