@@ -137,82 +137,9 @@ __device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double
   return r;
 }
 
-// kbc::collide() of one node (src/ulbm.cpp:91-126: eval_central_momenta :264-320, eval_gamma :138-148,
-// eval_delta_s :157-189, eval_delta_h :191-224 with its `ux2+uy` terms as written, eval_iequilibrium :226-244,
-// then S (cT - cT_eq), N^-1, -M^-1, + adve_f).  In: post-stream f and the iteration's m0, u.  Out: post-collision f.
-__device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double m0, double ux, double uy)
+// M^-1 of kbc::collide() step 4 (src/ulbm.cpp:114-122; the sign flip of :123 is left to the caller)
+__device__ __forceinline__ void kbc_minv(const double (&g)[9], double (&c)[9])
 {
-  constexpr double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0;
-  const double is2 = 1.0 / s2;
-  double cT[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) cT[k] = 0.0;
-#pragma unroll
-  for (int q = 0; q < 9; q++)
-  {
-    const double cmx = CX(q) == 0 ? -ux : (CX(q) > 0 ? 1.0 - ux : -1.0 - ux);
-    const double cmy = CY(q) == 0 ? -uy : (CY(q) > 0 ? 1.0 - uy : -1.0 - uy);
-    const double cmx2 = cmx * cmx, cmy2 = cmy * cmy;
-    cT[0] += f[q];
-    cT[1] += f[q] * cmx;
-    cT[2] += f[q] * cmy;
-    cT[3] += f[q] * (cmx2 + cmy2);
-    cT[4] += f[q] * (cmx2 - cmy2);
-    cT[5] += f[q] * cmx * cmy;
-    cT[6] += f[q] * cmx2 * cmy;
-    cT[7] += f[q] * cmx * cmy2;
-    cT[8] += f[q] * cmx2 * cmy2;
-  }
-  const double ux2 = ux * ux, uy2 = uy * uy;
-  const double C3 = cT[3], C4 = cT[4], C5 = cT[5], C6 = cT[6], C7 = cT[7], C8 = cT[8];
-  const double K3 = C3 - 2.0 * cs2 * m0;
-  double ds[9], dh[9], e[9];
-  ds[0] = -0.5 * C4 * (ux2 - uy2) + 4.0 * C5 * ux * uy - cs4 * m0 - m0 * (ux2 * uy2 - ux2 - uy2 + 1) + K3 * (0.5 * ux2 + 0.5 * uy2 - 1.0);
-  ds[1] = 0.25 * C4 * (ux2 - uy2 + ux + 1) - C5 * uy * (2.0 * ux + 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 + uy2 * ux - ux) - 0.25 * K3 * (ux2 + uy2 + ux - 1.0);
-  ds[2] = -0.25 * C4 * (-ux2 + uy2 + uy + 1) - C5 * ux * (2.0 * uy + 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - uy2 + ux2 * uy - uy) - 0.25 * K3 * (ux2 + uy2 + uy - 1.0);
-  ds[3] = 0.25 * C4 * (ux2 - uy2 - ux + 1) - C5 * uy * (2.0 * ux - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 - uy2 * ux + ux) - 0.25 * K3 * (ux2 + uy2 - ux - 1.0);
-  ds[4] = 0.25 * C4 * (ux2 - uy2 + uy - 1) - C5 * ux * (2.0 * uy - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - uy2 - ux2 * uy + uy) - 0.25 * K3 * (ux2 + uy2 - uy - 1.0);
-  ds[5] = -0.125 * C4 * (ux2 - uy2 + ux - uy) + C5 * (ux * uy + 0.5 * ux + 0.5 * uy + 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 * uy + uy2 * ux + ux * uy) + 0.125 * K3 * (ux2 + uy2 + ux + uy);
-  ds[6] = 0.125 * C4 * (-ux2 + uy2 + ux + uy) + C5 * (ux * uy + 0.5 * ux - 0.5 * uy - 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 * uy - uy2 * ux - ux * uy) + 0.125 * K3 * (ux2 + uy2 - ux + uy);
-  ds[7] = -0.125 * C4 * (ux2 - uy2 - ux + uy) + C5 * (ux * uy - 0.5 * ux - 0.5 * uy + 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 * uy - uy2 * ux + ux * uy) + 0.125 * K3 * (ux2 + uy2 - ux - uy);
-  ds[8] = -0.125 * C4 * (ux2 - uy2 + ux + uy) + C5 * (ux * uy - 0.5 * ux + 0.5 * uy - 0.25) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 * uy + uy2 * ux - ux * uy) + 0.125 * K3 * (ux2 + uy2 + ux - uy);
-  dh[0] = 2.0 * C6 * uy + 2.0 * C7 * ux + C8 - 2.0 * cs2 * m0 * (0.5 * ux2 + 0.5 * uy2 - 1.0) - cs4 * m0 - m0 * (ux2 * uy2 - ux2 - uy2 + 1.0);
-  dh[1] = -C6 * uy - C7 * (ux + 0.5) - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 + ux - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 + uy2 * ux - ux);
-  dh[2] = -C6 * (uy + 0.5) - C7 * ux - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 + uy - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 + ux2 * uy - uy2 - uy);
-  dh[3] = -C6 * uy - C7 * (ux - 0.5) - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 - ux - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 - uy2 * ux + ux);
-  dh[4] = -C6 * (uy - 0.5) - C7 * ux - 0.5 * C8 + 0.5 * cs2 * m0 * (ux2 + uy2 - uy - 1.0) + 0.5 * cs4 * m0 + 0.5 * m0 * (ux2 * uy2 - ux2 * uy - uy2 + uy);
-  // src/ulbm.cpp:211-223 as written: `ux2+uy`, not `ux2*uy`
-  dh[5] = C6 * (0.5 * uy + 0.25) + C7 * (0.5 * ux + 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 + ux + uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 + uy + uy2 * ux + ux * uy);
-  dh[6] = C6 * (0.5 * uy + 0.25) + C7 * (0.5 * ux - 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 - ux + uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 + ux2 + uy - uy2 * ux - ux * uy);
-  dh[7] = C6 * (0.5 * uy - 0.25) + C7 * (0.5 * ux - 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 - ux - uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 + uy - uy2 * ux + ux * uy);
-  dh[8] = C6 * (0.5 * uy - 0.25) + C7 * (0.5 * ux + 0.25) + 0.25 * C8 - 0.25 * cs2 * m0 * (ux2 + uy2 + ux - uy) - 0.25 * cs4 * m0 - 0.25 * m0 * (ux2 * uy2 - ux2 + uy + uy2 * ux - ux * uy);
-  kbc_eq_coef(ux, uy, ux2, uy2, e);
-  double num = 0.0, den = 0.0;
-#pragma unroll
-  for (int q = 0; q < 9; q++)
-  {
-    const double ie = 1.0 / (e[q] * m0);
-    num += ds[q] * dh[q] * ie;
-    den += dh[q] * dh[q] * ie;
-  }
-  const double gamma = is2 - (1.0 - is2) * num / den;
-  const double gs2 = gamma * s2;
-  cT[0] += -m0;
-  cT[3] += -2.0 * cs2 * m0;
-  cT[8] += -cs4 * m0;
-  cT[3] *= s2; cT[4] *= s2; cT[5] *= s2;
-  cT[6] *= gs2; cT[7] *= gs2; cT[8] *= gs2;
-  double g[9];
-  g[0] = cT[0];
-  g[1] = cT[0] * ux + cT[1];
-  g[2] = cT[0] * uy + cT[2];
-  g[3] = cT[0] * (ux2 + uy2) + 2.0 * cT[1] * ux + 2.0 * cT[2] * uy + cT[3];
-  g[4] = cT[0] * (ux2 - uy2) + 2.0 * cT[1] * ux - 2.0 * cT[2] * uy + cT[4];
-  g[5] = cT[0] * ux * uy + cT[1] * uy + cT[2] * ux + cT[5];
-  g[6] = cT[0] * ux2 * uy + 2.0 * cT[1] * ux * uy + cT[2] * ux2 + 0.5 * cT[3] * uy + 0.5 * cT[4] * uy + 2.0 * cT[5] * ux + cT[6];
-  g[7] = cT[0] * ux * uy2 + cT[1] * uy2 + 2.0 * cT[2] * ux * uy + 0.5 * cT[3] * ux - 0.5 * cT[4] * ux + 2.0 * cT[5] * uy + cT[7];
-  g[8] = cT[0] * ux2 * uy2 + 2.0 * cT[1] * ux * uy2 + 2.0 * cT[2] * ux2 * uy + 0.5 * cT[3] * (ux2 + uy2) - 0.5 * cT[4] * (ux2 - uy2) + 4.0 * cT[5] * ux * uy + 2.0 * cT[6] * uy + 2.0 * cT[7] * ux + cT[8];
-  double c[9];
   c[0] = g[0] - g[3] + g[8];
   c[1] = 0.5 * g[1] + 0.25 * g[3] + 0.25 * g[4] - 0.5 * g[7] - 0.5 * g[8];
   c[2] = 0.5 * g[2] + 0.25 * g[3] - 0.25 * g[4] - 0.5 * g[6] - 0.5 * g[8];
@@ -222,6 +149,120 @@ __device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double m0
   c[6] = 0.25 * (-g[5] + g[6] - g[7] + g[8]);
   c[7] = 0.25 * (g[5] - g[6] - g[7] + g[8]);
   c[8] = 0.25 * (-g[5] - g[6] + g[7] + g[8]);
+}
+
+// kbc::collide() of one node (src/ulbm.cpp:91-126: eval_central_momenta :264-320, eval_gamma :138-148,
+// eval_delta_s :157-189, eval_delta_h :191-224, eval_iequilibrium :226-244, then S (cT - cT_eq), N^-1, -M^-1,
+// + adve_f).  In: post-stream f and the iteration's m0, u.  Out: post-collision f.
+//
+// The reference spells delta_s, delta_h and 1/f_eq out as 27 polynomials and sums nine weighted products per
+// central moment (~630 fp64 instructions per node: fp64-bound at half the HBM roofline).  Here they are
+// evaluated through their structure, to rounding-level differences (T = M^-1 N^-1, the transform of steps 3-4):
+//   central moments  from the raw moments of opposite-direction pairs, shifted by u (binomial expansion)
+//   delta_s = T (-m0, 0, 0, cT3 - 2 cs2 m0, cT4, cT5, 0, 0, -cs4 m0)
+//   delta_h = T (-m0, 0, 0, -2 cs2 m0, 0, 0, cT6, cT7, cT8 - cs4 m0) + the reference's `ux2+uy` slips in entries
+//             5..8 (src/ulbm.cpp:211-223 adds ux2 and uy where the expansion has ux2*uy), kept as written
+//   collision = s2 T (0,0,0, cT3 - 2 cs2 m0, cT4, cT5, 0,0,0) + gamma s2 T (0,..,0, cT6, cT7, cT8 - cs4 m0)
+//             [+ T (cT0 - m0, cT1, cT2, 0,..) when the caller supplied m0, u: zero to rounding otherwise]
+//   so N^-1 runs once on the shear part P, once on the higher-order part H and on the two equilibrium-only
+//   vectors; delta_s, delta_h and the collision are combinations of those, and M^-1 runs three times;
+//   f_eq,q = m0 phi_x(c_qx) phi_y(c_qy), phi(0) = 1 - cs2 - u^2, phi(+-1) = (cs2 + u^2 +- u) / 2 (product form of
+//             :230-238): six reciprocals instead of nine, and m0 cancels in gamma's quotient.
+__device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double m0, double ux, double uy, bool given)
+{
+  constexpr double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0;
+  const double is2 = 1.0 / s2;
+  const double ux2 = ux * ux, uy2 = uy * uy, uxy = ux * uy;
+  // ---- raw moments m_ab = sum f cx^a cy^b from pair sums / differences, then central moments
+  const double A1 = f[1] + f[3], D1 = f[1] - f[3], A2 = f[2] + f[4], D2 = f[2] - f[4];
+  const double A57 = f[5] + f[7], D57 = f[5] - f[7], A68 = f[6] + f[8], D68 = f[6] - f[8];
+  const double m22 = A57 + A68, m11 = A57 - A68, m21 = D57 + D68, m12 = D57 - D68;
+  const double m20 = A1 + m22, m02 = A2 + m22;
+  const double m10 = D1 + m12, m01 = D2 + m21;
+  const double r00 = ((f[0] + A1) + A2) + m22;
+  const double k10 = m10 - ux * r00, k01 = m01 - uy * r00;
+  const double k20 = (m20 - 2.0 * ux * m10) + ux2 * r00;
+  const double k02 = (m02 - 2.0 * uy * m01) + uy2 * r00;
+  const double k11 = ((m11 - ux * m01) - uy * m10) + uxy * r00;
+  const double k21 = (((m21 - 2.0 * ux * m11) + ux2 * m01) - uy * m20) + (2.0 * uxy * m10 - ux2 * uy * r00);
+  const double k12 = (((m12 - 2.0 * uy * m11) + uy2 * m10) - ux * m02) + (2.0 * uxy * m01 - ux * uy2 * r00);
+  const double k22 = ((((m22 - 2.0 * ux * m12) + ux2 * m02) - 2.0 * uy * m21) + 4.0 * uxy * m11) +
+                     (((uy2 * m20 - 2.0 * ux2 * uy * m01) - 2.0 * ux * uy2 * m10) + ux2 * uy2 * r00);
+  const double K3 = (k20 + k02) - 2.0 * cs2 * m0, C4 = k20 - k02, C5 = k11, C6 = k21, C7 = k12, K8 = k22 - cs4 * m0;
+
+  // ---- N^-1 (src/ulbm.cpp:104-112) on P = (0,0,0,K3,C4,C5,0,0,0) and H = (0,...,0,C6,C7,K8)
+  double gP[9], gH[9];
+  gP[0] = gP[1] = gP[2] = 0.0;
+  gP[3] = K3; gP[4] = C4; gP[5] = C5;
+  gP[6] = 0.5 * (K3 + C4) * uy + 2.0 * C5 * ux;
+  gP[7] = 0.5 * (K3 - C4) * ux + 2.0 * C5 * uy;
+  gP[8] = (0.5 * K3 * (ux2 + uy2) - 0.5 * C4 * (ux2 - uy2)) + 4.0 * C5 * uxy;
+  gH[0] = gH[1] = gH[2] = gH[3] = gH[4] = gH[5] = 0.0;
+  gH[6] = C6; gH[7] = C7;
+  gH[8] = (2.0 * C6 * uy + 2.0 * C7 * ux) + K8;
+  // equilibrium-only vectors E0 = (-m0,0,..,0,-cs4 m0) (in delta_s) and E1 = (-m0,0,0,-2 cs2 m0,0,..,0) (in delta_h)
+  const double n0 = -m0;
+  double gE[9];  // N^-1 (-m0, 0, .., 0): common to both
+  gE[0] = n0; gE[1] = n0 * ux; gE[2] = n0 * uy; gE[3] = n0 * (ux2 + uy2); gE[4] = n0 * (ux2 - uy2); gE[5] = n0 * uxy;
+  gE[6] = gE[1] * uxy; gE[7] = gE[2] * uxy; gE[8] = n0 * ux2 * uy2;
+  const double e3 = -2.0 * cs2 * m0;  // v3 of E1: adds e3 to g3, 0.5 e3 uy to g6, 0.5 e3 ux to g7, 0.5 e3 (ux2+uy2) to g8
+  double gs[9], gh[9], ds[9], dh[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++)
+  {
+    gs[k] = gP[k] + gE[k];
+    gh[k] = gH[k] + gE[k];
+  }
+  gs[8] += -cs4 * m0;
+  gh[3] += e3;
+  gh[6] += 0.5 * e3 * uy;
+  gh[7] += 0.5 * e3 * ux;
+  gh[8] += 0.5 * e3 * (ux2 + uy2);
+  kbc_minv(gs, ds);
+  kbc_minv(gh, dh);
+  {
+    // entries 5..8 as the reference writes them: (.. + ux2 + uy ..) / (.. - ux2 + uy ..) where the expansion has +- ux2*uy
+    const double pp = ux2 * uy;
+    const double e56 = -0.25 * m0 * ((ux2 + uy) - pp), e78 = -0.25 * m0 * ((uy - ux2) + pp);
+    dh[5] += e56;
+    dh[6] += e56;
+    dh[7] += e78;
+    dh[8] += e78;
+  }
+  // ---- gamma (src/ulbm.cpp:138-148) with 1 / (f_eq / m0) in product form
+  const double ax = cs2 + ux2, ay = cs2 + uy2;
+  const double rx[3] = {1.0 / (1.0 - ax), 1.0 / (0.5 * (ax + ux)), 1.0 / (0.5 * (ax - ux))};  // c_x = 0, +1, -1
+  const double ry[3] = {1.0 / (1.0 - ay), 1.0 / (0.5 * (ay + uy)), 1.0 / (0.5 * (ay - uy))};
+  double num = 0.0, den = 0.0;
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    const double ie = rx[CX(q) == 0 ? 0 : (CX(q) > 0 ? 1 : 2)] * ry[CY(q) == 0 ? 0 : (CY(q) > 0 ? 1 : 2)];
+    const double w = dh[q] * ie;
+    num += ds[q] * w;
+    den += dh[q] * w;
+  }
+  const double gamma = is2 - (1.0 - is2) * num / den;
+  const double gs2 = gamma * s2;
+  // ---- collision: S (cT - cT_eq) through N^-1 and M^-1 (steps 1-5)
+  double g[9], c[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) g[k] = s2 * gP[k] + gs2 * gH[k];
+  if (given)
+  {
+    // cT0 - m0, cT1, cT2 (S = 1 on them) are not rounding noise when the caller's m0, u differ from the populations' own
+    const double r0 = r00 - m0, r1 = k10, r2 = k01;
+    g[0] += r0;
+    g[1] += r0 * ux + r1;
+    g[2] += r0 * uy + r2;
+    g[3] += (r0 * (ux2 + uy2) + 2.0 * r1 * ux) + 2.0 * r2 * uy;
+    g[4] += (r0 * (ux2 - uy2) + 2.0 * r1 * ux) - 2.0 * r2 * uy;
+    g[5] += (r0 * uxy + r1 * uy) + r2 * ux;
+    g[6] += (r0 * ux2 * uy + 2.0 * r1 * uxy) + r2 * ux2;
+    g[7] += (r0 * ux * uy2 + r1 * uy2) + 2.0 * r2 * uxy;
+    g[8] += (r0 * ux2 * uy2 + 2.0 * r1 * ux * uy2) + 2.0 * r2 * ux2 * uy;
+  }
+  kbc_minv(g, c);
 #pragma unroll
   for (int q = 0; q < 9; q++) f[q] = f[q] - c[q];
 }
@@ -250,10 +291,11 @@ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, 
     if (!given)
     {
       moments(f, rho, jx, jy);
-      ux = jx / rho;  // kbc.m1 = adve_f c^T / m0 (test/ulbm_double_shear_flow.cpp:145-146)
-      uy = jy / rho;
+      const double ir = 1.0 / rho;  // kbc.m1 = adve_f c^T / m0 (test/ulbm_double_shear_flow.cpp:145-146)
+      ux = jx * ir;
+      uy = jy * ir;
     }
-    kbc_collide(f, p.omega, rho, ux, uy);
+    kbc_collide(f, p.omega, rho, ux, uy, given);
     return;
   }
   moments(f, rho, jx, jy);
