@@ -168,6 +168,24 @@ k_bgk_interior(const double* __restrict__ fsrc, double* __restrict__ fdst, const
 
   if constexpr (MODE == MODE_PULL_ONLY)
   {
+    if (p.snap_rho != nullptr)
+    {
+      // snapshot: moments of the post-stream state straight from the pull (no AoS detour)
+      if (active)
+      {
+        double ra, uxa, uya, rb, uxb, uyb;
+        snapshot_moments<EQ, FORCE>(fa, p, ra, uxa, uya);
+        snapshot_moments<EQ, FORCE>(fb, p, rb, uxb, uyb);
+        const long long n = (long long)x * g.Y + y;
+        p.snap_rho[n] = ra;
+        p.snap_rho[n + 1] = rb;
+        p.snap_u[2 * n] = uxa;
+        p.snap_u[2 * n + 1] = uya;
+        p.snap_u[2 * n + 2] = uxb;
+        p.snap_u[2 * n + 3] = uyb;
+      }
+      return;
+    }
     if (active)
     {
       double* oa = out_f + ((long long)x * g.Y + y) * 9;
@@ -300,6 +318,16 @@ k_bgk_boundary(const double* __restrict__ fsrc, double* __restrict__ fdst, const
     // velocity of the NEW post-stream state, as rectangle_sedimentation_test.cpp:199-201 computes it
     ux = jx / rho;
     uy = jy / rho;
+    if (p.snap_rho != nullptr)
+    {
+      double sr, sx, sy;
+      snapshot_moments<EQ, FORCE>(f, p, sr, sx, sy);
+      const long long n = (long long)x * g.Y + y;
+      p.snap_rho[n] = sr;
+      p.snap_u[2 * n] = sx;
+      p.snap_u[2 * n + 1] = sy;
+      return;
+    }
     double* oa = out_f + ((long long)x * g.Y + y) * 9;
 #pragma unroll
     for (int q = 0; q < 9; q++) oa[q] = f[q];

@@ -71,7 +71,11 @@ struct BgkParams
   // members, test/ulbm_poiseuille.cpp:93) instead of the moments of the imported populations; nullptr otherwise
   const double* mom_in_rho;
   const double* mom_in_u;
-  int Y;           // row length of mom_in_*
+  int Y;           // row length of mom_in_* / snap_*
+  // MODE_PULL_ONLY: when set, the pass writes rho {Xl,Y} and u {Xl,Y,2} of the post-stream state (what the next
+  // iteration of the driver would compute: calc_rho, calc_u / calc_incomp_u, += Fg) instead of the populations
+  double* snap_rho;
+  double* snap_u;
 };
 
 // rho = sum_q f, (jx, jy) = sum_q f c_q in the q order of the reference's reductions
@@ -81,6 +85,21 @@ __device__ __forceinline__ void moments(const double (&f)[9], double& rho, doubl
   rho = ((((((((f[0] + f[1]) + f[2]) + f[3]) + f[4]) + f[5]) + f[6]) + f[7]) + f[8]);
   jx = (((((f[1] - f[3]) + f[5]) - f[6]) - f[7]) + f[8]);
   jy = (((((f[2] - f[4]) + f[5]) + f[6]) - f[7]) - f[8]);
+}
+
+// rho, u of a post-stream node with the conventions of the model's driver (lbm_get_moments)
+template <int EQ, int FORCE>
+__device__ __forceinline__ void snapshot_moments(const double (&f)[9], const BgkParams& p, double& rho, double& ux, double& uy)
+{
+  double jx, jy;
+  moments(f, rho, jx, jy);
+  ux = EQ == EQ_INCOMP ? jx : jx / rho;
+  uy = EQ == EQ_INCOMP ? jy : jy / rho;
+  if constexpr (FORCE == FORCE_UNIFORM)
+  {
+    ux += p.Fg0;
+    uy += p.Fg1;
+  }
 }
 
 // solver::equilibrium (src/solver.cpp:51-62)

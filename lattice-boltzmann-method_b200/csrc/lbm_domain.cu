@@ -107,6 +107,8 @@ struct LaunchArgs
   bool listed;          // run the listed-node kernel
   int slot;             // IBM force-field slot to read
   cudaStream_t stream;
+  double* snap_rho = nullptr;  // MODE_PULL_ONLY: write moments here instead of the AoS populations
+  double* snap_u = nullptr;
 };
 
 template <int MODE, int EQ, int FORCE, bool ADE>
@@ -124,6 +126,8 @@ static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
   p.mom_in_rho = (MODE == MODE_LOCAL && d->mom_in_valid) ? d->d_mom_in : nullptr;
   p.mom_in_u = p.mom_in_rho ? d->d_mom_in + (long long)d->g.Xl * d->g.Y : nullptr;
   p.Y = d->g.Y;
+  p.snap_rho = a.snap_rho;
+  p.snap_u = a.snap_u;
   if (a.rows && d->npairs > 0 && a.n_rows > 0)
   {
     ProfScope ps(d, LBM_PROF_INTERIOR, a.stream);
@@ -744,6 +748,21 @@ int commit_boundary_tables(lbm_domain* d)
   return LBM_OK;
 }
 
+// The staging buffer of the snapshot path doubles as the landing zone of host fields on their way in
+// (cudaMalloc / cudaFree per call cost 30-600 ms at 136 MB on this box: measured, hence persistent).
+int host_staging(lbm_domain* d, double** out)
+{
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  if (!d->d_mom_out) LBM_CUDA(cudaMalloc(&d->d_mom_out, 6 * N * sizeof(double)));
+  if (d->copy_pending)
+  {
+    LBM_CUDA(cudaEventSynchronize(d->ev_copied));
+    d->copy_pending = false;
+  }
+  *out = d->d_mom_out;
+  return LBM_OK;
+}
+
 // rho, u (and for two-phase models phase, rho_r, rho_b) of the current state into the staging buffer,
 // on the domain's stream.  A copy still draining the buffer (lbm_snapshot_async) is waited for first.
 int stage_fields(lbm_domain* d, int lattice)
@@ -758,6 +777,19 @@ int stage_fields(lbm_domain* d, int lattice)
   }
   if (d->copy_pending) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copied, 0));
   if (d->tp) return tp_stage_moments(d, d->d_mom_out);
+  if (lattice == 0 && !d->post_stream)
+  {
+    // straight from the stored post-collision state: one pull-only pass that writes rho, u (72 B read + 24 B written
+    // per node; no AoS scratch)
+    LBM_TRY(step_rows(d));
+    if (d->link_lo || d->link_hi) LBM_TRY(comm_link_refresh(d));
+    else LBM_TRY(step_prologue(d, true));
+    LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+    LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_all, d->g.Xl, true, d->ibm.used_slot, d->stream};
+    a.snap_rho = d->d_mom_out;
+    a.snap_u = d->d_mom_out + N;
+    return dispatch_bgk<MODE_PULL_ONLY>(d, a);
+  }
   LBM_TRY(export_post_stream(d));
   int incompressible = 0;
   double sx = 0.0, sy = 0.0;
@@ -967,16 +999,6 @@ int lbm_bc_get_mask(lbm_domain* d, int lattice, int32_t* mask)
 }
 
 // ---------------------------------------------------------------- state
-static int upload(lbm_domain* d, const double* host, size_t n, double** dev_out)
-{
-  double* p = nullptr;
-  LBM_CUDA(cudaMalloc(&p, n * sizeof(double)));
-  cudaError_t e = cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, d->stream);
-  if (e != cudaSuccess) { cudaFree(p); set_error("cudaMemcpyAsync H2D failed: %s", cudaGetErrorString(e)); return LBM_ERR_CUDA; }
-  *dev_out = p;
-  return LBM_OK;
-}
-
 int lbm_set_f(lbm_domain* d, int lattice, const double* f_aos)
 {
   if (!d || !f_aos || lattice < 0 || lattice >= d->nlat) { set_error("lbm_set_f: bad argument"); return LBM_ERR_INVALID; }
@@ -1071,16 +1093,16 @@ int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* 
   if (d->tp) { set_error("lbm_init_equilibrium: use lbm_init_two_phase for two-phase models"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   const long long N = (long long)d->g.Xl * d->g.Y;
-  double *d_rho = nullptr, *d_u = nullptr;
-  LBM_TRY(upload(d, rho, N, &d_rho));
-  LBM_TRY(upload(d, u, 2 * N, &d_u));
-  if (eq_kind < LBM_EQ_COMPRESSIBLE || eq_kind > LBM_EQ_KBC_FRESH) { cudaFree(d_rho); cudaFree(d_u); set_error("lbm_init_equilibrium: unknown equilibrium kind %d", eq_kind); return LBM_ERR_INVALID; }
+  if (eq_kind < LBM_EQ_COMPRESSIBLE || eq_kind > LBM_EQ_KBC_FRESH) { set_error("lbm_init_equilibrium: unknown equilibrium kind %d", eq_kind); return LBM_ERR_INVALID; }
+  double* stage = nullptr;
+  LBM_TRY(host_staging(d, &stage));
+  double *d_rho = stage, *d_u = stage + N;
+  LBM_CUDA(cudaMemcpyAsync(d_rho, rho, N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  LBM_CUDA(cudaMemcpyAsync(d_u, u, 2 * N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
   k_init_equilibrium<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[lattice][d->cur], d->g, eq_kind, d_rho, d_u);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
   LBM_CUDA(cudaStreamSynchronize(d->stream));
-  cudaFree(d_rho);
-  cudaFree(d_u);
   d->post_stream = true;
   d->have_state = true;
   d->side_ready = false;

@@ -164,7 +164,9 @@ namespace lbm
 {
 // lbm_domain.cu
 int ensure_aos_scratch(lbm_domain* d);
-void drop_graphs(lbm_domain* d);  // captured step pairs hold device pointers: drop them when tables / markers change
+void drop_graphs(lbm_domain* d);
+// persistent [6][Xl*Y] device staging for host fields on their way in or out (waits for a pending snapshot copy)
+int host_staging(lbm_domain* d, double** out);  // captured step pairs hold device pointers: drop them when tables / markers change
 // brackets a group of launches of one class with events when profiling is on
 struct ProfScope
 {

@@ -1082,14 +1082,13 @@ int lbm_set_u(lbm_domain* d, const double* u_aos)
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   const long long N = (long long)d->g.Xl * d->g.Y;
   double* tmp = nullptr;
-  LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 2 * N));
+  LBM_TRY(host_staging(d, &tmp));
   LBM_CUDA(cudaMemcpyAsync(tmp, u_aos, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, d->stream));
   k_tp_write_u<<<cdiv(N, 256), 256, 0, d->stream>>>(d->tp->mom, d->g, d->tp->mg, tmp);
   d->launches++;
   int s = tp_pad(d);
   if (s == LBM_OK) s = comm_exchange_moments(d);
   cudaStreamSynchronize(d->stream);
-  cudaFree(tmp);
   return s;
 }
 
@@ -1099,7 +1098,7 @@ int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, 
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   const long long N = (long long)d->g.Xl * d->g.Y;
   double* tmp = nullptr;
-  LBM_CUDA(cudaMalloc(&tmp, sizeof(double) * 4 * N));
+  LBM_TRY(host_staging(d, &tmp));  // [6][N] persistent staging: rho_r, rho_b, u use 4 N of it
   LBM_CUDA(cudaMemcpyAsync(tmp, rho_r, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
   LBM_CUDA(cudaMemcpyAsync(tmp + N, rho_b, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
   LBM_CUDA(cudaMemcpyAsync(tmp + 2 * N, u, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, d->stream));
@@ -1111,7 +1110,6 @@ int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, 
   int s = tp_pad(d);
   if (s == LBM_OK) s = comm_exchange_moments(d);
   cudaStreamSynchronize(d->stream);
-  cudaFree(tmp);
   if (s != LBM_OK) return s;
   d->post_stream = true;
   d->have_state = true;
