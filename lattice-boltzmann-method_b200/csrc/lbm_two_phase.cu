@@ -27,17 +27,10 @@
 #include "lbm_internal.hpp"
 #include "lbm_two_phase.cuh"
 
-// Cache hints of the fused kernel: streaming stores + evict-first on the second read.  Measured on B200:
-// RK 4096^2 16.5 -> 15.5 GLUPS, MRTCG 16384^2 13.06 -> 13.26 GLUPS (noise): off by default.
+// L2 eviction hints of the fused kernel (see tp_pull_at); compile-time switch.  A/B on B200: MRTCG 16384^2
+// 13.49 -> 13.60 GLUPS (DRAM reads 179 -> 169 B/node), RK 4096^2 16.49 -> 16.22 GLUPS: within noise, off by default.
 #ifndef LBM_TP_HINTS
 #define LBM_TP_HINTS 0
-#endif
-#if LBM_TP_HINTS
-#define LBM_TP_LDLAST(a) __ldcs(a)
-#define LBM_TP_ST(a, v) __stcs(a, v)
-#else
-#define LBM_TP_LDLAST(a) __ldg(a)
-#define LBM_TP_ST(a, v) (*(a) = (v))
 #endif
 
 namespace lbm
@@ -82,16 +75,40 @@ __device__ __forceinline__ void tp_load_interior(const double* __restrict__ src,
 // Pull through a per-thread node pointer (src + node_off(g, x, y)) plus WARP-UNIFORM offsets
 // q * plane - c_x * pitch - c_y: two integer instructions per access instead of a 64-bit index
 // rebuilt per thread and per population.
-// LAST = true: the block's second and final read of these lines (cache-streaming: evict first).
-template <bool LAST = false>
-__device__ __forceinline__ void tp_pull_at(const double* __restrict__ node, const SlabGeom& g, double (&f)[9])
+// L2 eviction policies for the two reads a block makes of every line: the FIRST one (moments of row r+H) marks the
+// line evict_last so that the SECOND one (collision of the same row, LAG iterations later) still finds it in L2;
+// the second marks it evict_first.  (ncu before: only ~60 % of the second reads hit L2.)
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ld_l2_hint(const double* a, unsigned long long pol)
+{
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+
+// pol = 0: plain read-only load
+__device__ __forceinline__ void tp_pull_at(const double* __restrict__ node, const SlabGeom& g, double (&f)[9], unsigned long long pol = 0ull)
 {
 #pragma unroll
   for (int q = 0; q < 9; q++)
   {
     const double* a = node + ((long long)q * g.plane - (long long)CX(q) * g.pitch - CY(q));
-    if constexpr (LAST) f[q] = LBM_TP_LDLAST(a);
-    else f[q] = __ldg(a);
+#if LBM_TP_HINTS
+    f[q] = ld_l2_hint(a, pol);
+#else
+    f[q] = __ldg(a);
+#endif
   }
 }
 
@@ -366,11 +383,17 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
   const double* pb = bsrc + o0;
   const long long back = (long long)LAG * g.pitch;
 
+#if LBM_TP_HINTS
+  const unsigned long long pol_first = l2_policy_evict_last(), pol_second = l2_policy_evict_first();
+#else
+  const unsigned long long pol_first = 0ull, pol_second = 0ull;
+#endif
+
   auto collide_row = [&](int sc) {
     // the second pull of this row (an L2 hit) first, so that its latency hides under the stencil arithmetic
     double fr[9], fb[9];
-    tp_pull_at<true>(pr - back, g, fr);
-    tp_pull_at<true>(pb - back, g, fb);
+    tp_pull_at(pr - back, g, fr, pol_second);
+    tp_pull_at(pb - back, g, fb, pol_second);
     TpStencil st;
     tp_ring_stencil<MODEL>(sm, sc, t, st);
     const double rr = S(C::F_RR, sc, t), rb = S(C::F_RB, sc, t);
@@ -381,8 +404,8 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
 #pragma unroll
     for (int q = 0; q < 9; q++)
     {
-      LBM_TP_ST(wr + (long long)q * g.plane, fr[q]);
-      LBM_TP_ST(wb + (long long)q * g.plane, fb[q]);
+      wr[(long long)q * g.plane] = fr[q];
+      wb[(long long)q * g.plane] = fb[q];
     }
   };
 
@@ -408,8 +431,8 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
       }
       else
       {
-        tp_pull_at(pr, g, fr);
-        tp_pull_at(pb, g, fb);
+        tp_pull_at(pr, g, fr, pol_first);
+        tp_pull_at(pb, g, fb, pol_first);
       }
     }
     // ---- B (pipelined): collision of row r - LAG
