@@ -471,6 +471,27 @@ k_pressure_apply(double* __restrict__ f, const SlabGeom g, int dst_lx, const dou
   }
 }
 
+// pack + apply in one launch when the source row and the written row live on the same slab (the single-GPU case:
+// two dependent tiny launches fewer on the side chain per pressure row)
+template <int EQ>
+static __global__ void __launch_bounds__(128)
+k_pressure_local(double* __restrict__ f, const SlabGeom g, int src_lx, int dst_lx, const int* __restrict__ src_bidx,
+                 const double* __restrict__ mom, double rho_bc, int y_lo, int y_hi)
+{
+  const int y = y_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= y_hi) return;
+  const long long os = node_off(g, src_lx, y), od = node_off(g, dst_lx, y);
+  const int j = src_bidx[y];
+  const double rho = mom[4 * j + 0], ux = mom[4 * j + 1], uy = mom[4 * j + 2];
+  const double uu = ux * ux + uy * uy;
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    const double t = feq_any<EQ == EQ_KBC ? EQ_INCOMP : EQ>(q, rho_bc * 1.0, ux, uy, uu);
+    f[q * g.plane + od] = (t + f[q * g.plane + os]) - feq_any<EQ>(q, rho, ux, uy, uu);
+  }
+}
+
 // ghost rows of a single slab that is its own neighbour (periodic wrap of solver::advect along
 // axis 0): row -1 <- row Xl-1 for c_x = +1 populations, row Xl <- row 0 for c_x = -1 populations.
 // With all_q != 0 every population is copied (models whose boundary rules read a whole opposite row).
