@@ -124,3 +124,20 @@ def test_double_shear_flow_reference_driver_golden():
         assert np.abs(uu[::st, ::st, 0] - g["ux"][k]).max() < tol, s
         assert np.abs(uu[::st, ::st, 1] - g["uy"][k]).max() < tol, s
         assert np.abs(rho[::st, ::st, 0] - g["rho"][k]).max() < tol, s
+
+
+@pytest.mark.parametrize("R,C", [(3, 3), (4, 5), (6, 131), (130, 7)])
+def test_tiny_and_ragged_grids(orc, R, C):
+    rng = np.random.default_rng(R * 100 + C)
+    m0 = 1.0 + 0.01 * rng.standard_normal((R, C))
+    u = 0.02 * rng.standard_normal((R, C, 2))
+    f = orc.kbc_equilibrium(m0, u, fresh_object=False)
+    for poiseuille in (None, (1.0003, 1.0)) if R >= 4 else (None,):
+        fo, a0, a1 = f.copy(), m0.copy(), u.copy()
+        d = cases.kbc(R, C, S2, poiseuille=poiseuille)
+        d.set_f(fo)
+        d.set_moments(a0[..., None], a1)
+        for _ in range(5):
+            orc.kbc_step(fo, a0, a1, S2, 0 if poiseuille is None else 1, *(poiseuille or (1.0, 1.0)))
+        d.step(5)
+        assert cases.relerr(d.get_f(), fo) < 1e-12, poiseuille

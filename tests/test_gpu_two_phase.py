@@ -207,3 +207,31 @@ def test_rk_fused_kernel_many_strips_and_bands(orc, Ln):
     assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
     rho, u = d.get_moments()
     assert np.abs(rho[..., 0] - st["rho"]).max() < 1e-12 and np.abs(u - st["u"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("R,C", [(5, 5), (6, 7), (7, 130), (9, 126), (131, 6)])
+def test_mrtcg_ragged_and_tiny_grids(orc, R, C):
+    """grids smaller than a band / narrower than a strip, strip edges at the domain edge, odd sizes"""
+    Fg = (6.25e-6, 0.0)
+    p = mrtcg_params(R, C, Fg, 1)
+    st = orc.mrtcg_init(p, "rt")
+    d = cases.mrtcg(R, C, Fg, 1)
+    d.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+    for _ in range(7):
+        orc.mrtcg_step(p, st)
+    d.step(7)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
+
+
+@pytest.mark.parametrize("Ln", [5, 8, 33, 129])
+def test_rk_ragged_and_tiny_grids(orc, Ln):
+    p = rk_params(Ln)
+    p.radius = max(1.5, Ln / 4.0)
+    st = orc.rk_init(p)
+    d = cases.rk(Ln)
+    d.set_f(st["r_adv"], 0)
+    d.set_f(st["b_adv"], 1)
+    for _ in range(6):
+        orc.rk_step(p, st)
+    d.step(6)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
