@@ -136,7 +136,7 @@ __device__ __forceinline__ void tp_stencil_global(const TpParams& p, const doubl
 {
   const long long o = mom_off(mg, x, y);
   const double* ph = mom + M_PH * mg.mplane;
-  st.gx = st.gy = st.rDxQx = st.rDyQy = st.bDxQx = st.bDyQy = 0.0;
+  st.gx = st.gy = st.DxQx = st.DyQy = 0.0;
   if constexpr (MODEL == TP_RK)
   {
     // rk_static_droplet_test.cpp:52-62: "x" kernel differentiates along axis 1, "y" kernel along axis 0
@@ -169,14 +169,12 @@ __device__ __forceinline__ void tp_stencil_global(const TpParams& p, const doubl
         if (a != 0)
         {
           st.gx += (w * (double)a) * phv;
-          st.rDxQx += (w * (double)a) * ((p.cr * rr) * ux);
-          st.bDxQx += (w * (double)a) * ((p.cb * rb) * ux);
+          st.DxQx += (w * (double)a) * ((p.cr * rr + p.cb * rb) * ux);
         }
         if (b != 0)
         {
           st.gy += (w * (double)b) * phv;
-          st.rDyQy += (w * (double)b) * ((p.cr * rr) * uy);
-          st.bDyQy += (w * (double)b) * ((p.cb * rb) * uy);
+          st.DyQy += (w * (double)b) * ((p.cr * rr + p.cb * rb) * uy);
         }
       }
   }
@@ -191,7 +189,7 @@ k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict_
                       double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom,
                       const TpParams p, int row_begin, int row_end)
 {
-  constexpr int NF = MODEL == TP_MRTCG ? 5 : 1;
+  constexpr int NF = MODEL == TP_MRTCG ? 3 : 1;
   __shared__ double sm[NF][SM_X][SM_Y + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int x_t = row_begin + blockIdx.y * TILE_X, y_t = 1 + blockIdx.x * TILE_Y;  // tile origin
@@ -208,10 +206,9 @@ k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict_
     {
       const double rr = mom[M_RR * mg.mplane + k], rb = mom[M_RB * mg.mplane + k];
       const double ux = mom[M_UX * mg.mplane + k], uy = mom[M_UY * mg.mplane + k];
-      sm[1][i][j] = (p.cr * rr) * ux;
-      sm[2][i][j] = (p.cr * rr) * uy;
-      sm[3][i][j] = (p.cb * rb) * ux;
-      sm[4][i][j] = (p.cb * rb) * uy;
+      const double cq = p.cr * rr + p.cb * rb;
+      sm[1][i][j] = cq * ux;
+      sm[2][i][j] = cq * uy;
     }
   }
   __syncthreads();
@@ -219,7 +216,7 @@ k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict_
   if (x >= row_end || y > g.Y - 2) return;
 
   TpStencil st;
-  st.gx = st.gy = st.rDxQx = st.rDyQy = st.bDxQx = st.bDyQy = 0.0;
+  st.gx = st.gy = st.DxQx = st.DyQy = 0.0;
   const int ci = ty + HALO, cj = tx + HALO;
   if constexpr (MODEL == TP_RK)
   {
@@ -246,14 +243,12 @@ k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict_
         if (a != 0)
         {
           st.gx += (w * (double)a) * sm[0][ci + a][cj + b];
-          st.rDxQx += (w * (double)a) * sm[1][ci + a][cj + b];
-          st.bDxQx += (w * (double)a) * sm[3][ci + a][cj + b];
+          st.DxQx += (w * (double)a) * sm[1][ci + a][cj + b];
         }
         if (b != 0)
         {
           st.gy += (w * (double)b) * sm[0][ci + a][cj + b];
-          st.rDyQy += (w * (double)b) * sm[2][ci + a][cj + b];
-          st.bDyQy += (w * (double)b) * sm[4][ci + a][cj + b];
+          st.DyQy += (w * (double)b) * sm[2][ci + a][cj + b];
         }
       }
   }
@@ -285,8 +280,8 @@ struct TpFused
 {
   static constexpr int H = MODEL == TP_MRTCG ? 2 : 1;   // stencil half-width
   static constexpr int NR = 2 * H + 2;                  // ring rows: 2H+1 live + the one being written
-  // ring fields: phase, [Q_rx, Q_ry, Q_bx, Q_by,] rho_r, rho_b, u_x, u_y
-  static constexpr int NF = MODEL == TP_MRTCG ? 9 : 5;
+  // ring fields: phase, [Q_x, Q_y,] rho_r, rho_b, u_x, u_y
+  static constexpr int NF = MODEL == TP_MRTCG ? 7 : 5;
   static constexpr int F_RR = NF - 4, F_RB = NF - 3, F_UX = NF - 2, F_UY = NF - 1;
   static constexpr int USEFUL = TPF_NT - 2 * H;         // columns a strip collides
   static constexpr size_t SMEM = sizeof(double) * NF * NR * TPF_NT;
@@ -299,7 +294,7 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
   using C = TpFused<MODEL>;
   constexpr int NR = C::NR, NT = TPF_NT;
   auto S = [&](int f, int slot, int col) -> double { return sm[(f * NR + slot) * NT + col]; };
-  st.gx = st.gy = st.rDxQx = st.rDyQy = st.bDxQx = st.bDyQy = 0.0;
+  st.gx = st.gy = st.DxQx = st.DyQy = 0.0;
   if constexpr (MODEL == TP_RK)
   {
 #pragma unroll
@@ -330,14 +325,12 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
         if (a != 0)
         {
           st.gx += (w * (double)a) * S(0, sa, t + b);
-          st.rDxQx += (w * (double)a) * S(1, sa, t + b);
-          st.bDxQx += (w * (double)a) * S(3, sa, t + b);
+          st.DxQx += (w * (double)a) * S(1, sa, t + b);
         }
         if (b != 0)
         {
           st.gy += (w * (double)b) * S(0, sa, t + b);
-          st.rDyQy += (w * (double)b) * S(2, sa, t + b);
-          st.bDyQy += (w * (double)b) * S(4, sa, t + b);
+          st.DyQy += (w * (double)b) * S(2, sa, t + b);
         }
       }
     }
@@ -360,7 +353,7 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
 #define LBM_TPF_MINB_RK 3
 #endif
 template <int MODEL, bool PIPE>
-__global__ void __launch_bounds__(TPF_NT, MODEL == TP_MRTCG ? LBM_TPF_MINB : LBM_TPF_MINB_RK)
+__global__ void __launch_bounds__(TPF_NT, MODEL == TP_MRTCG ? (PIPE ? LBM_TPF_MINB : LBM_TPF_MINB + 1) : LBM_TPF_MINB_RK)
 k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
            double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const TpParams p,
            const unsigned char* __restrict__ rowflag, int rows_per_block)
@@ -458,10 +451,9 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
       S(0, slot, t) = ph;
       if constexpr (MODEL == TP_MRTCG)
       {
-        S(1, slot, t) = (p.cr * rr) * ux;
-        S(2, slot, t) = (p.cr * rr) * uy;
-        S(3, slot, t) = (p.cb * rb) * ux;
-        S(4, slot, t) = (p.cb * rb) * uy;
+        const double cq = p.cr * rr + p.cb * rb;
+        S(1, slot, t) = cq * ux;
+        S(2, slot, t) = cq * uy;
       }
       S(C::F_RR, slot, t) = rr;
       S(C::F_RB, slot, t) = rb;

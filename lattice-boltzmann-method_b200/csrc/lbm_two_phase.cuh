@@ -149,7 +149,10 @@ __device__ __forceinline__ double tp_feq(int q, double rho_k, const double (&phi
 struct TpStencil
 {
   double gx, gy;               // grad(phase): MRTCG axis-0 / axis-1 derivatives; RK the driver's swapped pair
-  double rDxQx, rDyQy, bDxQx, bDyQy;  // MRTCG only
+  // MRTCG only: d/dx of Q_x and d/dy of Q_y, Q = Q_r + Q_b = (c_r rho_r + c_b rho_b) u.  update_C (:320-336) wants
+  // these per colour, but only the colour SUM of C enters the update (see tp_collide) and the differences are
+  // linear, so the two colours' momentum fields are added before they are differentiated.
+  double DxQx, DyQy;
 };
 
 // One two-colour collision in registers: fr/fb in = post-stream, out = post-collision.
@@ -223,8 +226,8 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
     // ---- m = S M d + C on the six non-conserved moments (M :130-142; S = diag(0,1.25,1.14,0,1.6,0,1.6,s_nu,s_nu)
     //      :384-387 + update_S; C: update_C :320-336, both colours)
     const double SA = s[0] + s[1], SD = s[2] + s[3];
-    const double DQ1 = (st.rDxQx + st.rDyQy) + (st.bDxQx + st.bDyQy);
-    const double DQ7 = (st.rDxQx - st.rDyQy) + (st.bDxQx - st.bDyQy);
+    const double DQ1 = st.DxQx + st.DyQy;
+    const double DQ7 = st.DxQx - st.DyQy;
     const double m_e = 1.25 * ((2.0 * SD - SA) - 4.0 * d0) + (3.0 * (1.0 - 0.5 * 1.25)) * DQ1;
     const double m_eps = 1.14 * ((SD - 2.0 * SA) + 4.0 * d0);
     const double m_qx = 1.6 * ((a[2] - a[3]) - 2.0 * a[0]);
