@@ -27,8 +27,9 @@
 #include "lbm_internal.hpp"
 #include "lbm_two_phase.cuh"
 
-// L2 eviction hints of the fused kernel (see tp_pull_at); compile-time switch.  A/B on B200: MRTCG 16384^2
-// 13.49 -> 13.60 GLUPS (DRAM reads 179 -> 169 B/node), RK 4096^2 16.49 -> 16.22 GLUPS: within noise, off by default.
+// L2 eviction hints of the fused kernel (see tp_pull_at); compile-time switch: 1 = the two reads, 2 = + evict_first
+// stores.  A/B on B200 (MRTCG 8192^2): DRAM reads 185 -> 165 -> 157 B/node (ideal 153), but 15.62 / 15.60 / 15.65 GLUPS
+// at 16384^2 and RK 16.84 / 16.59 / 16.27: the kernel is not DRAM-bound, the hints buy nothing.  Off by default.
 #ifndef LBM_TP_HINTS
 #define LBM_TP_HINTS 0
 #endif
@@ -398,8 +399,13 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
 #pragma unroll
     for (int q = 0; q < 9; q++)
     {
+#if LBM_TP_HINTS >= 2
+      asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(wr + (long long)q * g.plane), "d"(fr[q]), "l"(pol_second) : "memory");
+      asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(wb + (long long)q * g.plane), "d"(fb[q]), "l"(pol_second) : "memory");
+#else
       wr[(long long)q * g.plane] = fr[q];
       wb[(long long)q * g.plane] = fb[q];
+#endif
     }
   };
 
