@@ -340,7 +340,8 @@ def measured_hbm_peak():
 
 def ncu_traffic_per_launch(workload, X, Y):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture
-    (profiles/roofline_traffic.json), only when it was taken at this grid size"""
+    (profiles/roofline_traffic.json), only when it was taken at this grid size; on the same basis as `achieved`
+    (all of a step's launches of that kernel: the single-phase step has an early-rows and a bulk-rows launch)"""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
             return json.load(fh).get(f"{workload}_{X}x{Y}_bytes_per_launch")
