@@ -159,15 +159,22 @@ __device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double
 // M^-1 of kbc::collide() step 4 (src/ulbm.cpp:114-122; the sign flip of :123 is left to the caller)
 __device__ __forceinline__ void kbc_minv(const double (&g)[9], double (&c)[9])
 {
+  // the halves and quarters are exact scalings, taken once; each output is then a sum of a pair term and a shared term
+  const double h1 = 0.5 * g[1], h2 = 0.5 * g[2], h6 = 0.5 * g[6], h7 = 0.5 * g[7], h8 = 0.5 * g[8];
+  const double q3 = 0.25 * g[3], q4 = 0.25 * g[4];
+  const double a8 = (q3 + q4) - h8, b8 = (q3 - q4) - h8;
+  const double d17 = h1 - h7, d26 = h2 - h6;
   c[0] = g[0] - g[3] + g[8];
-  c[1] = 0.5 * g[1] + 0.25 * g[3] + 0.25 * g[4] - 0.5 * g[7] - 0.5 * g[8];
-  c[2] = 0.5 * g[2] + 0.25 * g[3] - 0.25 * g[4] - 0.5 * g[6] - 0.5 * g[8];
-  c[3] = -0.5 * g[1] + 0.25 * g[3] + 0.25 * g[4] + 0.5 * g[7] - 0.5 * g[8];
-  c[4] = -0.5 * g[2] + 0.25 * g[3] - 0.25 * g[4] + 0.5 * g[6] - 0.5 * g[8];
-  c[5] = 0.25 * (g[5] + g[6] + g[7] + g[8]);
-  c[6] = 0.25 * (-g[5] + g[6] - g[7] + g[8]);
-  c[7] = 0.25 * (g[5] - g[6] - g[7] + g[8]);
-  c[8] = 0.25 * (-g[5] - g[6] + g[7] + g[8]);
+  c[1] = a8 + d17;
+  c[3] = a8 - d17;
+  c[2] = b8 + d26;
+  c[4] = b8 - d26;
+  const double p58 = 0.25 * (g[5] + g[8]), m58 = 0.25 * (g[8] - g[5]);
+  const double p67 = 0.25 * (g[6] + g[7]), m67 = 0.25 * (g[6] - g[7]);
+  c[5] = p58 + p67;
+  c[7] = p58 - p67;
+  c[6] = m58 + m67;
+  c[8] = m58 - m67;
 }
 
 // kbc::collide() of one node (src/ulbm.cpp:91-126: eval_central_momenta :264-320, eval_gamma :138-148,
