@@ -358,10 +358,11 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
   for (int i = 0; i < n; i++)
   {
     if (!ds[i] || !ds[i]->have_state || !ds[i]->committed) { set_error("lbm_step_group: slab %d has no state / uncommitted rules", i); return LBM_ERR_INVALID; }
-    if (ds[i]->tp) { set_error("lbm_step_group: two-phase slabs are stepped over NCCL (lbm_comm_init), not linked"); return LBM_ERR_UNSUPPORTED; }
+    if ((ds[i]->tp != nullptr) != (ds[0]->tp != nullptr)) { set_error("lbm_step_group: slabs of different models"); return LBM_ERR_INVALID; }
     if (ds[i]->stages.size() != ds[0]->stages.size()) { set_error("lbm_step_group: slabs carry different rule lists"); return LBM_ERR_INVALID; }
     if (ds[i]->cur != ds[0]->cur || ds[i]->post_stream != ds[0]->post_stream) { set_error("lbm_step_group: slabs are out of step"); return LBM_ERR_INVALID; }
   }
+  if (ds[0]->tp) return tp_step_group(ds, n, n_steps);
   auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
   for (int i = 0; i < n; i++)
   {

@@ -1160,7 +1160,15 @@ int lbm_set_moments(lbm_domain* d, const double* rho, const double* u)
 }
 
 // ---------------------------------------------------------------- stepping
-static int step_once(lbm_domain* d) { return d->tp ? tp_step(d) : bgk_step_once(d); }
+static int step_once(lbm_domain* d)
+{
+  if (d->tp && (d->link_lo || d->link_hi))
+  {
+    set_error("lbm_step: this slab is linked to neighbours; advance the set with lbm_step_group");
+    return LBM_ERR_INVALID;
+  }
+  return d->tp ? tp_step(d) : bgk_step_once(d);
+}
 
 // One steady-state step PAIR captured into a CUDA graph (a pair returns every A/B toggle — buffers,
 // listed-node moments, IBM force slots — to where it started, so the graph replays as is).  For the

@@ -194,6 +194,7 @@ int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st);
 int tp_create(lbm_domain* d);
 int tp_destroy(lbm_domain* d);
 int tp_step(lbm_domain* d);
+int tp_step_group(lbm_domain* const* ds, int n, int n_steps);  // linked two-phase slabs in lock step
 int tp_commit(lbm_domain* d);
 int tp_export(lbm_domain* d);
 int tp_stage_moments(lbm_domain* d, double* stage);  // planes -> [6][N] staging (rho, u, phase, rho_r, rho_b)

@@ -950,24 +950,6 @@ static int tp_launch_fused(lbm_domain* d)
   TwoPhaseState* tp = d->tp;
   using C = TpFused<MODEL>;
   const int s = d->cur, t = d->cur ^ 1;
-  {
-    // moments of the thin region the planes stay authoritative for, its padding and the cut rows
-    ProfScope ps(d, LBM_PROF_MOMENTS);
-    if (tp->n_region > 0)
-    {
-      k_tp_moments_nodes<MODEL><<<cdiv(tp->n_region, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom,
-                                                                                tp->p, tp->d_region, tp->n_region);
-      d->launches++;
-    }
-    if (d->nb > 0)
-    {
-      k_tp_moments_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom,
-                                                                                    tp->p, table_of(d), nullptr, nullptr);
-      d->launches++;
-    }
-    LBM_TRY(tp_pad(d));
-    LBM_TRY(comm_exchange_moments(d));
-  }
   const int Yi = d->g.Y - 2;
   if (Yi > 0)
   {
@@ -992,13 +974,44 @@ static int tp_launch_fused(lbm_domain* d)
   return LBM_OK;
 }
 
-int tp_step(lbm_domain* d)
+// ---- the phases of one two-phase step.  lbm_step runs them back to back on one slab (NCCL halos inside);
+//      lbm_step_group interleaves them across linked slabs.
+// pre: the thin region of the moment planes that stays authoritative (listed nodes, their neighbourhood, edge and
+//      cut rows) and its replicate padding, from the stored post-collision state
+static int tp_phase_pre(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
   LBM_TRY(tp_build_region(d));
+  if (d->post_stream) return LBM_OK;  // first step after an import: the planes are full and hold the caller's u
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  const int s = d->cur;
+  if (tp->n_region > 0)
+  {
+    if (tp->model == TP_MRTCG)
+      k_tp_moments_nodes<TP_MRTCG><<<cdiv(tp->n_region, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, tp->d_region, tp->n_region);
+    else
+      k_tp_moments_nodes<TP_RK><<<cdiv(tp->n_region, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, tp->d_region, tp->n_region);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    if (tp->model == TP_MRTCG)
+      k_tp_moments_listed<TP_MRTCG, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr);
+    else
+      k_tp_moments_listed<TP_RK, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr);
+    d->launches++;
+  }
+  LBM_TRY(tp_pad(d));
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+// main: collision of every node (fused kernel + listed nodes; two-pass MODE_LOCAL for a post-stream state)
+static int tp_phase_main(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
   if (d->post_stream)
   {
-    // first step after an import: the caller's u lives in the (full) moment planes
     if (tp->model == TP_MRTCG) LBM_TRY((tp_launch_collide<TP_MRTCG, MODE_LOCAL>(d)));
     else LBM_TRY((tp_launch_collide<TP_RK, MODE_LOCAL>(d)));
   }
@@ -1010,11 +1023,111 @@ int tp_step(lbm_domain* d)
   d->cur ^= 1;
   d->post_stream = false;
   tp->planes_full = false;
+  return LBM_OK;
+}
+
+int tp_step(lbm_domain* d)
+{
+  LBM_TRY(tp_phase_pre(d));
+  if (!d->post_stream)
+  {
+    ProfScope ps(d, LBM_PROF_MOMENTS);
+    LBM_TRY(comm_exchange_moments(d));  // two plane rows across every cut (NCCL); nothing on a single slab
+  }
+  LBM_TRY(tp_phase_main(d));
   {
     // the next step pulls from the buffer just written: its ghost rows
     ProfScope ps(d, LBM_PROF_GHOST);
     if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->stream));
     else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
+  }
+  return LBM_OK;
+}
+
+// two rows of the five moment planes from the linked neighbours across every INTERNAL cut (the global edge replicates)
+static int tp_link_halo(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  const int pm = tp->mg.pm, Xl = d->g.Xl;
+  const size_t bytes = sizeof(double) * 2 * pm;
+  for (int f = 0; f < M_COUNT; f++)
+  {
+    double* pl = tp->mom + (long long)f * tp->mg.mplane;
+    if (d->cfg.x0 > 0 && d->link_lo)  // rows -2, -1 <- the lower slab's last two rows
+    {
+      lbm_domain* o = d->link_lo;
+      const double* src = o->tp->mom + (long long)f * o->tp->mg.mplane + (long long)o->g.Xl * o->tp->mg.pm;
+      if (o->cfg.device == d->cfg.device) LBM_CUDA(cudaMemcpyAsync(pl, src, bytes, cudaMemcpyDeviceToDevice, d->stream));
+      else LBM_CUDA(cudaMemcpyPeerAsync(pl, d->cfg.device, src, o->cfg.device, bytes, d->stream));
+      d->launches++;
+    }
+    if (d->cfg.x1 < d->cfg.X && d->link_hi)  // rows Xl, Xl+1 <- the upper slab's first two rows
+    {
+      lbm_domain* o = d->link_hi;
+      const double* src = o->tp->mom + (long long)f * o->tp->mg.mplane + (long long)2 * o->tp->mg.pm;
+      double* dst = pl + (long long)(Xl + 2) * pm;
+      if (o->cfg.device == d->cfg.device) LBM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d->stream));
+      else LBM_CUDA(cudaMemcpyPeerAsync(dst, d->cfg.device, src, o->cfg.device, bytes, d->stream));
+      d->launches++;
+    }
+  }
+  return LBM_OK;
+}
+
+// Linked two-phase slabs in lock step (lbm_step_group): the phases of tp_step interleaved across the slabs, every
+// cross-slab read ordered by events on the slabs' streams:
+//   pre_i   waits until the neighbours finished reading slab i's plane rows (their halo of the step before)
+//   halo_i  waits for the neighbours' pre;   main_i;   ghost_i waits for the neighbours' main
+int tp_step_group(lbm_domain* const* ds, int n, int n_steps)
+{
+  auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
+  auto wait_neighbours = [&](lbm_domain* d, cudaEvent_t lbm_domain::*ev) -> int {
+    for (lbm_domain* o : {d->link_lo, d->link_hi})
+      if (o && o != d) LBM_CUDA(cudaStreamWaitEvent(d->stream, o->*ev, 0));
+    return LBM_OK;
+  };
+  for (int i = 0; i < n; i++)
+  {
+    LBM_CUDA(on(ds[i]));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_begin, ds[i]->stream));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_packet, ds[i]->stream));  // "nobody is reading my planes"
+  }
+  for (int s = 0; s < n_steps; s++)
+  {
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(on(ds[i]));
+      LBM_TRY(wait_neighbours(ds[i], &lbm_domain::ev_packet));
+      LBM_TRY(tp_phase_pre(ds[i]));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_ready, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(on(ds[i]));
+      LBM_TRY(wait_neighbours(ds[i], &lbm_domain::ev_ready));
+      LBM_TRY(tp_link_halo(ds[i]));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_packet, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(on(ds[i]));
+      LBM_TRY(tp_phase_main(ds[i]));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_stage, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      lbm_domain* d = ds[i];
+      LBM_CUDA(on(d));
+      LBM_TRY(wait_neighbours(d, &lbm_domain::ev_stage));
+      ProfScope ps(d, LBM_PROF_GHOST);
+      if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur, d->stream));
+      else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
+    }
+  }
+  for (int i = 0; i < n; i++)
+  {
+    LBM_CUDA(on(ds[i]));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_end, ds[i]->stream));
   }
   return LBM_OK;
 }
