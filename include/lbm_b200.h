@@ -56,6 +56,9 @@ typedef enum
   LBM_MODEL_BGK_ADE = 1, /* fluid + advection-diffusion lattice: test/rectangle_sedimentation_test.cpp */
   LBM_MODEL_MRTCG = 2,   /* MRT colour gradient: test/mrtcg_rayleigh_taylor.cpp, test/mrtcg_static_droplet.cpp */
   LBM_MODEL_RK = 3,      /* Rothman-Keller droplet: test/rk_static_droplet_test.cpp */
+  LBM_MODEL_MRT_CSF = 5, /* MRT colour gradient with a continuum-surface-force perturbation: test/mrt_rayleigh_taylor.cpp
+                            (curvature of the interface normal, interfacial tension carried into the next velocity);
+                            one slab only */
   LBM_MODEL_KBC = 4      /* entropic central-moment collision ulbm::d2q9::kbc (src/ulbm.hpp:11-90, src/ulbm.cpp):
                             test/ulbm_double_shear_flow.cpp, test/ulbm_poiseuille.cpp; omega = the class's s2 */
 } lbm_model;
@@ -213,6 +216,8 @@ int lbm_snapshot_async(lbm_domain* d, int lattice, double* rho, double* u, doubl
 int lbm_snapshot_wait(lbm_domain* d);
 /* two-phase fields of the current state: phase {X,Y} (eval_phase_field), rho_r, rho_b {X,Y}     */
 int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b);
+/* LBM_MODEL_MRT_CSF: interf_tension {X,Y,2} of the last step (the driver snapshots it: mrt_rayleigh_taylor.cpp:485-486) */
+int lbm_get_interfacial_tension(lbm_domain* d, double* Fs_aos);
 /* two-phase models carry u between steps (mrtcg_rayleigh_taylor.cpp:476-477); initial value.      */
 int lbm_set_u(lbm_domain* d, const double* u_aos);
 /* LBM_MODEL_KBC: the class keeps m0 / m1 as members that its first collide() reads before they are recomputed

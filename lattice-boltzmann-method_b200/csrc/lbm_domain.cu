@@ -876,7 +876,7 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
   *out = nullptr;
   if (cfg->X < 3 || cfg->Y < 3) { set_error("lbm_create: grid %dx%d too small (need >= 3x3)", cfg->X, cfg->Y); return LBM_ERR_INVALID; }
   if (cfg->x0 < 0 || cfg->x1 > cfg->X || cfg->x1 <= cfg->x0) { set_error("lbm_create: bad slab rows [%d,%d) of %d", cfg->x0, cfg->x1, cfg->X); return LBM_ERR_INVALID; }
-  if (cfg->model < LBM_MODEL_BGK || cfg->model > LBM_MODEL_KBC) { set_error("lbm_create: unknown model %d", cfg->model); return LBM_ERR_INVALID; }
+  if (cfg->model < LBM_MODEL_BGK || cfg->model > LBM_MODEL_MRT_CSF) { set_error("lbm_create: unknown model %d", cfg->model); return LBM_ERR_INVALID; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
   {
@@ -932,7 +932,7 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
   LBM_CUDA(cudaEventCreate(&d->ev_end));
   for (cudaEvent_t* e : {&d->ev_ready, &d->ev_early, &d->ev_side, &d->ev_stage, &d->ev_packet})
     LBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-  if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK)
+  if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK || cfg->model == LBM_MODEL_MRT_CSF)
   {
     int s = tp_create(d);
     if (s != LBM_OK) { lbm_destroy(d); return s; }

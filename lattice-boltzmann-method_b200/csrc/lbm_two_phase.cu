@@ -52,6 +52,7 @@ struct TwoPhaseState
   int n_region = 0;
   int rows_per_block = 64;
   bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
+  double* aux = nullptr;               // TP_CSF: A_COUNT planes in the moment-plane geometry (normal n, interfacial tension Fs)
   int rpb_override = 0;
 };
 
@@ -597,12 +598,11 @@ k_tp_moments_listed(const double* __restrict__ rsrc, const double* __restrict__ 
 }
 
 // replicate padding of the moment planes: columns first (all owned rows), then rows (whole padded width)
-__global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const MomGeom mg)
+__global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int nplanes)
 {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= g.Xl) return;
-#pragma unroll
-  for (int f = 0; f < M_COUNT; f++)
+  for (int f = 0; f < nplanes; f++)
   {
     double* pl = mom + f * mg.mplane;
     const double lo = pl[mom_off(mg, x, 0)], hi = pl[mom_off(mg, x, g.Y - 1)];
@@ -615,13 +615,12 @@ __global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const 
 
 // lo_global / hi_global: this slab holds the global first / last row, where the padding replicates;
 // elsewhere the two ghost rows come from the neighbouring slab (lbm_comm.cu)
-__global__ void k_tp_pad_rows(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int lo_global, int hi_global)
+__global__ void k_tp_pad_rows(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int lo_global, int hi_global, int nplanes)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // padded column index 0 .. Y+3
   if (j >= g.Y + 4) return;
   const int y = j - 2;
-#pragma unroll
-  for (int f = 0; f < M_COUNT; f++)
+  for (int f = 0; f < nplanes; f++)
   {
     double* pl = mom + f * mg.mplane;
     if (lo_global)
@@ -747,7 +746,7 @@ int tp_create(lbm_domain* d)
 {
   TwoPhaseState* tp = new TwoPhaseState();
   d->tp = tp;
-  tp->model = d->cfg.model == LBM_MODEL_MRTCG ? TP_MRTCG : TP_RK;
+  tp->model = d->cfg.model == LBM_MODEL_MRTCG ? TP_MRTCG : (d->cfg.model == LBM_MODEL_MRT_CSF ? TP_CSF : TP_RK);
   tp->mg.pm = ((d->g.Y + 4 + 15) / 16) * 16;
   tp->mg.mplane = (long long)(d->g.Xl + 4) * tp->mg.pm;
   const size_t bytes = sizeof(double) * M_COUNT * tp->mg.mplane;
@@ -773,13 +772,22 @@ int tp_create(lbm_domain* d)
   p.Fg0 = c.Fg[0]; p.Fg1 = c.Fg[1];
   p.add_force = c.add_force;
   p.delta = c.delta;
-  if (tp->model == TP_MRTCG)
+  if (tp->model != TP_RK)
   {
     // relaxation_function{r, b, delta}: omegas from nu and the colour's own cs2 (mrtcg_rayleigh_taylor.cpp:57-66)
     p.r_val = 1.0 / (0.5 + c.red.nu / r_cs2);
     p.b_val = 1.0 / (0.5 + c.blue.nu / b_cs2);
+    // TP_CSF: omega2_k = A_k (1 - rlx_k / 2) eta with colour::rlx = 1 / (0.5 + nu / cs2) (src/colour.cpp:38-39)
+    p.w2sum = c.red.A * (1.0 - 0.5 * p.r_val) + c.blue.A * (1.0 - 0.5 * p.b_val);
   }
-  else
+  if (tp->model == TP_CSF)
+  {
+    p.add_force = 1;  // mrt_rayleigh_taylor.cpp:527-531
+    const size_t ab = sizeof(double) * 4 * tp->mg.mplane;
+    LBM_CUDA(cudaMalloc(&tp->aux, ab));
+    LBM_CUDA(cudaMemset(tp->aux, 0, ab));
+  }
+  if (tp->model == TP_RK)
   {
     // colour::init_omega with cs2 = 1/3, blended in tau space (rk_static_droplet_test.cpp:264-265,320-323)
     const double cs2 = 1.0 / 3.0;
@@ -812,6 +820,7 @@ int tp_destroy(lbm_domain* d)
 {
   if (!d->tp) return LBM_OK;
   cudaFree(d->tp->mom);
+  cudaFree(d->tp->aux);
   cudaFree(d->tp->d_rowflag);
   cudaFree(d->tp->d_region);
   delete d->tp;
@@ -834,9 +843,9 @@ static BoundaryTable table_of(lbm_domain* d)
 int tp_pad(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
   const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
-  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi);
+  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
   d->launches += 2;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
@@ -1026,8 +1035,12 @@ static int tp_phase_main(lbm_domain* d)
   return LBM_OK;
 }
 
+static int csf_step(lbm_domain* d);
+static int csf_fill_planes(lbm_domain* d);
+
 int tp_step(lbm_domain* d)
 {
+  if (d->tp->model == TP_CSF) return csf_step(d);
   LBM_TRY(tp_phase_pre(d));
   if (!d->post_stream)
   {
@@ -1080,6 +1093,12 @@ static int tp_link_halo(lbm_domain* d)
 //   halo_i  waits for the neighbours' pre;   main_i;   ghost_i waits for the neighbours' main
 int tp_step_group(lbm_domain* const* ds, int n, int n_steps)
 {
+  for (int i = 0; i < n; i++)
+    if (ds[i]->tp->model == TP_CSF)
+    {
+      set_error("lbm_step_group: LBM_MODEL_MRT_CSF runs on one slab (its curvature needs a 4-row halo that is not exchanged yet)");
+      return LBM_ERR_UNSUPPORTED;
+    }
   auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
   auto wait_neighbours = [&](lbm_domain* d, cudaEvent_t lbm_domain::*ev) -> int {
     for (lbm_domain* o : {d->link_lo, d->link_hi})
@@ -1138,6 +1157,7 @@ static int tp_fill_planes(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
   if (tp->planes_full || d->post_stream) return LBM_OK;
+  if (tp->model == TP_CSF) return csf_fill_planes(d);
   if (tp->model == TP_MRTCG) LBM_TRY(tp_launch_moments<TP_MRTCG>(d, d->cur, nullptr, nullptr));
   else LBM_TRY(tp_launch_moments<TP_RK>(d, d->cur, nullptr, nullptr));
   tp->planes_full = true;
@@ -1170,7 +1190,8 @@ int tp_export(lbm_domain* d)
     LBM_CUDA(cudaGetLastError());
     return LBM_OK;
   }
-  if (d->tp->model == TP_MRTCG) return tp_launch_moments<TP_MRTCG>(d, d->cur, d->d_aos[0], d->d_aos[1]);
+  // (with output pointers the pass only pulls: no model arithmetic)
+  if (d->tp->model != TP_RK) return tp_launch_moments<TP_MRTCG>(d, d->cur, d->d_aos[0], d->d_aos[1]);
   return tp_launch_moments<TP_RK>(d, d->cur, d->d_aos[0], d->d_aos[1]);
 }
 
@@ -1189,7 +1210,7 @@ int tp_stage_moments(lbm_domain* d, double* stage)
 int tp_refresh_moments(lbm_domain* d)
 {
   const long long N = (long long)d->g.Xl * d->g.Y;
-  if (d->tp->model == TP_MRTCG)
+  if (d->tp->model != TP_RK)  // TP_CSF: an import carries no interfacial tension (u = j / rho + Fg / (2 rho))
     k_tp_moments_local<TP_MRTCG><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p);
   else
     k_tp_moments_local<TP_RK><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p);
@@ -1197,6 +1218,234 @@ int tp_refresh_moments(lbm_domain* d)
   d->tp->planes_full = true;
   LBM_TRY(tp_pad(d));
   return comm_exchange_moments(d);
+}
+
+// ================================================================================================
+// TP_CSF — test/mrt_rayleigh_taylor.cpp.  First correct path: three passes per step over
+// full moment planes (moments -> normals -> collision), stencils straight from the padded planes.
+//   aux planes: A_NX, A_NY  n = -grad(phase) / (1e-20 + |grad|)  (padded like the moment planes: D differentiates them)
+//               A_FX, A_FY  interfacial tension Fs = -sigma/2 K grad(phase), carried into the next step's velocity
+// ================================================================================================
+enum AuxPlane { A_NX = 0, A_NY = 1, A_FX = 2, A_FY = 3 };
+
+// 5x5 isotropic differences of one padded plane at (x, y): dx along axis 0, dy along axis 1 (src/differential.hpp:9-40).
+// This model divides by 1e-20 + |grad(phase)| (mrt_rayleigh_taylor.cpp:508): where the phase field is constant to
+// machine precision the "normal" is the sign pattern of the ROUNDING RESIDUE of this sum, and the curvature of the
+// rim nodes differentiates it.  To stay on the CPU reference there as far as that is possible at all, the sum runs in
+// the order of a plain convolution loop (rows, then columns) with separately rounded products and additions — no
+// fused multiply-add — like the oracle's orc_diff5; an exactly constant neighbourhood then leaves the same residue.
+__device__ __forceinline__ void diff5_at(const double* __restrict__ pl, const MomGeom& mg, int x, int y, double& dx, double& dy)
+{
+  const long long o = mom_off(mg, x, y);
+  dx = dy = 0.0;
+#pragma unroll
+  for (int a = -2; a <= 2; a++)
+#pragma unroll
+    for (int b = -2; b <= 2; b++)
+    {
+      if (a == 0 && b == 0) continue;
+      const double v = pl[o + (long long)a * mg.pm + b];
+      const double w = XI5(a, b);
+      if (a != 0) dx = __dadd_rn(dx, __dmul_rn(w * (double)a, v));
+      if (b != 0) dy = __dadd_rn(dy, __dmul_rn(w * (double)b, v));
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_csf_moments_interior(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                       double* __restrict__ mom, const double* __restrict__ aux, const TpParams p)
+{
+  const int y = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (y > g.Y - 2) return;
+  double fr[9], fb[9];
+  tp_load_interior<MODE>(rsrc, g, x, y, fr);
+  tp_load_interior<MODE>(bsrc, g, x, y, fb);
+  const long long k = mom_off(mg, x, y);
+  double rr, rb, ux, uy, ph;
+  tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + k], aux[A_FY * mg.mplane + k]);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_csf_moments_listed(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                     double* __restrict__ mom, const double* __restrict__ aux, const TpParams p, const BoundaryTable t)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n) return;
+  const int x = t.x[i], y = t.y[i];
+  double fr[9], fb[9];
+  tp_load_listed<MODE>(rsrc, g, t, 0, i, x, y, fr);
+  tp_load_listed<MODE>(bsrc, g, t, 1, i, x, y, fb);
+  const long long k = mom_off(mg, x, y);
+  double rr, rb, ux, uy, ph;
+  tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + k], aux[A_FY * mg.mplane + k]);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
+// n = -grad(phase) / (1e-20 + |grad(phase)|)   (mrt_rayleigh_taylor.cpp:500-508)
+__global__ void __launch_bounds__(256)
+k_csf_normals(const double* __restrict__ mom, double* __restrict__ aux, const SlabGeom g, const MomGeom mg)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  double gx, gy;
+  diff5_at(mom + M_PH * mg.mplane, mg, x, y, gx, gy);
+  const double inv = 1.0 / (1e-20 + sqrt(gx * gx + gy * gy));
+  const long long k = mom_off(mg, x, y);
+  aux[A_NX * mg.mplane + k] = -gx * inv;
+  aux[A_NY * mg.mplane + k] = -gy * inv;
+}
+
+// collision of one node: stencils from the planes, curvature, interfacial tension (stored), tp_collide<TP_CSF>
+__device__ __forceinline__ void csf_collide_node(const TpParams& p, const double* __restrict__ mom, double* __restrict__ aux,
+                                                 const MomGeom& mg, int x, int y, double (&fr)[9], double (&fb)[9])
+{
+  TpStencil st;
+  tp_stencil_global<TP_MRTCG>(p, mom, mg, x, y, st);  // grad(phase), d/dx Q_x, d/dy Q_y
+  double dx_nx, dy_nx, dx_ny, dy_ny;
+  diff5_at(aux + A_NX * mg.mplane, mg, x, y, dx_nx, dy_nx);
+  diff5_at(aux + A_NY * mg.mplane, mg, x, y, dx_ny, dy_ny);
+  const long long k = mom_off(mg, x, y);
+  const double nx = aux[A_NX * mg.mplane + k], ny = aux[A_NY * mg.mplane + k];
+  // eval_local_curvature (:355-364); interf_tension = -0.5 sigma K grad (:510)
+  const double K = nx * ny * (dy_nx + dx_ny) - (nx * nx) * dy_ny - (ny * ny) * dx_nx;
+  st.Fsx = (-0.5 * p.sigma) * K * st.gx;
+  st.Fsy = (-0.5 * p.sigma) * K * st.gy;
+  aux[A_FX * mg.mplane + k] = st.Fsx;
+  aux[A_FY * mg.mplane + k] = st.Fsy;
+  const double rr = mom[M_RR * mg.mplane + k], rb = mom[M_RB * mg.mplane + k];
+  const double ux = mom[M_UX * mg.mplane + k], uy = mom[M_UY * mg.mplane + k], ph = mom[M_PH * mg.mplane + k];
+  tp_collide<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, st);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_csf_collide_interior(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
+                       double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom,
+                       double* __restrict__ aux, const TpParams p)
+{
+  const int y = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (y > g.Y - 2) return;
+  double fr[9], fb[9];
+  tp_load_interior<MODE>(rsrc, g, x, y, fr);
+  tp_load_interior<MODE>(bsrc, g, x, y, fb);
+  csf_collide_node(p, mom, aux, mg, x, y, fr, fb);
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    rdst[q * g.plane + o] = fr[q];
+    bdst[q * g.plane + o] = fb[q];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_csf_collide_listed(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
+                     double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom,
+                     double* __restrict__ aux, const TpParams p, const BoundaryTable t)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n) return;
+  const int x = t.x[i], y = t.y[i];
+  double fr[9], fb[9];
+  tp_load_listed<MODE>(rsrc, g, t, 0, i, x, y, fr);
+  tp_load_listed<MODE>(bsrc, g, t, 1, i, x, y, fb);
+  csf_collide_node(p, mom, aux, mg, x, y, fr, fb);
+  const long long o = node_off(g, x, y);
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    rdst[q * g.plane + o] = fr[q];
+    bdst[q * g.plane + o] = fb[q];
+  }
+}
+
+// rho_r, rho_b, u (with the stored interfacial tension), phase of the current post-stream state into the planes
+static int csf_fill_planes(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  const int Yi = d->g.Y - 2, w = d->cur;
+  if (Yi > 0)
+  {
+    dim3 grid(cdiv(Yi, 256), d->g.Xl);
+    k_csf_moments_interior<MODE_PULL><<<grid, 256, 0, d->stream>>>(d->buf[0][w], d->buf[1][w], d->g, tp->mg, tp->mom, tp->aux, tp->p);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    k_csf_moments_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][w], d->buf[1][w], d->g, tp->mg, tp->mom, tp->aux,
+                                                                            tp->p, table_of(d));
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  tp->planes_full = true;
+  return LBM_OK;
+}
+
+template <int MODE>
+static int csf_launch_collide(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  const int s = d->cur, t = d->cur ^ 1, Yi = d->g.Y - 2;
+  if (Yi > 0)
+  {
+    ProfScope ps(d, LBM_PROF_INTERIOR);
+    dim3 grid(cdiv(Yi, 128), d->g.Xl);
+    k_csf_collide_interior<MODE><<<grid, 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg, tp->mom,
+                                                             tp->aux, tp->p);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    ProfScope ps(d, LBM_PROF_BOUNDARY);
+    k_csf_collide_listed<MODE><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                       tp->mom, tp->aux, tp->p, table_of(d));
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+static int csf_step(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  if (comm_active(d) || d->link_lo || d->link_hi || d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X)
+  {
+    set_error("LBM_MODEL_MRT_CSF runs on one slab (its curvature needs a 4-row halo that is not exchanged yet)");
+    return LBM_ERR_UNSUPPORTED;
+  }
+  if (!d->post_stream && !tp->planes_full) LBM_TRY(csf_fill_planes(d));  // first step after an import: the caller's u
+  {
+    ProfScope ps(d, LBM_PROF_MOMENTS);
+    LBM_TRY(tp_pad(d));
+    const long long N = (long long)d->g.Xl * d->g.Y;
+    k_csf_normals<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg);
+    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 1, 1, 2);
+    d->launches += 3;
+  }
+  if (d->post_stream) LBM_TRY(csf_launch_collide<MODE_LOCAL>(d));
+  else LBM_TRY(csf_launch_collide<MODE_PULL>(d));
+  d->cur ^= 1;
+  d->post_stream = false;
+  tp->planes_full = false;
+  ProfScope ps(d, LBM_PROF_GHOST);
+  return wrap_ghost_rows_local(d, d->cur, d->stream);
 }
 
 }  // namespace lbm
@@ -1218,6 +1467,27 @@ int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b)
   if (rho_r) LBM_CUDA(cudaMemcpyAsync(rho_r, st + 4 * N, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
   if (rho_b) LBM_CUDA(cudaMemcpyAsync(rho_b, st + 5 * N, sizeof(double) * N, cudaMemcpyDeviceToHost, d->stream));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
+  return LBM_OK;
+}
+
+// interf_tension of the last step, {X,Y,2} (the driver snapshots it as gradx / grady, mrt_rayleigh_taylor.cpp:485-486)
+int lbm_get_interfacial_tension(lbm_domain* d, double* Fs_aos)
+{
+  if (!d || !d->tp || d->tp->model != TP_CSF || !Fs_aos) { set_error("lbm_get_interfacial_tension: LBM_MODEL_MRT_CSF domains only"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  const MomGeom mg = d->tp->mg;
+  const int Xl = d->g.Xl, Y = d->g.Y;
+  std::vector<double> fx((size_t)mg.mplane), fy((size_t)mg.mplane);
+  LBM_CUDA(cudaMemcpy(fx.data(), d->tp->aux + (long long)A_FX * mg.mplane, sizeof(double) * mg.mplane, cudaMemcpyDeviceToHost));
+  LBM_CUDA(cudaMemcpy(fy.data(), d->tp->aux + (long long)A_FY * mg.mplane, sizeof(double) * mg.mplane, cudaMemcpyDeviceToHost));
+  for (int x = 0; x < Xl; x++)
+    for (int y = 0; y < Y; y++)
+    {
+      const size_t k = (size_t)(x + 2) * mg.pm + (y + 2);
+      Fs_aos[2 * ((size_t)x * Y + y)] = fx[k];
+      Fs_aos[2 * ((size_t)x * Y + y) + 1] = fy[k];
+    }
   return LBM_OK;
 }
 
@@ -1247,7 +1517,8 @@ int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, 
   LBM_CUDA(cudaMemcpyAsync(tmp, rho_r, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
   LBM_CUDA(cudaMemcpyAsync(tmp + N, rho_b, sizeof(double) * N, cudaMemcpyHostToDevice, d->stream));
   LBM_CUDA(cudaMemcpyAsync(tmp + 2 * N, u, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, d->stream));
-  if (d->tp->model == TP_MRTCG)
+  if (d->tp->aux) LBM_CUDA(cudaMemsetAsync(d->tp->aux, 0, sizeof(double) * 4 * d->tp->mg.mplane, d->stream));
+  if (d->tp->model != TP_RK)
     k_tp_init<TP_MRTCG><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p, tmp, tmp + N, tmp + 2 * N);
   else
     k_tp_init<TP_RK><<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[0][d->cur], d->buf[1][d->cur], d->g, d->tp->mg, d->tp->mom, d->tp->p, tmp, tmp + N, tmp + 2 * N);

@@ -13,12 +13,16 @@
 namespace lbm
 {
 
-enum TpModel { TP_MRTCG = 0, TP_RK = 1 };
+// TP_CSF = test/mrt_rayleigh_taylor.cpp: the MRTCG model with the perturbation replaced by a continuum-surface-force
+// term (curvature from a second pass of the 5x5 differences over the interface normal) and the interfacial
+// tension carried into the next step's velocity
+enum TpModel { TP_MRTCG = 0, TP_RK = 1, TP_CSF = 2 };
 
 struct TpParams
 {
   double r_rho0, b_rho0, r_beta, b_beta, r_A, b_A;
   double r_irho0, b_irho0;    // 1 / rho0_k
+  double w2sum;               // TP_CSF: A_r (1 - rlx_r / 2) + A_b (1 - rlx_b / 2)   (mrt_rayleigh_taylor.cpp:512-513)
   double r_phi[3], b_phi[3];  // by |c|^2 class: q = 0, q = 1..4, q = 5..8  (src/colour.cpp:56-64)
   double r_eta[3], b_eta[3];  // src/colour.cpp:49-54
   double cr, cb;              // (1.8 alpha_k - 0.8)   (mrtcg_rayleigh_taylor.cpp:328-329)
@@ -104,15 +108,20 @@ __device__ __forceinline__ double relax_eval(const TpParams& p, double psi)
 // eval_phase_field (mrtcg_rayleigh_taylor.cpp:212-225)
 __device__ __forceinline__ double phase_of(const TpParams& p, double rr, double rb)
 {
-  const double a = rr * p.r_irho0, b = rb * p.b_irho0;
-  return (a - b) / (a + b);
+  // The two products are rounded on their own (no contraction into a - b / a + b): in the bulk of one fluid the other
+  // density is ~1e-22 of rounding residue, and the phase must come out as EXACTLY +-1 there, as it does in the
+  // reference — the models divide by 1e-20 + |grad(phase)|, so a 1-ulp ripple on the plateau would turn into an O(1)
+  // interface "normal".  (Observed: fma(3, RN(1/3), -+1e-22) straddles a rounding midpoint and gave 1 + 2^-52.)
+  const double a = __dmul_rn(rr, p.r_irho0), b = __dmul_rn(rb, p.b_irho0);
+  return __dsub_rn(a, b) / __dadd_rn(a, b);
 }
 
 // Moments of a freshly streamed node: what the drivers compute at the END of an iteration
 // (mrtcg_rayleigh_taylor.cpp:472-477 ; rk_static_droplet_test.cpp:602-609).
+// fsx, fsy: TP_CSF only, the interfacial tension of the step that produced this state (mrt_rayleigh_taylor.cpp:543-544)
 template <int MODEL>
 __device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)[9], const double (&fb)[9], double& rr,
-                                           double& rb, double& ux, double& uy, double& ph)
+                                           double& rb, double& ux, double& uy, double& ph, double fsx = 0.0, double fsy = 0.0)
 {
   double jx, jy, dummy;
   moments(fr, rr, jx, jy);
@@ -130,6 +139,11 @@ __device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)
     ux = ux + (0.5 * p.Fg0) * inv_rho;
     uy = uy + (0.5 * p.Fg1) * inv_rho;
   }
+  if constexpr (MODEL == TP_CSF)
+  {
+    ux = ux + (0.5 * (p.Fg0 + fsx)) * inv_rho;
+    uy = uy + (0.5 * (p.Fg1 + fsy)) * inv_rho;
+  }
   ph = phase_of(p, rr, rb);
 }
 
@@ -139,7 +153,7 @@ __device__ __forceinline__ double tp_feq(int q, double rho_k, const double (&phi
                                          double uy, double uu)
 {
   const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
-  if constexpr (MODEL == TP_MRTCG)  // mrtcg_rayleigh_taylor.cpp:233-247 (note 9 and 3, not 4.5 and 1.5)
+  if constexpr (MODEL != TP_RK)  // mrtcg_rayleigh_taylor.cpp:233-247 (note 9 and 3, not 4.5 and 1.5)
     return rho_k * (phi[QCLASS(q)] + W(q) * ((3.0 * ue) * eta[QCLASS(q)] + 9.0 * (ue * ue) - 3.0 * uu));
   else  // rk_static_droplet_test.cpp:183-199
     return rho_k * (phi[QCLASS(q)] + ((3.0 * ue + 4.5 * (ue * ue)) - 1.5 * uu) * W(q));
@@ -153,6 +167,7 @@ struct TpStencil
   // these per colour, but only the colour SUM of C enters the update (see tp_collide) and the differences are
   // linear, so the two colours' momentum fields are added before they are differentiated.
   double DxQx, DyQy;
+  double Fsx, Fsy;  // TP_CSF only: interfacial tension -sigma/2 K grad(phase) of this step (input of the collision)
 };
 
 // One two-colour collision in registers: fr/fb in = post-stream, out = post-collision.
@@ -198,6 +213,9 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
     const double k0 = (wr * wb) * rinv;                           // rho_r rho_b / (rho^2 (1e-20 + |grad|))
     const double A2 = (4.5 * p.sigma * s_nu) * (0.5 * gn) * 2.0;  // both colours: A = 4.5 sigma s_nu, xi = 0.5 |grad| (..)
     const double uF = ux * p.Fg0 + uy * p.Fg1;
+    // TP_CSF: omega2_k = A_k (1 - rlx_k / 2) eta, eta_q = w_q (3 (c_q - u) + 9 (u.c_q) c_q) . Fs   (eval_eta :366-385)
+    const double uFs = ux * st.Fsx + uy * st.Fsy;
+    const double Fse[4] = {st.Fsx, st.Fsy, st.Fsx + st.Fsy, st.Fsy - st.Fsx};
     const double pref = 1.0 - 0.5 * s_nu;
     constexpr double ISQ2 = 0.7071067811865476;
     constexpr double W1 = 1.0 / 9.0, W2 = 1.0 / 36.0;
@@ -242,7 +260,8 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
 
     // ---- perturbation, recolouring, force (eval_xi / eval_per_operator / eval_kappa / eval_rec_operator, :455-464)
     {
-      const double total = (fs0 + o1_0) + A2 * (4.0 / 27.0);  // q = 0: grad . c = 0, B_0 = -4/27
+      // q = 0: grad . c = 0, B_0 = -4/27  |  CSF: eta_0 = w_0 (-3 u.Fs)
+      const double total = (fs0 + o1_0) + (MODEL == TP_CSF ? p.w2sum * ((4.0 / 9.0) * (-3.0 * uFs)) : A2 * (4.0 / 27.0));
       double nr = wr * total, nb = wb * total;
       if (p.add_force)
       {
@@ -257,11 +276,22 @@ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], d
     for (int k = 0; k < 4; k++)
     {
       const double Wc = k < 2 ? W1 : W2, Bc = k < 2 ? 2.0 / 27.0 : 5.0 / 108.0, mx = k < 2 ? mix[1] : mix[2];
-      const double t = ge[k] * rinv;
-      const double o2x2 = A2 * (Wc * (t * t) - Bc);                   // even in c
-      const double kap = (k0 * (k < 2 ? ge[k] : ge[k] * ISQ2)) * mx;  // odd in c
-      const double totA = (fsA[k] + (o1E[k] + o1O[k])) + o2x2;
-      const double totB = (fsB[k] + (o1E[k] - o1O[k])) + o2x2;
+      double o2e, o2o, kap;  // omega2 summed over the colours: part even in c, part odd in c; kappa is odd in c
+      if constexpr (MODEL == TP_CSF)
+      {
+        o2e = (p.w2sum * Wc) * (9.0 * (ue[k] * Fse[k]) - 3.0 * uFs);
+        o2o = (p.w2sum * Wc) * (3.0 * Fse[k]);
+        kap = (k0 * ge[k]) * mx;  // eval_kappa with E, not unit_E (mrt_rayleigh_taylor.cpp:317)
+      }
+      else
+      {
+        const double t = ge[k] * rinv;
+        o2e = A2 * (Wc * (t * t) - Bc);
+        o2o = 0.0;
+        kap = (k0 * (k < 2 ? ge[k] : ge[k] * ISQ2)) * mx;
+      }
+      const double totA = (fsA[k] + (o1E[k] + o1O[k])) + (o2e + o2o);
+      const double totB = (fsB[k] + (o1E[k] - o1O[k])) + (o2e - o2o);
       const double kr = p.r_beta * kap, kb = p.b_beta * kap;
       double nrA = wr * totA + kr, nbA = wb * totA + kb;
       double nrB = wr * totB - kr, nbB = wb * totB - kb;

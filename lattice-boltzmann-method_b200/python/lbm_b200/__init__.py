@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG_DIR, "liblbm_b200.so")
 LBM_END = 2147483647
 
 # enums of include/lbm_b200.h
-MODEL_BGK, MODEL_BGK_ADE, MODEL_MRTCG, MODEL_RK, MODEL_KBC = 0, 1, 2, 3, 4
+MODEL_BGK, MODEL_BGK_ADE, MODEL_MRTCG, MODEL_RK, MODEL_KBC, MODEL_MRT_CSF = 0, 1, 2, 3, 4, 5
 EQ_COMPRESSIBLE, EQ_INCOMPRESSIBLE, EQ_KBC, EQ_KBC_FRESH = 0, 1, 2, 3
 FORCE_NONE, FORCE_UNIFORM, FORCE_IBM = 0, 1, 2
 BC_LINEAR, BC_ABB_FIXED, BC_ABB_EXTRAPOLATED, BC_ADE_INLET, BC_PRESSURE_PERIODIC, BC_COPY_PRE = range(6)
@@ -97,7 +97,7 @@ EXPORTS = [
     "lbm_differential3", "lbm_params_from_toml", "lbm_colour_from_toml", "lbm_two_phase_from_toml",
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
-    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments",
+    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -130,6 +130,7 @@ def load():
         _lib.lbm_save_pt.argtypes = [C.c_char_p, dp, C.POINTER(C.c_longlong), C.c_int]
         _lib.lbm_set_u.argtypes = [C.c_void_p, dp]
         _lib.lbm_set_moments.argtypes = [C.c_void_p, dp, dp]
+        _lib.lbm_get_interfacial_tension.argtypes = [C.c_void_p, dp]
         _lib.lbm_init_equilibrium.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
         _lib.lbm_init_two_phase.argtypes = [C.c_void_p, dp, dp, dp]
         _lib.lbm_ibm_set_markers.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
@@ -316,6 +317,11 @@ class Domain:
     def init_equilibrium(self, rho, u, kind=EQ_INCOMPRESSIBLE, lattice=0):
         r, rp = _in(rho); uu, up = _in(u)
         _chk(self.lib.lbm_init_equilibrium(self.h, lattice, kind, rp, up))
+
+    def get_interfacial_tension(self):
+        out = np.zeros((self.cfg.x1 - self.cfg.x0, self.cfg.Y, 2))
+        _chk(self.lib.lbm_get_interfacial_tension(self.h, out.ctypes.data_as(dp)))
+        return out
 
     def set_moments(self, rho, u):
         """MODEL_KBC: m0 / m1 the first step after an import uses (the ulbm drivers' members)"""

@@ -1161,6 +1161,177 @@ void orc_rk_step(const orc_rk_params* p, double* r_adv, double* b_adv, double* r
   free(gx); free(gy); free(r_col); free(b_col);
 }
 
+/* ------------------------------------------------------------------ test/mrt_rayleigh_taylor.cpp */
+
+void orc_csf_init(const orc_csf_params* p, double* r_rho, double* b_rho, double* rho, double* u, double* r_adv, double* b_adv)
+{
+  const int R = p->R, C = p->C;
+  const size_t N = (size_t)R * C;
+  const double middle = R / 2.0;
+  double cs2, rlx, rphi[9], reta[9], bphi[9], beta_[9];
+  colour_derive(p->r_alpha, p->r_nu, &cs2, &rlx, rphi, reta);
+  colour_derive(p->b_alpha, p->b_nu, &cs2, &rlx, bphi, beta_);
+  for (int r = 0; r < R; r++)
+    for (int c = 0; c < C; c++)
+    {
+      double s = middle + 0.1 * C * cos(2.0 * 3.141592 * c / C); /* :196 */
+      r_rho[(size_t)r * C + c] = p->r_rho0 * ((r < s) ? 1.0 : 0.0);
+      b_rho[(size_t)r * C + c] = p->b_rho0 * ((r >= s) ? 1.0 : 0.0);
+    }
+  for (size_t n = 0; n < N; n++)
+  {
+    rho[n] = r_rho[n] + b_rho[n];
+    u[n * 2] = 0.0 + 0.5 * p->Fg[0] / p->r_rho0; /* :464: shifted by the RED reference density, everywhere */
+    u[n * 2 + 1] = 0.0 + 0.5 * p->Fg[1] / p->r_rho0;
+    mrtcg_eq_node(r_rho[n], rphi, reta, u[n * 2], u[n * 2 + 1], r_adv + n * 9);
+    mrtcg_eq_node(b_rho[n], bphi, beta_, u[n * 2], u[n * 2 + 1], b_adv + n * 9);
+  }
+}
+
+void orc_csf_step(const orc_csf_params* p, double* r_adv, double* b_adv, double* r_rho, double* b_rho, double* rho,
+                  double* u, double* phase, double* s_nu, double* Fs)
+{
+  const int X = p->R, Y = p->C;
+  const size_t N = (size_t)X * Y;
+  double r_cs2, r_rlx, rphi[9], reta[9], b_cs2, b_rlx, bphi[9], beta_[9];
+  colour_derive(p->r_alpha, p->r_nu, &r_cs2, &r_rlx, rphi, reta);
+  colour_derive(p->b_alpha, p->b_nu, &b_cs2, &b_rlx, bphi, beta_);
+  relax_fn rf = relax_init(1.0 / (0.5 + p->r_nu / r_cs2), 1.0 / (0.5 + p->b_nu / b_cs2), p->delta);
+
+  double* Qx = dalloc(N);
+  double* Qy = dalloc(N);
+  double* tmp = dalloc(N);
+  double* rDxQx = dalloc(N);
+  double* rDyQy = dalloc(N);
+  double* bDxQx = dalloc(N);
+  double* bDyQy = dalloc(N);
+  double* gx = dalloc(N);
+  double* gy = dalloc(N);
+  double* nx = dalloc(N);
+  double* ny = dalloc(N);
+  double* dx_nx = dalloc(N);
+  double* dy_nx = dalloc(N);
+  double* dx_ny = dalloc(N);
+  double* dy_ny = dalloc(N);
+  double* r_col = dalloc(N * 9);
+  double* b_col = dalloc(N * 9);
+
+  for (size_t n = 0; n < N; n++)
+  {
+    phase[n] = (r_rho[n] / p->r_rho0 - b_rho[n] / p->b_rho0) / (r_rho[n] / p->r_rho0 + b_rho[n] / p->b_rho0);
+    s_nu[n] = relax_eval(&rf, phase[n], s_nu[n]);
+  }
+  for (size_t n = 0; n < N; n++)
+  {
+    Qx[n] = ((1.8 * p->r_alpha - 0.8) * r_rho[n]) * u[n * 2];
+    Qy[n] = ((1.8 * p->r_alpha - 0.8) * r_rho[n]) * u[n * 2 + 1];
+  }
+  orc_diff5(Qx, X, Y, rDxQx, tmp);
+  orc_diff5(Qy, X, Y, tmp, rDyQy);
+  for (size_t n = 0; n < N; n++)
+  {
+    Qx[n] = ((1.8 * p->b_alpha - 0.8) * b_rho[n]) * u[n * 2];
+    Qy[n] = ((1.8 * p->b_alpha - 0.8) * b_rho[n]) * u[n * 2 + 1];
+  }
+  orc_diff5(Qx, X, Y, bDxQx, tmp);
+  orc_diff5(Qy, X, Y, tmp, bDyQy);
+  orc_diff5(phase, X, Y, gx, gy);
+  /* n = -grad / (1e-20 + |grad|) (:508), curvature from D applied to n (:355-364) */
+  for (size_t n = 0; n < N; n++)
+  {
+    double gn = sqrt(gx[n] * gx[n] + gy[n] * gy[n]);
+    nx[n] = -gx[n] / (1e-20 + gn);
+    ny[n] = -gy[n] / (1e-20 + gn);
+  }
+  orc_diff5(nx, X, Y, dx_nx, dy_nx);
+  orc_diff5(ny, X, Y, dx_ny, dy_ny);
+
+  const double Sdiag[9] = {0.0, 1.25, 1.14, 0.0, 1.6, 0.0, 1.6, 0.0, 0.0};
+  const double w2r = p->r_A * (1.0 - 0.5 * r_rlx), w2b = p->b_A * (1.0 - 0.5 * b_rlx); /* :512-513 */
+#pragma omp parallel for
+  for (long n = 0; n < (long)N; n++)
+  {
+    double ux = u[n * 2], uy = u[n * 2 + 1];
+    double feq[9], m[9], om1[2][9], eta[9], kap[9], total[9];
+    double S[9];
+    for (int q = 0; q < 9; q++) S[q] = Sdiag[q];
+    S[7] = s_nu[n];
+    S[8] = s_nu[n];
+    for (int k = 0; k < 2; k++)
+    {
+      const double* fk = (k == 0 ? r_adv : b_adv) + n * 9;
+      double rk = (k == 0 ? r_rho[n] : b_rho[n]);
+      mrtcg_eq_node(rk, k == 0 ? rphi : bphi, k == 0 ? reta : beta_, ux, uy, feq);
+      double DxQx = (k == 0 ? rDxQx[n] : bDxQx[n]);
+      double DyQy = (k == 0 ? rDyQy[n] : bDyQy[n]);
+      double Ck[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      Ck[1] = 3.0 * (1.0 - 0.5 * 1.25) * (DxQx + DyQy);
+      Ck[7] = (1.0 - 0.5 * s_nu[n]) * (DxQx - DyQy);
+      for (int a = 0; a < 9; a++)
+      {
+        double s = 0.0;
+        for (int q = 0; q < 9; q++) s += MM[a][q] * (feq[q] - fk[q]);
+        m[a] = S[a] * s + Ck[a];
+      }
+      for (int q = 0; q < 9; q++)
+      {
+        double s = 0.0;
+        for (int a = 0; a < 9; a++) s += ((1.0 / 36.0) * MI36[q][a]) * m[a];
+        om1[k][q] = s;
+      }
+    }
+    double gn = sqrt(gx[n] * gx[n] + gy[n] * gy[n]);
+    /* eval_local_curvature; interf_tension = -0.5 sigma K grad (:509-510) */
+    double K = nx[n] * ny[n] * (dy_nx[n] + dx_ny[n]) - (nx[n] * nx[n]) * dy_ny[n] - (ny[n] * ny[n]) * dx_nx[n];
+    double fsx = (-0.5 * p->sigma) * K * gx[n], fsy = (-0.5 * p->sigma) * K * gy[n];
+    for (int q = 0; q < 9; q++)
+    {
+      double ue = ux * CXD[q] + uy * CYD[q];
+      /* eval_eta (:366-385): sum over the two components of (3 (E - u) + 9 (u.E) E) Fs, times W */
+      eta[q] = ((3.0 * (CXD[q] - ux) + 9.0 * (ue * CXD[q])) * fsx + (3.0 * (CYD[q] - uy) + 9.0 * (ue * CYD[q])) * fsy) * W9[q];
+      double ge = gx[n] * CXD[q] + gy[n] * CYD[q];
+      /* eval_kappa with E, not unit_E (:304-320) */
+      kap[q] = (((r_rho[n] * b_rho[n]) * ge) * (r_rho[n] * rphi[q] + b_rho[n] * bphi[q])) / ((rho[n] * rho[n]) * (1e-20 + gn));
+      total[q] = ((((r_adv[n * 9 + q] + om1[0][q]) + w2r * eta[q]) + b_adv[n * 9 + q]) + om1[1][q]) + w2b * eta[q]; /* :522 */
+    }
+    double uFg = ux * p->Fg[0] + uy * p->Fg[1];
+    for (int q = 0; q < 9; q++)
+    {
+      double o3r = r_rho[n] * total[q] / rho[n] + p->r_beta * kap[q];
+      double o3b = b_rho[n] * total[q] / rho[n] + p->b_beta * kap[q];
+      double ue = ux * CXD[q] + uy * CYD[q];
+      double Fe = p->Fg[0] * CXD[q] + p->Fg[1] * CYD[q];
+      double src = ((1 - 0.5 * s_nu[n]) * ((3.0 + 9.0 * ue) * Fe - 3.0 * uFg)) * W9[q]; /* :527-529 */
+      r_col[n * 9 + q] = o3r + src;
+      b_col[n * 9 + q] = o3b + src;
+    }
+    Fs[n * 2] = fsx;
+    Fs[n * 2 + 1] = fsy;
+  }
+  orc_advect(r_col, X, Y, r_adv);
+  orc_advect(b_col, X, Y, b_adv);
+  mrtcg_bc(r_adv, r_col, X, Y);
+  mrtcg_bc(b_adv, b_col, X, Y);
+  orc_calc_rho(r_adv, X, Y, r_rho);
+  orc_calc_rho(b_adv, X, Y, b_rho);
+  for (size_t n = 0; n < N; n++)
+  {
+    rho[n] = r_rho[n] + b_rho[n];
+    double sx = 0.0, sy = 0.0;
+    for (int q = 0; q < 9; q++)
+    {
+      double t = r_adv[n * 9 + q] + b_adv[n * 9 + q];
+      sx += t * CXD[q];
+      sy += t * CYD[q];
+    }
+    /* :543-544: u = calc_u + 0.5 (Fg + interf_tension) / rho */
+    u[n * 2] = sx / rho[n] + 0.5 * (p->Fg[0] + Fs[n * 2]) / rho[n];
+    u[n * 2 + 1] = sy / rho[n] + 0.5 * (p->Fg[1] + Fs[n * 2 + 1]) / rho[n];
+  }
+  free(Qx); free(Qy); free(tmp); free(rDxQx); free(rDyQy); free(bDxQx); free(bDyQy);
+  free(gx); free(gy); free(nx); free(ny); free(dx_nx); free(dy_nx); free(dx_ny); free(dy_ny); free(r_col); free(b_col);
+}
+
 /* ------------------------------------------------------------------ ulbm::d2q9::kbc */
 
 /* the nine polynomial factors of kbc::eval_equilibrium / eval_iequilibrium (src/ulbm.cpp:230-240, 250-258) */

@@ -119,6 +119,22 @@ void orc_rk_init(const orc_rk_params* p, const double* u0, double* r_adv, double
 void orc_rk_step(const orc_rk_params* p, double* r_adv, double* b_adv, double* r_rho, double* b_rho,
                  double* rho_mix, double* u, double* phase, double* relax, double* grad);
 
+/* ---- test/mrt_rayleigh_taylor.cpp: the MRT colour-gradient model with a continuum-surface-force perturbation
+ * (curvature from a second pass of `differential`) -- SURVEY 8(f) rank 2.  The driver only runs at
+ * 1024 x 256 (E_rep, :180); pinned against its own snapshots (tests/golden/mrt_csf_1024x256.npz). */
+typedef struct
+{
+  int R, C;
+  double r_rho0, r_alpha, r_nu, r_beta, r_A;
+  double b_rho0, b_alpha, b_nu, b_beta, b_A;
+  double sigma, delta, Fg[2];
+} orc_csf_params;
+/* init_rho_cosine (:184-210, interface at R/2 + 0.1 C cos), u = 0.5 Fg / rho_r0 (:464), adv_f = equilibrium */
+void orc_csf_init(const orc_csf_params* p, double* r_rho, double* b_rho, double* rho, double* u, double* r_adv, double* b_adv);
+/* one loop iteration (:490-545); Fs {R,C,2} = interf_tension carried into the next u, s_nu {R,C} */
+void orc_csf_step(const orc_csf_params* p, double* r_adv, double* b_adv, double* r_rho, double* b_rho, double* rho,
+                  double* u, double* phase, double* s_nu, double* Fs);
+
 /* ---- ulbm::d2q9::kbc (src/ulbm.hpp:11-90, src/ulbm.cpp) and its two drivers -- SURVEY 8(f) rank 3.
  * Pinned against the compiled reference: ref_kbc_run / ref_kbc_equilibrium of oracle/ref_harness.cpp
  * (tests/test_oracle_vs_reference.py) and the snapshots of test/ulbm_double_shear_flow.cpp

@@ -108,3 +108,11 @@ def double_shear_fields(R, C, u_max=0.02, alpha=80.0, delta=0.05):
     u[..., 0] = u_max * np.tanh(alpha * (0.25 * R - np.abs(c - 0.5 * R)))
     u[..., 1] = u_max * delta * np.sin(6.2832 * (r + 0.25 * R) / R)
     return np.ones((R, C)), u
+
+
+def csf(R, C, Fg=(6.25e-6, 0.0), sigma=0.1, **slab):
+    """test/mrt_rayleigh_taylor.cpp: MRT colour gradient with the continuum-surface-force perturbation"""
+    d = L.Domain(L.default_config(model=L.MODEL_MRT_CSF, X=R, Y=C, red=RED, blue=BLUE, sigma=sigma, delta=0.1, Fg=Fg,
+                                  add_force=1, **slab))
+    d.preset_mrtcg()
+    return d

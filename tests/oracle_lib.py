@@ -42,6 +42,15 @@ class MrtcgParams(C.Structure):
     ]
 
 
+class CsfParams(C.Structure):
+    _fields_ = [
+        ("R", C.c_int), ("C", C.c_int),
+        ("r_rho0", C.c_double), ("r_alpha", C.c_double), ("r_nu", C.c_double), ("r_beta", C.c_double), ("r_A", C.c_double),
+        ("b_rho0", C.c_double), ("b_alpha", C.c_double), ("b_nu", C.c_double), ("b_beta", C.c_double), ("b_A", C.c_double),
+        ("sigma", C.c_double), ("delta", C.c_double), ("Fg", C.c_double * 2),
+    ]
+
+
 class RkParams(C.Structure):
     _fields_ = [
         ("L", C.c_int), ("radius", C.c_double),
@@ -220,6 +229,19 @@ class Oracle:
     def mrtcg_step(self, p, st):
         self.lib.orc_mrtcg_step(C.byref(p), _p(st["r_adv"]), _p(st["b_adv"]), _p(st["r_rho"]), _p(st["b_rho"]),
                                 _p(st["rho"]), _p(st["u"]), _p(st["phase"]), _p(st["s_nu"]), _p(st["grad"]))
+
+    # ---- MRT colour gradient with continuum surface force (test/mrt_rayleigh_taylor.cpp)
+    def csf_init(self, p):
+        N = (p.R, p.C)
+        st = dict(r_rho=np.zeros(N + (1,)), b_rho=np.zeros(N + (1,)), rho=np.zeros(N + (1,)), u=np.zeros(N + (2,)),
+                  r_adv=np.zeros(N + (9,)), b_adv=np.zeros(N + (9,)), phase=np.zeros(N + (1,)), s_nu=np.zeros(N),
+                  Fs=np.zeros(N + (2,)))
+        self.lib.orc_csf_init(C.byref(p), _p(st["r_rho"]), _p(st["b_rho"]), _p(st["rho"]), _p(st["u"]), _p(st["r_adv"]), _p(st["b_adv"]))
+        return st
+
+    def csf_step(self, p, st):
+        self.lib.orc_csf_step(C.byref(p), _p(st["r_adv"]), _p(st["b_adv"]), _p(st["r_rho"]), _p(st["b_rho"]), _p(st["rho"]),
+                              _p(st["u"]), _p(st["phase"]), _p(st["s_nu"]), _p(st["Fs"]))
 
     # ---- ulbm::d2q9::kbc
     def kbc_equilibrium(self, m0, m1, fresh_object=True):

@@ -1,0 +1,102 @@
+"""GPU parity of LBM_MODEL_MRT_CSF (test/mrt_rayleigh_taylor.cpp) against the CPU oracle and
+against snapshots of the reference driver at its hard-wired 1024 x 256 grid.
+
+The reference algorithm is ill-conditioned from its third step on: the interface normal n = -grad / (1e-20 + |grad|)
+is O(1) rounding noise wherever the phase gradient is, and the curvature differentiates it (the oracle and the
+reference driver themselves differ by 1e-7 there, tests/golden/make_golden.py).  So: 1e-12 while the arithmetic is
+well conditioned (two steps), and afterwards the tolerance the oracle itself meets against the driver."""
+import numpy as np
+import pytest
+
+import cases
+import lbm_b200 as L
+from oracle_lib import CsfParams, Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def csf_params(R, C):
+    p = CsfParams()
+    p.R, p.C = R, C
+    p.r_rho0, p.r_alpha, p.r_nu, p.r_beta, p.r_A = 3.0, 0.7, 0.04, 0.7, 0.5
+    p.b_rho0, p.b_alpha, p.b_nu, p.b_beta, p.b_A = 1.0, 0.1, 0.04, -0.7, 0.5
+    p.sigma, p.delta = 0.1, 0.1
+    p.Fg[0], p.Fg[1] = 6.25e-6, 0.0
+    return p
+
+
+@pytest.mark.parametrize("R,C", [(96, 64), (41, 33), (12, 9)])
+def test_csf_vs_oracle(orc, R, C):
+    """the driver's own sharp-interface start: exact for the first step; afterwards no further from the oracle than
+    the oracle is from a twin whose initial populations were perturbed by 1e-15 (the algorithm's own conditioning)"""
+    p = csf_params(R, C)
+    st = orc.csf_init(p)
+    twin = orc.csf_init(p)
+    twin["r_adv"] *= 1.0 + 1e-15 * np.random.default_rng(7).standard_normal(twin["r_adv"].shape)
+    d = cases.csf(R, C)
+    d.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-15 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-15
+    for n in range(1, 13):
+        orc.csf_step(p, st)
+        orc.csf_step(p, twin)
+        d.step(1)
+        own = max(cases.relerr(twin["r_adv"], st["r_adv"]), cases.relerr(twin["b_adv"], st["b_adv"]), float(np.abs(twin["u"] - st["u"]).max()))
+        tol = 1e-12 if n == 1 else 1e-12 + 20.0 * own
+        assert cases.relerr(d.get_f(0), st["r_adv"]) < tol and cases.relerr(d.get_f(1), st["b_adv"]) < tol, (n, own)
+        rho, u = d.get_moments()
+        assert np.abs(rho - st["rho"]).max() < tol and np.abs(u - st["u"]).max() < tol, (n, own)
+
+
+def test_csf_smooth_interface_stays_on_the_oracle(orc):
+    """with a diffuse interface everywhere (no region of pure rounding-noise gradient) the whole run is well conditioned"""
+    R, C = 64, 48
+    p = csf_params(R, C)
+    st = orc.csf_init(p)
+    x = np.arange(R)[:, None] - R / 2 - 3.0 * np.cos(2 * np.pi * np.arange(C)[None, :] / C)
+    w = 0.5 * (1.0 - np.tanh(x / 14.0))                     # wide tanh profile: |grad phase| > 1e-4 everywhere
+    st["r_rho"][..., 0] = 3.0 * w
+    st["b_rho"][..., 0] = 1.0 * (1.0 - w)
+    # equilibrium populations of that state through the library itself, then the same populations into the oracle
+    d = cases.csf(R, C)
+    d.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+    st["r_adv"][...] = d.get_f(0); st["b_adv"][...] = d.get_f(1)
+    st["rho"][...] = st["r_rho"] + st["b_rho"]
+    for n in range(1, 41):
+        orc.csf_step(p, st)
+    d.step(40)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-10 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-10
+    rho, u = d.get_moments()
+    assert np.abs(rho - st["rho"]).max() < 1e-10 and np.abs(u - st["u"]).max() < 1e-10
+
+
+def test_csf_reference_driver_golden():
+    """snapshots written by the reference's own test/mrt_rayleigh_taylor.cpp at 1024 x 256 (strided view)"""
+    g = cases.golden("mrt_csf_1024x256")
+    R, C = 1024, 256
+    p = csf_params(R, C)
+    st = Oracle().csf_init(p)
+    d = cases.csf(R, C)
+    d.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+    sr, sc = (int(v) for v in g["stride"])
+    t = 0
+    for k, s in enumerate(int(s) for s in g["steps"]):
+        d.step(s - t)
+        t = s
+        tol = float(g["tol"][k])
+        rho, u = d.get_moments()   # snapshot s holds rho, u at the START of iteration s
+        assert np.abs(rho[::sr, ::sc, 0] - g["rhos"][k]).max() < tol, s
+        assert np.abs(u[::sr, ::sc, 0] - g["uxs"][k]).max() < tol and np.abs(u[::sr, ::sc, 1] - g["uys"][k]).max() < tol, s
+        Fs = d.get_interfacial_tension()   # ... and the interfacial tension of iteration s - 1 (saved as gradx / grady)
+        assert np.abs(Fs[::sr, ::sc, 0] - g["gradx"][k]).max() < tol and np.abs(Fs[::sr, ::sc, 1] - g["grady"][k]).max() < tol, s
+
+
+def test_csf_refuses_slabs():
+    d = cases.csf(64, 32, x0=0, x1=32)
+    d.init_two_phase(np.ones((32, 32)), np.ones((32, 32)), np.zeros((32, 32, 2)))
+    with pytest.raises(L.LbmError):
+        d.step(1)
