@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
     python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, rank 0 only)
-    python bench.py --workload mrtcg_rt|rk_droplet|sedimentation|poiseuille   (the other BASELINE.json configs)
+    python bench.py --workload mrtcg_rt|rk_droplet|sedimentation|poiseuille|kbc_shear|csf_rt|cylinder_bb   (the other BASELINE.json configs)
 
 A "step" is one lattice-Boltzmann time step of the whole grid.  Default workload at every N:
 configs[1] of BASELINE.json — flow past a cylinder, D2Q9 BGK, compressible equilibrium,
@@ -39,6 +39,12 @@ WORKLOADS = {
     # configs[1] — the headline: test/cylinder_test.cpp at 8192 x 8192 per GPU
     "cylinder": dict(X=8192, Y=8192, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,COMP,IBM>", driver="test/cylinder_test.cpp",
                      what="cylinder flow, D2Q9 BGK + IBM cylinder, ABB inlet/outlet, specular walls", cpu_sample=1024),
+    # configs[1] read literally ("flow past cylinder ... with bounce-back"): the same free-stream channel with a staircase
+    # cylinder under link-wise half-way bounce-back instead of the reference driver's immersed-boundary body
+    "cylinder_bb": dict(X=8192, Y=8192, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,COMP,NONE>",
+                        driver="test/cylinder_test.cpp (boundary rows/columns) + the obstacle-wall rule of test/rectangle_sedimentation_test.cpp:186-196",
+                        what="flow past a staircase cylinder, D2Q9 BGK compressible, half-way bounce-back links, ABB inlet/outlet, specular side columns",
+                        cpu_sample=1024),
     # configs[0] at the parameters.toml grid (the 21 x 21 reference case is a parity test)
     "poiseuille": dict(X=2700, Y=2100, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,INCOMP,NONE>",
                        driver="test/horizontal_poiseuille_test.cpp",
@@ -58,6 +64,12 @@ WORKLOADS = {
                           driver="test/rectangle_sedimentation_test.cpp",
                           what="rectangle sedimentation: fluid + advection-diffusion lattice, bounce-back rectangle walls",
                           cpu_sample=1024),
+    # not a BASELINE.json config: SURVEY §8(f) rank 2, the continuum-surface-force variant (three passes per step; bytes =
+    # both colours' populations read + written once (288) + the carried interfacial tension read + written (32))
+    "csf_rt": dict(X=8192, Y=8192, bytes=320.0, nlat=2, kernel="k_csf_collide_interior<PULL>",
+                   driver="test/mrt_rayleigh_taylor.cpp",
+                   what="MRT colour-gradient Rayleigh-Taylor with continuum surface force (curvature from nested 5x5 differences)",
+                   cpu_sample=512),
     # not a BASELINE.json config: the SURVEY §8(f) rank-3 collision (ulbm::d2q9::kbc), fully periodic double shear layer
     "kbc_shear": dict(X=8192, Y=8192, bytes=144.0, nlat=1, kernel="k_bgk_interior<PULL,KBC>",
                       driver="test/ulbm_double_shear_flow.cpp",
@@ -118,6 +130,16 @@ def cylinder_markers(X, Y):
     n = max(16, int(round(np.pi * D)))
     th = 2.0 * np.pi * np.arange(n) / n
     return X / 4.0 + 0.5 * D * np.cos(th) + 0.37, Y / 2.0 + 0.5 * D * np.sin(th) + 0.21
+
+
+def cylinder_solid(Xg, Y, X1):
+    """GLOBAL {Xg,Y} solid mask of the staircase cylinder: same centre and diameter as cylinder_markers of the first slab"""
+    D = max(8.0, X1 / 9.0)
+    solid = np.zeros((Xg, Y), dtype=np.uint8)
+    lo, hi = max(0, int(X1 / 4.0 - D)), min(Xg, int(X1 / 4.0 + D) + 1)
+    r2 = (np.arange(lo, hi)[:, None] - (X1 / 4.0 + 0.37)) ** 2 + (np.arange(Y)[None, :] - (Y / 2.0 + 0.21)) ** 2
+    solid[lo:hi] = r2 <= (0.5 * D) ** 2
+    return solid
 
 
 def write_markers_toml(path, xs, ys):
@@ -204,6 +226,30 @@ def cpu_reference_mlups(workload, edge, warmup, steps):
         orc.ibm_destroy(ib)
         return edge * edge / sec / 1e6, sec, "port", port_cores, desc
 
+    if workload == "cylinder_bb":
+        # collide + stream through the reference's own solver:: operators (oracle/_ref) where they compiled, the port
+        # otherwise; the bounce-back links are the driver-style slice assignments, done here with a mask per direction
+        have = oracle_lib.have_ref()
+        ops = oracle_lib.Ref() if have else oracle_lib.Oracle()
+        solid = cylinder_solid(edge, edge, edge)
+        opp = (0, 3, 4, 1, 2, 7, 8, 5, 6)
+        cuts = [(q, solid != np.roll(solid, (int(CX9[q]), int(CY9[q])), axis=(0, 1))) for q in range(1, 9)]
+        u = np.zeros((edge, edge, 2)); u[..., 0] = u_lb
+        state = [ops.incomp_equilibrium(u, np.ones((edge, edge, 1)))]
+
+        def bb_step():
+            f = state[0]
+            rho = ops.calc_rho(f)
+            coll = ops.collision(f, ops.equilibrium(ops.calc_u(f, rho), rho), omega)
+            adve = ops.advect(coll)
+            for q, cut in cuts:
+                adve[cut, q] = coll[cut, opp[q]]
+            state[0] = adve
+
+        sec = timed(bb_step)
+        return (edge * edge / sec / 1e6, sec, "reference" if have else "port", ops.num_threads() if have else port_cores,
+                f"{edge}x{edge} crop of the cylinder_bb workload (solver:: operators + bounce-back links; inlet/outlet rows left out)")
+
     orc = oracle_lib.Oracle()
     if workload == "poiseuille":
         om, rho_in, rho_out = channel_constants(edge, edge)
@@ -224,6 +270,15 @@ def cpu_reference_mlups(workload, edge, warmup, steps):
         p.add_force = 1
         st = orc.mrtcg_init(p, "rt")
         sec = timed(lambda: orc.mrtcg_step(p, st))
+    elif workload == "csf_rt":
+        p = oracle_lib.CsfParams()
+        p.R, p.C = edge, edge
+        p.r_rho0, p.r_alpha, p.r_nu, p.r_beta, p.r_A = RED["rho_0"], RED["alpha"], RED["nu"], RED["beta"], RED["A"]
+        p.b_rho0, p.b_alpha, p.b_nu, p.b_beta, p.b_A = BLUE["rho_0"], BLUE["alpha"], BLUE["nu"], BLUE["beta"], BLUE["A"]
+        p.sigma, p.delta = 0.1, 0.1
+        p.Fg[0], p.Fg[1] = RT_FG
+        st = orc.csf_init(p)
+        sec = timed(lambda: orc.csf_step(p, st))
     elif workload == "kbc_shear":
         r = np.arange(edge)[:, None] + 0.0 * np.arange(edge)[None, :]
         c = np.arange(edge)[None, :] + 0.0 * np.arange(edge)[:, None]
@@ -365,6 +420,8 @@ class Case:
         slab = dict(X=self.Xg, Y=self.Y, x0=self.x0, x1=self.x1, device=local)
         if self.name == "cylinder":
             cfg = L.default_config(model=L.MODEL_BGK, omega=self.omega, equilibrium=L.EQ_COMPRESSIBLE, force=L.FORCE_IBM, **slab)
+        elif self.name == "cylinder_bb":
+            cfg = L.default_config(model=L.MODEL_BGK, omega=self.omega, equilibrium=L.EQ_COMPRESSIBLE, **slab)
         elif self.name == "poiseuille":
             om, self.rho_in, self.rho_out = channel_constants(self.Xg, self.Y)
             cfg = L.default_config(model=L.MODEL_BGK, omega=om, equilibrium=L.EQ_INCOMPRESSIBLE, **slab)
@@ -373,6 +430,8 @@ class Case:
         elif self.name == "sedimentation":
             cfg = L.default_config(model=L.MODEL_BGK_ADE, omega=self.omega, omega_g=self.omega, equilibrium=L.EQ_COMPRESSIBLE,
                                    w_s=3e-3, **slab)
+        elif self.name == "csf_rt":
+            cfg = L.default_config(model=L.MODEL_MRT_CSF, red=RED, blue=BLUE, sigma=0.1, delta=0.1, Fg=RT_FG, add_force=1, **slab)
         elif self.name == "mrtcg_rt":
             cfg = L.default_config(model=L.MODEL_MRTCG, red=RED, blue=BLUE, sigma=0.1, delta=0.1, Fg=RT_FG, add_force=1, **slab)
         else:
@@ -389,11 +448,15 @@ class Case:
 
     def setup(self):
         d, X, Y = self.d, self.X, self.Y
-        if self.name == "cylinder":
+        if self.name in ("cylinder", "cylinder_bb"):
             d.preset_free_stream(self.u_lb, 0.0)
-            xs, ys = cylinder_markers(self.X, Y)  # the body sits in rank 0's slab
-            if self.rank == 0:
-                d.ibm_set_markers(xs, ys)
+            if self.name == "cylinder_bb":
+                d.bc_add_solid(cylinder_solid(self.Xg, Y, self.X))  # appended to the preset's rules; the body sits in rank 0's slab
+                d.bc_commit()
+            else:
+                xs, ys = cylinder_markers(self.X, Y)  # the body sits in rank 0's slab
+                if self.rank == 0:
+                    d.ibm_set_markers(xs, ys)
             # the drivers' f = incomp_equilibrium(u=(u_lb,0), rho=1) (cylinder_test.cpp:84-86): u and rho are the inputs
             self.ri_t, self.ri = self.pinned((X, Y, 1))
             self.ui_t, self.ui = self.pinned((X, Y, 2))
@@ -426,12 +489,12 @@ class Case:
             self.g[...] = 0.0
             self.g[:, 0, :] = C_w[self.x0:self.x1, None] * geq[None, :]
         else:
-            (d.preset_mrtcg if self.name == "mrtcg_rt" else d.preset_rk)()
+            (d.preset_rk if self.name == "rk_droplet" else d.preset_mrtcg)()
             self.rr_t, self.rr = self.pinned((X, Y))
             self.rb_t, self.rb = self.pinned((X, Y))
             self.u_t, self.u = self.pinned((X, Y, 2))
             self.u[...] = 0.0
-            if self.name == "mrtcg_rt":
+            if self.name != "rk_droplet":
                 self.rr[...], self.rb[...] = rt_densities(self.Xg, Y, self.x0, self.x1)
             else:
                 self.rr[...], self.rb[...] = droplet_densities(self.Xg, self.Xg / 4.0, self.x0, self.x1)
@@ -441,7 +504,7 @@ class Case:
     def import_state(self):
         """host -> device through the C ABI; returns the bytes copied"""
         d = self.d
-        if self.name in ("cylinder", "poiseuille"):
+        if self.name in ("cylinder", "cylinder_bb", "poiseuille"):
             d.init_equilibrium(self.ri, self.ui, self.L.EQ_INCOMPRESSIBLE)
             return self.ri.nbytes + self.ui.nbytes
         if self.name == "kbc_shear":
@@ -470,7 +533,7 @@ class Case:
 
     def dominant_nodes(self):
         """nodes per step the dominant kernel owns (the remaining edge columns are listed nodes)"""
-        if self.name in ("mrtcg_rt", "rk_droplet"):
+        if self.name in ("mrtcg_rt", "rk_droplet", "csf_rt"):
             return self.X * (self.Y - 2)
         return self.X * (2 * ((self.Y - 3) // 2))
 

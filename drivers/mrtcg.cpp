@@ -1,6 +1,7 @@
-// Mirrors of the two MRT colour-gradient drivers, selected by argv[1]:
+// Mirrors of the three MRT colour-gradient drivers, selected by argv[1]:
 //   mrtcg rayleigh-taylor <file.toml>   test/mrtcg_rayleigh_taylor.cpp (driver 16; needs [general])
 //   mrtcg static-droplet  <file.toml>   test/mrtcg_static_droplet.cpp  (driver 18; sigma = 0.1, Fg = (0,-6.25e-6), source not added)
+//   mrtcg csf             <file.toml>   test/mrt_rayleigh_taylor.cpp   (continuum-surface-force variant; also saves gradx / grady)
 #include <cstring>
 
 #include "common.hpp"
@@ -9,8 +10,9 @@ static double sigmoid(double x) { return 1.0 / (1.0 + std::exp(-x)); }
 
 int main(int argc, char* argv[])
 {
-  if (argc < 3) { std::cerr << "usage: mrtcg rayleigh-taylor|static-droplet <file.toml>\n"; return 1; }
-  const bool rt = std::strcmp(argv[1], "rayleigh-taylor") == 0;
+  if (argc < 3) { std::cerr << "usage: mrtcg rayleigh-taylor|static-droplet|csf <file.toml>\n"; return 1; }
+  const bool csf = std::strcmp(argv[1], "csf") == 0;
+  const bool rt = csf || std::strcmp(argv[1], "rayleigh-taylor") == 0;
   lbm_two_phase_params tp;
   DRV_CHECK(lbm_two_phase_from_toml(argv[2], rt ? 1 : 0, &tp));
   lbm_colour red, blue;
@@ -22,7 +24,7 @@ int main(int argc, char* argv[])
 
   lbm_config cfg;
   lbm_config_default(&cfg);
-  cfg.model = LBM_MODEL_MRTCG;
+  cfg.model = csf ? LBM_MODEL_MRT_CSF : LBM_MODEL_MRTCG;
   cfg.X = R; cfg.Y = C; cfg.x1 = R;
   cfg.red = {red.rho_0, red.alpha, red.A, red.nu, red.beta};
   cfg.blue = {blue.rho_0, blue.alpha, blue.A, blue.nu, blue.beta};
@@ -60,7 +62,8 @@ int main(int argc, char* argv[])
 
   const int S = tp.nr_snapshots;
   drv::Series rhos(R, C, S), uxs(R, C, S), uys(R, C, S), phases(R, C, S);
-  std::vector<double> rho(N), ph(N, 0.0);
+  drv::Series gradx(R, C, csf ? S : 0), grady(R, C, csf ? S : 0);
+  std::vector<double> rho(N), ph(N, 0.0), Fs(csf ? 2 * N : 0, 0.0);
   std::cout << "main loop" << std::endl;
   for (int t = 0; t < tp.time_steps; t++)
   {
@@ -70,14 +73,17 @@ int main(int argc, char* argv[])
       DRV_CHECK(lbm_get_moments(d, 0, rho.data(), u.data()));
       rhos.put(k, rho, 1, 0); uxs.put(k, u, 2, 0); uys.put(k, u, 2, 1);
       phases.put(k, ph, 1, 0);  // the driver stores the phase field of the PREVIOUS iteration (:421)
+      if (csf) { gradx.put(k, Fs, 2, 0); grady.put(k, Fs, 2, 1); }  // ... and its interfacial tension (mrt_rayleigh_taylor.cpp:485-486)
     }
     if ((t + 1) % tp.period_snapshots == 0) DRV_CHECK(lbm_get_phase(d, ph.data(), nullptr, nullptr));
     DRV_CHECK(lbm_step(d, 1));
+    if (csf && (t + 1) % tp.period_snapshots == 0) DRV_CHECK(lbm_get_interfacial_tension(d, Fs.data()));
   }
   DRV_CHECK(lbm_synchronize(d));
   std::cout << "save snapshots" << std::endl;
   const std::string pre = rt ? std::string(tp.name) + "-mrtcg-rayleigh-taylor-" : std::string("mrtcg-static-droplet-");
   rhos.save(pre + "rhos.pt"); uxs.save(pre + "uxs.pt"); uys.save(pre + "uys.pt"); phases.save(pre + "phases.pt");
+  if (csf) { gradx.save(pre + "gradx.pt"); grady.save(pre + "grady.pt"); }
   lbm_destroy(d);
   return 0;
 }

@@ -171,6 +171,13 @@ typedef struct
 void lbm_bc_op_default(lbm_bc_op* op);
 int lbm_bc_clear(lbm_domain* d);
 int lbm_bc_add(lbm_domain* d, const lbm_bc_op* op);
+/* Half-way bounce-back around an arbitrary (staircase) solid body: solid = {X,Y} GLOBAL mask, non-zero = solid.
+ * For every node n and direction q whose upstream neighbour n - c_q (periodic, like solver::advect) lies on the other
+ * side of the surface: f_adve[n, q] = f_coll[n, opp(q)] — the link-wise rule of the reference's obstacle walls
+ * (test/rectangle_sedimentation_test.cpp:186-196; BASELINE.json configs[1] "cylinder ... with bounce-back").
+ * Appends ordinary LBM_BC_LINEAR ops (one per run of columns); call lbm_bc_commit afterwards.  X, Y must be the
+ * domain's global size. */
+int lbm_bc_add_solid(lbm_domain* d, int lattice, const unsigned char* solid, int X, int Y);
 /* compiles the op list into per-node programs (must be called once before stepping) */
 int lbm_bc_commit(lbm_domain* d);
 /* bit-exact introspection of the compiled masks ("boundary-node masks ... bit-exact"):

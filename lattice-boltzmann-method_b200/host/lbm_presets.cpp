@@ -3,6 +3,11 @@
 // later assignments win at corners exactly as they do there.
 #include "../../include/lbm_b200.h"
 
+namespace lbm
+{
+void set_error(const char* fmt, ...);
+}
+
 namespace
 {
 struct Rules
@@ -78,6 +83,43 @@ void specular_columns(Rules& r)
 
 extern "C"
 {
+
+// Half-way bounce-back on every lattice link that joins a solid and a non-solid node: population q arriving at node n
+// from n - c_q on the other side of the surface is replaced by the node's own outgoing opposite population,
+//   f_adve[n, q] = f_coll[n, opp(q)]
+// — the rule the reference writes out slice by slice for its axis-aligned obstacle walls
+// (test/rectangle_sedimentation_test.cpp:186-196), applied to an arbitrary (staircase) body.  Both sides of the
+// surface get the rule, so the solid region is a closed enclosure that exchanges nothing with the flow.
+// Neighbours wrap periodically like solver::advect.  One LBM_BC_LINEAR op per run of consecutive columns.
+int lbm_bc_add_solid(lbm_domain* d, int lattice, const unsigned char* solid, int X, int Y)
+{
+  if (!d || !solid || X < 1 || Y < 1) { lbm::set_error("lbm_bc_add_solid: null argument or empty mask"); return LBM_ERR_INVALID; }
+  static const int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+  static const int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+  for (int x = 0; x < X; x++)
+    for (int q = 1; q < 9; q++)
+    {
+      const int sx = (x - cx[q] + X) % X;
+      int run = -1;
+      for (int y = 0; y <= Y; y++)
+      {
+        const bool cut = y < Y && (solid[(size_t)x * Y + y] != 0) != (solid[(size_t)sx * Y + (y - cy[q] + Y) % Y] != 0);
+        if (cut && run < 0) run = y;
+        if (!cut && run >= 0)
+        {
+          lbm_bc_op op;
+          lbm_bc_op_default(&op);
+          op.kind = LBM_BC_LINEAR; op.lattice = lattice;
+          op.x_begin = x; op.x_end = x + 1; op.y_begin = run; op.y_end = y;
+          op.dst_q = q; op.src_q = opp[q]; op.coef = 1.0;
+          const int s = lbm_bc_add(d, &op);
+          if (s != LBM_OK) return s;
+          run = -1;
+        }
+      }
+    }
+  return LBM_OK;
+}
 
 int lbm_preset_periodic(lbm_domain* d)
 {

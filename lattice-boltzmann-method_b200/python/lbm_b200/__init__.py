@@ -88,7 +88,7 @@ class TwoPhaseParams(C.Structure):
 
 EXPORTS = [
     "lbm_last_error", "lbm_version", "lbm_config_default", "lbm_create", "lbm_destroy", "lbm_bc_op_default",
-    "lbm_bc_clear", "lbm_bc_add", "lbm_bc_commit", "lbm_bc_get_mask", "lbm_set_f", "lbm_get_f", "lbm_get_moments",
+    "lbm_bc_clear", "lbm_bc_add", "lbm_bc_add_solid", "lbm_bc_commit", "lbm_bc_get_mask", "lbm_set_f", "lbm_get_f", "lbm_get_moments",
     "lbm_get_phase", "lbm_set_u", "lbm_init_equilibrium", "lbm_init_two_phase", "lbm_ibm_set_markers",
     "lbm_ibm_get_roi", "lbm_ibm_get_force", "lbm_ibm_force", "lbm_step", "lbm_synchronize", "lbm_last_step_ms",
     "lbm_kernel_launches", "lbm_get_stream", "lbm_use_graph", "lbm_comm_unique_id", "lbm_comm_init",
@@ -120,6 +120,7 @@ def load():
         for name in ("lbm_destroy", "lbm_bc_clear", "lbm_bc_commit", "lbm_synchronize"):
             getattr(_lib, name).argtypes = [C.c_void_p]
         _lib.lbm_bc_add.argtypes = [C.c_void_p, C.POINTER(BcOp)]
+        _lib.lbm_bc_add_solid.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_int]
         _lib.lbm_bc_get_mask.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
         _lib.lbm_set_f.argtypes = [C.c_void_p, C.c_int, dp]
         _lib.lbm_get_f.argtypes = [C.c_void_p, C.c_int, dp]
@@ -247,6 +248,13 @@ class Domain:
     def bc_add(self, **kw):
         op = bc_op(**kw)
         _chk(self.lib.lbm_bc_add(self.h, C.byref(op)))
+
+    def bc_add_solid(self, solid, lattice=0):
+        """half-way bounce-back around the non-zero nodes of the GLOBAL {X,Y} mask (staircase body)"""
+        m = np.ascontiguousarray(solid, dtype=np.uint8)
+        if m.shape != (self.cfg.X, self.cfg.Y):
+            raise ValueError("solid mask must have the global shape {X,Y}")
+        _chk(self.lib.lbm_bc_add_solid(self.h, lattice, m.ctypes.data_as(C.POINTER(C.c_ubyte)), m.shape[0], m.shape[1]))
 
     def bc_commit(self):
         _chk(self.lib.lbm_bc_commit(self.h))

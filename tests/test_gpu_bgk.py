@@ -88,6 +88,70 @@ def test_periodic_box_vs_oracle(orc, eq, X, Y):
     assert np.abs(rho_g - rho).max() < TOL_LONG and np.abs(u_g - u).max() < TOL_LONG
 
 
+CXI = (0, 1, 0, -1, 0, 1, -1, -1, 1)
+CYI = (0, 0, 1, 0, -1, 1, 1, -1, -1)
+OPPI = (0, 3, 4, 1, 2, 7, 8, 5, 6)
+
+
+def disc(X, Y, cx, cy, r):
+    return ((np.arange(X)[:, None] - cx) ** 2 + (np.arange(Y)[None, :] - cy) ** 2 <= r * r).astype(np.uint8)
+
+
+def bounce_back_step(orc, f, solid, omega):
+    """one step of BGK (compressible) + link-wise half-way bounce-back on the surface of `solid`, from the oracle's
+    granular operators: f_adve[n, q] = f_coll[n, opp q] where n - c_q is on the other side of the surface
+    (the rule of test/rectangle_sedimentation_test.cpp:186-196)"""
+    rho = orc.calc_rho(f)
+    u = orc.calc_u(f, rho)
+    coll = orc.collision(f, orc.equilibrium(u, rho), omega)
+    adve = orc.advect(coll)
+    for q in range(1, 9):
+        cut = solid != np.roll(solid, (CXI[q], CYI[q]), axis=(0, 1))   # roll: element n takes the value at n - c_q
+        adve[cut, q] = coll[cut, OPPI[q]]
+    return adve
+
+
+@pytest.mark.parametrize("X,Y,slabs", [(48, 40, 1), (97, 131, 1), (64, 66, 2), (96, 50, 3)])
+def test_staircase_bounce_back_vs_oracle(orc, X, Y, slabs):
+    """BASELINE.json configs[1] 'with bounce-back': an arbitrary solid mask (a disc, a bar touching the periodic wrap
+    and a disc across the slab cuts) compiled into link-wise rules; masks bit-exact, populations 1e-12 per step"""
+    omega = 1.7
+    solid = disc(X, Y, X / 2 - 0.5, Y / 3, min(X, Y) / 5) | disc(X, Y, X / 3, 0.8 * Y, 3.2)
+    solid[:2, Y // 2:Y // 2 + 5] = 1
+    solid[-1, Y // 2:Y // 2 + 3] = 1
+    f0 = rand_state(X, Y, 11)
+    want_mask = np.zeros((X, Y, 9), dtype=bool)
+    for q in range(1, 9):
+        want_mask[..., q] = solid != np.roll(solid, (CXI[q], CYI[q]), axis=(0, 1))
+    ds = []
+    for r in range(slabs):
+        x0, x1 = L.decompose_rows(X, slabs, r)
+        d = L.Domain(L.default_config(model=L.MODEL_BGK, X=X, Y=Y, omega=omega, equilibrium=L.EQ_COMPRESSIBLE, x0=x0, x1=x1))
+        d.bc_clear()
+        d.bc_add_solid(solid)
+        d.bc_commit()
+        assert np.array_equal(d.bc_mask() != 0, want_mask[x0:x1])
+        d.set_f(f0[x0:x1])
+        ds.append(d)
+    if slabs > 1:
+        for r, d in enumerate(ds):
+            d.link(ds[(r - 1) % slabs], ds[(r + 1) % slabs])
+    ref = f0.copy()
+    for n in range(1, 31):
+        ref = bounce_back_step(orc, ref, solid, omega)
+        if slabs > 1:
+            L.step_group(ds, 1)
+        else:
+            ds[0].step(1)
+        if n in (1, 2, 30):
+            got = np.concatenate([d.get_f() for d in ds], axis=0)
+            assert cases.relerr(got, ref) < TOL_STEP, f"step {n}"
+    # nothing crosses the surface: the mass inside the solid region and outside it are conserved separately
+    got = np.concatenate([d.get_f() for d in ds], axis=0)
+    assert abs(got[solid == 1].sum() - f0[solid == 1].sum()) < 1e-10 * f0.sum()
+    assert abs(got[solid == 0].sum() - f0[solid == 0].sum()) < 1e-10 * f0.sum()
+
+
 def test_poiseuille_golden_and_l2(orc):
     """config 1: the reference's own horizontal_poiseuille_test (21x21, 8301 steps, L2 <= 1e-11)."""
     g = cases.golden("poiseuille_21x21")
