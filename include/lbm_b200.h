@@ -240,7 +240,9 @@ int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, 
 /* ------------------------------------------------------------------------------------------------
  * Immersed boundary (src/ibm.hpp:21-34, src/ibm.cpp:60-190)
  * ---------------------------------------------------------------------------------------------- */
-/* replaces `ibm ib{tbl, name, dev}`: marker coordinates in GLOBAL lattice units */
+/* replaces `ibm ib{tbl, name, dev}`: marker coordinates in GLOBAL lattice units.  With slabs, hand EVERY slab the same
+ * list: a slab that owns none of the ROI rows ignores it (LBM_OK, no body), slabs that share the ROI exchange the moments
+ * of their own ROI nodes every step and keep identical force fields.  The ROI columns must be interior ([2, Y-2)). */
 int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n_markers, int m_max);
 /* ib.rows / ib.cols: roi = {row_start,row_stop,col_start,col_stop} */
 int lbm_ibm_get_roi(lbm_domain* d, long* roi4);

@@ -187,6 +187,32 @@ int comm_exchange_moments(lbm_domain* d)
   return LBM_OK;
 }
 
+// Immersed boundary across slab cuts: the moments of the active ROI nodes, one contiguous row segment per slab that owns
+// ROI rows, swapped between all of those slabs (usually two).  Every rank derives the same list from lbm_decompose_rows.
+int comm_ibm_share(lbm_domain* d, cudaStream_t st)
+{
+  CommState* c = d->comm;
+  IbmState& ib = d->ibm;
+  const int RC = (int)(ib.c1 - ib.c0);
+  LBM_NCCL(g_nccl.GroupStart());
+  for (int k = 0; k < c->n_ranks; k++)
+  {
+    if (k == c->rank) continue;
+    int kx0 = 0, kx1 = 0;
+    lbm_decompose_rows(d->cfg.X, c->n_ranks, k, &kx0, &kx1);
+    const long lo = std::max<long>(ib.r0, kx0) - ib.r0, hi = std::min<long>(ib.r1, kx1) - ib.r0;
+    if (hi <= lo) continue;  // rank k owns no ROI row
+    const size_t mine = (size_t)(ib.row_hi - ib.row_lo) * RC, theirs = (size_t)(hi - lo) * RC;
+    LBM_NCCL(g_nccl.Send(ib.d_rho + (size_t)ib.row_lo * RC, mine, ncclFloat64, k, c->comm, st));
+    LBM_NCCL(g_nccl.Send(ib.d_u + 2 * (size_t)ib.row_lo * RC, 2 * mine, ncclFloat64, k, c->comm, st));
+    LBM_NCCL(g_nccl.Recv(ib.d_rho + (size_t)lo * RC, theirs, ncclFloat64, k, c->comm, st));
+    LBM_NCCL(g_nccl.Recv(ib.d_u + 2 * (size_t)lo * RC, 2 * theirs, ncclFloat64, k, c->comm, st));
+  }
+  LBM_NCCL(g_nccl.GroupEnd());
+  d->launches++;
+  return LBM_OK;
+}
+
 // pressure packet of stage k: from the rank that owns the source row to the rank that owns the written row
 int comm_stage_transfer(lbm_domain* d, size_t k, cudaStream_t st)
 {
@@ -266,7 +292,7 @@ int comm_link_refresh(lbm_domain* d)
     }
     LBM_TRY(link_exchange(d, d->cur, d->side));
   }
-  LBM_TRY(step_prologue(d, false));  // IBM field if any, then ev_side (on the same side stream)
+  LBM_TRY(step_prologue(d, false, !d->ibm.split));  // IBM field if any, then ev_side (on the same side stream)
   return LBM_OK;
 }
 
@@ -350,6 +376,69 @@ int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper)
   return LBM_OK;
 }
 
+// Immersed-boundary pre-pass of linked slabs: (a) every slab computes the moments of the active ROI nodes on its own rows
+// from buffer `which`; (b) slabs that share a body copy each other's row segments; (c) each runs the forcing
+// iterations into its slot and signals ev_side.  use_next: the pre-pass belongs to the step after the one being
+// enqueued (side tail) rather than to this one (prologue).
+static int group_ibm(lbm_domain* const* ds, int n, bool tail)
+{
+  auto uses = [](const lbm_domain* d) { return d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM; };
+  auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
+  for (int i = 0; i < n; i++)
+  {
+    lbm_domain* d = ds[i];
+    if (!uses(d) || (!tail && d->side_ready)) continue;
+    LBM_CUDA(on(d));
+    if (d->ibm.split)  // the other owners may still be copying the segment of the pre-pass before
+      for (int j = 0; j < n; j++)
+        if (j != i && uses(ds[j]) && ds[j]->ibm.split) LBM_CUDA(cudaStreamWaitEvent(d->side, ds[j]->ev_side, 0));
+    ProfScope ps(d, LBM_PROF_IBM, d->side);
+    const int mode = tail ? MODE_PULL : (d->post_stream ? MODE_LOCAL : MODE_PULL);
+    LBM_TRY(ibm_roi_local(d, mode, tail ? d->cur ^ 1 : d->cur, d->side));
+    LBM_CUDA(cudaEventRecord(d->ev_ibm, d->side));
+  }
+  for (int i = 0; i < n; i++)
+  {
+    lbm_domain* d = ds[i];
+    if (!uses(d) || (!tail && d->side_ready)) continue;
+    LBM_CUDA(on(d));
+    ProfScope ps(d, LBM_PROF_IBM, d->side);
+    if (d->ibm.split)
+    {
+      const size_t RC = (size_t)(d->ibm.c1 - d->ibm.c0);
+      for (int j = 0; j < n; j++)
+      {
+        lbm_domain* o = ds[j];
+        if (j == i || !uses(o) || o->ibm.row_hi <= o->ibm.row_lo) continue;
+        if (o->ibm.r0 != d->ibm.r0 || o->ibm.r1 != d->ibm.r1 || o->ibm.n_markers != d->ibm.n_markers)
+        {
+          set_error("lbm_step_group: slabs %d and %d carry different immersed bodies (hand every slab the same marker list)", i, j);
+          return LBM_ERR_INVALID;
+        }
+        LBM_CUDA(cudaStreamWaitEvent(d->side, o->ev_ibm, 0));
+        const size_t lo = (size_t)o->ibm.row_lo * RC, cnt = (size_t)(o->ibm.row_hi - o->ibm.row_lo) * RC;
+        LBM_TRY(copy_rows(d, d->ibm.d_rho + lo, o, o->ibm.d_rho + lo, cnt, d->side));
+        LBM_TRY(copy_rows(d, d->ibm.d_u + 2 * lo, o, o->ibm.d_u + 2 * lo, 2 * cnt, d->side));
+      }
+    }
+    LBM_CUDA(cudaEventRecord(d->ev_ibm_got, d->side));
+  }
+  // (c) the forcing iterations update the ROI velocities in place: not before every co-owner has taken its copy
+  for (int i = 0; i < n; i++)
+  {
+    lbm_domain* d = ds[i];
+    if (!uses(d) || (!tail && d->side_ready)) continue;
+    LBM_CUDA(on(d));
+    ProfScope ps(d, LBM_PROF_IBM, d->side);
+    if (d->ibm.split)
+      for (int j = 0; j < n; j++)
+        if (j != i && uses(ds[j]) && ds[j]->ibm.split) LBM_CUDA(cudaStreamWaitEvent(d->side, ds[j]->ev_ibm_got, 0));
+    LBM_TRY(ibm_iterate(d, tail ? d->ibm.next_slot ^ 1 : d->ibm.next_slot, d->side));
+    LBM_CUDA(cudaEventRecord(d->ev_side, d->side));
+  }
+  return LBM_OK;
+}
+
 // Advance a set of linked slabs in lock step: the phases of one step (lbm_domain.cu) interleaved
 // across the slabs, with the ghost rows and pressure packets copied between the slabs' side streams.
 int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
@@ -395,8 +484,10 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
           if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur, d->side));
           else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->side));
         }
-        LBM_TRY(step_prologue(d, false));
+        LBM_TRY(step_prologue(d, false, false));
       }
+      LBM_TRY(group_ibm(ds, n, false));
+      for (int i = 0; i < n; i++) ds[i]->side_ready = true;
     }
     // ---- early rows, listed nodes
     for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_early(ds[i])); }
@@ -435,8 +526,9 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
         if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur ^ 1, d->side));
         else LBM_TRY(wrap_ghost_rows_local(d, d->cur ^ 1, d->side));
       }
-      LBM_TRY(step_side_tail(d, false));
+      LBM_TRY(step_side_tail(d, false, false));
     }
+    LBM_TRY(group_ibm(ds, n, true));
     // ---- bulk rows
     for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_bulk(ds[i])); }
   }

@@ -247,7 +247,7 @@ static bool uses_ibm(const lbm_domain* d) { return d->ibm.enabled && d->cfg.forc
 
 // Side chain for a state that no step has prepared (first step after an import, or an export):
 // ghost rows of buf[cur] and the IBM field the next step reads.
-int step_prologue(lbm_domain* d, bool exchange_local)
+int step_prologue(lbm_domain* d, bool exchange_local, bool with_ibm)
 {
   if (d->side_ready) return LBM_OK;
   const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
@@ -259,13 +259,13 @@ int step_prologue(lbm_domain* d, bool exchange_local)
     if (comm_active(d)) LBM_TRY(comm_exchange(d, d->cur, d->side));
     else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->side));
   }
-  if (uses_ibm(d))
+  if (with_ibm && uses_ibm(d))
   {
     ProfScope ps(d, LBM_PROF_IBM, d->side);
     LBM_TRY(ibm_prepass(d, mode, d->cur, d->ibm.next_slot, d->side));
   }
   LBM_CUDA(cudaEventRecord(d->ev_side, d->side));
-  d->side_ready = true;
+  d->side_ready = with_ibm || !uses_ibm(d);  // (linked slabs: lbm_step_group finishes the immersed-boundary part)
   return LBM_OK;
 }
 
@@ -350,7 +350,7 @@ static int stage_local(lbm_domain* d, size_t k)
 }
 
 // ghost rows of the NEW buffer and the IBM field of the NEXT step, then ev_side
-int step_side_tail(lbm_domain* d, bool exchange_local)
+int step_side_tail(lbm_domain* d, bool exchange_local, bool with_ibm)
 {
   const int t = d->cur ^ 1;
   if (exchange_local)
@@ -359,7 +359,7 @@ int step_side_tail(lbm_domain* d, bool exchange_local)
     if (comm_active(d)) LBM_TRY(comm_exchange(d, t, d->side));
     else LBM_TRY(wrap_ghost_rows_local(d, t, d->side));
   }
-  if (uses_ibm(d))
+  if (with_ibm && uses_ibm(d))
   {
     ProfScope ps(d, LBM_PROF_IBM, d->side);
     LBM_TRY(ibm_prepass(d, MODE_PULL, t, d->ibm.next_slot ^ 1, d->side));
@@ -390,7 +390,7 @@ static int bgk_step_once(lbm_domain* d)
     set_error("lbm_step: this slab is linked to neighbours; advance the set with lbm_step_group");
     return LBM_ERR_INVALID;
   }
-  LBM_TRY(step_prologue(d, true));
+  LBM_TRY(step_prologue(d, true, true));
   LBM_TRY(step_early(d));
   LBM_TRY(step_listed(d));
   for (size_t k = 0; k < d->stages.size(); k++)
@@ -405,7 +405,7 @@ static int bgk_step_once(lbm_domain* d)
     if (comm_active(d)) LBM_TRY(comm_stage_transfer(d, k, d->side));
     LBM_TRY(stage_apply(d, k));
   }
-  LBM_TRY(step_side_tail(d, true));
+  LBM_TRY(step_side_tail(d, true, true));
   return step_bulk(d);
 }
 
@@ -436,7 +436,7 @@ static int export_post_stream(lbm_domain* d)
   // pull-only pass over every row: the ghost rows of buf[cur] must be in place
   LBM_TRY(step_rows(d));
   if (d->link_lo || d->link_hi) LBM_TRY(comm_link_refresh(d));
-  else LBM_TRY(step_prologue(d, true));
+  else LBM_TRY(step_prologue(d, true, true));
   LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
   LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_all, d->g.Xl, true, d->ibm.used_slot, d->stream};
   return dispatch_bgk<MODE_PULL_ONLY>(d, a);
@@ -814,7 +814,7 @@ int stage_fields(lbm_domain* d, int lattice)
     // per node; no AoS scratch)
     LBM_TRY(step_rows(d));
     if (d->link_lo || d->link_hi) LBM_TRY(comm_link_refresh(d));
-    else LBM_TRY(step_prologue(d, true));
+    else LBM_TRY(step_prologue(d, true, true));
     LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
     LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_all, d->g.Xl, true, d->ibm.used_slot, d->stream};
     a.snap_rho = d->d_mom_out;
@@ -930,7 +930,7 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
   }
   LBM_CUDA(cudaEventCreate(&d->ev_begin));
   LBM_CUDA(cudaEventCreate(&d->ev_end));
-  for (cudaEvent_t* e : {&d->ev_ready, &d->ev_early, &d->ev_side, &d->ev_stage, &d->ev_packet})
+  for (cudaEvent_t* e : {&d->ev_ready, &d->ev_early, &d->ev_side, &d->ev_stage, &d->ev_packet, &d->ev_ibm, &d->ev_ibm_got})
     LBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK || cfg->model == LBM_MODEL_MRT_CSF)
   {
@@ -974,7 +974,7 @@ int lbm_destroy(lbm_domain* d)
   }
   if (d->ev_begin) cudaEventDestroy(d->ev_begin);
   if (d->ev_end) cudaEventDestroy(d->ev_end);
-  for (cudaEvent_t e : {d->ev_ready, d->ev_early, d->ev_side, d->ev_stage, d->ev_packet})
+  for (cudaEvent_t e : {d->ev_ready, d->ev_early, d->ev_side, d->ev_stage, d->ev_packet, d->ev_ibm, d->ev_ibm_got})
     if (e) cudaEventDestroy(e);
   cudaFree(d->d_rows_all); cudaFree(d->d_rows_early); cudaFree(d->d_rows_bulk);
   if (d->side) cudaStreamDestroy(d->side);

@@ -37,7 +37,7 @@ __global__ void k_ibm_roi_moments(const double* __restrict__ f, const SlabGeom g
                                   const int* __restrict__ active, double* __restrict__ u, double* __restrict__ rho)
 {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= na) return;
+  if (a >= na) return;  // active already points at this slab's part of the list
   const int n = active[a];
   const int i = n / RC, j = n % RC;
   const int x = r0 + i - g.xg0, y = c0 + j;
@@ -128,7 +128,7 @@ int ibm_release(lbm_domain* d)
 }
 
 // the four forcing iterations n = 1 .. m_max-1 on the ROI copies (src/ibm.cpp:166-187)
-static int ibm_iterate(lbm_domain* d, int slot, cudaStream_t st)
+int ibm_iterate(lbm_domain* d, int slot, cudaStream_t st)
 {
   IbmState& ib = d->ibm;
   const int RC = (int)(ib.c1 - ib.c0), nn = (int)(ib.r1 - ib.r0) * RC;
@@ -148,20 +148,38 @@ static int ibm_iterate(lbm_domain* d, int slot, cudaStream_t st)
   return LBM_OK;
 }
 
-// force field for the step that will read buffer `which` (mode: how that buffer is to be read)
-int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st)
+// u, rho of the active ROI nodes on this slab's rows, from buffer `which` (mode: how that buffer is to be read)
+int ibm_roi_local(lbm_domain* d, int mode, int which, cudaStream_t st)
 {
   IbmState& ib = d->ibm;
-  const int RC = (int)(ib.c1 - ib.c0);
+  const int RC = (int)(ib.c1 - ib.c0), na = ib.a_hi - ib.a_lo;
+  if (na <= 0) return LBM_OK;
   const double* f = d->buf[0][which];
   const bool comp = d->cfg.equilibrium == LBM_EQ_COMPRESSIBLE;
-#define LBM_ROI(M, E)                                                                                                   \
-  k_ibm_roi_moments<M, E><<<cdiv(ib.n_active, 128), 128, 0, st>>>(f, d->g, (int)ib.r0, (int)ib.c0, ib.n_active, RC, ib.d_active, \
-                                                                  ib.d_u, ib.d_rho)
+#define LBM_ROI(M, E)                                                                                                         \
+  k_ibm_roi_moments<M, E><<<cdiv(na, 128), 128, 0, st>>>(f, d->g, (int)ib.r0, (int)ib.c0, na, RC, ib.d_active + ib.a_lo, ib.d_u, ib.d_rho)
   if (mode == MODE_LOCAL) { if (comp) LBM_ROI(MODE_LOCAL, EQ_COMP); else LBM_ROI(MODE_LOCAL, EQ_INCOMP); }
   else { if (comp) LBM_ROI(MODE_PULL, EQ_COMP); else LBM_ROI(MODE_PULL, EQ_INCOMP); }
 #undef LBM_ROI
   d->launches++;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+// force field for the step that will read buffer `which`: one slab per process (lbm_step).  Linked slabs of one
+// process go through lbm_step_group, which runs the three phases itself with event-ordered copies in between.
+int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st)
+{
+  LBM_TRY(ibm_roi_local(d, mode, which, st));
+  if (d->ibm.split)
+  {
+    if (!comm_active(d))
+    {
+      set_error("immersed boundary across a slab cut: advance the slabs with lbm_step_group or join them with lbm_comm_init");
+      return LBM_ERR_INVALID;
+    }
+    LBM_TRY(comm_ibm_share(d, st));
+  }
   return ibm_iterate(d, slot, st);
 }
 
@@ -191,13 +209,25 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   ib.n_markers = n;
   ib.m_max = m_max;
   const int y_int_end = d->y_int_end;
-  if (ib.r0 < d->cfg.x0 || ib.r1 > d->cfg.x1 || ib.c0 < d->y_int_begin || ib.c1 > y_int_end)
+  if (ib.r0 < 0 || ib.r1 > d->cfg.X || ib.c0 < d->y_int_begin || ib.c1 > y_int_end)
   {
-    set_error("lbm_ibm_set_markers: ROI rows [%ld,%ld) cols [%ld,%ld) must lie inside this slab's rows [%d,%d) and interior columns [2,%d)",
-              ib.r0, ib.r1, ib.c0, ib.c1, d->cfg.x0, d->cfg.x1, y_int_end);
+    set_error("lbm_ibm_set_markers: ROI rows [%ld,%ld) cols [%ld,%ld) must lie inside the grid's rows [0,%d) and interior columns [2,%d)",
+              ib.r0, ib.r1, ib.c0, ib.c1, d->cfg.X, y_int_end);
     ib = IbmState();
     return LBM_ERR_UNSUPPORTED;
   }
+  if (ib.r1 <= d->cfg.x0 || ib.r0 >= d->cfg.x1)
+  {
+    // the body lies on other slabs: nothing to do here (every slab may be handed the same marker list)
+    ib = IbmState();
+    d->rows_dirty = true;
+    d->side_ready = false;
+    drop_graphs(d);
+    return LBM_OK;
+  }
+  ib.split = ib.r0 < d->cfg.x0 || ib.r1 > d->cfg.x1;
+  ib.row_lo = (int)(std::max<long>(ib.r0, d->cfg.x0) - ib.r0);
+  ib.row_hi = (int)(std::min<long>(ib.r1, d->cfg.x1) - ib.r0);
   const int RR = (int)(ib.r1 - ib.r0), RC = (int)(ib.c1 - ib.c0), nn = RR * RC;
   std::vector<int> mrow(n), mcol(n);
   std::vector<double> phi((size_t)n * 16);
@@ -227,6 +257,9 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   }
   ptr.push_back((int)em.size());
   ib.n_active = (int)active.size();
+  // the active list is sorted by node id (row-major), so the nodes on this slab's rows are one contiguous range
+  ib.a_lo = (int)(std::lower_bound(active.begin(), active.end(), ib.row_lo * RC) - active.begin());
+  ib.a_hi = (int)(std::lower_bound(active.begin(), active.end(), ib.row_hi * RC) - active.begin());
   LBM_CUDA(cudaMalloc(&ib.d_mrow, sizeof(int) * n));
   LBM_CUDA(cudaMalloc(&ib.d_mcol, sizeof(int) * n));
   LBM_CUDA(cudaMalloc(&ib.d_phi, sizeof(double) * n * 16));
@@ -238,6 +271,8 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   LBM_CUDA(cudaMalloc(&ib.d_ent_phi, sizeof(double) * std::max<size_t>(em.size(), 1)));
   LBM_CUDA(cudaMalloc(&ib.d_u, sizeof(double) * nn * 2));
   LBM_CUDA(cudaMalloc(&ib.d_rho, sizeof(double) * nn));
+  LBM_CUDA(cudaMemset(ib.d_u, 0, sizeof(double) * nn * 2));
+  LBM_CUDA(cudaMemset(ib.d_rho, 0, sizeof(double) * nn));
   for (int k = 0; k < 2; k++)
   {
     LBM_CUDA(cudaMalloc(&ib.d_Fx[k], sizeof(double) * nn));

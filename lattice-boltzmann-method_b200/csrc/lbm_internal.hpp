@@ -76,6 +76,12 @@ struct IbmState
   double* d_rho = nullptr; // [roi]
   double* d_Fx[2] = {nullptr, nullptr};  // [roi], double-buffered: the pre-pass of step t+1 runs while
   double* d_Fy[2] = {nullptr, nullptr};  // the bulk rows of step t still read the field of step t
+  // A body whose ROI rows cross a slab cut: every slab that owns ROI rows keeps the WHOLE solve (markers, lists, ROI
+  // fields); it computes the moments of the active nodes on its own rows, the slabs swap those row segments, and each
+  // runs the (tiny) forcing iterations redundantly — identical arithmetic, so the force field is the same on all of them.
+  bool split = false;
+  int row_lo = 0, row_hi = 0;  // ROI-local rows owned by this slab
+  int a_lo = 0, a_hi = 0;      // range of the active list that lies on those rows
   int next_slot = 0;  // slot the next step reads (filled by the last pre-pass)
   int used_slot = 0;  // slot the last enqueued step read (lbm_ibm_get_force)
 };
@@ -110,6 +116,8 @@ struct lbm_domain
   cudaEvent_t ev_early = nullptr;   // early rows of the step written (main stream)
   cudaEvent_t ev_side = nullptr;    // side chain done: listed nodes, stages, ghost rows, next IBM field
   cudaEvent_t ev_stage = nullptr;   // listed nodes + stages done (side stream), linked slabs
+  cudaEvent_t ev_ibm_got = nullptr; // ... and the co-owners' segments copied in
+  cudaEvent_t ev_ibm = nullptr;     // moments of this slab's active ROI nodes done (side stream), linked slabs sharing a body
   cudaEvent_t ev_packet = nullptr;  // pressure packet packed (side stream), linked slabs
   bool side_ready = false;          // ghost rows of buf[cur] and the IBM field for the next step are (being) prepared
   // row lists of the interior kernel
@@ -183,13 +191,16 @@ int step_early(lbm_domain* d);                           // main: wait side chai
 int step_listed(lbm_domain* d);                          // side: wait ev_early, listed-node kernel
 int stage_pack(lbm_domain* d, size_t k);                 // side: source half of stage k
 int stage_apply(lbm_domain* d, size_t k);                // side: writer half of stage k
-int step_side_tail(lbm_domain* d, bool exchange_local);  // side: ghost rows of the new buffer, next IBM field, ev_side
+int step_side_tail(lbm_domain* d, bool exchange_local, bool with_ibm);  // side: ghost rows of the new buffer, next IBM field, ev_side
 int step_bulk(lbm_domain* d);                            // main: bulk rows, then the buffer swap
-int step_prologue(lbm_domain* d, bool exchange_local);   // side chain for a state no step has prepared yet
+int step_prologue(lbm_domain* d, bool exchange_local, bool with_ibm);   // side chain for a state no step has prepared yet
 int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st);
 // lbm_ibm.cu
 int ibm_release(lbm_domain* d);
 int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st);
+int ibm_roi_local(lbm_domain* d, int mode, int which, cudaStream_t st);  // moments of the active ROI nodes on this slab's rows
+int ibm_iterate(lbm_domain* d, int slot, cudaStream_t st);               // forcing iterations on the complete ROI fields
+int comm_ibm_share(lbm_domain* d, cudaStream_t st);                      // NCCL: ROI row segments between the slabs that own ROI rows
 // lbm_two_phase.cu
 int tp_create(lbm_domain* d);
 int tp_destroy(lbm_domain* d);

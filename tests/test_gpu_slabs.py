@@ -113,6 +113,41 @@ def test_cylinder_slabs_equal_monolithic(P):
         assert np.array_equal(gather(slabs), mono.get_f())
 
 
+@pytest.mark.parametrize("P,shift", [(2, 0.0), (2, 3.0), (3, 0.0), (4, -11.0), (5, 0.0)])
+def test_cylinder_across_slab_cuts_equal_monolithic(P, shift):
+    """the ROI of the immersed body straddles one or several cuts.  Every slab that owns ROI rows keeps the
+    whole solve, the slabs swap the moments of their own active nodes, and the force field — hence the state — is the
+    monolithic one bit for bit.  Every slab is handed the same marker list; slabs away from the body ignore it."""
+    g = cases.golden("cylinder_99x77")
+    X, Y = int(g["X"]), int(g["Y"])
+    omega, u_lb = float(g["omega"]), float(g["u_lb"])
+    kw = dict(model=L.MODEL_BGK, Y=Y, omega=omega, equilibrium=L.EQ_COMPRESSIBLE, force=L.FORCE_IBM)
+    xs, ys = g["marker_x"] + shift, g["marker_y"]
+    mono = L.Domain(L.default_config(X=X, **kw))
+    mono.preset_free_stream(u_lb, 0.0)
+    mono.ibm_set_markers(xs, ys)
+    roi = mono.ibm_roi()
+
+    def setup(d):
+        d.preset_free_stream(u_lb, 0.0)
+        d.ibm_set_markers(xs, ys)
+
+    slabs = make_slabs(kw, X, P, setup)
+    owners = [d for d in slabs if d.cfg.x0 < roi[1] and roi[0] < d.cfg.x1]
+    assert len(owners) >= 2, "the body must cross a cut in this test"
+    mono.set_f(g["f0"]); scatter(slabs, g["f0"])
+    for n in (1, 2, 30):
+        mono.step(n); L.step_group(slabs, n)
+        assert np.array_equal(gather(slabs), mono.get_f())
+        for d in owners:
+            assert np.array_equal(d.ibm_get_force(), mono.ibm_get_force())
+    # an import in the middle of a run (the un-prepared-state path) and on
+    f = mono.get_f()
+    mono.set_f(f); scatter(slabs, f)
+    mono.step(3); L.step_group(slabs, 3)
+    assert np.array_equal(gather(slabs), mono.get_f())
+
+
 def test_sedimentation_slabs_equal_monolithic():
     g = cases.golden("sedimentation_176x264")
     X, Y = int(g["X"]), int(g["Y"])
