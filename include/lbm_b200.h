@@ -57,8 +57,7 @@ typedef enum
   LBM_MODEL_MRTCG = 2,   /* MRT colour gradient: test/mrtcg_rayleigh_taylor.cpp, test/mrtcg_static_droplet.cpp */
   LBM_MODEL_RK = 3,      /* Rothman-Keller droplet: test/rk_static_droplet_test.cpp */
   LBM_MODEL_MRT_CSF = 5, /* MRT colour gradient with a continuum-surface-force perturbation: test/mrt_rayleigh_taylor.cpp
-                            (curvature of the interface normal, interfacial tension carried into the next velocity);
-                            one slab only */
+                            (curvature of the interface normal, interfacial tension carried into the next velocity) */
   LBM_MODEL_KBC = 4      /* entropic central-moment collision ulbm::d2q9::kbc (src/ulbm.hpp:11-90, src/ulbm.cpp):
                             test/ulbm_double_shear_flow.cpp, test/ulbm_poiseuille.cpp; omega = the class's s2 */
 } lbm_model;

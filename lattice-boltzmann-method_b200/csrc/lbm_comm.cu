@@ -155,21 +155,21 @@ int comm_exchange(lbm_domain* d, int which, cudaStream_t st)
   return LBM_OK;
 }
 
-// two ghost rows of the moment planes across every INTERNAL cut (the global edge replicates)
-int comm_exchange_moments(lbm_domain* d)
+// two ghost rows of `nplanes` planes in the moment-plane geometry across every INTERNAL cut (the global edge replicates)
+int comm_exchange_planes(lbm_domain* d, double* base, int nplanes)
 {
   if (!d->tp || !comm_active(d)) return LBM_OK;
   CommState* c = d->comm;
   int pm = 0;
   long long mplane = 0;
-  double* mom = tp_moment_planes(d, &pm, &mplane);
+  tp_moment_planes(d, &pm, &mplane);
   const int Xl = d->g.Xl;
   const size_t n = (size_t)2 * pm;
   const bool has_dn = d->cfg.x0 > 0, has_up = d->cfg.x1 < d->cfg.X;
   LBM_NCCL(g_nccl.GroupStart());
-  for (int f = 0; f < 5; f++)
+  for (int f = 0; f < nplanes; f++)
   {
-    double* pl = mom + (long long)f * mplane;
+    double* pl = base + (long long)f * mplane;
     // storage row r holds slab row r - 2
     if (has_up)
     {
@@ -185,6 +185,14 @@ int comm_exchange_moments(lbm_domain* d)
   LBM_NCCL(g_nccl.GroupEnd());
   d->launches++;
   return LBM_OK;
+}
+
+int comm_exchange_moments(lbm_domain* d)
+{
+  if (!d->tp) return LBM_OK;
+  int pm = 0;
+  long long mplane = 0;
+  return comm_exchange_planes(d, tp_moment_planes(d, &pm, &mplane), 5);
 }
 
 // Immersed boundary across slab cuts: the moments of the active ROI nodes, one contiguous row segment per slab that owns

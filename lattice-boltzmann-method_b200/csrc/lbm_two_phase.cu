@@ -1057,19 +1057,20 @@ int tp_step(lbm_domain* d)
   return LBM_OK;
 }
 
-// two rows of the five moment planes from the linked neighbours across every INTERNAL cut (the global edge replicates)
-static int tp_link_halo(lbm_domain* d)
+// two rows of `nplanes` planes (moment-plane geometry) from the linked neighbours across every INTERNAL cut (the global
+// edge replicates): the five moment planes, or the CSF model's normal field
+static int tp_link_halo_planes(lbm_domain* d, double* TwoPhaseState::*field, int nplanes)
 {
   TwoPhaseState* tp = d->tp;
   const int pm = tp->mg.pm, Xl = d->g.Xl;
   const size_t bytes = sizeof(double) * 2 * pm;
-  for (int f = 0; f < M_COUNT; f++)
+  for (int f = 0; f < nplanes; f++)
   {
-    double* pl = tp->mom + (long long)f * tp->mg.mplane;
+    double* pl = tp->*field + (long long)f * tp->mg.mplane;
     if (d->cfg.x0 > 0 && d->link_lo)  // rows -2, -1 <- the lower slab's last two rows
     {
       lbm_domain* o = d->link_lo;
-      const double* src = o->tp->mom + (long long)f * o->tp->mg.mplane + (long long)o->g.Xl * o->tp->mg.pm;
+      const double* src = o->tp->*field + (long long)f * o->tp->mg.mplane + (long long)o->g.Xl * o->tp->mg.pm;
       if (o->cfg.device == d->cfg.device) LBM_CUDA(cudaMemcpyAsync(pl, src, bytes, cudaMemcpyDeviceToDevice, d->stream));
       else LBM_CUDA(cudaMemcpyPeerAsync(pl, d->cfg.device, src, o->cfg.device, bytes, d->stream));
       d->launches++;
@@ -1077,7 +1078,7 @@ static int tp_link_halo(lbm_domain* d)
     if (d->cfg.x1 < d->cfg.X && d->link_hi)  // rows Xl, Xl+1 <- the upper slab's first two rows
     {
       lbm_domain* o = d->link_hi;
-      const double* src = o->tp->mom + (long long)f * o->tp->mg.mplane + (long long)2 * o->tp->mg.pm;
+      const double* src = o->tp->*field + (long long)f * o->tp->mg.mplane + (long long)2 * o->tp->mg.pm;
       double* dst = pl + (long long)(Xl + 2) * pm;
       if (o->cfg.device == d->cfg.device) LBM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d->stream));
       else LBM_CUDA(cudaMemcpyPeerAsync(dst, d->cfg.device, src, o->cfg.device, bytes, d->stream));
@@ -1087,18 +1088,17 @@ static int tp_link_halo(lbm_domain* d)
   return LBM_OK;
 }
 
+static int tp_link_halo(lbm_domain* d) { return tp_link_halo_planes(d, &TwoPhaseState::mom, M_COUNT); }
+
+static int csf_step_group(lbm_domain* const* ds, int n, int n_steps);
+
 // Linked two-phase slabs in lock step (lbm_step_group): the phases of tp_step interleaved across the slabs, every
 // cross-slab read ordered by events on the slabs' streams:
 //   pre_i   waits until the neighbours finished reading slab i's plane rows (their halo of the step before)
 //   halo_i  waits for the neighbours' pre;   main_i;   ghost_i waits for the neighbours' main
 int tp_step_group(lbm_domain* const* ds, int n, int n_steps)
 {
-  for (int i = 0; i < n; i++)
-    if (ds[i]->tp->model == TP_CSF)
-    {
-      set_error("lbm_step_group: LBM_MODEL_MRT_CSF runs on one slab (its curvature needs a 4-row halo that is not exchanged yet)");
-      return LBM_ERR_UNSUPPORTED;
-    }
+  if (ds[0]->tp->model == TP_CSF) return csf_step_group(ds, n, n_steps);
   auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
   auto wait_neighbours = [&](lbm_domain* d, cudaEvent_t lbm_domain::*ev) -> int {
     for (lbm_domain* o : {d->link_lo, d->link_hi})
@@ -1421,31 +1421,121 @@ static int csf_launch_collide(lbm_domain* d)
   return LBM_OK;
 }
 
-static int csf_step(lbm_domain* d)
+// The step in three phases; slabs put a two-row halo between them (normals differentiate the phase field, the
+// curvature differentiates the normals: together the 4-row reach of SURVEY §8(f) rank 2):
+//   moments   (pull)  rho_k, u (with the stored Fs), phase -> planes, columns padded      | halo: 5 moment planes
+//   normals           global edge rows padded, n = -grad / (1e-20 + |grad|), columns padded | halo: n_x, n_y
+//   collide           global edge rows of n padded, K, Fs, collision                        | ghost rows of the populations
+static int csf_phase_moments(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
-  if (comm_active(d) || d->link_lo || d->link_hi || d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X)
-  {
-    set_error("LBM_MODEL_MRT_CSF runs on one slab (its curvature needs a 4-row halo that is not exchanged yet)");
-    return LBM_ERR_UNSUPPORTED;
-  }
-  if (!d->post_stream && !tp->planes_full) LBM_TRY(csf_fill_planes(d));  // first step after an import: the caller's u
+  if (!d->post_stream && !tp->planes_full) LBM_TRY(csf_fill_planes(d));  // (post-stream state: the import's planes, the caller's u)
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
+  d->launches++;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+static int csf_phase_normals(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
+  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  k_csf_normals<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
+  d->launches += 3;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+static int csf_phase_collide(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
   {
     ProfScope ps(d, LBM_PROF_MOMENTS);
-    LBM_TRY(tp_pad(d));
-    const long long N = (long long)d->g.Xl * d->g.Y;
-    k_csf_normals<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg);
-    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
-    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 1, 1, 2);
-    d->launches += 3;
+    const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, lo, hi, 2);
+    d->launches++;
   }
   if (d->post_stream) LBM_TRY(csf_launch_collide<MODE_LOCAL>(d));
   else LBM_TRY(csf_launch_collide<MODE_PULL>(d));
   d->cur ^= 1;
   d->post_stream = false;
   tp->planes_full = false;
+  return LBM_OK;
+}
+
+static int csf_step(lbm_domain* d)
+{
+  LBM_TRY(csf_phase_moments(d));
+  LBM_TRY(comm_exchange_planes(d, d->tp->mom, M_COUNT));  // NCCL ring; nothing on a single slab
+  LBM_TRY(csf_phase_normals(d));
+  LBM_TRY(comm_exchange_planes(d, d->tp->aux, 2));
+  LBM_TRY(csf_phase_collide(d));
   ProfScope ps(d, LBM_PROF_GHOST);
+  if (comm_active(d)) return comm_exchange(d, d->cur, d->stream);
   return wrap_ghost_rows_local(d, d->cur, d->stream);
+}
+
+// linked slabs: the three phases interleaved across the slabs; ev_ready = planes written, ev_packet = normals written,
+// ev_stage = collision done.  A slab's next moments pass comes after its wait for the neighbours' ev_stage, by which
+// time they have finished copying rows out of its planes.
+static int csf_step_group(lbm_domain* const* ds, int n, int n_steps)
+{
+  auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
+  auto wait_neighbours = [&](lbm_domain* d, cudaEvent_t lbm_domain::*ev) -> int {
+    for (lbm_domain* o : {d->link_lo, d->link_hi})
+      if (o && o != d) LBM_CUDA(cudaStreamWaitEvent(d->stream, o->*ev, 0));
+    return LBM_OK;
+  };
+  for (int i = 0; i < n; i++)
+  {
+    LBM_CUDA(on(ds[i]));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_begin, ds[i]->stream));
+  }
+  for (int s = 0; s < n_steps; s++)
+  {
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(on(ds[i]));
+      LBM_TRY(csf_phase_moments(ds[i]));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_ready, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(on(ds[i]));
+      LBM_TRY(wait_neighbours(ds[i], &lbm_domain::ev_ready));
+      LBM_TRY(tp_link_halo_planes(ds[i], &TwoPhaseState::mom, M_COUNT));
+      LBM_TRY(csf_phase_normals(ds[i]));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_packet, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      LBM_CUDA(on(ds[i]));
+      LBM_TRY(wait_neighbours(ds[i], &lbm_domain::ev_packet));
+      LBM_TRY(tp_link_halo_planes(ds[i], &TwoPhaseState::aux, 2));
+      LBM_TRY(csf_phase_collide(ds[i]));
+      LBM_CUDA(cudaEventRecord(ds[i]->ev_stage, ds[i]->stream));
+    }
+    for (int i = 0; i < n; i++)
+    {
+      lbm_domain* d = ds[i];
+      LBM_CUDA(on(d));
+      LBM_TRY(wait_neighbours(d, &lbm_domain::ev_stage));
+      ProfScope ps(d, LBM_PROF_GHOST);
+      if (d->link_lo || d->link_hi) LBM_TRY(link_exchange(d, d->cur, d->stream));
+      else LBM_TRY(wrap_ghost_rows_local(d, d->cur, d->stream));
+    }
+  }
+  for (int i = 0; i < n; i++)
+  {
+    LBM_CUDA(on(ds[i]));
+    LBM_CUDA(cudaEventRecord(ds[i]->ev_end, ds[i]->stream));
+  }
+  return LBM_OK;
 }
 
 }  // namespace lbm

@@ -115,6 +115,33 @@ def main():
             failures.append("rk")
     d.close()
 
+    # ---- continuum-surface-force variant: halos of the moment planes and of the normal field across the ring
+    R, Cc = 96, 40
+    x0, x1 = L.decompose_rows(R, world, rank)
+    import ctypes  # noqa: F401
+    from oracle_lib import CsfParams, Oracle
+    p = CsfParams()
+    p.R, p.C = R, Cc
+    p.r_rho0, p.r_alpha, p.r_nu, p.r_beta, p.r_A = 3.0, 0.7, 0.04, 0.7, 0.5
+    p.b_rho0, p.b_alpha, p.b_nu, p.b_beta, p.b_A = 1.0, 0.1, 0.04, -0.7, 0.5
+    p.sigma, p.delta = 0.1, 0.1
+    p.Fg[0], p.Fg[1] = 6.25e-6, 0.0
+    st = Oracle().csf_init(p)
+    d = cases.csf(R, Cc, x0=x0, x1=x1, device=local)
+    d.comm_init(fresh_id(), world, rank)
+    d.init_two_phase(st["r_rho"][x0:x1], st["b_rho"][x0:x1], st["u"][x0:x1])
+    d.step(15)
+    got_r, got_b = gather(d.get_f(0)), gather(d.get_f(1))
+    if rank == 0:
+        mono = cases.csf(R, Cc, device=local)
+        mono.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+        mono.step(15)
+        ok = np.array_equal(got_r, mono.get_f(0)) and np.array_equal(got_b, mono.get_f(1))
+        print(f"csf ring of {world}: bit-exact vs monolithic after 15 steps = {ok}")
+        if not ok:
+            failures.append("csf")
+    d.close()
+
     # ---- cylinder: IBM body in rank 0's slab, ABB rows at the two global ends, specular columns
     g = cases.golden("cylinder_99x77")
     X, Y = int(g["X"]), int(g["Y"])
