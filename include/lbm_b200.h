@@ -243,6 +243,13 @@ int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, 
  * list: a slab that owns none of the ROI rows ignores it (LBM_OK, no body), slabs that share the ROI exchange the moments
  * of their own ROI nodes every step and keep identical force fields.  The ROI columns must be interior ([2, Y-2)). */
 int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n_markers, int m_max);
+/* A constant body force on a rectangle of nodes, entering through the source term only (no velocity shift):
+ *   f_coll[region] += (1 - omega/2) ((ics2 + ics4 u.c_q)(F.c_q) - ics2 u.F) w_q
+ * test/decompose_domain_loop.cpp:66-69,151-158 (F = (3e-3, 0), ics2 = 3, ics4 = 9, rows L/4+5 .. L/4+55 of block A).
+ * Slices are GLOBAL with torch semantics (clamped).  Occupies the force-field slot of the immersed boundary: the domain
+ * must have been created with force = LBM_FORCE_IBM, and markers and a region force exclude each other. */
+int lbm_set_force_region(lbm_domain* d, int x_begin, int x_end, int y_begin, int y_end, double Fx, double Fy, double ics2,
+                         double ics4);
 /* ib.rows / ib.cols: roi = {row_start,row_stop,col_start,col_stop} */
 int lbm_ibm_get_roi(lbm_domain* d, long* roi4);
 /* last Eulerian force density F {roi_rows, roi_cols, 2} computed inside lbm_step (cylinder_test.cpp:110) */
@@ -293,6 +300,16 @@ int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks
 int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper);
 /* advance a set of linked slabs in lock step (what decompose_domain.cpp's loop does for A and B) */
 int lbm_step_group(lbm_domain* const* domains, int n_domains, int n_steps);
+/* Multi-block binding across a COLUMN face — the "Bind the domains" lines of test/decompose_domain_loop.cpp:232-261, one
+ * call per direction.  The three populations that enter block d through its edge column (`side` 0 = first column,
+ * populations 2, 5, 6; `side` 1 = last column, populations 4, 7, 8) on rows [row_begin, row_begin + n_rows) stream in from
+ * the facing edge column of `other` (its last column for side 0, its first for side 1), rows
+ * [other_row_begin, other_row_begin + n_rows):
+ *   f_adve[row_begin + k, col, q] = other.f_coll[other_row_begin + k - c_qx, col', q]     for 0 <= k - c_qx < n_rows,
+ * i.e. the diagonal populations keep the block's own (wall) rule at the two ends of the face, as in the reference.
+ * Blocks keep their own coordinates and rule lists (like the reference's `domain A{L, L4}; domain B{L4, L2}; ...`), must own
+ * all their rows, and are advanced together with lbm_step_group.  Call lbm_bc_commit after the last binding. */
+int lbm_link_face(lbm_domain* d, int side, int row_begin, int n_rows, lbm_domain* other, int other_row_begin);
 /* bit-exact decomposition indexing: rows [x0,x1) for `rank` of `n_ranks` over X rows */
 int lbm_decompose_rows(int X, int n_ranks, int rank, int* x0, int* x1);
 

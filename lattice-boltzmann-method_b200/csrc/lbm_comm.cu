@@ -304,6 +304,19 @@ int comm_link_refresh(lbm_domain* d)
   return LBM_OK;
 }
 
+int faces_release(lbm_domain* d)
+{
+  for (auto& fl : d->faces)
+  {
+    if (fl.other) cudaSetDevice(fl.other->cfg.device);
+    cudaFree(fl.d_packet);
+    if (fl.ev) cudaEventDestroy(fl.ev);
+  }
+  d->faces.clear();
+  cudaSetDevice(d->cfg.device);
+  return LBM_OK;
+}
+
 }  // namespace lbm
 
 using namespace lbm;
@@ -384,13 +397,108 @@ int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper)
   return LBM_OK;
 }
 
+int lbm_link_face(lbm_domain* d, int side, int row_begin, int n_rows, lbm_domain* other, int other_row_begin)
+{
+  if (!d || !other || (side != 0 && side != 1) || n_rows < 1) { set_error("lbm_link_face: bad argument"); return LBM_ERR_INVALID; }
+  if (d->tp || other->tp || d->nlat != other->nlat)
+  {
+    set_error("lbm_link_face: column faces are built for the single-phase models (the two-phase moment planes have no column halo)");
+    return LBM_ERR_UNSUPPORTED;
+  }
+  if (d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X || other->cfg.x0 != 0 || other->cfg.x1 != other->cfg.X)
+  {
+    set_error("lbm_link_face: a block bound across a column face must own all of its rows (no row slabs)");
+    return LBM_ERR_UNSUPPORTED;
+  }
+  if (row_begin < 0 || row_begin + n_rows > d->cfg.X || other_row_begin < 0 || other_row_begin + n_rows > other->cfg.X)
+  {
+    set_error("lbm_link_face: rows [%d,%d) / [%d,%d) outside the blocks", row_begin, row_begin + n_rows, other_row_begin, other_row_begin + n_rows);
+    return LBM_ERR_INVALID;
+  }
+  for (const auto& fl : d->faces)
+    if (fl.side == side && row_begin < fl.rb + fl.n && fl.rb < row_begin + n_rows)
+    {
+      set_error("lbm_link_face: rows [%d,%d) of side %d are already bound", row_begin, row_begin + n_rows, side);
+      return LBM_ERR_INVALID;
+    }
+  FaceLink fl;
+  fl.side = side; fl.rb = row_begin; fl.n = n_rows; fl.orb = other_row_begin; fl.other = other;
+  LBM_CUDA(cudaSetDevice(other->cfg.device));
+  LBM_CUDA(cudaMalloc(&fl.d_packet, sizeof(double) * d->nlat * 3 * n_rows));
+  LBM_CUDA(cudaEventCreateWithFlags(&fl.ev, cudaEventDisableTiming));
+  if (other->cfg.device != d->cfg.device)
+  {
+    int can = 0;
+    LBM_CUDA(cudaDeviceCanAccessPeer(&can, d->cfg.device, other->cfg.device));
+    if (can)
+    {
+      LBM_CUDA(cudaSetDevice(d->cfg.device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(other->cfg.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) LBM_CUDA(e);
+      cudaGetLastError();
+    }
+  }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  d->faces.push_back(fl);
+  d->committed = false;  // the edge-column programs change: lbm_bc_commit again
+  d->side_ready = false;
+  drop_graphs(d);
+  return LBM_OK;
+}
+
+// packet[lattice][qi][k] = f_coll(lattice)[row0 + k, col, face_q(side, qi)]
+__global__ void k_face_pack(const double* __restrict__ f0, const double* __restrict__ f1, const SlabGeom g, int col, int row0,
+                            int n, int side, int nlat, double* __restrict__ packet)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nlat * 3 * n) return;
+  const int k = idx % n, qi = (idx / n) % 3, l = idx / (3 * n);
+  const double* f = l == 0 ? f0 : f1;
+  packet[idx] = f[(long long)face_q(side, qi) * g.plane + node_off(g, row0 + k, col)];
+}
+
+// Face tails of every bound block: the facing edge columns of the other blocks (written by their listed-node kernels on
+// their side streams) packed there, copied here on this block's side stream ahead of its next listed-node kernel.
+// new_buffer: the buffers being written by the step in flight (cur ^ 1) rather than the current ones.
+static int group_faces(lbm_domain* const* ds, int n, bool new_buffer)
+{
+  for (int i = 0; i < n; i++)
+  {
+    lbm_domain* d = ds[i];
+    for (auto& fl : d->faces)
+    {
+      lbm_domain* o = fl.other;
+      bool member = false;
+      for (int j = 0; j < n; j++) member = member || ds[j] == o;
+      if (!member || !o->have_state) { set_error("lbm_step_group: a block is bound to a block outside the group"); return LBM_ERR_INVALID; }
+      const int ow = new_buffer ? o->cur ^ 1 : o->cur, dw = new_buffer ? d->cur ^ 1 : d->cur;
+      LBM_CUDA(cudaSetDevice(o->cfg.device));
+      LBM_CUDA(cudaStreamWaitEvent(o->side, d->ev_side, 0));  // the copy out of this packet one step ago
+      const int total = d->nlat * 3 * fl.n;
+      k_face_pack<<<(total + 127) / 128, 128, 0, o->side>>>(o->buf[0][ow], o->buf[1][ow], o->g, fl.side == 0 ? o->g.Y - 1 : 0, fl.orb,
+                                                           fl.n, fl.side, d->nlat, fl.d_packet);
+      o->launches++;
+      LBM_CUDA(cudaGetLastError());
+      LBM_CUDA(cudaEventRecord(fl.ev, o->side));
+      LBM_CUDA(cudaSetDevice(d->cfg.device));
+      LBM_CUDA(cudaStreamWaitEvent(d->side, fl.ev, 0));
+      ProfScope ps(d, LBM_PROF_GHOST, d->side);
+      for (int l = 0; l < d->nlat; l++)
+        for (int qi = 0; qi < 3; qi++)
+          LBM_TRY(copy_rows(d, d->buf[l][dw] + face_tail_off(d->g, fl.side, qi, fl.rb), o, fl.d_packet + (size_t)(l * 3 + qi) * fl.n,
+                            (size_t)fl.n, d->side));
+    }
+  }
+  return LBM_OK;
+}
+
 // Immersed-boundary pre-pass of linked slabs: (a) every slab computes the moments of the active ROI nodes on its own rows
 // from buffer `which`; (b) slabs that share a body copy each other's row segments; (c) each runs the forcing
 // iterations into its slot and signals ev_side.  use_next: the pre-pass belongs to the step after the one being
 // enqueued (side tail) rather than to this one (prologue).
 static int group_ibm(lbm_domain* const* ds, int n, bool tail)
 {
-  auto uses = [](const lbm_domain* d) { return d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM; };
+  auto uses = [](const lbm_domain* d) { return d->ibm.enabled && !d->ibm.fixed && d->cfg.force == LBM_FORCE_IBM; };
   auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
   for (int i = 0; i < n; i++)
   {
@@ -459,6 +567,13 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
     if (ds[i]->stages.size() != ds[0]->stages.size()) { set_error("lbm_step_group: slabs carry different rule lists"); return LBM_ERR_INVALID; }
     if (ds[i]->cur != ds[0]->cur || ds[i]->post_stream != ds[0]->post_stream) { set_error("lbm_step_group: slabs are out of step"); return LBM_ERR_INVALID; }
   }
+  for (int i = 0; i < n; i++)
+    for (const auto& fl : ds[i]->faces)
+    {
+      bool member = false;
+      for (int j = 0; j < n; j++) member = member || ds[j] == fl.other;
+      if (!member) { set_error("lbm_step_group: block %d is bound across a column face to a block outside the group", i); return LBM_ERR_INVALID; }
+    }
   if (ds[0]->tp) return tp_step_group(ds, n, n_steps);
   auto on = [](lbm_domain* d) { return cudaSetDevice(d->cfg.device); };
   for (int i = 0; i < n; i++)
@@ -494,12 +609,19 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
         }
         LBM_TRY(step_prologue(d, false, false));
       }
+      if (!ds[0]->post_stream)
+      {
+        LBM_TRY(group_faces(ds, n, false));
+        for (int i = 0; i < n; i++)
+          if (!ds[i]->faces.empty()) { LBM_CUDA(on(ds[i])); LBM_CUDA(cudaEventRecord(ds[i]->ev_side, ds[i]->side)); }
+      }
       LBM_TRY(group_ibm(ds, n, false));
       for (int i = 0; i < n; i++) ds[i]->side_ready = true;
     }
     // ---- early rows, listed nodes
     for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_early(ds[i])); }
     for (int i = 0; i < n; i++) { LBM_CUDA(on(ds[i])); LBM_TRY(step_listed(ds[i])); }
+    LBM_TRY(group_faces(ds, n, true));  // the edge columns just written feed the bound blocks' next step
     // ---- pre-stream stages, packets handed from the source owner to the writer
     for (size_t k = 0; k < ds[0]->stages.size(); k++)
     {

@@ -67,6 +67,8 @@ struct BgkParams
   int roi_r0, roi_r1, roi_c0, roi_c1;
   const double* Fx;
   const double* Fy;
+  double ics2, ics4;  // constants of the source term as the driver names them: 1/3, 1/9 (gravity_test.cpp:143-144,
+                      // cylinder_test.cpp:112-113) or 3, 9 (decompose_domain_loop.cpp:68-69)
   // LBM_MODEL_KBC, first step after an import: rho {Xl,Y}, u {Xl,Y,2} supplied by the caller (the drivers' m0 / m1
   // members, test/ulbm_poiseuille.cpp:93) instead of the moments of the imported populations; nullptr otherwise
   const double* mom_in_rho;
@@ -349,7 +351,7 @@ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, 
   }
   else
   {
-    constexpr double ics2 = 1.0 / 3.0, ics4 = 1.0 / 9.0;
+    const double ics2 = p.ics2, ics4 = p.ics4;
     double fx = Fx, fy = Fy;
     if constexpr (FORCE == FORCE_UNIFORM)
     {

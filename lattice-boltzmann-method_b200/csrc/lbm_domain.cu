@@ -123,6 +123,8 @@ static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
   p.roi_r0 = (int)d->ibm.r0; p.roi_r1 = (int)d->ibm.r1; p.roi_c0 = (int)d->ibm.c0; p.roi_c1 = (int)d->ibm.c1;
   p.Fx = d->ibm.d_Fx[a.slot];
   p.Fy = d->ibm.d_Fy[a.slot];
+  p.ics2 = d->ics2;
+  p.ics4 = d->ics4;
   p.mom_in_rho = (MODE == MODE_LOCAL && d->mom_in_valid) ? d->d_mom_in : nullptr;
   p.mom_in_u = p.mom_in_rho ? d->d_mom_in + (long long)d->g.Xl * d->g.Y : nullptr;
   p.Y = d->g.Y;
@@ -217,7 +219,7 @@ int step_rows(lbm_domain* d)
   early[0] = early[Xl - 1] = 1;
   for (int x = 0; x < Xl && x < (int)d->row_has_listed.size(); x++)
     if (d->row_has_listed[x]) early[x] = 1;
-  if (d->ibm.enabled)
+  if (d->ibm.enabled && !d->ibm.fixed)
     for (long gx = d->ibm.r0 - 1; gx < d->ibm.r1 + 1; gx++)
     {
       const long x = gx - d->cfg.x0;
@@ -243,7 +245,7 @@ int step_rows(lbm_domain* d)
   return LBM_OK;
 }
 
-static bool uses_ibm(const lbm_domain* d) { return d->ibm.enabled && d->cfg.force == LBM_FORCE_IBM; }
+static bool uses_ibm(const lbm_domain* d) { return d->ibm.enabled && !d->ibm.fixed && d->cfg.force == LBM_FORCE_IBM; }
 
 // Side chain for a state that no step has prepared (first step after an import, or an export):
 // ghost rows of buf[cur] and the IBM field the next step reads.
@@ -385,6 +387,11 @@ int step_bulk(lbm_domain* d)
 
 static int bgk_step_once(lbm_domain* d)
 {
+  if (!d->faces.empty())
+  {
+    set_error("lbm_step: this block is bound to others across a column face; advance the set with lbm_step_group");
+    return LBM_ERR_INVALID;
+  }
   if (d->link_lo || d->link_hi)
   {
     set_error("lbm_step: this slab is linked to neighbours; advance the set with lbm_step_group");
@@ -713,6 +720,33 @@ int commit_boundary_tables(lbm_domain* d)
     }
   }
 
+  // ---- column-face bindings (lbm_link_face), after every op like "Bind the domains" at the end of the reference's loop
+  // body (test/decompose_domain_loop.cpp:230-261): population q entering through the edge column on row rb + k comes
+  // from row k - c_qx of the facing column; where that row is outside the bound range the wall rule stays
+  for (size_t j = 0; j < d->faces.size(); j++)
+  {
+    const FaceLink& fl = d->faces[j];
+    const int col = fl.side == 0 ? 0 : Y - 1;
+    for (int k = 0; k < fl.n; k++)
+    {
+      const int i = index.at((long long)(fl.rb + k) * Y + col);
+      for (int qi = 0; qi < 3; qi++)
+      {
+        const int q = face_q(fl.side, qi);
+        const int ks = k - CX(q);
+        if (ks < 0 || ks >= fl.n) continue;
+        for (int l = 0; l < d->nlat; l++)
+        {
+          BcEntry e;
+          e.src = face_tail_off(g, fl.side, qi, fl.rb + ks);
+          e.coef = 1.0; e.cst = 0.0; e.kind = OP_LINEAR; e.sq = q; e.aux0 = e.aux1 = 0;
+          ent[((size_t)l * 9 + q) * nb + i] = e;
+          d->mask[l][((size_t)(fl.rb + k) * Y + col) * 9 + q] = (int32_t)(d->ops.size() + 1 + j);
+        }
+      }
+    }
+  }
+
   // rows the interior kernel must finish before the listed-node kernel / the stages touch them
   d->row_has_listed.assign(Xl, 0);
   for (auto& kv : index)
@@ -907,7 +941,7 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
     d->y_int_begin = 1;
     d->y_int_end = cfg->Y - 1;
   }
-  const size_t bytes = (size_t)9 * d->g.plane * sizeof(double);
+  const size_t bytes = ((size_t)9 * d->g.plane + (size_t)6 * d->g.Xl) * sizeof(double);  // nine planes + the face tail
   for (int l = 0; l < d->nlat; l++)
     for (int b = 0; b < 2; b++)
     {
@@ -948,6 +982,7 @@ int lbm_destroy(lbm_domain* d)
   if (d->stream) cudaStreamSynchronize(d->stream);
   if (d->side) cudaStreamSynchronize(d->side);
   release_compiled(d);
+  faces_release(d);
   ibm_release(d);
   tp_destroy(d);
   comm_release(d);

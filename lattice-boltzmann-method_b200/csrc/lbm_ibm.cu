@@ -195,6 +195,8 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   if (!d || !xs || !ys || n <= 0 || m_max < 1) { set_error("lbm_ibm_set_markers: bad argument"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   ibm_release(d);
+  d->ics2 = 1.0 / 3.0;  // cylinder_test.cpp:112-113
+  d->ics4 = 1.0 / 9.0;
   IbmState& ib = d->ibm;
   // ROI: src/ibm.cpp:122-156
   long r_min = 1000000, r_max = 0, c_min = 1000000, c_max = 0;
@@ -287,6 +289,50 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   LBM_CUDA(cudaMemcpy(ib.d_ent_marker, em.data(), sizeof(int) * em.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(ib.d_ent_phi, ephi.data(), sizeof(double) * ephi.size(), cudaMemcpyHostToDevice));
   ib.enabled = true;
+  d->rows_dirty = true;
+  d->side_ready = false;
+  drop_graphs(d);
+  return LBM_OK;
+}
+
+// torch::indexing::Slice(b, e) over n entries (negative = from the end, LBM_END = None, clamped)
+static void clamp_slice(int b, int e, int n, long& lo, long& hi)
+{
+  lo = b < 0 ? b + n : b;
+  hi = e == LBM_END ? n : (e < 0 ? e + n : e);
+  lo = std::min<long>(std::max<long>(lo, 0), n);
+  hi = std::min<long>(std::max<long>(hi, lo), n);
+}
+
+int lbm_set_force_region(lbm_domain* d, int x_begin, int x_end, int y_begin, int y_end, double Fx, double Fy, double ics2, double ics4)
+{
+  if (!d) { set_error("lbm_set_force_region: null domain"); return LBM_ERR_INVALID; }
+  if (d->cfg.force != LBM_FORCE_IBM || d->tp || d->cfg.model == LBM_MODEL_KBC)
+  {
+    set_error("lbm_set_force_region: the region force uses the force-field slot of the BGK kernels (create the domain with force = LBM_FORCE_IBM)");
+    return LBM_ERR_INVALID;
+  }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  LBM_CUDA(cudaStreamSynchronize(d->side));
+  ibm_release(d);
+  IbmState& ib = d->ibm;
+  clamp_slice(x_begin, x_end, d->cfg.X, ib.r0, ib.r1);
+  clamp_slice(y_begin, y_end, d->cfg.Y, ib.c0, ib.c1);
+  const size_t nn = (size_t)(ib.r1 - ib.r0) * (size_t)(ib.c1 - ib.c0);
+  if (nn == 0) { ib = IbmState(); return LBM_OK; }
+  std::vector<double> hx(nn, Fx), hy(nn, Fy);
+  for (int k = 0; k < 2; k++)
+  {
+    LBM_CUDA(cudaMalloc(&ib.d_Fx[k], sizeof(double) * nn));
+    LBM_CUDA(cudaMalloc(&ib.d_Fy[k], sizeof(double) * nn));
+    LBM_CUDA(cudaMemcpy(ib.d_Fx[k], hx.data(), sizeof(double) * nn, cudaMemcpyHostToDevice));
+    LBM_CUDA(cudaMemcpy(ib.d_Fy[k], hy.data(), sizeof(double) * nn, cudaMemcpyHostToDevice));
+  }
+  ib.fixed = true;
+  ib.enabled = true;
+  d->ics2 = ics2;
+  d->ics4 = ics4;
   d->rows_dirty = true;
   d->side_ready = false;
   drop_graphs(d);

@@ -79,6 +79,8 @@ struct IbmState
   // A body whose ROI rows cross a slab cut: every slab that owns ROI rows keeps the WHOLE solve (markers, lists, ROI
   // fields); it computes the moments of the active nodes on its own rows, the slabs swap those row segments, and each
   // runs the (tiny) forcing iterations redundantly — identical arithmetic, so the force field is the same on all of them.
+  // lbm_set_force_region: the field is a constant the caller gave (no markers, no pre-pass)
+  bool fixed = false;
   bool split = false;
   int row_lo = 0, row_hi = 0;  // ROI-local rows owned by this slab
   int a_lo = 0, a_hi = 0;      // range of the active list that lies on those rows
@@ -95,6 +97,23 @@ struct ProfRec
 struct TwoPhaseState;  // lbm_two_phase.cu
 struct CommState;      // lbm_comm.cu
 
+}  // namespace lbm
+
+namespace lbm
+{
+// test/decompose_domain_loop.cpp:232-261, one direction of one face: rows [rb, rb + n) of this block's edge column
+// `side` (0 = first column: populations 2, 5, 6 enter; 1 = last column: 4, 7, 8) are fed by rows [orb, orb + n) of the
+// facing edge column of `other`
+struct FaceLink
+{
+  int side = 0, rb = 0, n = 0, orb = 0;
+  lbm_domain* other = nullptr;
+  double* d_packet = nullptr;  // [lattice][3][n] on other's device
+  cudaEvent_t ev = nullptr;    // packet packed (other's side stream)
+};
+// the three populations that enter through the first (side 0: c_y = +1) / last (side 1: c_y = -1) column
+__host__ __device__ inline int face_q(int side, int qi) { return side == 0 ? (qi == 0 ? 2 : (qi == 1 ? 5 : 6)) : (qi == 0 ? 4 : (qi == 1 ? 7 : 8)); }
+inline long long face_tail_off(const SlabGeom& g, int side, int qi, int row) { return 9 * g.plane + (long long)(side * 3 + qi) * g.Xl + row; }
 }  // namespace lbm
 
 struct lbm_domain
@@ -152,6 +171,10 @@ struct lbm_domain
   bool copy_pending = false;
 
   lbm::IbmState ibm;
+  double ics2 = 1.0 / 3.0, ics4 = 1.0 / 9.0;  // source-term constants (lbm_set_force_region overrides them)
+  // column-face bindings to other blocks (lbm_link_face): the populations entering through an edge column are read
+  // from a tail appended to every lattice buffer, [side][3 populations][Xl] behind the nine planes
+  std::vector<lbm::FaceLink> faces;
   lbm::TwoPhaseState* tp = nullptr;
   lbm::CommState* comm = nullptr;
   lbm_domain *link_lo = nullptr, *link_hi = nullptr;
@@ -200,7 +223,8 @@ int ibm_release(lbm_domain* d);
 int ibm_prepass(lbm_domain* d, int mode, int which, int slot, cudaStream_t st);
 int ibm_roi_local(lbm_domain* d, int mode, int which, cudaStream_t st);  // moments of the active ROI nodes on this slab's rows
 int ibm_iterate(lbm_domain* d, int slot, cudaStream_t st);               // forcing iterations on the complete ROI fields
-int comm_ibm_share(lbm_domain* d, cudaStream_t st);                      // NCCL: ROI row segments between the slabs that own ROI rows
+int comm_ibm_share(lbm_domain* d, cudaStream_t st);
+int faces_release(lbm_domain* d);                      // NCCL: ROI row segments between the slabs that own ROI rows
 // lbm_two_phase.cu
 int tp_create(lbm_domain* d);
 int tp_destroy(lbm_domain* d);

@@ -97,7 +97,7 @@ EXPORTS = [
     "lbm_differential3", "lbm_params_from_toml", "lbm_colour_from_toml", "lbm_two_phase_from_toml",
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
-    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension",
+    "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension", "lbm_link_face", "lbm_set_force_region",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -148,6 +148,8 @@ def load():
         _lib.lbm_comm_unique_id.argtypes = [C.c_char_p]
         _lib.lbm_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.lbm_link_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.lbm_link_face.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _lib.lbm_set_force_region.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         _lib.lbm_step_group.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
         _lib.lbm_decompose_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.lbm_calc_rho.argtypes = [dp, C.c_int, C.c_int, dp]
@@ -399,6 +401,13 @@ class Domain:
     # ---- multi-GPU
     def comm_init(self, unique_id, n_ranks, rank):
         _chk(self.lib.lbm_comm_init(self.h, unique_id, n_ranks, rank))
+
+    def link_face(self, side, row_begin, n_rows, other, other_row_begin):
+        """bind rows [row_begin, row_begin + n_rows) of the first (side 0) / last (side 1) column to the facing column of `other`"""
+        _chk(self.lib.lbm_link_face(self.h, side, row_begin, n_rows, other.h, other_row_begin))
+
+    def set_force_region(self, x_begin, x_end, y_begin, y_end, Fx, Fy, ics2=3.0, ics4=9.0):
+        _chk(self.lib.lbm_set_force_region(self.h, x_begin, x_end, y_begin, y_end, Fx, Fy, ics2, ics4))
 
     def link(self, lower, upper):
         _chk(self.lib.lbm_link_neighbours(self.h, lower.h if lower else None, upper.h if upper else None))

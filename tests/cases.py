@@ -116,3 +116,38 @@ def csf(R, C, Fg=(6.25e-6, 0.0), sigma=0.1, **slab):
                                   add_force=1, **slab))
     d.preset_mrtcg()
     return d
+
+
+def loop_blocks(Ln, omega, F=(3e-3, 0.0), device=0):
+    """test/decompose_domain_loop.cpp: four blocks A {L, L/4}, B {L/4, L/2}, C {L, L/4}, D {L/4, L/2} closing a square
+    channel; each block keeps its own coordinates and wall rules (:171-230), the column faces are bound pairwise
+    (:232-261), block A carries the body force on rows L/4+5 .. L/4+55 (:66-69)."""
+    L4, L2, END = Ln // 4, Ln // 2, L.LBM_END
+    dom = {}
+    for k, (R, Cc) in (("A", (Ln, L4)), ("B", (L4, L2)), ("C", (Ln, L4)), ("D", (L4, L2))):
+        dom[k] = L.Domain(L.default_config(model=L.MODEL_BGK, X=R, Y=Cc, omega=omega, equilibrium=L.EQ_COMPRESSIBLE,
+                                           force=L.FORCE_IBM if k == "A" else L.FORCE_NONE, device=device))
+
+    def wall(d, xb, xe, yb, ye, pairs):
+        for q, qs in pairs:
+            d.bc_add(kind=L.BC_LINEAR, lattice=0, x_begin=xb, x_end=xe, y_begin=yb, y_end=ye, dst_q=q, src_q=qs, coef=1.0)
+
+    top, bottom = [(8, 6), (1, 3), (5, 7)], [(7, 5), (3, 1), (6, 8)]
+    left, right = [(2, 4), (5, 7), (6, 8)], [(4, 2), (7, 5), (8, 6)]
+    for k, d in dom.items():
+        d.bc_clear()
+        wall(d, 0, 1, 0, END, top)
+        wall(d, -1, END, 0, END, bottom)
+    wall(dom["A"], L4, -L4, 0, 1, left)
+    wall(dom["A"], 1, -1, -1, END, right)
+    wall(dom["C"], 1, -1, 0, 1, left)
+    wall(dom["C"], L4, -L4, -1, END, right)
+    A, B, Cb, D = dom["A"], dom["B"], dom["C"], dom["D"]
+    A.link_face(0, Ln - L4, L4, B, 0); B.link_face(1, 0, L4, A, Ln - L4)      # A-B
+    B.link_face(0, 0, L4, Cb, Ln - L4); Cb.link_face(1, Ln - L4, L4, B, 0)    # B-C
+    Cb.link_face(1, 0, L4, D, 0); D.link_face(0, 0, L4, Cb, 0)                # C-D
+    D.link_face(1, 0, L4, A, 0); A.link_face(0, 0, L4, D, 0)                  # D-A
+    A.set_force_region(L4 + 5, L4 + 55, 0, END, F[0], F[1], 3.0, 9.0)
+    for d in dom.values():
+        d.bc_commit()
+    return dom

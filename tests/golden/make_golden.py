@@ -161,6 +161,45 @@ def case_decompose():
          fB=np.stack([B[..., t] for t in keep]), omega=omega, rho_in=rho_in, rho_out=rho_out)
 
 
+def case_loop_blocks():
+    """test/decompose_domain_loop.cpp with L = 128, T = 400 (oracle/Makefile: the same translation unit, two constants
+    lowered): m_1, m_0 of the four blocks every 50 iterations.  Pins oracle/blocks_oracle.py."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import blocks_oracle as BO
+    d = workdir("loop")
+    if not os.path.exists(os.path.join(d, "D-domain-decomp-hpt-rho.pt")):
+        r = run_ref_driver("decompose_domain_loop_small", [], d)
+        assert r.returncode == 0, r.stderr
+    Ln = 128
+    omega = 1.0 / (np.sqrt(3.0 / 16.0) + 0.5)
+    ref = {k: {f: load_pt(os.path.join(d, f"{k}-domain-decomp-hpt-{f}.pt")) for f in ("ux", "uy", "rho")} for k in "ABCD"}
+    T = ref["A"]["ux"].shape[-1]
+    st = BO.init(ORC, Ln)
+    worst = 0.0
+    for t in range(50 * (T - 1) + 1):
+        if t % 50 == 0:   # the snapshot at the top of iteration t: m_0, m_1 of iteration t - 1, with F added on A's forced rows
+            ts = t // 50
+            for k in "ABCD":
+                u = st[k]["u"].copy()
+                if k == "A":
+                    u[BO.force_rows(Ln), :, 0] += 3e-3
+                worst = max(worst, np.abs(u[..., 0] - ref[k]["ux"][..., ts]).max(), np.abs(u[..., 1] - ref[k]["uy"][..., ts]).max(),
+                            np.abs(st[k]["rho"][..., 0] - ref[k]["rho"][..., ts]).max())
+        if t == 0:
+            # the driver adds F to m_1 at the top of EVERY iteration and only iteration t's calc_u overwrites it (:116,143):
+            # at t = 0 nothing has been computed yet, m_1 = F on the forced rows, which the snapshot shows and calc_u discards
+            pass
+        BO.step(ORC, st, Ln, omega)
+    print(f"  oracle vs reference driver over {T} snapshots (L = {Ln}): worst abs err {worst:.3e}")
+    assert worst < 1e-12
+    out = {}
+    keep = [0, 1, 2, T - 1]
+    for k in "ABCD":
+        for f in ("ux", "uy", "rho"):
+            out[f"{k}_{f}"] = np.moveaxis(ref[k][f], -1, 0)[keep]
+    save("loop_blocks_128", L=Ln, omega=omega, steps=np.array(keep) * 50, **out)
+
+
 # ------------------------------------------------------------------ TOML-driven drivers
 PARAMS_TOML = """\
 [flow]
@@ -544,7 +583,7 @@ def case_kbc_double_shear():
          rho=np.array(out["rho"]), tol=np.array(out["tol"]), s2=s2, stride=st)
 
 
-CASES = dict(mrt_csf=case_mrt_csf, kbc_double_shear=case_kbc_double_shear, poiseuille=case_poiseuille, specular=case_specular, gravity=case_gravity, decompose=case_decompose,
+CASES = dict(loop_blocks=case_loop_blocks, mrt_csf=case_mrt_csf, kbc_double_shear=case_kbc_double_shear, poiseuille=case_poiseuille, specular=case_specular, gravity=case_gravity, decompose=case_decompose,
              free_stream=case_free_stream, cylinder=case_cylinder, sedimentation=case_sedimentation,
              mrtcg_rt=case_mrtcg_rt, mrtcg_droplet=case_mrtcg_droplet, rk=case_rk)
 
