@@ -392,6 +392,11 @@ static int bgk_step_once(lbm_domain* d)
     set_error("lbm_step: this block is bound to others across a column face; advance the set with lbm_step_group");
     return LBM_ERR_INVALID;
   }
+  if (uses_ibm(d) && d->ibm.split && !comm_active(d))
+  {
+    set_error("lbm_step: the immersed body crosses this slab's edge; advance the slabs with lbm_step_group or join them with lbm_comm_init");
+    return LBM_ERR_INVALID;
+  }
   if (d->link_lo || d->link_hi)
   {
     set_error("lbm_step: this slab is linked to neighbours; advance the set with lbm_step_group");

@@ -49,12 +49,23 @@ def test_rule_validation():
     assert st == 1 and "lattice" in msg
 
 
-def test_ibm_roi_must_fit_the_slab():
+def test_ibm_roi_across_a_cut_needs_the_group_or_the_ring():
+    """a body that crosses the slab's edge is accepted (the slabs share the solve), but such a slab cannot be stepped on
+    its own; a body outside the grid or on the listed edge columns is refused; a body on other slabs is ignored"""
     d = L.Domain(L.default_config(model=L.MODEL_BGK, X=64, Y=64, x0=0, x1=32, force=L.FORCE_IBM))
     d.preset_free_stream(0.05)
     th = 2 * np.pi * np.arange(40) / 40
-    st, msg = status_of(lambda: d.ibm_set_markers(30.0 + 6 * np.cos(th), 32.0 + 6 * np.sin(th)))
-    assert st in (1, 4) and "slab" in msg
+    d.ibm_set_markers(30.0 + 6 * np.cos(th), 32.0 + 6 * np.sin(th))
+    d.set_f(np.full((32, 64, 9), 0.1))
+    st, msg = status_of(lambda: d.step(1))
+    assert st == 1 and "lbm_step_group" in msg
+    st, msg = status_of(lambda: d.ibm_set_markers(60.0 + 6 * np.cos(th), 32.0 + 6 * np.sin(th)))
+    assert st == 4 and "grid" in msg
+    st, msg = status_of(lambda: d.ibm_set_markers(16.0 + 6 * np.cos(th), 5.0 + 6 * np.sin(th)))
+    assert st == 4 and "interior columns" in msg
+    d.ibm_set_markers(48.0 + 6 * np.cos(th), 32.0 + 6 * np.sin(th))   # rows 40..56: another slab's body
+    st, msg = status_of(lambda: d.ibm_roi())
+    assert st == 1 and "no immersed boundary" in msg
 
 
 def test_linked_slab_refuses_plain_step():
