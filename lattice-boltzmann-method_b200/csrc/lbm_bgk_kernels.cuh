@@ -218,7 +218,7 @@ k_bgk_interior(const double* __restrict__ fsrc, double* __restrict__ fdst, const
     double rho_a, ux_a, uy_a, rho_b, ux_b, uy_b;
     bool roi_a = false, roi_b = false;
     double Fxa = 0.0, Fya = 0.0, Fxb = 0.0, Fyb = 0.0;
-    if constexpr (FORCE == FORCE_IBM)
+    if constexpr (FORCE == FORCE_IBM || FORCE == FORCE_REGION)
     {
       const int xg = x + g.xg0;
       if (active && xg >= p.roi_r0 && xg < p.roi_r1)
@@ -336,7 +336,7 @@ k_bgk_boundary(const double* __restrict__ fsrc, double* __restrict__ fdst, const
   {
     bool in_roi = false;
     double Fx = 0.0, Fy = 0.0;
-    if constexpr (FORCE == FORCE_IBM)
+    if constexpr (FORCE == FORCE_IBM || FORCE == FORCE_REGION)
     {
       const int xg = x + g.xg0;
       if (xg >= p.roi_r0 && xg < p.roi_r1 && y >= p.roi_c0 && y < p.roi_c1)

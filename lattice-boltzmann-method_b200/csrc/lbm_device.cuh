@@ -40,7 +40,9 @@ enum Mode
 // EQ_KBC selects the entropic central-moment collision of ulbm::d2q9::kbc (src/ulbm.cpp) and its
 // product-form equilibrium; it is the third "equilibrium kind" of the single-phase kernel family.
 enum EqKind { EQ_COMP = 0, EQ_INCOMP = 1, EQ_KBC = 2 };
-enum ForceKind { FORCE_NONE = 0, FORCE_UNIFORM = 1, FORCE_IBM = 2 };
+// FORCE_REGION: the FORCE_IBM data path (a force field on a rectangle) with the source-term constants read from the
+// parameters instead of folded in (lbm_set_force_region); internal, selected when the field is a fixed one
+enum ForceKind { FORCE_NONE = 0, FORCE_UNIFORM = 1, FORCE_IBM = 2, FORCE_REGION = 3 };
 
 // Everything a step kernel needs to know about one slab.
 struct SlabGeom
@@ -67,8 +69,8 @@ struct BgkParams
   int roi_r0, roi_r1, roi_c0, roi_c1;
   const double* Fx;
   const double* Fy;
-  double ics2, ics4;  // constants of the source term as the driver names them: 1/3, 1/9 (gravity_test.cpp:143-144,
-                      // cylinder_test.cpp:112-113) or 3, 9 (decompose_domain_loop.cpp:68-69)
+  double ics2, ics4;  // FORCE_REGION: constants of the source term as the driver names them, 3 and 9 in
+                      // decompose_domain_loop.cpp:68-69 (1/3, 1/9 of gravity_test / cylinder_test are compile-time)
   // LBM_MODEL_KBC, first step after an import: rho {Xl,Y}, u {Xl,Y,2} supplied by the caller (the drivers' m0 / m1
   // members, test/ulbm_poiseuille.cpp:93) instead of the moments of the imported populations; nullptr otherwise
   const double* mom_in_rho;
@@ -351,7 +353,8 @@ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, 
   }
   else
   {
-    const double ics2 = p.ics2, ics4 = p.ics4;
+    // compile-time constants on the drivers' standard path: as run-time parameters they cost the cylinder workload 3 %
+    const double ics2 = FORCE == FORCE_REGION ? p.ics2 : 1.0 / 3.0, ics4 = FORCE == FORCE_REGION ? p.ics4 : 1.0 / 9.0;
     double fx = Fx, fy = Fy;
     if constexpr (FORCE == FORCE_UNIFORM)
     {

@@ -165,7 +165,7 @@ template <int MODE>
 static int dispatch_bgk(lbm_domain* d, const LaunchArgs& a)
 {
   const bool ade = d->cfg.model == LBM_MODEL_BGK_ADE;
-  const int eq = d->cfg.equilibrium, fo = d->cfg.force;
+  const int eq = d->cfg.equilibrium, fo = (d->cfg.force == LBM_FORCE_IBM && d->ibm.fixed) ? (int)FORCE_REGION : d->cfg.force;
   if (ade) return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, a);
   if (d->cfg.model == LBM_MODEL_KBC) return launch_bgk<MODE, EQ_KBC, FORCE_NONE, false>(d, a);
 #define LBM_CASE(E, F) \
@@ -176,6 +176,8 @@ static int dispatch_bgk(lbm_domain* d, const LaunchArgs& a)
   LBM_CASE(EQ_INCOMP, FORCE_NONE)
   LBM_CASE(EQ_INCOMP, FORCE_UNIFORM)
   LBM_CASE(EQ_INCOMP, FORCE_IBM)
+  LBM_CASE(EQ_COMP, FORCE_REGION)
+  LBM_CASE(EQ_INCOMP, FORCE_REGION)
 #undef LBM_CASE
   set_error("unsupported equilibrium/force combination (%d, %d)", eq, fo);
   return LBM_ERR_INVALID;
