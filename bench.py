@@ -66,7 +66,7 @@ WORKLOADS = {
                           cpu_sample=1024),
     # not a BASELINE.json config: SURVEY §8(f) rank 2, the continuum-surface-force variant (three passes per step; bytes =
     # both colours' populations read + written once (288) + the carried interfacial tension read + written (32))
-    "csf_rt": dict(X=8192, Y=8192, bytes=320.0, nlat=2, kernel="k_csf_collide_interior<PULL>",
+    "csf_rt": dict(X=8192, Y=8192, bytes=320.0, nlat=2, kernel="k_csf_collide_ring<PULL>",
                    driver="test/mrt_rayleigh_taylor.cpp",
                    what="MRT colour-gradient Rayleigh-Taylor with continuum surface force (curvature from nested 5x5 differences)",
                    cpu_sample=512),
