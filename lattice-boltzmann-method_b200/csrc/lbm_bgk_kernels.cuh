@@ -149,13 +149,12 @@ __device__ __forceinline__ void load_streamed_pair(const double* __restrict__ ba
 
 // grid: x = ceil(npairs / blockDim.x), y = number of rows in `rows` (the launch's row list: the
 // "early" rows whose results feed the ghost exchange / IBM pre-pass of the next step, or the bulk)
-// Resident blocks the KBC instantiation is compiled for.  Measured on B200 (8192^2): 1 (126 registers, 4 blocks fit)
-// 35.9 GLUPS; 5 (spills 224 B) 31.4; 6 (404 B) 24.8; 8 (608 B) 18.4 — the collision needs its registers.
-#ifndef LBM_KBC_MINB
-#define LBM_KBC_MINB 1
-#endif
+// No minimum-blocks argument: with one, ptxas sizes every instantiation for that occupancy — (128, 1) let the BGK+IBM
+// kernel grow from 76 to 126 registers and cost the cylinder workload 8 %.  For the KBC instantiation (126 registers,
+// 4 blocks/SM) forcing more resident blocks was measured at 8192^2: 5 blocks (spills 224 B) 31.4 GLUPS, 6 (404 B) 24.8,
+// 8 (608 B) 18.4, against 35.9 as compiled here — that collision needs its registers.
 template <int MODE, int EQ, int FORCE, bool ADE>
-__global__ void __launch_bounds__(128, EQ == EQ_KBC ? LBM_KBC_MINB : 1)
+__global__ void __launch_bounds__(128)
 k_bgk_interior(const double* __restrict__ fsrc, double* __restrict__ fdst, const double* __restrict__ gsrc,
                double* __restrict__ gdst, const SlabGeom g, const BgkParams p, const int* __restrict__ rows, int npairs,
                double* __restrict__ out_f, double* __restrict__ out_g)
