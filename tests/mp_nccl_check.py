@@ -7,6 +7,8 @@ Every rank owns one slab; the gathered result must equal the monolithic single-G
 import os
 import sys
 
+import functools
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -16,6 +18,9 @@ sys.path.insert(0, os.path.join(ROOT, "lattice-boltzmann-method_b200", "python")
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 import lbm_b200 as L  # noqa: E402
+
+
+print = functools.partial(print, flush=True)  # the launcher's pipe would hold the lines back until exit
 
 
 def main():
@@ -142,7 +147,7 @@ def main():
             failures.append("csf")
     d.close()
 
-    # ---- cylinder: IBM body in rank 0's slab, ABB rows at the two global ends, specular columns
+    # ---- cylinder: small IBM body near the inlet (inside rank 0's slab on 2 and 4 ranks), ABB rows at the two global ends, specular columns
     g = cases.golden("cylinder_99x77")
     X, Y = int(g["X"]), int(g["Y"])
     omega, u_lb = float(g["omega"]), float(g["u_lb"])
@@ -153,8 +158,10 @@ def main():
     d = L.Domain(L.default_config(x0=x0, x1=x1, device=local, **kw))
     d.comm_init(fresh_id(), world, rank)
     d.preset_free_stream(u_lb, 0.0)
-    if rank == 0:
-        d.ibm_set_markers(xs, ys)
+    # EVERY rank gets the marker list: a rank that owns none of the ROI rows ignores it, and on rings where the ROI
+    # (rows 6..23) crosses a cut (8 ranks: 12-13 rows each) the co-owners must all know about the body — handing it to
+    # rank 0 alone would leave rank 0 waiting for a partner that never posts its half of the exchange
+    d.ibm_set_markers(xs, ys)
     d.set_f(g["f0"][x0:x1])
     d.step(40)
     got = gather(d.get_f())

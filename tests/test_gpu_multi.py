@@ -1,6 +1,6 @@
 """GPU (>= 2 devices): one process per GPU over NCCL — tests/mp_nccl_check.py under torchrun.  Poiseuille
-(pressure packets across the ring) and cylinder (IBM) must equal the monolithic run bit for bit; MRTCG and
-RK (moment-plane halos) must stay on the oracle to 1e-12."""
+(pressure packets across the ring), cylinder (IBM, also with the body across the cut) and the CSF model must equal
+the monolithic run bit for bit; MRTCG and RK (moment-plane halos) must stay on the oracle to 1e-12."""
 import os
 import subprocess
 import sys
@@ -23,5 +23,6 @@ def test_nccl_slab_ring_two_ranks():
            "--master-port", "29541", os.path.join("tests", "mp_nccl_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    for case in ("poiseuille", "mrtcg", "rk", "cylinder"):
+    for case in ("poiseuille", "mrtcg", "rk", "csf", "cylinder"):
         assert f"{case} ring of 2" in r.stdout
+    assert "cylinder across the cuts, ring of 2: bit-exact vs monolithic = True" in r.stdout
