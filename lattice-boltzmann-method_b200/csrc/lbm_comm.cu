@@ -308,7 +308,7 @@ int faces_release(lbm_domain* d)
 {
   for (auto& fl : d->faces)
   {
-    if (fl.other) cudaSetDevice(fl.other->cfg.device);
+    cudaSetDevice(fl.other_device);
     cudaFree(fl.d_packet);
     if (fl.ev) cudaEventDestroy(fl.ev);
   }
@@ -423,6 +423,7 @@ int lbm_link_face(lbm_domain* d, int side, int row_begin, int n_rows, lbm_domain
     }
   FaceLink fl;
   fl.side = side; fl.rb = row_begin; fl.n = n_rows; fl.orb = other_row_begin; fl.other = other;
+  fl.other_device = other->cfg.device;
   LBM_CUDA(cudaSetDevice(other->cfg.device));
   LBM_CUDA(cudaMalloc(&fl.d_packet, sizeof(double) * d->nlat * 3 * n_rows));
   LBM_CUDA(cudaEventCreateWithFlags(&fl.ev, cudaEventDisableTiming));

@@ -108,6 +108,7 @@ struct FaceLink
 {
   int side = 0, rb = 0, n = 0, orb = 0;
   lbm_domain* other = nullptr;
+  int other_device = 0;        // kept separately: `other` may be destroyed before this block is
   double* d_packet = nullptr;  // [lattice][3][n] on other's device
   cudaEvent_t ev = nullptr;    // packet packed (other's side stream)
 };
