@@ -62,6 +62,7 @@ __device__ __forceinline__ long long node_off(const SlabGeom& g, int x, int y)
 struct BgkParams
 {
   double omega;    // fluid relaxation (params::lattice::omega)
+  double inv_omega;  // 1 / omega (the KBC collision's 1 / s2)
   double omega_g;  // ADE lattice relaxation
   double Fg0, Fg1; // uniform force (test/gravity_test.cpp:85)
   double w_s;      // settling velocity (test/rectangle_sedimentation_test.cpp:89)
@@ -84,7 +85,7 @@ struct BgkParams
 
 // rho = sum_q f, (jx, jy) = sum_q f c_q in the q order of the reference's reductions
 // (solver::calc_rho / calc_incomp_u, src/solver.cpp:23-31).
-__device__ __forceinline__ void moments(const double (&f)[9], double& rho, double& jx, double& jy)
+__host__ __device__ __forceinline__ void moments(const double (&f)[9], double& rho, double& jx, double& jy)
 {
   rho = ((((((((f[0] + f[1]) + f[2]) + f[3]) + f[4]) + f[5]) + f[6]) + f[7]) + f[8]);
   jx = (((((f[1] - f[3]) + f[5]) - f[6]) - f[7]) + f[8]);
@@ -161,7 +162,7 @@ __device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double
 }
 
 // M^-1 of kbc::collide() step 4 (src/ulbm.cpp:114-122; the sign flip of :123 is left to the caller)
-__device__ __forceinline__ void kbc_minv(const double (&g)[9], double (&c)[9])
+__host__ __device__ __forceinline__ void kbc_minv(const double (&g)[9], double (&c)[9])
 {
   // the halves and quarters are exact scalings, taken once; each output is then a sum of a pair term and a shared term
   const double h1 = 0.5 * g[1], h2 = 0.5 * g[2], h6 = 0.5 * g[6], h7 = 0.5 * g[7], h8 = 0.5 * g[8];
@@ -197,11 +198,10 @@ __device__ __forceinline__ void kbc_minv(const double (&g)[9], double (&c)[9])
 //   so N^-1 runs once on the shear part P, once on the higher-order part H and on the two equilibrium-only
 //   vectors; delta_s, delta_h and the collision are combinations of those, and M^-1 runs three times;
 //   f_eq,q = m0 phi_x(c_qx) phi_y(c_qy), phi(0) = 1 - cs2 - u^2, phi(+-1) = (cs2 + u^2 +- u) / 2 (product form of
-//             :230-238): six reciprocals instead of nine, and m0 cancels in gamma's quotient.
-__device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double m0, double ux, double uy, bool given)
+//             :230-238); in gamma's quotient m0 and the common denominator cancel: no reciprocal at all.
+__host__ __device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double is2, double m0, double ux, double uy, bool given)
 {
-  constexpr double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0;
-  const double is2 = 1.0 / s2;
+  constexpr double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0;  // is2 = 1 / s2, taken once on the host
   const double ux2 = ux * ux, uy2 = uy * uy, uxy = ux * uy;
   // ---- raw moments m_ab = sum f cx^a cy^b from pair sums / differences, then central moments
   const double A1 = f[1] + f[3], D1 = f[1] - f[3], A2 = f[2] + f[4], D2 = f[2] - f[4];
@@ -259,10 +259,14 @@ __device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double m0
     dh[7] += e78;
     dh[8] += e78;
   }
-  // ---- gamma (src/ulbm.cpp:138-148) with 1 / (f_eq / m0) in product form
+  // ---- gamma (src/ulbm.cpp:138-148).  1 / f_eq,q = 1 / (m0 phi_x(c_qx) phi_y(c_qy)) weighs both sums of the quotient, so m0
+  // and the common factor 1 / (prod_a phi_x(a) prod_b phi_y(b)) cancel: the weight of q becomes the product of the OTHER
+  // two phi_x times the OTHER two phi_y, and the six reciprocals (an fp64 reciprocal is a dozen instructions) are gone.
   const double ax = cs2 + ux2, ay = cs2 + uy2;
-  const double rx[3] = {1.0 / (1.0 - ax), 1.0 / (0.5 * (ax + ux)), 1.0 / (0.5 * (ax - ux))};  // c_x = 0, +1, -1
-  const double ry[3] = {1.0 / (1.0 - ay), 1.0 / (0.5 * (ay + uy)), 1.0 / (0.5 * (ay - uy))};
+  const double fx0 = 1.0 - ax, fx1 = 0.5 * (ax + ux), fx2 = 0.5 * (ax - ux);  // phi_x of c_x = 0, +1, -1
+  const double fy0 = 1.0 - ay, fy1 = 0.5 * (ay + uy), fy2 = 0.5 * (ay - uy);
+  const double rx[3] = {fx1 * fx2, fx0 * fx2, fx0 * fx1};
+  const double ry[3] = {fy1 * fy2, fy0 * fy2, fy0 * fy1};
   double num = 0.0, den = 0.0;
 #pragma unroll
   for (int q = 0; q < 9; q++)
@@ -325,7 +329,7 @@ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, 
       ux = jx * ir;
       uy = jy * ir;
     }
-    kbc_collide(f, p.omega, rho, ux, uy, given);
+    kbc_collide(f, p.omega, p.inv_omega, rho, ux, uy, given);
     return;
   }
   moments(f, rho, jx, jy);

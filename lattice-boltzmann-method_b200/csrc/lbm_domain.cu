@@ -116,6 +116,7 @@ static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
 {
   BgkParams p;
   p.omega = d->cfg.omega;
+  p.inv_omega = 1.0 / d->cfg.omega;
   p.omega_g = d->cfg.omega_g;
   p.Fg0 = d->cfg.Fg[0];
   p.Fg1 = d->cfg.Fg[1];
