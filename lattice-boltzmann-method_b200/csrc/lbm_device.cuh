@@ -199,10 +199,11 @@ __host__ __device__ __forceinline__ void kbc_minv(const double (&g)[9], double (
 //   vectors; delta_s, delta_h and the collision are combinations of those, and M^-1 runs three times;
 //   f_eq,q = m0 phi_x(c_qx) phi_y(c_qy), phi(0) = 1 - cs2 - u^2, phi(+-1) = (cs2 + u^2 +- u) / 2 (product form of
 //             :230-238); in gamma's quotient m0 and the common denominator cancel: no reciprocal at all.
-__host__ __device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double is2, double m0, double ux, double uy, bool given)
+// given = false: m0, ux, uy are OUTPUTS — the populations' own moments (kbc.m0 = adve_f.sum, kbc.m1 = adve_f c^T / m0,
+// test/ulbm_double_shear_flow.cpp:143-146), taken from the pair sums the central moments need anyway.
+__host__ __device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, double is2, double& m0, double& ux, double& uy, bool given)
 {
   constexpr double cs2 = 1.0 / 3.0, cs4 = 1.0 / 9.0;  // is2 = 1 / s2, taken once on the host
-  const double ux2 = ux * ux, uy2 = uy * uy, uxy = ux * uy;
   // ---- raw moments m_ab = sum f cx^a cy^b from pair sums / differences, then central moments
   const double A1 = f[1] + f[3], D1 = f[1] - f[3], A2 = f[2] + f[4], D2 = f[2] - f[4];
   const double A57 = f[5] + f[7], D57 = f[5] - f[7], A68 = f[6] + f[8], D68 = f[6] - f[8];
@@ -210,6 +211,14 @@ __host__ __device__ __forceinline__ void kbc_collide(double (&f)[9], double s2, 
   const double m20 = A1 + m22, m02 = A2 + m22;
   const double m10 = D1 + m12, m01 = D2 + m21;
   const double r00 = ((f[0] + A1) + A2) + m22;
+  if (!given)
+  {
+    const double ir = 1.0 / r00;
+    m0 = r00;
+    ux = m10 * ir;
+    uy = m01 * ir;
+  }
+  const double ux2 = ux * ux, uy2 = uy * uy, uxy = ux * uy;
   const double k10 = m10 - ux * r00, k01 = m01 - uy * r00;
   const double k20 = (m20 - 2.0 * ux * m10) + ux2 * r00;
   const double k02 = (m02 - 2.0 * uy * m01) + uy2 * r00;
@@ -322,14 +331,7 @@ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, 
   double jx, jy;
   if constexpr (EQ == EQ_KBC)
   {
-    if (!given)
-    {
-      moments(f, rho, jx, jy);
-      const double ir = 1.0 / rho;  // kbc.m1 = adve_f c^T / m0 (test/ulbm_double_shear_flow.cpp:145-146)
-      ux = jx * ir;
-      uy = jy * ir;
-    }
-    kbc_collide(f, p.omega, p.inv_omega, rho, ux, uy, given);
+    kbc_collide(f, p.omega, p.inv_omega, rho, ux, uy, given);  // given = false: rho, ux, uy come back as the populations' moments
     return;
   }
   moments(f, rho, jx, jy);

@@ -7,24 +7,17 @@ extern "C"
 {
 
 // kbc::collide() of N nodes in place; given = 0: m0, u are the populations' own moments (computed here like
-// bgk_collide<EQ_KBC> does), given = 1: the caller's m0 {N}, u {N,2}
+// kbc_collide does itself), given = 1: the caller's m0 {N}, u {N,2}
 void host_kbc_collide(double* f, const double* m0, const double* u, int given, long N, double s2)
 {
   for (long n = 0; n < N; n++)
   {
     double v[9];
     for (int q = 0; q < 9; q++) v[q] = f[9 * n + q];
-    double rho, ux, uy;
+    double rho = 0.0, ux = 0.0, uy = 0.0;
     if (given)
     {
       rho = m0[n]; ux = u[2 * n]; uy = u[2 * n + 1];
-    }
-    else
-    {
-      double jx, jy;
-      lbm::moments(v, rho, jx, jy);
-      const double ir = 1.0 / rho;
-      ux = jx * ir; uy = jy * ir;
     }
     lbm::kbc_collide(v, s2, 1.0 / s2, rho, ux, uy, given != 0);
     for (int q = 0; q < 9; q++) f[9 * n + q] = v[q];
