@@ -733,15 +733,6 @@ __global__ void k_tp_write_u(double* __restrict__ mom, const SlabGeom g, const M
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static void fill_colour(const lbm_colour_desc& c, double (&phi)[3], double (&eta)[3], double& cs2)
-{
-  cs2 = 3.0 * (1.0 - c.alpha) / 5.0;  // src/colour.cpp:37
-  phi[0] = c.alpha;
-  phi[1] = 0.2 * (1.0 - c.alpha);
-  phi[2] = 0.05 * (1.0 - c.alpha);
-  for (int k = 0; k < 3; k++) eta[k] = 1.0 + 0.5 * (3.0 * cs2 - 1.0) * (3.0 * (double)k - 4.0);
-}
-
 static int csf_configure();
 
 int tp_create(lbm_domain* d)
@@ -761,47 +752,13 @@ int tp_create(lbm_domain* d)
     set_error("two-phase model: red/blue initial_density and delta must be positive");
     return LBM_ERR_INVALID;
   }
-  double r_cs2, b_cs2;
-  fill_colour(c.red, p.r_phi, p.r_eta, r_cs2);
-  fill_colour(c.blue, p.b_phi, p.b_eta, b_cs2);
-  p.r_rho0 = c.red.rho_0; p.b_rho0 = c.blue.rho_0;
-  p.r_irho0 = 1.0 / c.red.rho_0; p.b_irho0 = 1.0 / c.blue.rho_0;
-  p.r_beta = c.red.beta; p.b_beta = c.blue.beta;
-  p.r_A = c.red.A; p.b_A = c.blue.A;
-  p.cr = 1.8 * c.red.alpha - 0.8;
-  p.cb = 1.8 * c.blue.alpha - 0.8;
-  p.sigma = c.sigma;
-  p.Fg0 = c.Fg[0]; p.Fg1 = c.Fg[1];
-  p.add_force = c.add_force;
-  p.delta = c.delta;
-  if (tp->model != TP_RK)
-  {
-    // relaxation_function{r, b, delta}: omegas from nu and the colour's own cs2 (mrtcg_rayleigh_taylor.cpp:57-66)
-    p.r_val = 1.0 / (0.5 + c.red.nu / r_cs2);
-    p.b_val = 1.0 / (0.5 + c.blue.nu / b_cs2);
-    // TP_CSF: omega2_k = A_k (1 - rlx_k / 2) eta with colour::rlx = 1 / (0.5 + nu / cs2) (src/colour.cpp:38-39)
-    p.w2sum = c.red.A * (1.0 - 0.5 * p.r_val) + c.blue.A * (1.0 - 0.5 * p.b_val);
-  }
+  tp_fill_params(c, (TpModel)tp->model, p);
   if (tp->model == TP_CSF)
   {
-    p.add_force = 1;  // mrt_rayleigh_taylor.cpp:527-531
     const size_t ab = sizeof(double) * 4 * tp->mg.mplane;
     LBM_CUDA(cudaMalloc(&tp->aux, ab));
     LBM_CUDA(cudaMemset(tp->aux, 0, ab));
   }
-  if (tp->model == TP_RK)
-  {
-    // colour::init_omega with cs2 = 1/3, blended in tau space (rk_static_droplet_test.cpp:264-265,320-323)
-    const double cs2 = 1.0 / 3.0;
-    const double r_om = 1.0 / (0.5 + c.red.nu / cs2), b_om = 1.0 / (0.5 + c.blue.nu / cs2);
-    p.r_val = 1.0 / r_om;
-    p.b_val = 1.0 / b_om;
-  }
-  p.s1 = 2.0 * p.r_val * p.b_val / (p.r_val + p.b_val);
-  p.s2 = 2.0 * (p.r_val - p.s1) / p.delta;
-  p.s3 = -p.s2 / (2.0 * p.delta);
-  p.t2 = 2.0 * (p.s1 - p.b_val) / p.delta;
-  p.t3 = p.t2 / (2.0 * p.delta);
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));

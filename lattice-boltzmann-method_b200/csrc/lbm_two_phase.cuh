@@ -8,6 +8,7 @@
 // side — the padding of the reference's replicate-mode Conv2d (src/differential.cpp:8-9) — so the
 // 5x5 / 3x3 finite differences never clamp an index.
 #pragma once
+#include "../../include/lbm_b200.h"
 #include "lbm_device.cuh"
 
 namespace lbm
@@ -31,6 +32,58 @@ struct TpParams
   // relaxation blend (mrtcg_rayleigh_taylor.cpp:34-100 in omega; rk_static_droplet_test.cpp:287-359 in tau)
   double delta, r_val, b_val, s1, s2, s3, t2, t3;
 };
+
+// Per-fluid constants of class colour (src/colour.cpp:37,49-64) by |c|^2 class
+inline void tp_fill_colour(const lbm_colour_desc& c, double (&phi)[3], double (&eta)[3], double& cs2)
+{
+  cs2 = 3.0 * (1.0 - c.alpha) / 5.0;  // src/colour.cpp:37
+  phi[0] = c.alpha;
+  phi[1] = 0.2 * (1.0 - c.alpha);
+  phi[2] = 0.05 * (1.0 - c.alpha);
+  for (int k = 0; k < 3; k++) eta[k] = 1.0 + 0.5 * (3.0 * cs2 - 1.0) * (3.0 * (double)k - 4.0);
+}
+
+// Everything the kernels need from an lbm_config, in host fp64 with the drivers' formula order.  A header function so
+// that the CPU test of the collision arithmetic (tests/host_kernels) derives its constants with the product's own code.
+inline void tp_fill_params(const lbm_config& c, TpModel model, TpParams& p)
+{
+  double r_cs2, b_cs2;
+  tp_fill_colour(c.red, p.r_phi, p.r_eta, r_cs2);
+  tp_fill_colour(c.blue, p.b_phi, p.b_eta, b_cs2);
+  p.r_rho0 = c.red.rho_0; p.b_rho0 = c.blue.rho_0;
+  p.r_irho0 = 1.0 / c.red.rho_0; p.b_irho0 = 1.0 / c.blue.rho_0;
+  p.r_beta = c.red.beta; p.b_beta = c.blue.beta;
+  p.r_A = c.red.A; p.b_A = c.blue.A;
+  p.cr = 1.8 * c.red.alpha - 0.8;
+  p.cb = 1.8 * c.blue.alpha - 0.8;
+  p.sigma = c.sigma;
+  p.Fg0 = c.Fg[0]; p.Fg1 = c.Fg[1];
+  p.add_force = c.add_force;
+  p.delta = c.delta;
+  p.w2sum = 0.0;
+  if (model != TP_RK)
+  {
+    // relaxation_function{r, b, delta}: omegas from nu and the colour's own cs2 (mrtcg_rayleigh_taylor.cpp:57-66)
+    p.r_val = 1.0 / (0.5 + c.red.nu / r_cs2);
+    p.b_val = 1.0 / (0.5 + c.blue.nu / b_cs2);
+    // TP_CSF: omega2_k = A_k (1 - rlx_k / 2) eta with colour::rlx = 1 / (0.5 + nu / cs2) (src/colour.cpp:38-39)
+    p.w2sum = c.red.A * (1.0 - 0.5 * p.r_val) + c.blue.A * (1.0 - 0.5 * p.b_val);
+  }
+  else
+  {
+    // colour::init_omega with cs2 = 1/3, blended in tau space (rk_static_droplet_test.cpp:264-265,320-323)
+    const double cs2 = 1.0 / 3.0;
+    const double r_om = 1.0 / (0.5 + c.red.nu / cs2), b_om = 1.0 / (0.5 + c.blue.nu / cs2);
+    p.r_val = 1.0 / r_om;
+    p.b_val = 1.0 / b_om;
+  }
+  if (model == TP_CSF) p.add_force = 1;  // mrt_rayleigh_taylor.cpp:527-531
+  p.s1 = 2.0 * p.r_val * p.b_val / (p.r_val + p.b_val);
+  p.s2 = 2.0 * (p.r_val - p.s1) / p.delta;
+  p.s3 = -p.s2 / (2.0 * p.delta);
+  p.t2 = 2.0 * (p.s1 - p.b_val) / p.delta;
+  p.t3 = p.t2 / (2.0 * p.delta);
+}
 
 struct MomGeom
 {
@@ -90,7 +143,7 @@ __host__ __device__ __forceinline__ constexpr double MI36(int q, int a)
 
 // relaxation_function::eval; a NaN phase matches no branch (the reference then keeps the previous
 // value, zero on the first step)
-__device__ __forceinline__ double relax_eval(const TpParams& p, double psi)
+__host__ __device__ __forceinline__ double relax_eval(const TpParams& p, double psi)
 {
   double s = 0.0;
   if (psi > p.delta) s = p.r_val;
@@ -106,21 +159,26 @@ __device__ __forceinline__ double relax_eval(const TpParams& p, double psi)
 // <= 1 ulp per operation, far inside the parity tolerance (1e-12 relative after one step).
 
 // eval_phase_field (mrtcg_rayleigh_taylor.cpp:212-225)
-__device__ __forceinline__ double phase_of(const TpParams& p, double rr, double rb)
+__host__ __device__ __forceinline__ double phase_of(const TpParams& p, double rr, double rb)
 {
   // The two products are rounded on their own (no contraction into a - b / a + b): in the bulk of one fluid the other
   // density is ~1e-22 of rounding residue, and the phase must come out as EXACTLY +-1 there, as it does in the
   // reference — the models divide by 1e-20 + |grad(phase)|, so a 1-ulp ripple on the plateau would turn into an O(1)
   // interface "normal".  (Observed: fma(3, RN(1/3), -+1e-22) straddles a rounding midpoint and gave 1 + 2^-52.)
+#ifdef __CUDA_ARCH__
   const double a = __dmul_rn(rr, p.r_irho0), b = __dmul_rn(rb, p.b_irho0);
   return __dsub_rn(a, b) / __dadd_rn(a, b);
+#else  // host build (tests/host_kernels): nothing contracts there
+  const double a = rr * p.r_irho0, b = rb * p.b_irho0;
+  return (a - b) / (a + b);
+#endif
 }
 
 // Moments of a freshly streamed node: what the drivers compute at the END of an iteration
 // (mrtcg_rayleigh_taylor.cpp:472-477 ; rk_static_droplet_test.cpp:602-609).
 // fsx, fsy: TP_CSF only, the interfacial tension of the step that produced this state (mrt_rayleigh_taylor.cpp:543-544)
 template <int MODEL>
-__device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)[9], const double (&fb)[9], double& rr,
+__host__ __device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)[9], const double (&fb)[9], double& rr,
                                            double& rb, double& ux, double& uy, double& ph, double fsx = 0.0, double fsy = 0.0)
 {
   double jx, jy, dummy;
@@ -149,7 +207,7 @@ __device__ __forceinline__ void tp_moments(const TpParams& p, const double (&fr)
 
 // eval_equilibrium of one colour
 template <int MODEL>
-__device__ __forceinline__ double tp_feq(int q, double rho_k, const double (&phi)[3], const double (&eta)[3], double ux,
+__host__ __device__ __forceinline__ double tp_feq(int q, double rho_k, const double (&phi)[3], const double (&eta)[3], double ux,
                                          double uy, double uu)
 {
   const double ue = (double)CX(q) * ux + (double)CY(q) * uy;
@@ -172,7 +230,7 @@ struct TpStencil
 
 // One two-colour collision in registers: fr/fb in = post-stream, out = post-collision.
 template <int MODEL>
-__device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], double (&fb)[9], double rr, double rb,
+__host__ __device__ __forceinline__ void tp_collide(const TpParams& p, double (&fr)[9], double (&fb)[9], double rr, double rb,
                                            double ux, double uy, double ph, const TpStencil& st)
 {
   const double uu = ux * ux + uy * uy;

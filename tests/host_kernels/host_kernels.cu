@@ -2,6 +2,7 @@
 // suite can hold it against the oracle without a GPU: the functions are __host__ __device__, the same source the
 // kernels inline.  (Host code has no fused multiply-add: results differ from the device's in the last bits only.)
 #include "../../lattice-boltzmann-method_b200/csrc/lbm_device.cuh"
+#include "../../lattice-boltzmann-method_b200/csrc/lbm_two_phase.cuh"
 
 extern "C"
 {
@@ -22,6 +23,63 @@ void host_kbc_collide(double* f, const double* m0, const double* u, int given, l
     lbm::kbc_collide(v, s2, 1.0 / s2, rho, ux, uy, given != 0);
     for (int q = 0; q < 9; q++) f[9 * n + q] = v[q];
   }
+}
+
+// ---- two-phase models (csrc/lbm_two_phase.cuh).  model: 0 = MRT colour gradient, 1 = Rothman-Keller, 2 = MRT + CSF.
+// Constants from the product's own tp_fill_params.
+
+// moments of freshly streamed populations: rr, rb {N}, u {N,2}, ph {N};  Fs {N,2} (model 2) or null
+void host_tp_moments(int model, const lbm_config* cfg, const double* fr, const double* fb, const double* Fs, long N,
+                     double* rr, double* rb, double* u, double* ph)
+{
+  lbm::TpParams p;
+  lbm::tp_fill_params(*cfg, (lbm::TpModel)model, p);
+  for (long n = 0; n < N; n++)
+  {
+    double a[9], b[9];
+    for (int q = 0; q < 9; q++) { a[q] = fr[9 * n + q]; b[q] = fb[9 * n + q]; }
+    const double fsx = Fs ? Fs[2 * n] : 0.0, fsy = Fs ? Fs[2 * n + 1] : 0.0;
+    if (model == 0) lbm::tp_moments<lbm::TP_MRTCG>(p, a, b, rr[n], rb[n], u[2 * n], u[2 * n + 1], ph[n]);
+    else if (model == 1) lbm::tp_moments<lbm::TP_RK>(p, a, b, rr[n], rb[n], u[2 * n], u[2 * n + 1], ph[n]);
+    else lbm::tp_moments<lbm::TP_CSF>(p, a, b, rr[n], rb[n], u[2 * n], u[2 * n + 1], ph[n], fsx, fsy);
+  }
+}
+
+void host_tp_phase(int model, const lbm_config* cfg, const double* rr, const double* rb, long N, double* ph)
+{
+  lbm::TpParams p;
+  lbm::tp_fill_params(*cfg, (lbm::TpModel)model, p);
+  for (long n = 0; n < N; n++) ph[n] = lbm::phase_of(p, rr[n], rb[n]);
+}
+
+// collision of N nodes in place (fr, fb: post-stream in, post-collision out); st4 {N,4} = grad_x, grad_y of the phase
+// field and d/dx Q_x, d/dy Q_y of the colour-summed momentum field; Fs {N,2} (model 2) or null
+void host_tp_collide(int model, const lbm_config* cfg, double* fr, double* fb, const double* rr, const double* rb,
+                     const double* u, const double* ph, const double* st4, const double* Fs, long N)
+{
+  lbm::TpParams p;
+  lbm::tp_fill_params(*cfg, (lbm::TpModel)model, p);
+  for (long n = 0; n < N; n++)
+  {
+    double a[9], b[9];
+    for (int q = 0; q < 9; q++) { a[q] = fr[9 * n + q]; b[q] = fb[9 * n + q]; }
+    lbm::TpStencil st;
+    st.gx = st4[4 * n]; st.gy = st4[4 * n + 1]; st.DxQx = st4[4 * n + 2]; st.DyQy = st4[4 * n + 3];
+    st.Fsx = Fs ? Fs[2 * n] : 0.0; st.Fsy = Fs ? Fs[2 * n + 1] : 0.0;
+    if (model == 0) lbm::tp_collide<lbm::TP_MRTCG>(p, a, b, rr[n], rb[n], u[2 * n], u[2 * n + 1], ph[n], st);
+    else if (model == 1) lbm::tp_collide<lbm::TP_RK>(p, a, b, rr[n], rb[n], u[2 * n], u[2 * n + 1], ph[n], st);
+    else lbm::tp_collide<lbm::TP_CSF>(p, a, b, rr[n], rb[n], u[2 * n], u[2 * n + 1], ph[n], st);
+    for (int q = 0; q < 9; q++) { fr[9 * n + q] = a[q]; fb[9 * n + q] = b[q]; }
+  }
+}
+
+// the constants themselves, for a direct look: {cr, cb, r_val, b_val, s1, s2, s3, t2, t3, w2sum}
+void host_tp_constants(int model, const lbm_config* cfg, double* out)
+{
+  lbm::TpParams p;
+  lbm::tp_fill_params(*cfg, (lbm::TpModel)model, p);
+  const double v[10] = {p.cr, p.cb, p.r_val, p.b_val, p.s1, p.s2, p.s3, p.t2, p.t3, p.w2sum};
+  for (int k = 0; k < 10; k++) out[k] = v[k];
 }
 
 }  // extern "C"

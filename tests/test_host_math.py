@@ -15,7 +15,8 @@ from oracle_lib import Oracle
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_kernels", "host_kernels.cu")
 OUT = os.path.join(HERE, "host_kernels", "_build", "libhost_kernels.so")
-DEPS = [SRC, os.path.join(os.path.dirname(HERE), "lattice-boltzmann-method_b200", "csrc", "lbm_device.cuh")]
+CSRC = os.path.join(os.path.dirname(HERE), "lattice-boltzmann-method_b200", "csrc")
+DEPS = [SRC, os.path.join(CSRC, "lbm_device.cuh"), os.path.join(CSRC, "lbm_two_phase.cuh")]
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 CXI = (0, 1, 0, -1, 0, 1, -1, -1, 1)
@@ -73,3 +74,125 @@ def test_kbc_collision_on_the_host_matches_the_oracle(host, given):
         host.host_kbc_collide(ptr(c), ptr(mine_m0), ptr(mine_u), 1 if (given and step == 0) else 0, c.size // 9, s2)
         mine = advect(c)
         assert cases.relerr(mine, ref_f) < 1e-13, step
+
+
+# ------------------------------------------------------------------------------------------------
+# two-phase models: tp_moments / tp_collide / tp_fill_params of csrc/lbm_two_phase.cuh on the host
+# ------------------------------------------------------------------------------------------------
+TP_MRTCG, TP_RK, TP_CSF = 0, 1, 2   # enum TpModel of csrc/lbm_two_phase.cuh
+
+
+def tp_api(lib):
+    import lbm_b200 as L
+    dp = C.POINTER(C.c_double)
+    cp = C.POINTER(L.Config)
+    lib.host_tp_moments.argtypes = [C.c_int, cp, dp, dp, dp, C.c_long, dp, dp, dp, dp]
+    lib.host_tp_phase.argtypes = [C.c_int, cp, dp, dp, C.c_long, dp]
+    lib.host_tp_collide.argtypes = [C.c_int, cp, dp, dp, dp, dp, dp, dp, dp, dp, C.c_long]
+    lib.host_tp_constants.argtypes = [C.c_int, cp, dp]
+    return L
+
+
+def mrtcg_bc(adv, col):
+    """test/mrtcg_rayleigh_taylor.cpp:495-533: periodic columns on the inner rows, bounce-back on the first / last row"""
+    X, Y = adv.shape[:2]
+    inner = slice(1, X - 1)
+    for q in (2, 5, 6):
+        adv[inner, 0, q] = col[inner, Y - 1, q]
+    for q in (4, 8, 7):
+        adv[inner, Y - 1, q] = col[inner, 0, q]
+    for q, qs in ((3, 1), (7, 5), (6, 8)):
+        adv[X - 1, :, q] = col[X - 1, :, qs]
+    for q, qs in ((1, 3), (5, 7), (8, 6)):
+        adv[0, :, q] = col[0, :, qs]
+
+
+def rk_bc(adv, col):
+    """test/rk_static_droplet_test.cpp:204-211: whole nodes copied across both pairs of edges"""
+    X, Y = adv.shape[:2]
+    inner = slice(1, X - 1)
+    adv[inner, 0, :] = col[inner, Y - 1, :]
+    adv[inner, Y - 1, :] = col[inner, 0, :]
+    adv[0, :, :] = col[X - 1, :, :]
+    adv[X - 1, :, :] = col[0, :, :]
+
+
+def tp_emulated_step(host, orc, L, model, cfg, fr, fb, rr, rb, u, Fs=None):
+    """one step of a two-phase model: the product's moments-to-collision arithmetic on the host, the differences through
+    the oracle's operators, streaming and the drivers' boundary rules in numpy.  Returns the new populations and moments."""
+    shape = rr.shape
+    N = rr.size
+    k = np.zeros(10)
+    host.host_tp_constants(model, C.byref(cfg), ptr(k))
+    ph = np.zeros(shape)
+    host.host_tp_phase(model, C.byref(cfg), ptr(rr), ptr(rb), N, ptr(ph))
+    st4 = np.zeros(shape + (4,))
+    if model == TP_RK:
+        st4[..., 0], st4[..., 1] = orc.diff3(ph)
+    else:
+        cq = k[0] * rr + k[1] * rb
+        st4[..., 0], st4[..., 1] = orc.diff5(ph)
+        st4[..., 2] = orc.diff5(np.ascontiguousarray(cq * u[..., 0]))[0]
+        st4[..., 3] = orc.diff5(np.ascontiguousarray(cq * u[..., 1]))[1]
+    cr, cb = np.ascontiguousarray(fr).copy(), np.ascontiguousarray(fb).copy()
+    host.host_tp_collide(model, C.byref(cfg), ptr(cr), ptr(cb), ptr(rr), ptr(rb), ptr(np.ascontiguousarray(u)), ptr(ph), ptr(st4),
+                         ptr(Fs) if Fs is not None else None, N)
+    nr, nb = advect(cr), advect(cb)
+    (rk_bc if model == TP_RK else mrtcg_bc)(nr, cr)
+    (rk_bc if model == TP_RK else mrtcg_bc)(nb, cb)
+    nr, nb = np.ascontiguousarray(nr), np.ascontiguousarray(nb)
+    rr2, rb2, u2, ph2 = np.zeros(shape), np.zeros(shape), np.zeros(shape + (2,)), np.zeros(shape)
+    host.host_tp_moments(model, C.byref(cfg), ptr(nr), ptr(nb), None, N, ptr(rr2), ptr(rb2), ptr(u2), ptr(ph2))
+    return nr, nb, rr2, rb2, u2
+
+
+@pytest.mark.parametrize("kind", ["rt", "droplet"])
+def test_mrtcg_collision_on_the_host_matches_the_oracle(host, kind):
+    """MRT colour gradient (test/mrtcg_rayleigh_taylor.cpp, mrtcg_static_droplet.cpp), 10 steps from the drivers' own
+    initial states: populations and velocity at 1e-12 (the droplet's recolouring divides by a noise-level gradient at the
+    centre of the drop: 1e-10 there, as for the oracle itself against the reference, tests/golden/make_golden.py)"""
+    from oracle_lib import MrtcgParams
+    L = tp_api(host)
+    orc = Oracle()
+    R, Cc = (48, 40) if kind == "rt" else (56, 56)
+    Fg, add_force = ((6.25e-6, 0.0), 1) if kind == "rt" else ((0.0, -6.25e-6), 0)
+    p = MrtcgParams()
+    p.R, p.C = R, Cc
+    p.r_rho0, p.r_alpha, p.r_nu, p.r_beta = 3.0, 0.7, 0.04, 0.7
+    p.b_rho0, p.b_alpha, p.b_nu, p.b_beta = 1.0, 0.1, 0.04, -0.7
+    p.sigma, p.delta = 0.1, 0.1
+    p.Fg[0], p.Fg[1] = Fg
+    p.add_force = add_force
+    st = orc.mrtcg_init(p, kind)
+    cfg = L.default_config(model=L.MODEL_MRTCG, X=R, Y=Cc, red=cases.RED, blue=cases.BLUE, sigma=0.1, delta=0.1, Fg=Fg,
+                           add_force=add_force)
+    fr, fb = st["r_adv"].copy(), st["b_adv"].copy()
+    rr, rb, u = st["r_rho"][..., 0].copy(), st["b_rho"][..., 0].copy(), st["u"].copy()
+    tol = 1e-12 if kind == "rt" else 1e-10
+    for step in range(10):
+        fr, fb, rr, rb, u = tp_emulated_step(host, orc, L, TP_MRTCG, cfg, fr, fb, rr, rb, u)
+        orc.mrtcg_step(p, st)
+        assert cases.relerr(fr, st["r_adv"]) < tol and cases.relerr(fb, st["b_adv"]) < tol, step
+        assert np.abs(u - st["u"]).max() < tol and np.abs(rr - st["r_rho"][..., 0]).max() < tol, step
+
+
+def test_rk_collision_on_the_host_matches_the_oracle(host):
+    """Rothman-Keller static droplet (test/rk_static_droplet_test.cpp), 10 steps"""
+    from oracle_lib import RkParams
+    L = tp_api(host)
+    orc = Oracle()
+    Ln = 48
+    p = RkParams()
+    p.L, p.radius = Ln, Ln / 4.0
+    p.r_rho0, p.r_alpha, p.r_A, p.r_nu = 1.2, 1.0 / 3.0, 1e-4, 0.16
+    p.b_rho0, p.b_alpha, p.b_A, p.b_nu = 1.0, 0.2, 1e-4, 0.14
+    p.delta = 0.98
+    st = orc.rk_init(p)
+    cfg = L.default_config(model=L.MODEL_RK, X=Ln, Y=Ln, red=cases.RK_RED, blue=cases.RK_BLUE, delta=0.98)
+    fr, fb = st["r_adv"].copy(), st["b_adv"].copy()
+    rr, rb, u = st["r_rho"].copy(), st["b_rho"].copy(), st["u"].copy()
+    for step in range(10):
+        fr, fb, rr, rb, u = tp_emulated_step(host, orc, L, TP_RK, cfg, fr, fb, rr, rb, u)
+        orc.rk_step(p, st)
+        assert cases.relerr(fr, st["r_adv"]) < 1e-12 and cases.relerr(fb, st["b_adv"]) < 1e-12, step
+        assert np.abs(u - st["u"]).max() < 1e-12 and np.abs(rr - st["r_rho"]).max() < 1e-12, step
