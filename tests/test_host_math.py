@@ -196,3 +196,56 @@ def test_rk_collision_on_the_host_matches_the_oracle(host):
         orc.rk_step(p, st)
         assert cases.relerr(fr, st["r_adv"]) < 1e-12 and cases.relerr(fb, st["b_adv"]) < 1e-12, step
         assert np.abs(u - st["u"]).max() < 1e-12 and np.abs(rr - st["r_rho"]).max() < 1e-12, step
+
+
+def test_csf_collision_on_the_host_matches_the_oracle(host):
+    """MRT colour gradient with continuum surface force (test/mrt_rayleigh_taylor.cpp), 6 steps from the driver's sharp
+    interface: normals, curvature and interfacial tension assembled here from the oracle's difference operator (the same
+    routine the oracle's own step uses, so the rounding-residue normals of the bulk agree), collision and moments from the
+    product's source"""
+    from oracle_lib import CsfParams
+    L = tp_api(host)
+    orc = Oracle()
+    R, Cc = 64, 40
+    p = CsfParams()
+    p.R, p.C = R, Cc
+    p.r_rho0, p.r_alpha, p.r_nu, p.r_beta, p.r_A = 3.0, 0.7, 0.04, 0.7, 0.5
+    p.b_rho0, p.b_alpha, p.b_nu, p.b_beta, p.b_A = 1.0, 0.1, 0.04, -0.7, 0.5
+    p.sigma, p.delta = 0.1, 0.1
+    p.Fg[0], p.Fg[1] = 6.25e-6, 0.0
+    st = orc.csf_init(p)
+    cfg = L.default_config(model=L.MODEL_MRT_CSF, X=R, Y=Cc, red=cases.RED, blue=cases.BLUE, sigma=0.1, delta=0.1,
+                           Fg=(6.25e-6, 0.0), add_force=1)
+    k = np.zeros(10)
+    host.host_tp_constants(TP_CSF, C.byref(cfg), ptr(k))
+    fr, fb = st["r_adv"].copy(), st["b_adv"].copy()
+    rr, rb, u = st["r_rho"][..., 0].copy(), st["b_rho"][..., 0].copy(), st["u"].copy()
+    N = rr.size
+    for step in range(6):
+        ph = np.zeros((R, Cc))
+        host.host_tp_phase(TP_CSF, C.byref(cfg), ptr(rr), ptr(rb), N, ptr(ph))
+        gx, gy = orc.diff5(ph)
+        gn = np.sqrt(gx * gx + gy * gy)
+        nx, ny = np.ascontiguousarray(-gx / (1e-20 + gn)), np.ascontiguousarray(-gy / (1e-20 + gn))
+        dx_nx, dy_nx = orc.diff5(nx)
+        dx_ny, dy_ny = orc.diff5(ny)
+        K = nx * ny * (dy_nx + dx_ny) - (nx * nx) * dy_ny - (ny * ny) * dx_nx      # eval_local_curvature (:355-364)
+        Fs = np.ascontiguousarray(np.stack([(-0.5 * 0.1) * K * gx, (-0.5 * 0.1) * K * gy], -1))   # (:510)
+        cq = k[0] * rr + k[1] * rb
+        st4 = np.zeros((R, Cc, 4))
+        st4[..., 0], st4[..., 1] = gx, gy
+        st4[..., 2] = orc.diff5(np.ascontiguousarray(cq * u[..., 0]))[0]
+        st4[..., 3] = orc.diff5(np.ascontiguousarray(cq * u[..., 1]))[1]
+        cr, cb = np.ascontiguousarray(fr).copy(), np.ascontiguousarray(fb).copy()
+        host.host_tp_collide(TP_CSF, C.byref(cfg), ptr(cr), ptr(cb), ptr(rr), ptr(rb), ptr(np.ascontiguousarray(u)), ptr(ph),
+                             ptr(st4), ptr(Fs), N)
+        fr, fb = advect(cr), advect(cb)
+        mrtcg_bc(fr, cr)
+        mrtcg_bc(fb, cb)
+        fr, fb = np.ascontiguousarray(fr), np.ascontiguousarray(fb)
+        rr, rb, u = np.zeros((R, Cc)), np.zeros((R, Cc)), np.zeros((R, Cc, 2))
+        host.host_tp_moments(TP_CSF, C.byref(cfg), ptr(fr), ptr(fb), ptr(Fs), N, ptr(rr), ptr(rb), ptr(u), ptr(ph))
+        orc.csf_step(p, st)
+        tol = 1e-12 if step < 2 else 1e-9   # later steps: the algorithm's own conditioning (DESIGN §8d)
+        assert cases.relerr(fr, st["r_adv"]) < tol and cases.relerr(fb, st["b_adv"]) < tol, step
+        assert np.abs(u - st["u"]).max() < tol and np.abs(Fs - st["Fs"]).max() < tol, step
