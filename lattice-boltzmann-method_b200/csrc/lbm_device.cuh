@@ -94,7 +94,7 @@ __host__ __device__ __forceinline__ void moments(const double (&f)[9], double& r
 
 // rho, u of a post-stream node with the conventions of the model's driver (lbm_get_moments)
 template <int EQ, int FORCE>
-__device__ __forceinline__ void snapshot_moments(const double (&f)[9], const BgkParams& p, double& rho, double& ux, double& uy)
+__host__ __device__ __forceinline__ void snapshot_moments(const double (&f)[9], const BgkParams& p, double& rho, double& ux, double& uy)
 {
   double jx, jy;
   moments(f, rho, jx, jy);
@@ -108,7 +108,7 @@ __device__ __forceinline__ void snapshot_moments(const double (&f)[9], const Bgk
 }
 
 // solver::equilibrium (src/solver.cpp:51-62)
-__device__ __forceinline__ double feq_comp(int q, double rho, double ux, double uy, double uu)
+__host__ __device__ __forceinline__ double feq_comp(int q, double rho, double ux, double uy, double uu)
 {
   const double cu = (double)CX(q) * ux + (double)CY(q) * uy;
   const double A = 1.0 + 3.0 * cu + 4.5 * (cu * cu) - 1.5 * uu;
@@ -116,16 +116,16 @@ __device__ __forceinline__ double feq_comp(int q, double rho, double ux, double 
 }
 
 // solver::incomp_equilibrium (src/solver.cpp:39-49)
-__device__ __forceinline__ double feq_incomp(int q, double rho, double ux, double uy)
+__host__ __device__ __forceinline__ double feq_incomp(int q, double rho, double ux, double uy)
 {
   const double cu = (double)CX(q) * ux + (double)CY(q) * uy;
   return (rho + 3.0 * cu) * W(q);
 }
 
-__device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double uy);
+__host__ __device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double uy);
 
 template <int EQ>
-__device__ __forceinline__ double feq_any(int q, double rho, double ux, double uy, double uu)
+__host__ __device__ __forceinline__ double feq_any(int q, double rho, double ux, double uy, double uu)
 {
   if constexpr (EQ == EQ_COMP) return feq_comp(q, rho, ux, uy, uu);
   else if constexpr (EQ == EQ_KBC) return feq_kbc_q(q, rho, ux, uy);
@@ -150,7 +150,7 @@ __host__ __device__ __forceinline__ void kbc_eq_coef(double ux, double uy, doubl
 
 // f_equi as test/ulbm_poiseuille.cpp:117 hands it to its pressure rule: kbc.iequi_f.pow(-1), i.e. the
 // reciprocal of the stored reciprocal 1 / (e_q m0)
-__device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double uy)
+__host__ __device__ __forceinline__ double feq_kbc_q(int q, double rho, double ux, double uy)
 {
   double e[9];
   kbc_eq_coef(ux, uy, ux * ux, uy * uy, e);
@@ -328,7 +328,7 @@ __host__ __device__ __forceinline__ double abb_term(int q, double uwx, double uw
 //   EQ_KBC        ulbm::d2q9::kbc::collide               (src/ulbm.cpp:91-126), omega = s2; `given` = the
 //                 caller's m0, u for the first step after an import (passed in through rho, ux, uy)
 template <int EQ, int FORCE>
-__device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, bool in_roi, double Fx, double Fy,
+__host__ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, bool in_roi, double Fx, double Fy,
                                             double& rho, double& ux, double& uy, bool given = false)
 {
   double jx, jy;
@@ -390,7 +390,7 @@ __device__ __forceinline__ void bgk_collide(double (&f)[9], const BgkParams& p, 
 
 // Second lattice of the sedimentation driver (test/rectangle_sedimentation_test.cpp:125,131):
 // g_coll = (1-w) g + w * equilibrium(u + w_s, C), with the scalar w_s added to both components.
-__device__ __forceinline__ void ade_collide(double (&g)[9], double omega_g, double ux, double uy, double w_s, double& C)
+__host__ __device__ __forceinline__ void ade_collide(double (&g)[9], double omega_g, double ux, double uy, double w_s, double& C)
 {
   double jx, jy;
   moments(g, C, jx, jy);

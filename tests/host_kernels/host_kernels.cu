@@ -25,6 +25,30 @@ void host_kbc_collide(double* f, const double* m0, const double* u, int given, l
   }
 }
 
+// ---- single-phase family: bgk_collide<EQ, FORCE> of N nodes in place.  eq: 0 compressible, 1 incompressible;
+// force: 0 none, 1 uniform (Fg added to u, gravity_test), 2 field F {N,2} with the 1/3, 1/9 constants (cylinder_test),
+// 3 field F with run-time ics2, ics4 (decompose_domain_loop).  rho {N}, u {N,2}: the iteration's moments, out.
+void host_bgk_collide(int eq, int force, double* f, long N, double omega, double Fg0, double Fg1, const double* F, double ics2,
+                      double ics4, double* rho, double* u)
+{
+  lbm::BgkParams p = {};
+  p.omega = omega; p.inv_omega = 1.0 / omega; p.Fg0 = Fg0; p.Fg1 = Fg1; p.ics2 = ics2; p.ics4 = ics4;
+  for (long n = 0; n < N; n++)
+  {
+    double v[9];
+    for (int q = 0; q < 9; q++) v[q] = f[9 * n + q];
+    const double Fx = F ? F[2 * n] : 0.0, Fy = F ? F[2 * n + 1] : 0.0;
+    double r, ux, uy;
+#define HK_CASE(E, FO) if (eq == E && force == FO) lbm::bgk_collide<E, FO>(v, p, true, Fx, Fy, r, ux, uy);
+    HK_CASE(lbm::EQ_COMP, lbm::FORCE_NONE) HK_CASE(lbm::EQ_COMP, lbm::FORCE_UNIFORM) HK_CASE(lbm::EQ_COMP, lbm::FORCE_IBM)
+    HK_CASE(lbm::EQ_COMP, lbm::FORCE_REGION) HK_CASE(lbm::EQ_INCOMP, lbm::FORCE_NONE) HK_CASE(lbm::EQ_INCOMP, lbm::FORCE_UNIFORM)
+    HK_CASE(lbm::EQ_INCOMP, lbm::FORCE_IBM) HK_CASE(lbm::EQ_INCOMP, lbm::FORCE_REGION)
+#undef HK_CASE
+    for (int q = 0; q < 9; q++) f[9 * n + q] = v[q];
+    rho[n] = r; u[2 * n] = ux; u[2 * n + 1] = uy;
+  }
+}
+
 // ---- two-phase models (csrc/lbm_two_phase.cuh).  model: 0 = MRT colour gradient, 1 = Rothman-Keller, 2 = MRT + CSF.
 // Constants from the product's own tp_fill_params.
 

@@ -249,3 +249,81 @@ def test_csf_collision_on_the_host_matches_the_oracle(host):
         tol = 1e-12 if step < 2 else 1e-9   # later steps: the algorithm's own conditioning
         assert cases.relerr(fr, st["r_adv"]) < tol and cases.relerr(fb, st["b_adv"]) < tol, step
         assert np.abs(u - st["u"]).max() < tol and np.abs(Fs - st["Fs"]).max() < tol, step
+
+
+# ------------------------------------------------------------------------------------------------
+# single-phase family: bgk_collide<EQ, FORCE> on the host
+# ------------------------------------------------------------------------------------------------
+W9 = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+
+
+def bgk_api(lib):
+    dp = C.POINTER(C.c_double)
+    lib.host_bgk_collide.argtypes = [C.c_int, C.c_int, dp, C.c_long, C.c_double, C.c_double, C.c_double, dp, C.c_double,
+                                     C.c_double, dp, dp]
+
+
+def near_equilibrium(orc, X, Y, seed):
+    rng = np.random.default_rng(seed)
+    rho = 1.0 + 0.02 * rng.standard_normal((X, Y, 1))
+    u = 0.05 * rng.standard_normal((X, Y, 2))
+    return orc.equilibrium(u, rho) * (1.0 + 1e-2 * rng.standard_normal((X, Y, 9)))
+
+
+@pytest.mark.parametrize("eq", [0, 1])
+def test_bgk_collision_on_the_host_matches_the_operators(host, eq):
+    """solver::calc_rho / calc_u / calc_incomp_u / equilibrium / incomp_equilibrium / collision fused in bgk_collide"""
+    bgk_api(host)
+    orc = Oracle()
+    f = near_equilibrium(orc, 24, 20, 1)
+    omega = 1.37
+    rho = orc.calc_rho(f)
+    u = orc.calc_u(f, rho) if eq == 0 else orc.calc_incomp_u(f)
+    want = orc.collision(f, orc.equilibrium(u, rho) if eq == 0 else orc.incomp_equilibrium(u, rho), omega)
+    got = f.copy()
+    r, uu = np.zeros(f.shape[:2]), np.zeros(f.shape[:2] + (2,))
+    host.host_bgk_collide(eq, 0, ptr(got), got.size // 9, omega, 0.0, 0.0, None, 0.0, 0.0, ptr(r), ptr(uu))
+    assert cases.relerr(got, want) < 1e-15
+    assert np.abs(r - rho[..., 0]).max() < 1e-15 and np.abs(uu - u).max() < 1e-15
+
+
+@pytest.mark.parametrize("force,ics2,ics4", [(2, 1.0 / 3.0, 1.0 / 9.0), (3, 3.0, 9.0)])
+def test_bgk_force_field_source_term_on_the_host(host, force, ics2, ics4):
+    """f + (-omega (f - feq)) + (1 - omega/2) ((ics2 + ics4 u.c)(F.c) - ics2 u.F) w: cylinder_test.cpp:112-127 with 1/3, 1/9
+    (compile-time in the kernels) and decompose_domain_loop.cpp:66-69,151-158 with 3, 9 (lbm_set_force_region)"""
+    bgk_api(host)
+    orc = Oracle()
+    f = near_equilibrium(orc, 20, 18, 2)
+    omega = 1.21
+    F = np.ascontiguousarray(1e-3 * np.random.default_rng(9).standard_normal(f.shape[:2] + (2,)))
+    rho = orc.calc_rho(f)
+    u = orc.calc_u(f, rho)
+    feq = orc.equilibrium(u, rho)
+    CX = np.array(CXI, dtype=float); CY = np.array(CYI, dtype=float)
+    cu = u[..., 0:1] * CX + u[..., 1:2] * CY
+    cF = F[..., 0:1] * CX + F[..., 1:2] * CY
+    uF = u[..., 0:1] * F[..., 0:1] + u[..., 1:2] * F[..., 1:2]
+    want = f + (-omega * (f - feq)) + ((1.0 - 0.5 * omega) * ((ics2 + ics4 * cu) * cF - ics2 * uF)) * W9
+    got = f.copy()
+    r, uu = np.zeros(f.shape[:2]), np.zeros(f.shape[:2] + (2,))
+    host.host_bgk_collide(0, force, ptr(got), got.size // 9, omega, 0.0, 0.0, ptr(F), ics2, ics4, ptr(r), ptr(uu))
+    assert cases.relerr(got, want) < 1e-15
+
+
+def test_bgk_uniform_force_on_the_host_matches_the_gravity_driver(host):
+    """test/gravity_test.cpp: one collision of the oracle's gravity step (u += Fg before the equilibrium, source term with
+    1/3 and 1/9), isolated by undoing the streaming on a periodic box away from the driver's boundary rows / columns"""
+    bgk_api(host)
+    orc = Oracle()
+    X = Y = 16
+    f = near_equilibrium(orc, X, Y, 3)
+    omega, Fg = 1.1, (-3e-4, 1e-4)
+    got = f.copy()
+    r, uu = np.zeros((X, Y)), np.zeros((X, Y, 2))
+    host.host_bgk_collide(1, 1, ptr(got), X * Y, omega, Fg[0], Fg[1], None, 0.0, 0.0, ptr(r), ptr(uu))
+    ref = f.copy()
+    u = np.zeros((X, Y, 2)); rho = np.ones((X, Y, 1))
+    orc.gravity_step(ref, u, rho, omega, 1.0, 1.0, np.array(Fg))
+    mine = advect(got)
+    inner = (slice(3, X - 3), slice(3, Y - 3))     # nodes whose nine sources no boundary rule of the driver touches
+    assert cases.relerr(mine[inner], ref[inner]) < 1e-14
