@@ -250,6 +250,23 @@ def cpu_reference_mlups(workload, edge, warmup, steps):
         return (edge * edge / sec / 1e6, sec, "reference" if have else "port", ops.num_threads() if have else port_cores,
                 f"{edge}x{edge} crop of the cylinder_bb workload (solver:: operators + bounce-back links; inlet/outlet rows left out)")
 
+    if workload == "kbc_shear" and oracle_lib.have_ref():
+        # the reference's own ulbm::d2q9::kbc object stepped like test/ulbm_double_shear_flow.cpp does (oracle/ref_harness.cpp)
+        ref = oracle_lib.Ref()
+        r = np.arange(edge)[:, None] + 0.0 * np.arange(edge)[None, :]
+        c = np.arange(edge)[None, :] + 0.0 * np.arange(edge)[:, None]
+        u = np.zeros((edge, edge, 2))
+        u[..., 0] = 0.02 * np.tanh(80.0 * (0.25 * edge - np.abs(c - 0.5 * edge)))
+        u[..., 1] = 0.02 * 0.05 * np.sin(6.2832 * (r + 0.25 * edge) / edge)
+        m0 = np.ones((edge, edge))
+        f = ref.kbc_equilibrium(m0, u)
+        s2 = 1.0 / (0.5 + 3.0 * 1.70766666e-4)
+        ref.kbc_run(f, m0, u, s2, max(warmup, 1))
+        t0 = time.perf_counter()
+        ref.kbc_run(f, m0, u, s2, steps)
+        sec = (time.perf_counter() - t0) / max(steps, 1)
+        return edge * edge / sec / 1e6, sec, "reference", ref.num_threads(), f"{edge}x{edge} crop of the kbc_shear workload"
+
     orc = oracle_lib.Oracle()
     if workload == "poiseuille":
         om, rho_in, rho_out = channel_constants(edge, edge)
