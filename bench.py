@@ -267,6 +267,12 @@ def cpu_reference_mlups(workload, edge, warmup, steps):
         sec = (time.perf_counter() - t0) / max(steps, 1)
         return edge * edge / sec / 1e6, sec, "reference", ref.num_threads(), f"{edge}x{edge} crop of the kbc_shear workload"
 
+    if workload == "poiseuille" and oracle_lib.have_ref() and hasattr(oracle_lib.Ref().lib, "ref_poiseuille_loop"):
+        ref = oracle_lib.Ref()
+        om, rho_in, rho_out = channel_constants(edge, edge)
+        sec, _ = ref.poiseuille_loop(edge, edge, om, rho_in, rho_out, max(warmup, 1), steps)
+        return edge * edge / sec / 1e6, sec, "reference", ref.num_threads(), f"{edge}x{edge} crop of the poiseuille workload"
+
     orc = oracle_lib.Oracle()
     if workload == "poiseuille":
         om, rho_in, rho_out = channel_constants(edge, edge)

@@ -289,6 +289,51 @@ int ref_cylinder_loop(int X, int Y, double omega, double u_lb, const char* marke
   REF_CATCH
 }
 
+// The time loop of test/horizontal_poiseuille_test.cpp:100-153 (moments, incompressible equilibrium, solver::collision,
+// the pressure-periodic rows of :25-45, solver::advect, bounce-back columns; snapshots and the convergence check left
+// out) on an {H,W} grid, every operator the reference's own.  CPU baseline of bench.py's poiseuille workload.
+int ref_poiseuille_loop(int H, int W, double omega, double rho_inlet, double rho_outlet, int warmup, int steps,
+                        double* seconds_per_step, double* checksum)
+{
+  REF_TRY
+  using torch::Tensor;
+  using torch::indexing::Slice;
+  using torch::indexing::Ellipsis;
+  const torch::Device dev = torch::kCPU;
+  Tensor f_equi = torch::zeros({H, W, 9}, dev);
+  Tensor f_coll = torch::zeros_like(f_equi);
+  Tensor f_adve = torch::zeros_like(f_equi);
+  Tensor u = torch::zeros({H, W, 2}, dev);
+  Tensor rho = torch::ones({H, W, 1}, dev);
+  Tensor temp_equi = torch::zeros({1, W, 9}, dev);
+  Tensor temp_rho = torch::ones({1, W, 1}, dev);
+  solver::incomp_equilibrium(f_adve, u, rho);
+  std::chrono::steady_clock::time_point t0;
+  for (int t = 0; t < warmup + steps; t++)
+  {
+    if (t == warmup) t0 = std::chrono::steady_clock::now();
+    solver::calc_rho(rho, f_adve);
+    solver::calc_incomp_u(u, f_adve);
+    solver::incomp_equilibrium(f_equi, u, rho);
+    solver::collision(f_coll, f_adve, f_equi, omega);
+    solver::incomp_equilibrium(temp_equi, u.index({-2, Ellipsis}).unsqueeze(0), rho_inlet * temp_rho);
+    f_coll.index({0, Ellipsis}) = (temp_equi + f_coll.index({-2, Ellipsis}) - f_equi.index({-2, Ellipsis})).squeeze(0).clone().detach();
+    solver::incomp_equilibrium(temp_equi, u.index({1, Ellipsis}).unsqueeze(0), rho_outlet * temp_rho);
+    f_coll.index({-1, Ellipsis}) = (temp_equi + f_coll.index({1, Ellipsis}) - f_equi.index({1, Ellipsis})).squeeze(0).clone().detach();
+    solver::advect(f_adve, f_coll);
+    f_adve.index({Slice(), -1, 4}) = f_coll.index({Slice(), -1, 2}).clone().detach();
+    f_adve.index({Slice(), -1, 7}) = f_coll.index({Slice(), -1, 5}).clone().detach();
+    f_adve.index({Slice(), -1, 8}) = f_coll.index({Slice(), -1, 6}).clone().detach();
+    f_adve.index({Slice(), 0, 2}) = f_coll.index({Slice(), 0, 4}).clone().detach();
+    f_adve.index({Slice(), 0, 5}) = f_coll.index({Slice(), 0, 7}).clone().detach();
+    f_adve.index({Slice(), 0, 6}) = f_coll.index({Slice(), 0, 8}).clone().detach();
+  }
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *seconds_per_step = dt / steps;
+  *checksum = f_adve.sum().item<double>();
+  REF_CATCH
+}
+
 // struct domain (src/domain.cpp:3-12): shapes of the five buffers, 15 ints.
 int ref_domain_shapes(int R, int C, long* shapes15)
 {

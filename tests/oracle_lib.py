@@ -372,6 +372,15 @@ class Ref:
                                              warmup, steps, C.byref(sec), C.byref(chk)))
         return sec.value, chk.value
 
+    def poiseuille_loop(self, H, W, omega, rho_in, rho_out, warmup, steps):
+        """seconds per step and checksum of the loop body of test/horizontal_poiseuille_test.cpp:100-153 on CPU libtorch"""
+        if not hasattr(self.lib, "ref_poiseuille_loop"):
+            raise RuntimeError("oracle/_ref/libref_harness.so predates ref_poiseuille_loop: rebuild it (make -C oracle ref)")
+        sec = C.c_double(); chk = C.c_double()
+        self._chk(self.lib.ref_poiseuille_loop(H, W, C.c_double(omega), C.c_double(rho_in), C.c_double(rho_out), warmup, steps,
+                                               C.byref(sec), C.byref(chk)))
+        return sec.value, chk.value
+
     def kbc_run(self, f, m0, m1, s2, steps, bc=0, rho_in=1.0, rho_out=1.0):
         """ulbm::d2q9::kbc stepped like its drivers (in place on f = adve_f, m0, m1)"""
         X, Y, _ = f.shape

@@ -132,3 +132,17 @@ def test_kbc_class_and_driver_loops(libs):
             o.kbc_step(fo, ao, bo, s2, 1, 1.0004, 1.0)
         r.kbc_run(fr, ar, br, s2, n, 1, 1.0004, 1.0)
         assert np.abs(fo - fr).max() < 1e-12, n
+
+
+def test_poiseuille_loop_of_the_reference_matches_the_port(libs):
+    """the timed loop bench.py uses as the CPU arm of the poiseuille workload (oracle/ref_harness.cpp: the reference's own
+    operators in the order of test/horizontal_poiseuille_test.cpp:100-153) lands where the C port's step does"""
+    orc, ref = libs
+    H, W, steps = 21, 21, 60
+    omega, rho_in, rho_out = cases.channel_constants(H, W, 1.030985714e-1)
+    _, chk = ref.poiseuille_loop(H, W, omega, rho_in, rho_out, 0, steps)
+    u = np.zeros((H, W, 2)); rho = np.ones((H, W, 1))
+    f = orc.incomp_equilibrium(u, rho)
+    for _ in range(steps):
+        orc.poiseuille_step(f, u, rho, omega, rho_in, rho_out)
+    assert abs(chk - f.sum()) < 1e-11 * abs(f.sum())
