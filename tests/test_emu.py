@@ -1,0 +1,58 @@
+"""The `-m gpu` parity tests, run on host cores against the library's own CUDA sources compiled by the SIMT emulator of
+tests/cpu_emu/ (fibers for the threads of a block, typed waits for __syncthreads and the warp shuffles, an
+immediately-executing CUDA runtime whose fresh allocations are NaN-filled).  TEST INFRASTRUCTURE: it checks the kernels'
+indexing, shared-memory rings, barriers, boundary tables and the host-side step schedule where there is no GPU; it says
+nothing about speed, and rounding differs from the device's (no FMA contraction), so it is no substitute for the
+`-m gpu` run on the B200.  The product never loads the emulated library (tests/conftest.py, LBM_EMU=1 only).
+
+The default CPU suite runs every GPU test except the 10^4-step ones and two long golden runs;
+`LBM_EMU=1 python -m pytest tests -m gpu` runs all of them (about ten minutes on eight cores)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "cpu_emu")
+SLOW = [
+    "tests/test_gpu_long_horizon.py",
+    "tests/test_gpu_kbc.py::test_double_shear_flow_reference_driver_golden",
+    "tests/test_gpu_bgk.py::test_poiseuille_golden_and_l2",
+]
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    if sys.platform != "linux":
+        pytest.skip("the emulated build is set up for Linux")
+    r = subprocess.run(["make", "-C", EMU_DIR, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    path = os.path.join(EMU_DIR, "_build", "liblbm_b200_emu.so")
+    assert os.path.exists(path)
+    return path
+
+
+def run_emulated(args, timeout):
+    env = dict(os.environ, LBM_EMU="1", OMP_WAIT_POLICY="passive")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + args
+    return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_gpu_parity_tests_pass_on_the_emulated_device(emu_lib):
+    args = ["tests"]
+    for s in SLOW:
+        args += ["--deselect", s]
+    r = run_emulated(args, 1500)
+    tail = r.stdout[-4000:]
+    assert r.returncode == 0, tail
+    last = r.stdout.strip().splitlines()[-1]
+    assert " passed" in last and "failed" not in last, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 80, last  # the emulated run really ran the parity tests
+
+
+def test_the_product_binding_does_not_know_the_emulated_library():
+    src = open(os.path.join(ROOT, "lattice-boltzmann-method_b200", "python", "lbm_b200", "__init__.py")).read()
+    assert "emu" not in src.lower() and "LBM_EMU" not in src
+    for name in ("bench.py", "__graft_entry__.py"):
+        assert "cpu_emu" not in open(os.path.join(ROOT, name)).read()

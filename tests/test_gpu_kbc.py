@@ -47,25 +47,34 @@ def test_double_shear_flow_vs_oracle(orc, R, C):
 
 
 def test_poiseuille_cold_start_vs_oracle(orc):
-    """test/ulbm_poiseuille.cpp: adve_f = 0, m0 = 1, m1 = 0 at t = 0; pressure rows on coll_f, bounce-back columns"""
+    """test/ulbm_poiseuille.cpp: adve_f = 0, m0 = 1, m1 = 0 at t = 0; pressure rows on coll_f, bounce-back columns.
+    1e-12 on the first three steps.  The cold start is a violent transient that amplifies rounding (the oracle itself
+    departs from a twin perturbed by 1e-15 after step 1 by 2e-11 at step 20 and 7e-13 at step 300), so from then on the
+    bound is the algorithm's own conditioning: no further from the oracle than 5 x the oracle is from that twin."""
     R, C = 48, 40
     nu = 1e-4
     s2 = 1.0 / (0.5 + 3.0 * nu)
     rho_out = 1.0
     rho_in = 3.0 * (R - 1) * (8.0 * nu * 0.05 / (C * C)) + rho_out
     f = np.zeros((R, C, 9)); m0 = np.ones((R, C)); u = np.zeros((R, C, 2))
+    tf, tm0, tu = f.copy(), m0.copy(), u.copy()
     d = cases.kbc(R, C, s2, poiseuille=(rho_in, rho_out))
     d.set_f(f)
     d.set_moments(m0[..., None], u)
     done = 0
     for upto in (1, 2, 3, 20, 300):
-        for _ in range(upto - done):
+        for n in range(done, upto):
             orc.kbc_step(f, m0, u, s2, 1, rho_in, rho_out)
+            orc.kbc_step(tf, tm0, tu, s2, 1, rho_in, rho_out)
+            if n == 0:
+                tf *= 1.0 + 1e-15 * np.random.default_rng(7).standard_normal(tf.shape)
         d.step(upto - done)
         done = upto
-        assert cases.relerr(d.get_f(), f) < 1e-12, upto
+        own = cases.relerr(tf, f)
+        tol = 1e-12 if upto <= 3 else max(1e-12, 5.0 * own)
+        assert tol < 1e-9 and cases.relerr(d.get_f(), f) < tol, (upto, own)
     rho, uu = d.get_moments()
-    assert np.abs(rho[..., 0] - m0).max() < 1e-12 and np.abs(uu - u).max() < 1e-12
+    assert np.abs(rho[..., 0] - m0).max() < tol and np.abs(uu - u).max() < tol
 
 
 def test_without_set_moments_the_populations_decide(orc):
