@@ -106,6 +106,7 @@ struct Block
   int alive = 0, arrived = 0;   // block barrier
   unsigned gen = 0;
   std::vector<WarpState> warps;
+  std::vector<int> order;       // the order threads start (and resume) in: EMU_ORDER = forward | reverse | shuffle[:seed]
   Context main_ctx;
   Fiber* current = nullptr;
   std::vector<Fiber*> pool, running;
@@ -141,7 +142,7 @@ void fiber_main()
   Fiber* f = b.current;
   while (b.next < b.total)
   {
-    const int lin = b.next++;
+    const int lin = b.order[b.next++];
     f->lin = lin;
     f->tid.x = lin % b.dim.x;
     f->tid.y = (lin / b.dim.x) % b.dim.y;
@@ -153,6 +154,29 @@ void fiber_main()
   f->finished = true;
   ctx_switch(f->ctx, b.main_ctx);
   std::abort();  // a finished fiber is never resumed
+}
+
+// Thread order inside a block.  A kernel that is correct on the device does not depend on it; a missing barrier
+// around a shared-memory ring usually does, so the parity tests are run under several orders (tests/test_emu.py).
+void fill_order(Block& b)
+{
+  static const char* mode = std::getenv("EMU_ORDER");
+  b.order.resize(b.total);
+  for (int i = 0; i < b.total; i++) b.order[i] = i;
+  if (!mode || !std::strncmp(mode, "forward", 7)) return;
+  if (!std::strncmp(mode, "reverse", 7))
+  {
+    for (int i = 0; i < b.total; i++) b.order[i] = b.total - 1 - i;
+    return;
+  }
+  // shuffle[:seed] — warps stay together only by chance, as on the device nothing orders them
+  static thread_local uint64_t state = 0;
+  if (state == 0) state = 0x9E3779B97F4A7C15ull ^ (std::strlen(mode) > 8 ? std::strtoull(mode + 8, nullptr, 10) : 1ull);
+  for (int i = b.total - 1; i > 0; i--)
+  {
+    state ^= state << 13; state ^= state >> 7; state ^= state << 17;
+    std::swap(b.order[i], b.order[(int)(state % (uint64_t)(i + 1))]);
+  }
 }
 
 Fiber* take_fiber(Block& b)
@@ -192,6 +216,7 @@ void run_block(Block& b)
   b.warps.assign(nw, WarpState{});
   for (int w = 0; w < nw; w++) b.warps[w].alive = std::min(32, b.total - 32 * w);
   b.running.clear();
+  fill_order(b);
   while (true)
   {
     bool progressed = false;

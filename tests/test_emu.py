@@ -33,8 +33,8 @@ def emu_lib():
     return path
 
 
-def run_emulated(args, timeout):
-    env = dict(os.environ, LBM_EMU="1", OMP_WAIT_POLICY="passive")
+def run_emulated(args, timeout, order="forward"):
+    env = dict(os.environ, LBM_EMU="1", OMP_WAIT_POLICY="passive", EMU_ORDER=order)
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + args
     return subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
 
@@ -49,6 +49,14 @@ def test_gpu_parity_tests_pass_on_the_emulated_device(emu_lib):
     last = r.stdout.strip().splitlines()[-1]
     assert " passed" in last and "failed" not in last, tail
     assert int(last.split(" passed")[0].split()[-1]) >= 80, last  # the emulated run really ran the parity tests
+
+
+@pytest.mark.parametrize("order", ["reverse", "shuffle:3"])
+def test_shared_memory_ring_kernels_do_not_depend_on_thread_order(emu_lib, order):
+    """The threads of a block start and resume in reversed / shuffled order.  A missing barrier around the shared-memory
+    rings of k_tp_fused / k_csf_collide_ring makes these runs fail (checked by deleting the ring's __syncthreads)."""
+    r = run_emulated(["tests/test_gpu_two_phase.py", "tests/test_gpu_csf.py", "tests/test_gpu_slabs.py"], 900, order)
+    assert r.returncode == 0, r.stdout[-4000:]
 
 
 def test_the_product_binding_does_not_know_the_emulated_library():
