@@ -1161,6 +1161,87 @@ void orc_rk_step(const orc_rk_params* p, double* r_adv, double* b_adv, double* r
   free(gx); free(gy); free(r_col); free(b_col);
 }
 
+/* The per-iteration diagnostic fields driver 17 snapshots next to the state (test/rk_static_droplet_test.cpp:546-600):
+ * everything is a function of the state at the TOP of loop iteration t (r_adv, r_rho, b_rho, rho_mix, u), so calling
+ * this and then orc_rk_step reproduces iteration t.  None of it feeds the state update (step() only uses
+ * omega3 = omega1 + omega2 of grad and |grad|, :213-237).
+ *   phase :547 (rhons) ; grad, norm :550-558 ; n = -normalize(grad where |grad| > 0.1 max|grad| else 0) :559-567 ;
+ *   K eval_local_curvature :440-446 ; Fs = sigma/2 K grad :572 ; eta eval_eta :398-413 ; kappa eval_kappa :415-438 ;
+ *   rparams = 1 / tau(phase) :587-589 (in-out like orc_rk_step's relax) ; omega1, omega2 of the RED colour :255-262, :239-245.
+ * Any output pointer may be NULL. */
+void orc_rk_diagnostics(const orc_rk_params* p, double sigma, const double* r_adv, const double* r_rho, const double* b_rho,
+                        const double* rho_mix, const double* u, double* phase_o, double* grad_o, double* norm_o, double* n_o,
+                        double* K_o, double* Fs_o, double* eta_o, double* kappa_o, double* relax_io, double* omega1_o,
+                        double* omega2_o)
+{
+  const int X = p->L, Y = p->L;
+  const size_t N = (size_t)X * Y;
+  const double cs2 = 1.0 / 3.0, ics2 = 3.0;
+  double rphi[9];
+  rk_phi(p->r_alpha, rphi);
+  double r_om = 1.0 / (0.5 + p->r_nu / cs2), b_om = 1.0 / (0.5 + p->b_nu / cs2);
+  relax_fn rf = relax_init(1.0 / r_om, 1.0 / b_om, p->delta);
+  double* phase = dalloc(N);
+  double* gx = dalloc(N); double* gy = dalloc(N); double* gn = dalloc(N);
+  double* nx = dalloc(N); double* ny = dalloc(N);
+  double* x_nx = dalloc(N); double* y_nx = dalloc(N); double* x_ny = dalloc(N); double* y_ny = dalloc(N);
+  for (size_t n = 0; n < N; n++)
+    phase[n] = (r_rho[n] / p->r_rho0 - b_rho[n] / p->b_rho0) / (r_rho[n] / p->r_rho0 + b_rho[n] / p->b_rho0);
+  orc_diff3(phase, X, Y, gx, gy); /* grad[...,0] = partial.x = along axis 1, grad[...,1] = partial.y = along axis 0 */
+  double gmax = 0.0;
+  for (size_t n = 0; n < N; n++)
+  {
+    gn[n] = sqrt(pow(gx[n], 2.0) + pow(gy[n], 2.0));
+    if (gn[n] > gmax) gmax = gn[n];
+  }
+  for (size_t n = 0; n < N; n++)
+  {
+    /* torch::where(norm <= 0.1 max, 0, grad), then F::normalize: v / max(||v||_2, 1e-12), negated */
+    double cx = gn[n] <= 0.1 * gmax ? 0.0 : gx[n], cy = gn[n] <= 0.1 * gmax ? 0.0 : gy[n];
+    double den = sqrt(cx * cx + cy * cy);
+    if (den < 1e-12) den = 1e-12;
+    nx[n] = -(cx / den);
+    ny[n] = -(cy / den);
+  }
+  orc_diff3(nx, X, Y, x_nx, y_nx);
+  orc_diff3(ny, X, Y, x_ny, y_ny);
+  for (size_t n = 0; n < N; n++)
+  {
+    const double K = nx[n] * ny[n] * (y_nx[n] + x_ny[n]) - pow(nx[n], 2.0) * y_ny[n] - pow(ny[n], 2.0) * x_nx[n];
+    const double Fsx = 0.5 * sigma * K * gx[n], Fsy = 0.5 * sigma * K * gy[n];
+    const double ux = u[n * 2], uy = u[n * 2 + 1];
+    if (phase_o) phase_o[n] = phase[n];
+    if (grad_o) { grad_o[n * 2] = gx[n]; grad_o[n * 2 + 1] = gy[n]; }
+    if (norm_o) norm_o[n] = gn[n];
+    if (n_o) { n_o[n * 2] = nx[n]; n_o[n * 2 + 1] = ny[n]; }
+    if (K_o) K_o[n] = K;
+    if (Fs_o) { Fs_o[n * 2] = Fsx; Fs_o[n * 2 + 1] = Fsy; }
+    double relax = 0.0;
+    if (relax_io)
+    {
+      double tau = relax_eval(&rf, phase[n], relax_io[n]);
+      relax = pow(tau, -1.0);
+      relax_io[n] = relax;
+    }
+    double feq[9];
+    rk_eq_node(r_rho[n], rphi, ux, uy, feq);
+    for (int q = 0; q < 9; q++)
+    {
+      const double ue = ux * CXD[q] + uy * CYD[q];
+      if (eta_o) /* sum over the two components of (ics2 (E - u) + ics2 (u.E) E) Fs, times W */
+        eta_o[n * 9 + q] = ((ics2 * (CXD[q] - ux) + ics2 * (ue * CXD[q])) * Fsx + (ics2 * (CYD[q] - uy) + ics2 * (ue * CYD[q])) * Fsy) * W9[q];
+      if (kappa_o) kappa_o[n * 9 + q] = (r_rho[n] * b_rho[n] / rho_mix[n]) * (((-nx[n]) * CXD[q] + (-ny[n]) * CYD[q]) * W9[q]);
+      if (omega1_o && relax_io) omega1_o[n * 9 + q] = relax * (feq[q] - r_adv[n * 9 + q]);
+      if (omega2_o)
+      {
+        const double fe = gx[n] * CXD[q] + gy[n] * CYD[q];
+        omega2_o[n * 9 + q] = ((0.5 * p->r_A) * gn[n]) * ((pow(fe, 2.0) / (1e-20 + pow(gn[n], 2.0))) * W9[q] - BB9[q]);
+      }
+    }
+  }
+  free(phase); free(gx); free(gy); free(gn); free(nx); free(ny); free(x_nx); free(y_nx); free(x_ny); free(y_ny);
+}
+
 /* ------------------------------------------------------------------ test/mrt_rayleigh_taylor.cpp */
 
 void orc_csf_init(const orc_csf_params* p, double* r_rho, double* b_rho, double* rho, double* u, double* r_adv, double* b_adv)

@@ -118,6 +118,12 @@ void orc_rk_init(const orc_rk_params* p, const double* u0, double* r_adv, double
                  double* r_rho, double* b_rho, double* rho_mix);
 void orc_rk_step(const orc_rk_params* p, double* r_adv, double* b_adv, double* r_rho, double* b_rho,
                  double* rho_mix, double* u, double* phase, double* relax, double* grad);
+/* the diagnostic fields the driver snapshots per iteration (:546-600), from the state at the top of the iteration;
+ * relax_io is in-out like orc_rk_step's relax; omega1 / omega2 are the red colour's; NULL outputs are skipped */
+void orc_rk_diagnostics(const orc_rk_params* p, double sigma, const double* r_adv, const double* r_rho, const double* b_rho,
+                        const double* rho_mix, const double* u, double* phase_o, double* grad_o, double* norm_o, double* n_o,
+                        double* K_o, double* Fs_o, double* eta_o, double* kappa_o, double* relax_io, double* omega1_o,
+                        double* omega2_o);
 
 /* ---- test/mrt_rayleigh_taylor.cpp: the MRT colour-gradient model with a continuum-surface-force perturbation
  * (curvature from a second pass of `differential`) -- SURVEY 8(f) rank 2.  The driver only runs at

@@ -270,6 +270,19 @@ class Oracle:
         self.lib.orc_rk_step(C.byref(p), _p(st["r_adv"]), _p(st["b_adv"]), _p(st["r_rho"]), _p(st["b_rho"]),
                              _p(st["rho"]), _p(st["u"]), _p(st["phase"]), _p(st["relax"]), _p(st["grad"]))
 
+    def rk_diagnostics(self, p, st, sigma=5e-3):
+        """the fields driver 17 snapshots per iteration, from the state BEFORE rk_step (relax is not advanced: a copy)"""
+        L = p.L
+        out = dict(phase=np.zeros((L, L)), grad=np.zeros((L, L, 2)), norm=np.zeros((L, L)), n=np.zeros((L, L, 2)),
+                   K=np.zeros((L, L)), Fs=np.zeros((L, L, 2)), eta=np.zeros((L, L, 9)), kappa=np.zeros((L, L, 9)),
+                   rparams=st["relax"].copy(), omega1=np.zeros((L, L, 9)), omega2=np.zeros((L, L, 9)))
+        self.lib.orc_rk_diagnostics.argtypes = [C.c_void_p, C.c_double] + [dp] * 16
+        self.lib.orc_rk_diagnostics(C.byref(p), sigma, _p(st["r_adv"]), _p(st["r_rho"]), _p(st["b_rho"]), _p(st["rho"]), _p(st["u"]),
+                                    _p(out["phase"]), _p(out["grad"]), _p(out["norm"]), _p(out["n"]), _p(out["K"]), _p(out["Fs"]),
+                                    _p(out["eta"]), _p(out["kappa"]), _p(out["rparams"]), _p(out["omega1"]), _p(out["omega2"]))
+        out["omega3"] = out["omega1"] + out["omega2"]
+        return out
+
 
 def have_ref():
     return os.path.exists(REF_SO)
