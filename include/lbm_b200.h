@@ -224,6 +224,19 @@ int lbm_snapshot_wait(lbm_domain* d);
 int lbm_get_phase(lbm_domain* d, double* phase, double* rho_r, double* rho_b);
 /* LBM_MODEL_MRT_CSF: interf_tension {X,Y,2} of the last step (the driver snapshots it: mrt_rayleigh_taylor.cpp:485-486) */
 int lbm_get_interfacial_tension(lbm_domain* d, double* Fs_aos);
+/* LBM_MODEL_RK: the diagnostic fields test/rk_static_droplet_test.cpp snapshots at the top of every iteration (:546-600) —
+ * functions of the CURRENT state only, none feeds the step (it uses grad and |grad| alone, :213-237).  Call before
+ * lbm_step(d, 1) to reproduce iteration t of the driver.  Host buffers in the reference's tensor layouts; NULL = skip.
+ *   phase {X,Y} (rhons)   grad {X,Y,2} (gradxs, gradys: [0] = the driver's partial.x, along axis 1)   norm {X,Y} (norms)
+ *   n {X,Y,2} (nxs, nys) = -normalize(grad where |grad| > 0.1 max|grad|, else 0)   K {X,Y} (Ks, eval_local_curvature :440-446)
+ *   Fs {X,Y,2} (Fsxs, Fsys) = sigma/2 K grad   eta {X,Y,9} (eval_eta :398-413)   kappa {X,Y,9} (kappas, eval_kappa :415-438)
+ *   rparams {X,Y} = 1/tau(phase)   omega1, omega2, omega3 {X,Y,9}: the RED colour's operators (:255-262, :239-245, :232-236)
+ * Monolithic domains only (the cut needs the global max|grad|); LBM_ERR_UNSUPPORTED on a slab.                              */
+typedef struct lbm_rk_diag
+{
+  double *phase, *grad, *norm, *n, *K, *Fs, *eta, *kappa, *rparams, *omega1, *omega2, *omega3;
+} lbm_rk_diag;
+int lbm_rk_diagnostics(lbm_domain* d, double sigma, const lbm_rk_diag* out);
 /* two-phase models carry u between steps (mrtcg_rayleigh_taylor.cpp:476-477); initial value.      */
 int lbm_set_u(lbm_domain* d, const double* u_aos);
 /* LBM_MODEL_KBC: the class keeps m0 / m1 as members that its first collide() reads before they are recomputed

@@ -1589,6 +1589,115 @@ static int csf_step_group(lbm_domain* const* ds, int n, int n_steps)
   return LBM_OK;
 }
 
+// ================================================================================================
+// Diagnostic fields of driver 17 (test/rk_static_droplet_test.cpp:546-600): interface normal with the driver's
+// 0.1 max|grad| cut, local curvature, interfacial tension, eta, kappa, 1/tau, and the red colour's omega1 / omega2.
+// Functions of the current post-stream state only; nothing here feeds the step.
+// Planes in the moment-plane geometry: D_NX, D_NY (padded: the curvature differentiates them).
+// ================================================================================================
+// grad(phase) (the driver's swapped pair: [0] along axis 1, [1] along axis 0), its norm, and the global maximum of the
+// norm: non-negative doubles order like their bit patterns, so one atomicMax on the bits per block does it
+__global__ void __launch_bounds__(256)
+k_rk_diag_grad(const double* __restrict__ mom, const SlabGeom g, const MomGeom mg, const TpParams p, double* __restrict__ grad,
+               double* __restrict__ norm, unsigned long long* __restrict__ gmax_bits)
+{
+  __shared__ double smax[256];
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double gn = 0.0;
+  if (n < (long long)g.Xl * g.Y)
+  {
+    const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+    TpStencil st;
+    tp_stencil_global<TP_RK>(p, mom, mg, x, y, st);
+    gn = sqrt(st.gx * st.gx + st.gy * st.gy);
+    grad[2 * n] = st.gx;
+    grad[2 * n + 1] = st.gy;
+    norm[n] = gn;
+  }
+  smax[threadIdx.x] = gn == gn ? gn : 0.0;  // a NaN does not take part (torch's max would propagate it; the cut is then moot)
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1)
+  {
+    if ((int)threadIdx.x < w) smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(smax[0]));
+}
+
+// n = -normalize(grad where |grad| > 0.1 max|grad|, else 0), F::normalize's eps = 1e-12 (:559-567)
+__global__ void __launch_bounds__(256)
+k_rk_diag_normal(const double* __restrict__ grad, const double* __restrict__ norm, const SlabGeom g, const MomGeom mg,
+                 const unsigned long long* __restrict__ gmax_bits, double* __restrict__ nplanes)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const double gmax = __longlong_as_double((long long)*gmax_bits);
+  const bool cut = norm[n] <= 0.1 * gmax;
+  const double cx = cut ? 0.0 : grad[2 * n], cy = cut ? 0.0 : grad[2 * n + 1];
+  const double den = fmax(sqrt(cx * cx + cy * cy), 1e-12);
+  const long long k = mom_off(mg, x, y);
+  nplanes[k] = -(cx / den);
+  nplanes[mg.mplane + k] = -(cy / den);
+}
+
+struct RkDiagOut  // device AoS buffers in the reference's tensor layouts; nullptr = not wanted
+{
+  double *K, *Fs, *eta, *kappa, *rparams, *omega1, *omega2, *omega3;
+};
+
+__global__ void __launch_bounds__(128)
+k_rk_diag_final(const double* __restrict__ mom, const double* __restrict__ nplanes, const double* __restrict__ grad,
+                const double* __restrict__ norm, const double* __restrict__ r_aos, const SlabGeom g, const MomGeom mg,
+                const TpParams p, double sigma, RkDiagOut o)
+{
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= (long long)g.Xl * g.Y) return;
+  const int x = (int)(n / g.Y), y = (int)(n % g.Y);
+  const long long k = mom_off(mg, x, y);
+  // eval_local_curvature (:440-446) with the driver's 3x3 kernels: x(.) along axis 1, y(.) along axis 0
+  double x_nx = 0.0, y_nx = 0.0, x_ny = 0.0, y_ny = 0.0;
+#pragma unroll
+  for (int a = -1; a <= 1; a++)
+#pragma unroll
+    for (int b = -1; b <= 1; b++)
+    {
+      const double vx = nplanes[k + (long long)a * mg.pm + b], vy = nplanes[mg.mplane + k + (long long)a * mg.pm + b];
+      const double wa = a == 0 ? 1.0 / 9.0 : 1.0 / 36.0, wb = b == 0 ? 1.0 / 9.0 : 1.0 / 36.0;
+      if (b != 0) { x_nx += (3.0 * (wa * (double)b)) * vx; x_ny += (3.0 * (wa * (double)b)) * vy; }
+      if (a != 0) { y_nx += (3.0 * (wb * (double)a)) * vx; y_ny += (3.0 * (wb * (double)a)) * vy; }
+    }
+  const double nx = nplanes[k], ny = nplanes[mg.mplane + k];
+  const double K = nx * ny * (y_nx + x_ny) - (nx * nx) * y_ny - (ny * ny) * x_nx;
+  const double gx = grad[2 * n], gy = grad[2 * n + 1], gn = norm[n];
+  const double Fsx = 0.5 * sigma * K * gx, Fsy = 0.5 * sigma * K * gy;  // :572
+  const double rr = mom[M_RR * mg.mplane + k], rb = mom[M_RB * mg.mplane + k];
+  const double ux = mom[M_UX * mg.mplane + k], uy = mom[M_UY * mg.mplane + k], ph = mom[M_PH * mg.mplane + k];
+  const double relax = 1.0 / relax_eval(p, ph);  // :587-589
+  if (o.K) o.K[n] = K;
+  if (o.Fs) { o.Fs[2 * n] = Fsx; o.Fs[2 * n + 1] = Fsy; }
+  if (o.rparams) o.rparams[n] = relax;
+  const double uu = ux * ux + uy * uy;
+  const double kap = rr * rb / (rr + rb);
+  const double ign2 = 1.0 / (1e-20 + gn * gn);
+#pragma unroll
+  for (int q = 0; q < 9; q++)
+  {
+    const double ex = (double)CX(q), ey = (double)CY(q);
+    const double ue = ux * ex + uy * ey;
+    // eval_eta (:398-413): ((ics2 (E - u) + ics2 (u.E) E) . Fs) W with ics2 = 3 in both terms, as written
+    if (o.eta) o.eta[9 * n + q] = ((3.0 * (ex - ux) + 3.0 * (ue * ex)) * Fsx + (3.0 * (ey - uy) + 3.0 * (ue * ey)) * Fsy) * W(q);
+    // eval_kappa (:415-438): rho_r rho_b / rho * ((-n) . E) W
+    if (o.kappa) o.kappa[9 * n + q] = kap * (((-nx) * ex + (-ny) * ey) * W(q));
+    const double o1 = relax * (tp_feq<TP_RK>(q, rr, p.r_phi, p.r_eta, ux, uy, uu) - r_aos[9 * n + q]);  // :255-262
+    const double fe = gx * ex + gy * ey;
+    const double o2 = ((0.5 * p.r_A) * gn) * (((fe * fe) * ign2) * W(q) - BQ(q));  // :239-245
+    if (o.omega1) o.omega1[9 * n + q] = o1;
+    if (o.omega2) o.omega2[9 * n + q] = o2;
+    if (o.omega3) o.omega3[9 * n + q] = o1 + o2;  // :232-236
+  }
+}
+
 }  // namespace lbm
 
 using namespace lbm;
@@ -1630,6 +1739,83 @@ int lbm_get_interfacial_tension(lbm_domain* d, double* Fs_aos)
       Fs_aos[2 * ((size_t)x * Y + y) + 1] = fy[k];
     }
   return LBM_OK;
+}
+
+int lbm_rk_diagnostics(lbm_domain* d, double sigma, const lbm_rk_diag* out)
+{
+  if (!d || !d->tp || d->tp->model != TP_RK || !out) { set_error("lbm_rk_diagnostics: LBM_MODEL_RK domains only"); return LBM_ERR_INVALID; }
+  if (!d->have_state || !d->committed) { set_error("lbm_rk_diagnostics: no state or boundary rules not committed"); return LBM_ERR_INVALID; }
+  if (d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X)
+  {
+    // the normal's cut needs max|grad| over the whole grid and the curvature a halo of the normal planes
+    set_error("lbm_rk_diagnostics: monolithic domains only (a slab holds rows %d..%d of %d)", d->cfg.x0, d->cfg.x1, d->cfg.X);
+    return LBM_ERR_UNSUPPORTED;
+  }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  TwoPhaseState* tp = d->tp;
+  const long long N = (long long)d->g.Xl * d->g.Y;
+  const MomGeom mg = tp->mg;
+  LBM_TRY(tp_fill_planes(d));
+  LBM_TRY(tp_pad(d));
+  LBM_TRY(ensure_aos_scratch(d));
+  LBM_TRY(tp_export(d));  // post-stream populations (adv_f) of both colours in the reference layout
+  // one scratch allocation per call: this is a diagnostic path, not the time loop
+  const size_t n_planes = 2 * (size_t)mg.mplane, n_nodes = (size_t)N * (2 + 1 + 1 + 2 + 9 + 9 + 1 + 27);
+  double* scratch = nullptr;
+  unsigned long long* gmax = nullptr;
+  LBM_CUDA(cudaMalloc(&scratch, (n_planes + n_nodes) * sizeof(double)));
+  if (cudaMalloc(&gmax, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(scratch); set_error("lbm_rk_diagnostics: out of device memory"); return LBM_ERR_CUDA; }
+  double* npl = scratch;
+  double* grad = npl + n_planes;
+  double* norm = grad + 2 * N;
+  RkDiagOut o;
+  o.K = norm + N; o.Fs = o.K + N; o.eta = o.Fs + 2 * N; o.kappa = o.eta + 9 * N; o.rparams = o.kappa + 9 * N;
+  o.omega1 = o.rparams + N; o.omega2 = o.omega1 + 9 * N; o.omega3 = o.omega2 + 9 * N;
+  int rc = LBM_OK;
+  auto run = [&]() -> int {
+    LBM_CUDA(cudaMemsetAsync(gmax, 0, sizeof(unsigned long long), d->stream));
+    k_rk_diag_grad<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, d->g, mg, tp->p, grad, norm, gmax);
+    k_rk_diag_normal<<<cdiv(N, 256), 256, 0, d->stream>>>(grad, norm, d->g, mg, gmax, npl);
+    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(npl, d->g, mg, 2);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(npl, d->g, mg, 1, 1, 2);
+    k_rk_diag_final<<<cdiv(N, 128), 128, 0, d->stream>>>(tp->mom, npl, grad, norm, d->d_aos[0], d->g, mg, tp->p, sigma, o);
+    d->launches += 5;
+    LBM_CUDA(cudaGetLastError());
+    auto back = [&](double* host, const double* dev, long long count) -> int {
+      if (host) LBM_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, d->stream));
+      return LBM_OK;
+    };
+    LBM_TRY(back(out->grad, grad, 2 * N));
+    LBM_TRY(back(out->norm, norm, N));
+    LBM_TRY(back(out->K, o.K, N));
+    LBM_TRY(back(out->Fs, o.Fs, 2 * N));
+    LBM_TRY(back(out->eta, o.eta, 9 * N));
+    LBM_TRY(back(out->kappa, o.kappa, 9 * N));
+    LBM_TRY(back(out->rparams, o.rparams, N));
+    LBM_TRY(back(out->omega1, o.omega1, 9 * N));
+    LBM_TRY(back(out->omega2, o.omega2, 9 * N));
+    LBM_TRY(back(out->omega3, o.omega3, 9 * N));
+    LBM_CUDA(cudaStreamSynchronize(d->stream));
+    if (out->n || out->phase)
+    {
+      // the normal and the phase live in padded planes: unpad on the host
+      std::vector<double> pl(out->n ? n_planes : 0), ph(out->phase ? (size_t)mg.mplane : 0);
+      if (out->n) LBM_CUDA(cudaMemcpy(pl.data(), npl, sizeof(double) * n_planes, cudaMemcpyDeviceToHost));
+      if (out->phase) LBM_CUDA(cudaMemcpy(ph.data(), tp->mom + (long long)M_PH * mg.mplane, sizeof(double) * mg.mplane, cudaMemcpyDeviceToHost));
+      for (int x = 0; x < d->g.Xl; x++)
+        for (int y = 0; y < d->g.Y; y++)
+        {
+          const size_t k = (size_t)(x + 2) * mg.pm + (y + 2), n = (size_t)x * d->g.Y + y;
+          if (out->n) { out->n[2 * n] = pl[k]; out->n[2 * n + 1] = pl[(size_t)mg.mplane + k]; }
+          if (out->phase) out->phase[n] = ph[k];
+        }
+    }
+    return LBM_OK;
+  };
+  rc = run();
+  cudaFree(scratch);
+  cudaFree(gmax);
+  return rc;
 }
 
 int lbm_set_u(lbm_domain* d, const double* u_aos)

@@ -48,6 +48,13 @@ class Config(C.Structure):
     ]
 
 
+class RkDiag(C.Structure):
+    """lbm_rk_diag: host output pointers of lbm_rk_diagnostics"""
+    FIELDS = (("phase", ()), ("grad", (2,)), ("norm", ()), ("n", (2,)), ("K", ()), ("Fs", (2,)), ("eta", (9,)), ("kappa", (9,)),
+              ("rparams", ()), ("omega1", (9,)), ("omega2", (9,)), ("omega3", (9,)))
+    _fields_ = [(name, C.POINTER(C.c_double)) for name, _ in FIELDS]
+
+
 class BcOp(C.Structure):
     _fields_ = [
         ("kind", C.c_int), ("lattice", C.c_int), ("x_begin", C.c_int), ("x_end", C.c_int), ("y_begin", C.c_int),
@@ -98,6 +105,7 @@ EXPORTS = [
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
     "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension", "lbm_link_face", "lbm_set_force_region",
+    "lbm_rk_diagnostics",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -130,6 +138,7 @@ def load():
         _lib.lbm_snapshot_wait.argtypes = [C.c_void_p]
         _lib.lbm_save_pt.argtypes = [C.c_char_p, dp, C.POINTER(C.c_longlong), C.c_int]
         _lib.lbm_set_u.argtypes = [C.c_void_p, dp]
+        _lib.lbm_rk_diagnostics.argtypes = [C.c_void_p, C.c_double, C.POINTER(RkDiag)]
         _lib.lbm_set_moments.argtypes = [C.c_void_p, dp, dp]
         _lib.lbm_get_interfacial_tension.argtypes = [C.c_void_p, dp]
         _lib.lbm_init_equilibrium.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp]
@@ -319,6 +328,13 @@ class Domain:
         ph = np.empty((self.Xl, self.Y)); rr = np.empty((self.Xl, self.Y)); rb = np.empty((self.Xl, self.Y))
         _chk(self.lib.lbm_get_phase(self.h, ph.ctypes.data_as(dp), rr.ctypes.data_as(dp), rb.ctypes.data_as(dp)))
         return ph, rr, rb
+
+    def rk_diagnostics(self, sigma=5e-3):
+        """the fields test/rk_static_droplet_test.cpp snapshots at the top of an iteration, of the current state"""
+        out = {name: np.empty((self.Xl, self.Y) + tail) for name, tail in RkDiag.FIELDS}
+        arg = RkDiag(**{name: a.ctypes.data_as(dp) for name, a in out.items()})
+        _chk(self.lib.lbm_rk_diagnostics(self.h, C.c_double(sigma), C.byref(arg)))
+        return out
 
     def set_u(self, u):
         a, p = _in(u)

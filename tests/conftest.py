@@ -22,17 +22,18 @@ if os.environ.get("LBM_EMU") == "1":
     import lbm_b200
 
     lbm_b200.LIB_PATH = os.path.join(ROOT, "tests", "cpu_emu", "_build", "liblbm_b200_emu.so")
+    # the drivers' binaries (RUNPATH to liblbm_b200.so) resolve the same soname to the emulated build first
+    os.environ["LD_LIBRARY_PATH"] = os.path.join(ROOT, "tests", "cpu_emu", "_build", "drv") + ":" + os.environ.get("LD_LIBRARY_PATH", "")
 
 
-# what the emulated runtime does not provide: stream capture (CUDA graphs) and the host drivers' binaries, which link
-# the real liblbm_b200.so
-EMU_SKIPS = ("test_gpu_graph.py", "slabs_and_graph", "driver_writes")
+# what the emulated runtime does not provide: stream capture (CUDA graphs)
+EMU_SKIPS = ("test_gpu_graph.py", "slabs_and_graph")
 
 
 def pytest_collection_modifyitems(config, items):
     if os.environ.get("LBM_EMU") != "1":
         return
-    skip = pytest.mark.skip(reason="needs a real device (CUDA graphs / the drivers' binaries): not emulated")
+    skip = pytest.mark.skip(reason="needs a real device (CUDA graphs): not emulated")
     for item in items:
         if any(k in item.nodeid for k in EMU_SKIPS):
             item.add_marker(skip)

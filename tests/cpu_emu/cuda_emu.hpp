@@ -92,6 +92,14 @@ inline double atomicAdd(double* a, double v)
     std::memcpy(&old, &o, 8);
   } while (true);
 }
+inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v)
+{
+  unsigned long long old = __atomic_load_n(a, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+inline long long __double_as_longlong(double x) { long long r; std::memcpy(&r, &x, 8); return r; }
+inline double __longlong_as_double(long long x) { double r; std::memcpy(&r, &x, 8); return r; }
 inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* a, unsigned v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
 
