@@ -64,6 +64,12 @@ WORKLOADS = {
                           driver="test/rectangle_sedimentation_test.cpp",
                           what="rectangle sedimentation: fluid + advection-diffusion lattice, bounce-back rectangle walls",
                           cpu_sample=1024),
+    # configs[4] as BASELINE.json words it ("with immersed-boundary coupling (ibm)"): driver 15 has no ibm object (SURVEY §8
+    # notes), so this is driver 15's loop plus a cylinder coupled the way driver 11 couples one; not a reference driver
+    "sedimentation_ibm": dict(X=4096, Y=8192, bytes=288.0, nlat=2, kernel="k_bgk_interior<PULL,COMP,IBM,ADE>",
+                              driver="test/rectangle_sedimentation_test.cpp + ibm as in test/cylinder_test.cpp",
+                              what="rectangle sedimentation with an immersed cylinder: fluid (Guo-forced) + advection-diffusion lattice",
+                              cpu_sample=1024),
     # not a BASELINE.json config: SURVEY §8(f) rank 2, the continuum-surface-force variant (three passes per step; bytes =
     # both colours' populations read + written once (288) + the carried interfacial tension read + written (32))
     "csf_rt": dict(X=8192, Y=8192, bytes=320.0, nlat=2, kernel="k_csf_collide_ring<PULL>",
@@ -140,6 +146,15 @@ def cylinder_solid(Xg, Y, X1):
     r2 = (np.arange(lo, hi)[:, None] - (X1 / 4.0 + 0.37)) ** 2 + (np.arange(Y)[None, :] - (Y / 2.0 + 0.21)) ** 2
     solid[lo:hi] = r2 <= (0.5 * D) ** 2
     return solid
+
+
+def sedimentation_body(X, Y):
+    """sedimentation_ibm: a cylinder of diameter ~X/9 upstream of the rectangle (the flow runs along axis 1), centred at
+    (X/2, Y/4) of the first slab, markers about one lattice unit apart"""
+    D = max(8.0, X / 9.0)
+    n = max(16, int(round(np.pi * D)))
+    th = 2.0 * np.pi * np.arange(n) / n
+    return X / 2.0 + 0.5 * D * np.cos(th) + 0.37, Y / 4.0 + 0.5 * D * np.sin(th) + 0.21
 
 
 def write_markers_toml(path, xs, ys):
@@ -279,10 +294,13 @@ def cpu_reference_mlups(workload, edge, warmup, steps):
         u = np.zeros((edge, edge, 2)); rho = np.ones((edge, edge, 1))
         f = orc.incomp_equilibrium(u, rho)
         sec = timed(lambda: orc.poiseuille_step(f, u, rho, om, rho_in, rho_out))
-    elif workload == "sedimentation":
+    elif workload in ("sedimentation", "sedimentation_ibm"):
         R23, C28, C38, C_w = sedimentation_geometry(edge, edge)
         f, g, u, rho, Cc = orc.sedimentation_init(edge, edge, u_lb, C_w)
-        sec = timed(lambda: orc.sedimentation_step(f, g, u, rho, Cc, omega, u_lb, 3e-3, C_w, R23, C28, C38))
+        ib = orc.ibm_create(*sedimentation_body(edge, edge)) if workload == "sedimentation_ibm" else None
+        sec = timed(lambda: orc.sedimentation_step(f, g, u, rho, Cc, omega, u_lb, 3e-3, C_w, R23, C28, C38, ib=ib))
+        if ib is not None:
+            orc.ibm_destroy(ib)
     elif workload == "mrtcg_rt":
         p = oracle_lib.MrtcgParams()
         p.R, p.C = edge, edge
@@ -460,9 +478,9 @@ class Case:
             cfg = L.default_config(model=L.MODEL_BGK, omega=om, equilibrium=L.EQ_INCOMPRESSIBLE, **slab)
         elif self.name == "kbc_shear":
             cfg = L.default_config(model=L.MODEL_KBC, omega=1.0 / (0.5 + 3.0 * 1.70766666e-4), **slab)
-        elif self.name == "sedimentation":
+        elif self.name in ("sedimentation", "sedimentation_ibm"):
             cfg = L.default_config(model=L.MODEL_BGK_ADE, omega=self.omega, omega_g=self.omega, equilibrium=L.EQ_COMPRESSIBLE,
-                                   w_s=3e-3, **slab)
+                                   w_s=3e-3, force=L.FORCE_IBM if self.name == "sedimentation_ibm" else L.FORCE_NONE, **slab)
         elif self.name == "csf_rt":
             cfg = L.default_config(model=L.MODEL_MRT_CSF, red=RED, blue=BLUE, sigma=0.1, delta=0.1, Fg=RT_FG, add_force=1, **slab)
         elif self.name == "mrtcg_rt":
@@ -510,9 +528,11 @@ class Case:
             r = np.arange(self.x0, self.x1)[:, None]; c = np.arange(Y)[None, :]
             self.ui[..., 0] = 0.02 * np.tanh(80.0 * (0.25 * self.Xg - np.abs(c - 0.5 * self.Xg))) + 0.0 * r
             self.ui[..., 1] = 0.02 * 0.05 * np.sin(6.2832 * (r + 0.25 * self.Xg) / self.Xg) + 0.0 * c
-        elif self.name == "sedimentation":
+        elif self.name in ("sedimentation", "sedimentation_ibm"):
             R23, C28, C38, C_w = sedimentation_geometry(self.Xg, Y)
             d.preset_sedimentation(self.u_lb, C_w, R23, C28, C38)
+            if self.name == "sedimentation_ibm" and self.rank == 0:
+                d.ibm_set_markers(*sedimentation_body(self.X, Y))  # the body sits in rank 0's slab
             # rectangle_sedimentation_test.cpp:84-103: u = (0, u_lb); f = incomp_eq(u, 1); g = eq(u, C), C = C_w on column 0
             self.f_t, self.f = self.pinned((X, Y, 9))
             self.g_t, self.g = self.pinned((X, Y, 9))
@@ -544,7 +564,7 @@ class Case:
             d.init_equilibrium(self.ri, self.ui, self.L.EQ_KBC_FRESH)
             d.set_moments(self.ri, self.ui)
             return 2 * (self.ri.nbytes + self.ui.nbytes)
-        if self.name == "sedimentation":
+        if self.name in ("sedimentation", "sedimentation_ibm"):
             d.set_f(self.f, 0)
             d.set_f(self.g, 1)
             return self.f.nbytes + self.g.nbytes

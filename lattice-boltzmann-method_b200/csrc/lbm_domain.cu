@@ -167,7 +167,13 @@ static int dispatch_bgk(lbm_domain* d, const LaunchArgs& a)
 {
   const bool ade = d->cfg.model == LBM_MODEL_BGK_ADE;
   const int eq = d->cfg.equilibrium, fo = (d->cfg.force == LBM_FORCE_IBM && d->ibm.fixed) ? (int)FORCE_REGION : d->cfg.force;
-  if (ade) return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, a);
+  if (ade)
+  {
+    // with an immersed body (BASELINE configs[4] "with immersed-boundary coupling"): the cylinder driver's force term on the
+    // fluid lattice, the ADE lattice advected by the same u
+    if (fo == FORCE_IBM) return launch_bgk<MODE, EQ_COMP, FORCE_IBM, true>(d, a);
+    return launch_bgk<MODE, EQ_COMP, FORCE_NONE, true>(d, a);
+  }
   if (d->cfg.model == LBM_MODEL_KBC) return launch_bgk<MODE, EQ_KBC, FORCE_NONE, false>(d, a);
 #define LBM_CASE(E, F) \
   if (eq == E && fo == F) return launch_bgk<MODE, E, F, false>(d, a);

@@ -633,9 +633,9 @@ void orc_sedimentation_init(double* f, double* g, double* u, double* rho, double
   orc_calc_u(f, rho, X, Y, u);
 }
 
-void orc_sedimentation_step(double* f, double* g, double* u, double* rho, double* C, int X, int Y,
-                            double omega, double u_lb, double w_s, const double* C_w, int R23, int C28,
-                            int C38)
+static void sedimentation_step_impl(double* f, double* g, double* u, double* rho, double* C, int X, int Y,
+                                    double omega, double u_lb, double w_s, const double* C_w, int R23, int C28,
+                                    int C38, orc_ibm* ib)
 {
   size_t N = (size_t)X * Y;
   double* feq = dalloc(N * 9);
@@ -648,7 +648,32 @@ void orc_sedimentation_step(double* f, double* g, double* u, double* rho, double
   orc_equilibrium(u, rho, X, Y, feq);
   for (size_t n = 0; n < N * 2; n++) us[n] = u[n] + w_s;
   orc_equilibrium(us, C, X, Y, geq);
-  orc_collision(f, feq, omega, X, Y, fc);
+  if (!ib) orc_collision(f, feq, omega, X, Y, fc);
+  else
+  {
+    /* BASELINE configs[4] "with immersed-boundary coupling": the collision of test/cylinder_test.cpp:110-127 (force
+     * density from u, rho; f_coll = f + (-omega (f - f_eq)) + S inside the ROI) in place of solver::collision */
+    const long RR = ib->r1 - ib->r0, RC = ib->c1 - ib->c0;
+    double* F = dalloc((size_t)RR * RC * 2);
+    orc_ibm_force(ib, u, rho, X, Y, F);
+    for (size_t n = 0; n < N * 9; n++) fc[n] = f[n] + (-omega * (f[n] - feq[n]));
+    const double ics2 = 1.0 / 3.0, ics4 = 1.0 / 9.0;
+    for (long i = 0; i < RR; i++)
+      for (long j = 0; j < RC; j++)
+      {
+        size_t gg = N2(ib->r0 + i, ib->c0 + j);
+        double ux = u[gg * 2], uy = u[gg * 2 + 1];
+        double Fx = F[(i * RC + j) * 2], Fy = F[(i * RC + j) * 2 + 1];
+        double uF = ux * Fx + uy * Fy;
+        for (int q = 0; q < 9; q++)
+        {
+          double cu = ux * CXD[q] + uy * CYD[q];
+          double cF = Fx * CXD[q] + Fy * CYD[q];
+          fc[gg * 9 + q] += ((1 - 0.5 * omega) * ((ics2 + ics4 * cu) * cF - ics2 * uF)) * W9[q];
+        }
+      }
+    free(F);
+  }
   orc_collision(g, geq, omega / 1.0, X, Y, gc);
   /* zero gradient :137-141 */
   for (int y = 0; y < Y; y++)
@@ -743,6 +768,23 @@ void orc_sedimentation_step(double* f, double* g, double* u, double* rho, double
   /* :237 */
   orc_calc_rho(g, X, Y, C);
   free(feq); free(geq); free(fc); free(gc); free(us);
+}
+
+void orc_sedimentation_step(double* f, double* g, double* u, double* rho, double* C, int X, int Y,
+                            double omega, double u_lb, double w_s, const double* C_w, int R23, int C28,
+                            int C38)
+{
+  sedimentation_step_impl(f, g, u, rho, C, X, Y, omega, u_lb, w_s, C_w, R23, C28, C38, NULL);
+}
+
+/* NOT a reference driver: the sedimentation loop with an immersed body added the way test/cylinder_test.cpp couples one
+ * (BASELINE configs[4] words the case "with immersed-boundary coupling (ibm)"; driver 15 itself has none).  Composed of
+ * the two pinned steps, itself unpinned. */
+void orc_sedimentation_ibm_step(double* f, double* g, double* u, double* rho, double* C, int X, int Y,
+                                double omega, double u_lb, double w_s, const double* C_w, int R23, int C28,
+                                int C38, orc_ibm* ib)
+{
+  sedimentation_step_impl(f, g, u, rho, C, X, Y, omega, u_lb, w_s, C_w, R23, C28, C38, ib);
 }
 
 /* ------------------------------------------------------------------ drivers 16 / 18 (MRT colour gradient) */

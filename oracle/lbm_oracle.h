@@ -84,6 +84,11 @@ void orc_sedimentation_init(double* f, double* g, double* u, double* rho, double
 void orc_sedimentation_step(double* f, double* g, double* u, double* rho, double* C, int X, int Y,
                             double omega, double u_lb, double w_s, const double* C_w,
                             int R23, int C28, int C38);
+/* the same loop with an immersed body coupled as in test/cylinder_test.cpp:110-127 (BASELINE configs[4] as worded;
+ * not a reference driver: composed of the two pinned steps, itself unpinned) */
+void orc_sedimentation_ibm_step(double* f, double* g, double* u, double* rho, double* C, int X, int Y,
+                                double omega, double u_lb, double w_s, const double* C_w, int R23, int C28,
+                                int C38, orc_ibm* ib);
 
 /* ---- drivers 16/18: test/mrtcg_rayleigh_taylor.cpp:413-478, test/mrtcg_static_droplet.cpp:463-528 */
 typedef struct

@@ -59,9 +59,9 @@ def cylinder(X, Y, omega, u_lb, xs, ys):
     return d
 
 
-def sedimentation(X, Y, omega, u_lb, w_s, C_w, walls):
+def sedimentation(X, Y, omega, u_lb, w_s, C_w, walls, ibm=False, **slab):
     d = L.Domain(L.default_config(model=L.MODEL_BGK_ADE, X=X, Y=Y, omega=omega, omega_g=omega / 1.0,
-                                  equilibrium=L.EQ_COMPRESSIBLE, w_s=w_s))
+                                  equilibrium=L.EQ_COMPRESSIBLE, w_s=w_s, force=L.FORCE_IBM if ibm else L.FORCE_NONE, **slab))
     d.preset_sedimentation(u_lb, C_w, int(walls[0]), int(walls[1]), int(walls[2]))
     return d
 

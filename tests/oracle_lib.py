@@ -205,8 +205,14 @@ class Oracle:
         self.lib.orc_sedimentation_init(_p(f), _p(g), _p(u), _p(rho), _p(Cc), X, Y, C.c_double(u_lb), _p(C_w))
         return f, g, u, rho, Cc
 
-    def sedimentation_step(self, f, g, u, rho, Cc, omega, u_lb, w_s, C_w, R23, C28, C38):
+    def sedimentation_step(self, f, g, u, rho, Cc, omega, u_lb, w_s, C_w, R23, C28, C38, ib=None):
         X, Y, _ = f.shape
+        if ib is not None:  # with an immersed body (not a reference driver; see lbm_oracle.h)
+            self.lib.orc_sedimentation_ibm_step.argtypes = [dp] * 5 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp,
+                                                               C.c_int, C.c_int, C.c_int, C.c_void_p]
+            self.lib.orc_sedimentation_ibm_step(_p(f), _p(g), _p(u), _p(rho), _p(Cc), X, Y, omega, u_lb, w_s, _p(C_w),
+                                                int(R23), int(C28), int(C38), ib)
+            return
         self.lib.orc_sedimentation_step(_p(f), _p(g), _p(u), _p(rho), _p(Cc), X, Y, C.c_double(omega),
                                         C.c_double(u_lb), C.c_double(w_s), _p(C_w), int(R23), int(C28), int(C38))
 

@@ -59,6 +59,14 @@ def test_shared_memory_ring_kernels_do_not_depend_on_thread_order(emu_lib, order
     assert r.returncode == 0, r.stdout[-4000:]
 
 
+def test_every_bench_workload_sets_up_and_steps_on_the_emulated_device(emu_lib):
+    env = dict(os.environ, OMP_WAIT_POLICY="passive")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "bench_cases.py")], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok") >= 9, r.stdout
+
+
 def test_the_product_binding_does_not_know_the_emulated_library():
     src = open(os.path.join(ROOT, "lattice-boltzmann-method_b200", "python", "lbm_b200", "__init__.py")).read()
     assert "emu" not in src.lower() and "LBM_EMU" not in src

@@ -13,7 +13,7 @@ case "$what" in
     timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
     ;;
   bench)
-    for w in cylinder cylinder_bb kbc_shear poiseuille sedimentation rk_droplet mrtcg_rt csf_rt; do
+    for w in cylinder cylinder_bb kbc_shear poiseuille sedimentation sedimentation_ibm rk_droplet mrtcg_rt csf_rt; do
       s=100; [ "$w" = mrtcg_rt ] && s=20; [ "$w" = csf_rt ] && s=30
       timeout 300 python bench.py --workload $w --steps $s --warmup 5 2> gpurun_out/bench_$w.err | tail -1 > gpurun_out/bench_$w.json
       python - "$w" <<'PY'
