@@ -21,9 +21,11 @@ def pytest_configure(config):
 if os.environ.get("LBM_EMU") == "1":
     import lbm_b200
 
-    lbm_b200.LIB_PATH = os.path.join(ROOT, "tests", "cpu_emu", "_build", "liblbm_b200_emu.so")
+    # LBM_EMU_ASAN=1: the AddressSanitizer build (make -C tests/cpu_emu SAN=1; run python with libasan preloaded)
+    _emu_build = os.path.join(ROOT, "tests", "cpu_emu", "_build_asan" if os.environ.get("LBM_EMU_ASAN") == "1" else "_build")
+    lbm_b200.LIB_PATH = os.path.join(_emu_build, "liblbm_b200_emu.so")
     # the drivers' binaries (RUNPATH to liblbm_b200.so) resolve the same soname to the emulated build first
-    os.environ["LD_LIBRARY_PATH"] = os.path.join(ROOT, "tests", "cpu_emu", "_build", "drv") + ":" + os.environ.get("LD_LIBRARY_PATH", "")
+    os.environ["LD_LIBRARY_PATH"] = os.path.join(_emu_build, "drv") + ":" + os.environ.get("LD_LIBRARY_PATH", "")
 
 
 # what the emulated runtime does not provide: stream capture (CUDA graphs)
