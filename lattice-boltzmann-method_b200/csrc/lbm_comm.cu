@@ -17,7 +17,9 @@
 //          tested on a single GPU.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "lbm_internal.hpp"
 
@@ -47,13 +49,25 @@ static NcclApi g_nccl;
 
 static int load_nccl()
 {
+  static std::mutex mu;  // several host threads (one per GPU) may create their communicators at once
+  std::lock_guard<std::mutex> lock(mu);
   if (g_nccl.handle) return LBM_OK;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   void* h = nullptr;
+  // LBM_NCCL_LIB: path of the NCCL build to bind instead (a site's own libnccl; tests/cpu_emu points it at its stand-in)
+  if (const char* path = std::getenv("LBM_NCCL_LIB"))
+  {
+    h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h)
+    {
+      set_error("cannot load LBM_NCCL_LIB=%s: %s", path, dlerror());
+      return LBM_ERR_COMM;
+    }
+  }
   for (const char* n : names)
   {
-    h = dlopen(n, RTLD_NOW | RTLD_NOLOAD);  // the copy the host process (e.g. torch) already loaded
     if (h) break;
+    h = dlopen(n, RTLD_NOW | RTLD_NOLOAD);  // the copy the host process (e.g. torch) already loaded
   }
   for (const char* n : names)
   {

@@ -10,8 +10,6 @@ import sys
 import functools
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "lattice-boltzmann-method_b200", "python"))
@@ -23,21 +21,10 @@ import lbm_b200 as L  # noqa: E402
 print = functools.partial(print, flush=True)  # the launcher's pipe would hold the lines back until exit
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    def fresh_id():
-        """one NCCL unique id per communicator: rank 0 creates it, everyone receives it"""
-        ident = [L.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        return ident[0]
-
-    def gather(a):
-        out = [None] * world
-        dist.all_gather_object(out, a)
-        return np.concatenate(out, axis=0)
-
+def run_checks(rank, world, local, fresh_id, gather, barrier):
+    """Every check of the ring on one rank.  fresh_id() hands all ranks one new communicator id, gather(a) returns the
+    row-concatenation of every rank's array, barrier() joins the ranks — torch.distributed under torchrun (main below),
+    threads of one process on the emulated device (tests/cpu_emu/ring_threads.py).  Returns rank 0's list of failures."""
     failures = []
 
     # ---- Poiseuille: pressure packets cross the ring (row 0 <- row X-2)
@@ -198,7 +185,30 @@ def main():
             failures.append("cylinder-straddling")
     d.close()
 
-    dist.barrier()
+    barrier()
+    return failures
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def fresh_id():
+        """one NCCL unique id per communicator: rank 0 creates it, everyone receives it"""
+        ident = [L.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        return ident[0]
+
+    def gather(a):
+        out = [None] * world
+        dist.all_gather_object(out, a)
+        return np.concatenate(out, axis=0)
+
+    failures = run_checks(rank, world, local, fresh_id, gather, dist.barrier)
     flag = [len(failures)]
     dist.broadcast_object_list(flag, src=0)
     dist.destroy_process_group()

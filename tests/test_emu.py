@@ -76,6 +76,18 @@ def test_kernels_under_address_sanitizer():
     assert r.returncode == 0 and "AddressSanitizer" not in r.stdout + r.stderr, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+def test_slab_ring_over_the_nccl_stand_in(emu_lib, world):
+    """tests/mp_nccl_check.py's own checks (the GPU box runs them under torchrun over real NCCL) with one thread per rank on
+    the emulated device: Poiseuille pressure packets across the ring, MRTCG / RK / CSF halos, an immersed body inside one
+    slab and across every cut — bit-exact against the monolithic run at ring sizes the GPU budget never reached (8)."""
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", OMP_NUM_THREADS="2", FAKE_NCCL_TIMEOUT_S="120")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "ring_threads.py"), str(world)], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "failures: []" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(f"ring of {world}") == 6, r.stdout
+
+
 def test_every_bench_workload_sets_up_and_steps_on_the_emulated_device(emu_lib):
     env = dict(os.environ, OMP_WAIT_POLICY="passive")
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "bench_cases.py")], cwd=ROOT, env=env, capture_output=True, text=True,
