@@ -347,8 +347,21 @@ def cpu_baseline_leg(workload, edge, target_seconds=12.0):
     _, sec, _, _, _ = cpu_reference_mlups(workload, edge, 1, 2)
     steps = int(min(400, max(5, round(target_seconds / max(sec, 1e-6)))))
     mlups, sec, kind, cores, desc = cpu_reference_mlups(workload, edge, 1, steps)
-    return {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": kind,
-            "sample": f"{desc}, {steps} steps after 1 warm-up ({sec * steps:.1f} s of CPU work)", "ms_per_step": sec * 1e3}
+    out = {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": kind,
+           "sample": f"{desc}, {steps} steps after 1 warm-up ({sec * steps:.1f} s of CPU work)", "ms_per_step": sec * 1e3}
+    if kind == "reference":
+        # the reference also on ONE host thread (at::set_num_threads(1)), a few steps of the same crop
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+
+        ref = oracle_lib.Ref()
+        ref.lib.ref_set_num_threads(1)
+        try:
+            one, _, _, _, _ = cpu_reference_mlups(workload, edge, 1, int(min(steps, max(2, round(4.0 / max(sec * cores, 1e-6))))))
+            out["single_thread"] = {"value": one, "unit": "MLUPS", "cores": 1}
+        finally:
+            ref.lib.ref_set_num_threads(cores)
+    return out
 
 
 def run_reference_arm(args):
