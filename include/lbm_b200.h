@@ -308,6 +308,11 @@ int lbm_profile_read(lbm_domain* d, int prof_class, double* total_ms, long long*
 int lbm_comm_unique_id(char id[LBM_UNIQUE_ID_BYTES]);
 /* joins the slab ring: neighbours are rank-1 and rank+1 (periodic, like solver::advect) */
 int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank);
+/* Collective consistency check of the ring (optional; every rank calls it after its setup, before the first lbm_step):
+ * grids, model, force mode, and that every slab owning rows of an immersed body's ROI was handed that body's marker list —
+ * the misuse that otherwise leaves ranks waiting for a row exchange nobody posts.  LBM_ERR_COMM on every rank, with the
+ * difference in lbm_last_error(), instead of a hang.  LBM_OK without a communicator.                                    */
+int lbm_comm_check(lbm_domain* d);
 /* single-process alternative: link two domains on the same host process; ghost rows are exchanged with
  * cudaMemcpyPeerAsync (what decompose_domain.cpp's "bind" does between tensors) */
 int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper);

@@ -380,6 +380,76 @@ int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks
   return LBM_OK;
 }
 
+// Collective over the ring: every rank calls it once its setup is complete (rules committed, markers set), before the
+// first lbm_step.  Each rank hands every other rank a ten-number record of what it was set up with; a difference that
+// would make the ring wait for a message nobody sends (an immersed body whose ROI rows a slab owns but whose marker list
+// that slab was never given; different grids, models or force modes) comes back as LBM_ERR_COMM on every rank instead.
+int lbm_comm_check(lbm_domain* d)
+{
+  if (!d) { set_error("lbm_comm_check: null domain"); return LBM_ERR_INVALID; }
+  if (!comm_active(d)) return LBM_OK;
+  CommState* c = d->comm;
+  constexpr int NREC = 10;
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  const int P = c->n_ranks;
+  std::vector<double> rec((size_t)P * NREC, 0.0);
+  double* mine = rec.data() + (size_t)c->rank * NREC;
+  mine[0] = d->cfg.X; mine[1] = d->cfg.Y; mine[2] = d->cfg.model; mine[3] = d->cfg.force; mine[4] = d->cfg.equilibrium;
+  mine[5] = d->ibm_given.n; mine[6] = (double)d->ibm_given.r0; mine[7] = (double)d->ibm_given.r1;
+  mine[8] = (double)(d->ibm_given.hash >> 32); mine[9] = (double)(d->ibm_given.hash & 0xffffffffull);  // exact in fp64
+  double* dev = nullptr;
+  LBM_CUDA(cudaMalloc(&dev, sizeof(double) * rec.size()));
+  auto exchange = [&]() -> int {
+    LBM_CUDA(cudaMemcpyAsync(dev + (size_t)c->rank * NREC, mine, sizeof(double) * NREC, cudaMemcpyHostToDevice, d->stream));
+    LBM_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < P; k++)
+    {
+      if (k == c->rank) continue;
+      LBM_NCCL(g_nccl.Send(dev + (size_t)c->rank * NREC, NREC, ncclFloat64, k, c->comm, d->stream));
+      LBM_NCCL(g_nccl.Recv(dev + (size_t)k * NREC, NREC, ncclFloat64, k, c->comm, d->stream));
+    }
+    LBM_NCCL(g_nccl.GroupEnd());
+    LBM_CUDA(cudaMemcpyAsync(rec.data(), dev, sizeof(double) * rec.size(), cudaMemcpyDeviceToHost, d->stream));
+    LBM_CUDA(cudaStreamSynchronize(d->stream));
+    return LBM_OK;
+  };
+  const int rc = exchange();
+  cudaFree(dev);
+  if (rc != LBM_OK) return rc;
+  const char* names[5] = {"X", "Y", "model", "force", "equilibrium"};
+  for (int k = 0; k < P; k++)
+  {
+    const double* r = rec.data() + (size_t)k * NREC;
+    for (int f = 0; f < 5; f++)
+      if (r[f] != rec[f])
+      {
+        set_error("lbm_comm_check: rank %d was created with %s = %g, rank 0 with %g", k, names[f], r[f], rec[f]);
+        return LBM_ERR_COMM;
+      }
+  }
+  // every slab that owns rows of some rank's ROI must hold that very marker list
+  for (int k = 0; k < P; k++)
+  {
+    const double* r = rec.data() + (size_t)k * NREC;
+    if (r[5] == 0.0) continue;
+    for (int j = 0; j < P; j++)
+    {
+      int jx0 = 0, jx1 = 0;
+      lbm_decompose_rows(d->cfg.X, P, j, &jx0, &jx1);
+      if ((double)jx1 <= r[6] || (double)jx0 >= r[7]) continue;  // rank j owns none of these ROI rows
+      const double* q = rec.data() + (size_t)j * NREC;
+      if (q[5] != r[5] || q[8] != r[8] || q[9] != r[9])
+      {
+        set_error("lbm_comm_check: the immersed body rank %d was given (%d markers, ROI rows [%d,%d)) crosses the slab of rank %d, "
+                  "which was given %s: hand lbm_ibm_set_markers the same list on every rank of the ring",
+                  k, (int)r[5], (int)r[6], (int)r[7], j, q[5] == 0.0 ? "no markers" : "a different list");
+        return LBM_ERR_COMM;
+      }
+    }
+  }
+  return LBM_OK;
+}
+
 int lbm_link_neighbours(lbm_domain* d, lbm_domain* lower, lbm_domain* upper)
 {
   if (!d) { set_error("lbm_link_neighbours: null domain"); return LBM_ERR_INVALID; }

@@ -195,6 +195,7 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   if (!d || !xs || !ys || n <= 0 || m_max < 1) { set_error("lbm_ibm_set_markers: bad argument"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   ibm_release(d);
+  d->ibm_given = IbmGiven();
   d->ics2 = 1.0 / 3.0;  // cylinder_test.cpp:112-113
   d->ics4 = 1.0 / 9.0;
   IbmState& ib = d->ibm;
@@ -209,6 +210,20 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
   }
   ib.r0 = r_min; ib.r1 = r_max + 1; ib.c0 = c_min; ib.c1 = c_max + 1;
   ib.n_markers = n;
+  {
+    // FNV-1a over the coordinates as given: lbm_comm_check compares it across the ring
+    unsigned long long h = 1469598103934665603ull;
+    auto eat = [&](const double* a) {
+      const unsigned char* b = reinterpret_cast<const unsigned char*>(a);
+      for (size_t k = 0; k < sizeof(double) * (size_t)n; k++) { h ^= b[k]; h *= 1099511628211ull; }
+    };
+    eat(xs);
+    eat(ys);
+    d->ibm_given.n = n;
+    d->ibm_given.r0 = ib.r0;
+    d->ibm_given.r1 = ib.r1;
+    d->ibm_given.hash = h;
+  }
   ib.m_max = m_max;
   const int y_int_end = d->y_int_end;
   if (ib.r0 < 0 || ib.r1 > d->cfg.X || ib.c0 < d->y_int_begin || ib.c1 > y_int_end)
@@ -216,6 +231,7 @@ int lbm_ibm_set_markers(lbm_domain* d, const double* xs, const double* ys, int n
     set_error("lbm_ibm_set_markers: ROI rows [%ld,%ld) cols [%ld,%ld) must lie inside the grid's rows [0,%d) and interior columns [2,%d)",
               ib.r0, ib.r1, ib.c0, ib.c1, d->cfg.X, y_int_end);
     ib = IbmState();
+    d->ibm_given = IbmGiven();
     return LBM_ERR_UNSUPPORTED;
   }
   if (ib.r1 <= d->cfg.x0 || ib.r0 >= d->cfg.x1)

@@ -88,6 +88,15 @@ struct IbmState
   int used_slot = 0;  // slot the last enqueued step read (lbm_ibm_get_force)
 };
 
+// the marker list as lbm_ibm_set_markers was handed it (kept on slabs that own none of its ROI rows too): what
+// lbm_comm_check compares across the ring
+struct IbmGiven
+{
+  int n = 0;
+  long r0 = 0, r1 = 0;
+  unsigned long long hash = 0;
+};
+
 struct ProfRec
 {
   cudaEvent_t a, b;
@@ -172,6 +181,7 @@ struct lbm_domain
   bool copy_pending = false;
 
   lbm::IbmState ibm;
+  lbm::IbmGiven ibm_given;
   double ics2 = 1.0 / 3.0, ics4 = 1.0 / 9.0;  // source-term constants (lbm_set_force_region overrides them)
   // column-face bindings to other blocks (lbm_link_face): the populations entering through an edge column are read
   // from a tail appended to every lattice buffer, [side][3 populations][Xl] behind the nine planes

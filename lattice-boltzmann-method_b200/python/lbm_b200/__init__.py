@@ -105,7 +105,7 @@ EXPORTS = [
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
     "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension", "lbm_link_face", "lbm_set_force_region",
-    "lbm_rk_diagnostics",
+    "lbm_rk_diagnostics", "lbm_comm_check",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -335,6 +335,9 @@ class Domain:
         arg = RkDiag(**{name: a.ctypes.data_as(dp) for name, a in out.items()})
         _chk(self.lib.lbm_rk_diagnostics(self.h, C.c_double(sigma), C.byref(arg)))
         return out
+
+    def comm_check(self):
+        _chk(self.lib.lbm_comm_check(self.h))
 
     def set_u(self, u):
         a, p = _in(u)

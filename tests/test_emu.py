@@ -87,6 +87,16 @@ def test_slab_ring_over_the_nccl_stand_in(emu_lib, world):
     assert r.stdout.count(f"ring of {world}") == 6, r.stdout
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_comm_check_turns_the_missing_marker_list_into_an_error(emu_lib, world):
+    """lbm_comm_check on a ring of threads: a body across a cut handed to rank 0 only is LBM_ERR_COMM on every rank (it
+    hung an eight-GPU run once); both correct usages pass"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", FAKE_NCCL_TIMEOUT_S="60")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "ring_check_misuse.py"), str(world)], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"misuse reported on all {world} ranks" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_every_bench_workload_sets_up_and_steps_on_the_emulated_device(emu_lib):
     env = dict(os.environ, OMP_WAIT_POLICY="passive")
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "bench_cases.py")], cwd=ROOT, env=env, capture_output=True, text=True,
