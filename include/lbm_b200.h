@@ -231,7 +231,8 @@ int lbm_get_interfacial_tension(lbm_domain* d, double* Fs_aos);
  *   n {X,Y,2} (nxs, nys) = -normalize(grad where |grad| > 0.1 max|grad|, else 0)   K {X,Y} (Ks, eval_local_curvature :440-446)
  *   Fs {X,Y,2} (Fsxs, Fsys) = sigma/2 K grad   eta {X,Y,9} (eval_eta :398-413)   kappa {X,Y,9} (kappas, eval_kappa :415-438)
  *   rparams {X,Y} = 1/tau(phase)   omega1, omega2, omega3 {X,Y,9}: the RED colour's operators (:255-262, :239-245, :232-236)
- * Monolithic domains only (the cut needs the global max|grad|); LBM_ERR_UNSUPPORTED on a slab.                              */
+ * Monolithic domains, or every rank of an lbm_comm_init ring at once (the cut's max|grad| is reduced over the ring, the
+ * normal planes swap halos: SURVEY 8(e)); LBM_ERR_UNSUPPORTED on linked slabs of one process.                              */
 typedef struct lbm_rk_diag
 {
   double *phase, *grad, *norm, *n, *K, *Fs, *eta, *kappa, *rparams, *omega1, *omega2, *omega3;

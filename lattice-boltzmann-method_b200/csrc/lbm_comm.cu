@@ -201,6 +201,39 @@ int comm_exchange_planes(lbm_domain* d, double* base, int nplanes)
   return LBM_OK;
 }
 
+// max over the ring of one non-negative double held on the device: every rank hands its value to every other, the
+// reduction runs on the host.  Diagnostic paths only (lbm_rk_diagnostics: the normal's cut at 0.1 max|grad|).
+int comm_allreduce_max(lbm_domain* d, double* dev_value)
+{
+  if (!comm_active(d)) return LBM_OK;
+  CommState* c = d->comm;
+  const int P = c->n_ranks;
+  double* all = nullptr;
+  LBM_CUDA(cudaMalloc(&all, sizeof(double) * P));
+  auto run = [&]() -> int {
+    LBM_CUDA(cudaMemcpyAsync(all + c->rank, dev_value, sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
+    LBM_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < P; k++)
+    {
+      if (k == c->rank) continue;
+      LBM_NCCL(g_nccl.Send(dev_value, 1, ncclFloat64, k, c->comm, d->stream));
+      LBM_NCCL(g_nccl.Recv(all + k, 1, ncclFloat64, k, c->comm, d->stream));
+    }
+    LBM_NCCL(g_nccl.GroupEnd());
+    std::vector<double> host(P);
+    LBM_CUDA(cudaMemcpyAsync(host.data(), all, sizeof(double) * P, cudaMemcpyDeviceToHost, d->stream));
+    LBM_CUDA(cudaStreamSynchronize(d->stream));
+    double m = 0.0;
+    for (double v : host) m = v > m ? v : m;
+    LBM_CUDA(cudaMemcpyAsync(dev_value, &m, sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    LBM_CUDA(cudaStreamSynchronize(d->stream));
+    return LBM_OK;
+  };
+  const int rc = run();
+  cudaFree(all);
+  return rc;
+}
+
 int comm_exchange_moments(lbm_domain* d)
 {
   if (!d->tp) return LBM_OK;

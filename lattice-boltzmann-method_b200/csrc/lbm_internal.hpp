@@ -252,6 +252,7 @@ bool comm_active(const lbm_domain* d);
 int link_exchange(lbm_domain* d, int which, cudaStream_t st);  // ghost rows from linked neighbours
 int comm_exchange(lbm_domain* d, int which, cudaStream_t st);  // population ghost rows over NCCL
 int comm_exchange_planes(lbm_domain* d, double* base, int nplanes);  // 2 ghost rows of planes in the moment-plane geometry
+int comm_allreduce_max(lbm_domain* d, double* dev_value);  // ring-wide max of one non-negative device double (diagnostics)
 int comm_exchange_moments(lbm_domain* d);  // two-phase: 2 ghost rows of the moment planes at slab cuts
 int comm_stage_transfer(lbm_domain* d, size_t k, cudaStream_t st);  // pressure packet of stage k between ranks
 int comm_link_refresh(lbm_domain* d);                             // linked slabs: ghost rows of buf[cur] outside lbm_step_group               // pressure packet of stage k between ranks

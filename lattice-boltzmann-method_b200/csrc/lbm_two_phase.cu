@@ -1745,10 +1745,13 @@ int lbm_rk_diagnostics(lbm_domain* d, double sigma, const lbm_rk_diag* out)
 {
   if (!d || !d->tp || d->tp->model != TP_RK || !out) { set_error("lbm_rk_diagnostics: LBM_MODEL_RK domains only"); return LBM_ERR_INVALID; }
   if (!d->have_state || !d->committed) { set_error("lbm_rk_diagnostics: no state or boundary rules not committed"); return LBM_ERR_INVALID; }
-  if (d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X)
+  const bool slab = d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X;
+  if (slab && !comm_active(d))
   {
-    // the normal's cut needs max|grad| over the whole grid and the curvature a halo of the normal planes
-    set_error("lbm_rk_diagnostics: monolithic domains only (a slab holds rows %d..%d of %d)", d->cfg.x0, d->cfg.x1, d->cfg.X);
+    // the normal's cut needs max|grad| over the whole grid and the curvature a halo of the normal planes: over the NCCL
+    // ring both are exchanges (every rank calls this function); linked slabs of one process have no such collective
+    set_error("lbm_rk_diagnostics: monolithic domains or the ranks of an lbm_comm_init ring only (this slab holds rows %d..%d of %d)",
+              d->cfg.x0, d->cfg.x1, d->cfg.X);
     return LBM_ERR_UNSUPPORTED;
   }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
@@ -1757,6 +1760,7 @@ int lbm_rk_diagnostics(lbm_domain* d, double sigma, const lbm_rk_diag* out)
   const MomGeom mg = tp->mg;
   LBM_TRY(tp_fill_planes(d));
   LBM_TRY(tp_pad(d));
+  LBM_TRY(comm_exchange_moments(d));  // ring: the two ghost rows of the moment planes at the cuts
   LBM_TRY(ensure_aos_scratch(d));
   LBM_TRY(tp_export(d));  // post-stream populations (adv_f) of both colours in the reference layout
   // one scratch allocation per call: this is a diagnostic path, not the time loop
@@ -1775,9 +1779,11 @@ int lbm_rk_diagnostics(lbm_domain* d, double sigma, const lbm_rk_diag* out)
   auto run = [&]() -> int {
     LBM_CUDA(cudaMemsetAsync(gmax, 0, sizeof(unsigned long long), d->stream));
     k_rk_diag_grad<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, d->g, mg, tp->p, grad, norm, gmax);
+    LBM_TRY(comm_allreduce_max(d, reinterpret_cast<double*>(gmax)));  // grad_norm.max() over the whole grid
     k_rk_diag_normal<<<cdiv(N, 256), 256, 0, d->stream>>>(grad, norm, d->g, mg, gmax, npl);
     k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(npl, d->g, mg, 2);
-    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(npl, d->g, mg, 1, 1, 2);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(npl, d->g, mg, d->cfg.x0 == 0, d->cfg.x1 == d->cfg.X, 2);
+    LBM_TRY(comm_exchange_planes(d, npl, 2));  // the curvature differentiates the normal across the cuts
     k_rk_diag_final<<<cdiv(N, 128), 128, 0, d->stream>>>(tp->mom, npl, grad, norm, d->d_aos[0], d->g, mg, tp->p, sigma, o);
     d->launches += 5;
     LBM_CUDA(cudaGetLastError());

@@ -43,7 +43,7 @@ def main(world):
             return out
 
         try:
-            results[rank] = mp_nccl_check.run_checks(rank, world, 0, fresh_id, gather, sync.wait)
+            results[rank] = mp_nccl_check.run_checks(rank, world, 0, fresh_id, gather, sync.wait, extra=True)
         except BaseException as e:  # noqa: BLE001  (a failed rank must not leave the others at a barrier)
             results[rank] = [f"rank {rank}: {type(e).__name__}: {e}"]
             sync.abort()

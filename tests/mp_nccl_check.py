@@ -21,10 +21,12 @@ import lbm_b200 as L  # noqa: E402
 print = functools.partial(print, flush=True)  # the launcher's pipe would hold the lines back until exit
 
 
-def run_checks(rank, world, local, fresh_id, gather, barrier):
+def run_checks(rank, world, local, fresh_id, gather, barrier, extra=False):
     """Every check of the ring on one rank.  fresh_id() hands all ranks one new communicator id, gather(a) returns the
     row-concatenation of every rank's array, barrier() joins the ranks — torch.distributed under torchrun (main below),
-    threads of one process on the emulated device (tests/cpu_emu/ring_threads.py).  Returns rank 0's list of failures."""
+    threads of one process on the emulated device (tests/cpu_emu/ring_threads.py).  Returns rank 0's list of failures.
+    extra: the checks whose collectives (an all-to-all group of small sends) have only run over the stand-in so far —
+    lbm_comm_check and the RK diagnostics on a ring; LBM_RING_EXTRA=1 adds them under torchrun."""
     failures = []
 
     # ---- Poiseuille: pressure packets cross the ring (row 0 <- row X-2)
@@ -185,6 +187,30 @@ def run_checks(rank, world, local, fresh_id, gather, barrier):
             failures.append("cylinder-straddling")
     d.close()
 
+    if extra:
+        # ---- RK diagnostics on the ring: max|grad| reduced over the ranks, halos of the moment and normal planes
+        x0, x1 = L.decompose_rows(Ln, world, rank)
+        rst = orc.rk_init(rp)
+        d = cases.rk(Ln, x0=x0, x1=x1, device=local)
+        d.comm_init(fresh_id(), world, rank)
+        d.set_f(rst["r_adv"][x0:x1], 0)
+        d.set_f(rst["b_adv"][x0:x1], 1)
+        d.comm_check()
+        worst = 0.0
+        for n in range(4):
+            got = d.rk_diagnostics(5e-3)
+            want = orc.rk_diagnostics(rp, rst)
+            for k in ("phase", "grad", "norm", "n", "K", "Fs", "kappa", "rparams", "omega1", "omega2", "omega3"):
+                worst = max(worst, float(np.abs(got[k] - want[k][x0:x1]).max()) / max(float(np.abs(want[k]).max()), 1e-3))
+            orc.rk_step(rp, rst)
+            d.step(1)
+        worst = float(gather(np.array([worst])).max())
+        if rank == 0:
+            print(f"rk diagnostics ring of {world}: worst scaled err vs oracle over 4 steps = {worst:.2e}")
+            if not worst < 1e-12:
+                failures.append("rk-diagnostics")
+        d.close()
+
     barrier()
     return failures
 
@@ -208,7 +234,7 @@ def main():
         dist.all_gather_object(out, a)
         return np.concatenate(out, axis=0)
 
-    failures = run_checks(rank, world, local, fresh_id, gather, dist.barrier)
+    failures = run_checks(rank, world, local, fresh_id, gather, dist.barrier, extra=os.environ.get("LBM_RING_EXTRA") == "1")
     flag = [len(failures)]
     dist.broadcast_object_list(flag, src=0)
     dist.destroy_process_group()

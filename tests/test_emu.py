@@ -84,7 +84,7 @@ def test_slab_ring_over_the_nccl_stand_in(emu_lib, world):
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "ring_threads.py"), str(world)], cwd=ROOT, env=env, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0 and "failures: []" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(f"ring of {world}") == 6, r.stdout
+    assert r.stdout.count(f"ring of {world}") == 7, r.stdout  # six checks + the RK diagnostics on the ring
 
 
 @pytest.mark.parametrize("world", [2, 8])
