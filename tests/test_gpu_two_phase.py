@@ -153,44 +153,6 @@ def test_rk_droplet_vs_oracle_and_golden(orc):
         assert np.abs(u[..., 0] - g["ux"][k]).max() < 1e-12 and np.abs(u[..., 1] - g["uy"][k]).max() < 1e-12, sstep
 
 
-def test_rk_diagnostic_fields_vs_oracle_and_golden(orc):
-    """lbm_rk_diagnostics: the fields driver 17 snapshots at the top of every iteration (normal with the 0.1 max|grad|
-    cut, curvature, interfacial tension, eta, kappa, 1/tau, the red colour's omega1/2/3), against the oracle at every
-    step and against the reference driver's own nx / ny / ks / norms / fx / fy / kappas / omegas1 / omegas2 files"""
-    from test_oracle_golden import rk_diag_fields
-
-    g = cases.golden("rk_droplet_101")
-    p = rk_params(101)
-    st = orc.rk_init(p)
-    d = cases.rk(101)
-    d.set_f(st["r_adv"], 0)
-    d.set_f(st["b_adv"], 1)
-    steps = [int(v) for v in g["steps"]]
-    for n in range(steps[-2] + 1):
-        want = orc.rk_diagnostics(p, st)
-        got = d.rk_diagnostics(5e-3)
-        scale = {k: max(float(np.abs(v).max()), 1e-30) for k, v in want.items()}
-        for k in ("phase", "grad", "norm", "n", "K", "Fs", "eta", "kappa", "rparams", "omega1", "omega2", "omega3"):
-            # absolute 1e-12 on O(1) fields, relative on the small ones (Fs ~ 1e-5, omega2 ~ 1e-6)
-            assert np.abs(got[k] - want[k]).max() < 1e-12 * max(scale[k], 1e-3), (n, k)
-        if n in steps:
-            for name, a in rk_diag_fields(got).items():
-                assert np.abs(a - g[name][steps.index(n)]).max() < 1e-12, (n, name)
-        orc.rk_step(p, st)
-        d.step(1)
-    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12  # asking for diagnostics between steps does not disturb the state
-
-
-def test_rk_diagnostics_error_behaviour():
-    d = cases.mrtcg(16, 16, (0.0, 0.0), 0)
-    with pytest.raises(L.LbmError, match="LBM_MODEL_RK"):
-        d.rk_diagnostics()
-    slab = cases.rk(32, x0=0, x1=16)
-    slab.init_two_phase(np.ones((16, 32)), np.ones((16, 32)), np.zeros((16, 32, 2)))
-    with pytest.raises(L.LbmError, match="monolithic domains or the ranks"):
-        slab.rk_diagnostics()  # a slab outside a ring: no way to reduce max|grad| or to swap the normal's halo
-
-
 def test_rk_long_run_stays_on_the_oracle(orc):
     """static droplet, 1500 steps: <= 1e-9 on density / velocity / phase (north-star long-run tolerance)"""
     Ln = 64
