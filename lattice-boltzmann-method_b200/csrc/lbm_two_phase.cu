@@ -54,6 +54,14 @@ struct TwoPhaseState
   bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
   double* aux = nullptr;               // TP_CSF: A_COUNT planes in the moment-plane geometry (normal n, interfacial tension Fs)
   int rpb_override = 0;
+  // TP_CSF single-pass variant (LBM_CSF_FUSED=1, off by default until it has been measured on the device)
+  bool csf_fused = false;
+  double* aux_next = nullptr;          // second aux set: a fused step reads Fs from aux and writes it here, then the two swap
+  unsigned char* d_csf_flags = nullptr;  // [Xl] bit 0: moments of the whole row from the planes; bit 1: normals too
+  int* d_csf_list4 = nullptr;          // interior-column nodes whose moments the pre-pass writes to the planes
+  int* d_csf_list2 = nullptr;          // nodes (any column) whose normals the pre-pass writes to the planes
+  int n_csf_list4 = 0, n_csf_list2 = 0;
+  bool csf_lists_dirty = true;
 };
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -758,6 +766,12 @@ int tp_create(lbm_domain* d)
     const size_t ab = sizeof(double) * 4 * tp->mg.mplane;
     LBM_CUDA(cudaMalloc(&tp->aux, ab));
     LBM_CUDA(cudaMemset(tp->aux, 0, ab));
+    if (const char* e = getenv("LBM_CSF_FUSED")) tp->csf_fused = atoi(e) != 0;
+    if (tp->csf_fused)
+    {
+      LBM_CUDA(cudaMalloc(&tp->aux_next, ab));
+      LBM_CUDA(cudaMemset(tp->aux_next, 0, ab));
+    }
   }
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
@@ -781,6 +795,10 @@ int tp_destroy(lbm_domain* d)
   if (!d->tp) return LBM_OK;
   cudaFree(d->tp->mom);
   cudaFree(d->tp->aux);
+  cudaFree(d->tp->aux_next);
+  cudaFree(d->tp->d_csf_flags);
+  cudaFree(d->tp->d_csf_list4);
+  cudaFree(d->tp->d_csf_list2);
   cudaFree(d->tp->d_rowflag);
   cudaFree(d->tp->d_region);
   delete d->tp;
@@ -1133,6 +1151,7 @@ int tp_commit(lbm_domain* d)
       return LBM_ERR_UNSUPPORTED;
     }
   d->tp->region_dirty = true;
+  d->tp->csf_lists_dirty = true;
   return commit_boundary_tables(d);
 }
 
@@ -1269,8 +1288,9 @@ k_csf_normals(const double* __restrict__ mom, double* __restrict__ aux, const Sl
 }
 
 // collision of one node: stencils from the planes, curvature, interfacial tension (stored), tp_collide<TP_CSF>
-__device__ __forceinline__ void csf_collide_node(const TpParams& p, const double* __restrict__ mom, double* __restrict__ aux,
-                                                 const MomGeom& mg, int x, int y, double (&fr)[9], double (&fb)[9])
+__device__ __forceinline__ void csf_collide_node(const TpParams& p, const double* __restrict__ mom, const double* __restrict__ aux,
+                                                 double* __restrict__ aux_out, const MomGeom& mg, int x, int y, double (&fr)[9],
+                                                 double (&fb)[9])
 {
   TpStencil st;
   tp_stencil_global<TP_MRTCG>(p, mom, mg, x, y, st);  // grad(phase), d/dx Q_x, d/dy Q_y
@@ -1283,8 +1303,8 @@ __device__ __forceinline__ void csf_collide_node(const TpParams& p, const double
   const double K = nx * ny * (dy_nx + dx_ny) - (nx * nx) * dy_ny - (ny * ny) * dx_nx;
   st.Fsx = (-0.5 * p.sigma) * K * st.gx;
   st.Fsy = (-0.5 * p.sigma) * K * st.gy;
-  aux[A_FX * mg.mplane + k] = st.Fsx;
-  aux[A_FY * mg.mplane + k] = st.Fsy;
+  aux_out[A_FX * mg.mplane + k] = st.Fsx;  // (aux_out == aux in the three-pass step: other planes of the same set)
+  aux_out[A_FY * mg.mplane + k] = st.Fsy;
   const double rr = mom[M_RR * mg.mplane + k], rb = mom[M_RB * mg.mplane + k];
   const double ux = mom[M_UX * mg.mplane + k], uy = mom[M_UY * mg.mplane + k], ph = mom[M_PH * mg.mplane + k];
   tp_collide<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, st);
@@ -1399,7 +1419,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128)
 k_csf_collide_listed(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
                      double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom,
-                     double* __restrict__ aux, const TpParams p, const BoundaryTable t)
+                     const double* __restrict__ aux, double* __restrict__ aux_out, const TpParams p, const BoundaryTable t)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.n) return;
@@ -1407,7 +1427,7 @@ k_csf_collide_listed(const double* __restrict__ rsrc, const double* __restrict__
   double fr[9], fb[9];
   tp_load_listed<MODE>(rsrc, g, t, 0, i, x, y, fr);
   tp_load_listed<MODE>(bsrc, g, t, 1, i, x, y, fb);
-  csf_collide_node(p, mom, aux, mg, x, y, fr, fb);
+  csf_collide_node(p, mom, aux, aux_out, mg, x, y, fr, fb);
   const long long o = node_off(g, x, y);
 #pragma unroll
   for (int q = 0; q < 9; q++)
@@ -1417,10 +1437,243 @@ k_csf_collide_listed(const double* __restrict__ rsrc, const double* __restrict__
   }
 }
 
+// ================================================================================================
+// TP_CSF in ONE pass over the populations (LBM_CSF_FUSED=1; monolithic domains).  Row-marching column strips like
+// k_tp_fused, with two lags: the moments of row r enter a ring, the normal of row r-2 is formed from the ring's phase
+// rows r-4 .. r, and row r-5 is collided from the moment rows r-7 .. r-3 and the normal rows r-7 .. r-3.  The
+// populations are pulled twice (the second time out of L2, five rows later); nothing but the interfacial tension is
+// written besides them: 320 B/node of DRAM traffic against the 584 B of the three-pass step.
+//   planes stay authoritative (a pre-pass fills them) where the kernel cannot form a value itself:
+//     moments  listed nodes, the padding, rows within 4 of a row with listed nodes or of the global edge rows 0..2
+//     normals  listed nodes, the padding (replicated NORMALS, not normals of the replicated phase), rows within 2 of ...
+//   Fs is double-buffered (aux -> aux_next): a neighbouring strip's halo still reads the previous step's value.
+// ================================================================================================
+struct CsfFused
+{
+  static constexpr int HC = 4;                 // halo columns per side: 2 for the curvature's normals + 2 for their phase
+  static constexpr int NRM = 9, NRN = 6;       // ring rows: moments r-7 .. r + the one being written; normals r-7 .. r-2
+  static constexpr int LAG_N = 2, LAG_C = 5;
+  static constexpr int USEFUL = TPF_NT - 2 * HC;
+  static constexpr size_t SMEM = sizeof(double) * (3 * NRM + 2 * NRN) * TPF_NT;
+};
+
+// pre-pass: moments of listed interior-column nodes' neighbourhoods (with the carried interfacial tension) into the planes
+__global__ void __launch_bounds__(128)
+k_csf_moments_nodes(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                    double* __restrict__ mom, const double* __restrict__ aux, const TpParams p, const int* __restrict__ nodes, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = nodes[i] / g.Y, y = nodes[i] % g.Y;
+  double fr[9], fb[9];
+  tp_load_interior<MODE_PULL>(rsrc, g, x, y, fr);
+  tp_load_interior<MODE_PULL>(bsrc, g, x, y, fb);
+  const long long k = mom_off(mg, x, y);
+  double rr, rb, ux, uy, ph;
+  tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + k], aux[A_FY * mg.mplane + k]);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
+// pre-pass: normals of a node list from the (padded) phase plane
+__global__ void __launch_bounds__(128)
+k_csf_normals_nodes(const double* __restrict__ mom, double* __restrict__ aux, const SlabGeom g, const MomGeom mg,
+                    const int* __restrict__ nodes, int n)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = nodes[i] / g.Y, y = nodes[i] % g.Y;
+  double gx, gy;
+  diff5_at(mom + M_PH * mg.mplane, mg, x, y, gx, gy);
+  const double inv = 1.0 / (1e-20 + sqrt(gx * gx + gy * gy));
+  const long long k = mom_off(mg, x, y);
+  aux[A_NX * mg.mplane + k] = -gx * inv;
+  aux[A_NY * mg.mplane + k] = -gy * inv;
+}
+
+__global__ void __launch_bounds__(TPF_NT, 3)
+k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst, double* __restrict__ bdst,
+            const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const double* __restrict__ aux,
+            double* __restrict__ aux_out, const TpParams p, const unsigned char* __restrict__ rowflags, int rows_per_block)
+{
+  using C = CsfFused;
+  constexpr int NT = TPF_NT, NRM = C::NRM, NRN = C::NRN, HC = C::HC;
+  extern __shared__ double sm[];  // moments [3][NRM][NT] (phase, Q_x, Q_y), then normals [2][NRN][NT]
+  double* smn = sm + 3 * NRM * NT;
+  auto M = [&](int f, int slot, int col) -> double& { return sm[(f * NRM + slot) * NT + col]; };
+  auto N = [&](int f, int slot, int col) -> double& { return smn[(f * NRN + slot) * NT + col]; };
+  const int t = threadIdx.x;
+  const int y = 1 + blockIdx.x * C::USEFUL - HC + t;
+  const int xb = blockIdx.y * rows_per_block;
+  const int xe = min(xb + rows_per_block, g.Xl);
+  const bool col_ok = y >= -2 && y <= g.Y + 1;      // inside the padded planes
+  const bool col_plane = y < 1 || y > g.Y - 2;      // listed edge columns and the padding
+  const bool normal_thread = t >= 2 && t < NT - 2;  // has the phase of its columns y-2 .. y+2 in the ring
+  const bool collider = t >= HC && t < NT - HC && y >= 1 && y <= g.Y - 2;
+
+  __shared__ unsigned char sflag[128 + 16];  // flags of rows xb-4 .. xe+4 (outside the slab: everything from the planes)
+  for (int k = t; k < xe - xb + 9; k += NT)
+  {
+    const int r = xb - 4 + k;
+    sflag[k] = (r < 0 || r >= g.Xl) ? 3 : rowflags[r];
+  }
+  __syncthreads();
+  auto flag_of = [&](int r) -> int { return sflag[r - (xb - 4)]; };
+
+  for (int r = xb - 4; r <= xe + 4; r++)
+  {
+    // ---- A: moments of (r, y) -> moment ring
+    if (col_ok && r >= -2 && r <= g.Xl + 1)
+    {
+      double rr, rb, ux, uy, ph;
+      const long long k = mom_off(mg, r, y);
+      if (col_plane || (flag_of(r) & 1))
+      {
+        rr = mom[M_RR * mg.mplane + k];
+        rb = mom[M_RB * mg.mplane + k];
+        ux = mom[M_UX * mg.mplane + k];
+        uy = mom[M_UY * mg.mplane + k];
+        ph = mom[M_PH * mg.mplane + k];
+      }
+      else
+      {
+        double fr[9], fb[9];
+        tp_pull_at(rsrc + node_off(g, r, y), g, fr);
+        tp_pull_at(bsrc + node_off(g, r, y), g, fb);
+        tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + k], aux[A_FY * mg.mplane + k]);
+      }
+      const int slot = (r + 4 * NRM) % NRM;
+      const double cq = p.cr * rr + p.cb * rb;
+      M(0, slot, t) = ph;
+      M(1, slot, t) = cq * ux;
+      M(2, slot, t) = cq * uy;
+    }
+    __syncthreads();
+    // ---- B: normal of (r - 2, y) -> normal ring
+    {
+      const int rn = r - C::LAG_N;
+      if (col_ok && rn >= xb - 2 && rn <= xe + 1 && rn >= -2 && rn <= g.Xl + 1)
+      {
+        double nx = 0.0, ny = 0.0;
+        bool have = false;
+        if (col_plane || (flag_of(rn) & 2))
+        {
+          const long long k = mom_off(mg, rn, y);
+          nx = aux[A_NX * mg.mplane + k];
+          ny = aux[A_NY * mg.mplane + k];
+          have = true;
+        }
+        else if (normal_thread)
+        {
+          // the summation order of diff5_at (k_csf_normals): rows, then columns, separately rounded products and sums
+          double gx = 0.0, gy = 0.0;
+#pragma unroll
+          for (int a = -2; a <= 2; a++)
+          {
+            const int sa = (rn + a + 4 * NRM) % NRM;
+#pragma unroll
+            for (int b = -2; b <= 2; b++)
+            {
+              if (a == 0 && b == 0) continue;
+              const double v = M(0, sa, t + b);
+              const double w = XI5(a, b);
+              if (a != 0) gx = __dadd_rn(gx, __dmul_rn(w * (double)a, v));
+              if (b != 0) gy = __dadd_rn(gy, __dmul_rn(w * (double)b, v));
+            }
+          }
+          const double inv = 1.0 / (1e-20 + sqrt(gx * gx + gy * gy));
+          nx = -gx * inv;
+          ny = -gy * inv;
+          have = true;
+        }
+        if (have)
+        {
+          const int slot = (rn + 4 * NRN) % NRN;
+          N(0, slot, t) = nx;
+          N(1, slot, t) = ny;
+        }
+      }
+    }
+    // ---- C: collision of (r - 5, y) from moment rows r-7 .. r-3 and normal rows r-7 .. r-3 (written before this barrier)
+    {
+      const int x = r - C::LAG_C;
+      if (x >= xb && x < xe && collider)
+      {
+        double fr[9], fb[9];
+        tp_pull_at(rsrc + node_off(g, x, y), g, fr);
+        tp_pull_at(bsrc + node_off(g, x, y), g, fb);
+        const long long k = mom_off(mg, x, y);
+        double rr, rb, ux, uy, ph;
+        // the same arithmetic on the same inputs as stage A / the pre-pass: identical values, no ring rows for them
+        tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + k], aux[A_FY * mg.mplane + k]);
+        TpStencil st;
+        st.gx = st.gy = st.DxQx = st.DyQy = 0.0;
+        double dx_nx = 0.0, dy_nx = 0.0, dx_ny = 0.0, dy_ny = 0.0;
+#pragma unroll
+        for (int a = -2; a <= 2; a++)
+        {
+          const int sa = (x + a + 4 * NRM) % NRM;
+#pragma unroll
+          for (int b = -2; b <= 2; b++)
+          {
+            if (a == 0 && b == 0) continue;
+            const double w = XI5(a, b);
+            if (a != 0)
+            {
+              st.gx += (w * (double)a) * M(0, sa, t + b);
+              st.DxQx += (w * (double)a) * M(1, sa, t + b);
+            }
+            if (b != 0)
+            {
+              st.gy += (w * (double)b) * M(0, sa, t + b);
+              st.DyQy += (w * (double)b) * M(2, sa, t + b);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = -2; a <= 2; a++)
+        {
+          const int na = (x + a + 4 * NRN) % NRN;
+#pragma unroll
+          for (int b = -2; b <= 2; b++)
+          {
+            if (a == 0 && b == 0) continue;
+            const double w = XI5(a, b);
+            const double vx = N(0, na, t + b), vy = N(1, na, t + b);
+            if (a != 0) { dx_nx += (w * (double)a) * vx; dx_ny += (w * (double)a) * vy; }
+            if (b != 0) { dy_nx += (w * (double)b) * vx; dy_ny += (w * (double)b) * vy; }
+          }
+        }
+        const int nc = (x + 4 * NRN) % NRN;
+        const double nx = N(0, nc, t), ny = N(1, nc, t);
+        const double K = nx * ny * (dy_nx + dx_ny) - (nx * nx) * dy_ny - (ny * ny) * dx_nx;  // eval_local_curvature (:355-364)
+        st.Fsx = (-0.5 * p.sigma) * K * st.gx;                                              // interf_tension (:510)
+        st.Fsy = (-0.5 * p.sigma) * K * st.gy;
+        aux_out[A_FX * mg.mplane + k] = st.Fsx;
+        aux_out[A_FY * mg.mplane + k] = st.Fsy;
+        tp_collide<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, st);
+        const long long o = node_off(g, x, y);
+#pragma unroll
+        for (int q = 0; q < 9; q++)
+        {
+          rdst[q * g.plane + o] = fr[q];
+          bdst[q * g.plane + o] = fb[q];
+        }
+      }
+    }
+    // no second barrier: the next iteration writes moment slot (r+1) mod 9 = (r-8) mod 9 and, after ITS barrier, normal slot
+    // (r-1) mod 6 = (r-7) mod 6 — the moment rows read above are r-7 .. r, the normal rows read after that barrier r-6 .. r-2
+  }
+}
+
 static int csf_configure()
 {
   LBM_CUDA(cudaFuncSetAttribute(k_csf_collide_ring<MODE_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfRing::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_csf_collide_ring<MODE_PULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfRing::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfFused::SMEM));
   return LBM_OK;
 }
 
@@ -1465,7 +1718,7 @@ static int csf_launch_collide(lbm_domain* d)
   {
     ProfScope ps(d, LBM_PROF_BOUNDARY);
     k_csf_collide_listed<MODE><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
-                                                                       tp->mom, tp->aux, tp->p, table_of(d));
+                                                                       tp->mom, tp->aux, tp->aux, tp->p, table_of(d));
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
@@ -1519,8 +1772,107 @@ static int csf_phase_collide(lbm_domain* d)
   return LBM_OK;
 }
 
+// ---- single-pass step (LBM_CSF_FUSED=1)
+// flags and node lists: which rows / nodes keep their moments and normals in the planes (see k_csf_fused)
+static int csf_build_lists(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  if (!tp->csf_lists_dirty) return LBM_OK;
+  const int Xl = d->g.Xl, Y = d->g.Y;
+  std::vector<unsigned char> near2(Xl, 0), near4(Xl, 0);
+  auto mark = [&](std::vector<unsigned char>& v, int x) { if (x >= 0 && x < Xl) v[x] = 1; };
+  // the replicate padding of the normals copies rows 0 and Xl-1, whose own normals need the phase of rows 0 .. 2 / Xl-3 .. Xl-1
+  for (int x : {0, Xl - 1}) mark(near2, x);
+  for (int x : {0, 1, 2, Xl - 3, Xl - 2, Xl - 1}) mark(near4, x);
+  // listed nodes differentiate the normals of their 5x5 neighbourhood, and those the phase of theirs
+  for (int x = 0; x < Xl && x < (int)d->row_has_listed.size(); x++)
+    if (d->row_has_listed[x])
+      for (int k = -4; k <= 4; k++)
+      {
+        mark(near4, x + k);
+        if (k >= -2 && k <= 2) mark(near2, x + k);
+      }
+  std::vector<unsigned char> flags(Xl);
+  std::vector<int> list4, list2;
+  for (int x = 0; x < Xl; x++)
+  {
+    flags[x] = (unsigned char)((near4[x] ? 1 : 0) | (near2[x] ? 2 : 0));
+    for (int y = 1; y <= Y - 2; y++)
+      if (near4[x] || y <= 4 || y >= Y - 5) list4.push_back(x * Y + y);   // the edge columns 0, Y-1 are listed nodes
+    for (int y = 0; y <= Y - 1; y++)
+      if (near2[x] || y <= 2 || y >= Y - 3) list2.push_back(x * Y + y);
+  }
+  cudaFree(tp->d_csf_flags); cudaFree(tp->d_csf_list4); cudaFree(tp->d_csf_list2);
+  tp->d_csf_flags = nullptr; tp->d_csf_list4 = nullptr; tp->d_csf_list2 = nullptr;
+  LBM_CUDA(cudaMalloc(&tp->d_csf_flags, Xl));
+  LBM_CUDA(cudaMemcpy(tp->d_csf_flags, flags.data(), Xl, cudaMemcpyHostToDevice));
+  tp->n_csf_list4 = (int)list4.size();
+  tp->n_csf_list2 = (int)list2.size();
+  LBM_CUDA(cudaMalloc(&tp->d_csf_list4, sizeof(int) * std::max<size_t>(list4.size(), 1)));
+  LBM_CUDA(cudaMalloc(&tp->d_csf_list2, sizeof(int) * std::max<size_t>(list2.size(), 1)));
+  LBM_CUDA(cudaMemcpy(tp->d_csf_list4, list4.data(), sizeof(int) * list4.size(), cudaMemcpyHostToDevice));
+  LBM_CUDA(cudaMemcpy(tp->d_csf_list2, list2.data(), sizeof(int) * list2.size(), cudaMemcpyHostToDevice));
+  tp->csf_lists_dirty = false;
+  return LBM_OK;
+}
+
+static bool csf_can_fuse(const lbm_domain* d)
+{
+  // monolithic only: a slab would need four-row halos of the moment planes (the planes carry two)
+  return d->tp->csf_fused && !d->post_stream && d->cfg.x0 == 0 && d->cfg.x1 == d->cfg.X && !d->link_lo && !d->link_hi &&
+         !comm_active(d) && d->g.Xl >= 8 && d->g.Y >= 12;
+}
+
+static int csf_step_fused(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  LBM_TRY(csf_build_lists(d));
+  const int s = d->cur, t = d->cur ^ 1, Yi = d->g.Y - 2;
+  {
+    ProfScope ps(d, LBM_PROF_MOMENTS);
+    // pre-pass: the thin part of the planes that stays authoritative, from the stored post-collision state
+    if (tp->n_csf_list4 > 0)
+      k_csf_moments_nodes<<<cdiv(tp->n_csf_list4, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
+                                                                            tp->p, tp->d_csf_list4, tp->n_csf_list4);
+    if (d->nb > 0)
+      k_csf_moments_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
+                                                                              tp->p, table_of(d));
+    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, 1, 1, M_COUNT);
+    k_csf_normals_nodes<<<cdiv(tp->n_csf_list2, 128), 128, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg, tp->d_csf_list2, tp->n_csf_list2);
+    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 1, 1, 2);
+    d->launches += 7;
+    LBM_CUDA(cudaGetLastError());
+  }
+  if (Yi > 0)
+  {
+    ProfScope ps(d, LBM_PROF_INTERIOR);
+    const int rpb = tp->rpb_override > 0 ? std::min(128, tp->rpb_override) : 64;
+    dim3 grid(cdiv(Yi, CsfFused::USEFUL), cdiv(d->g.Xl, rpb));
+    k_csf_fused<<<grid, TPF_NT, CsfFused::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg, tp->mom,
+                                                            tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
+    d->launches++;
+  }
+  if (d->nb > 0)
+  {
+    ProfScope ps(d, LBM_PROF_BOUNDARY);
+    k_csf_collide_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g,
+                                                                            tp->mg, tp->mom, tp->aux, tp->aux_next, tp->p, table_of(d));
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  std::swap(tp->aux, tp->aux_next);  // the interfacial tension just written is what the next step (and the getters) read
+  d->cur ^= 1;
+  d->post_stream = false;
+  tp->planes_full = false;
+  ProfScope ps(d, LBM_PROF_GHOST);
+  return wrap_ghost_rows_local(d, d->cur, d->stream);
+}
+
 static int csf_step(lbm_domain* d)
 {
+  if (csf_can_fuse(d)) return csf_step_fused(d);
   LBM_TRY(csf_phase_moments(d));
   LBM_TRY(comm_exchange_planes(d, d->tp->mom, M_COUNT));  // NCCL ring; nothing on a single slab
   LBM_TRY(csf_phase_normals(d));
