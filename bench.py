@@ -707,7 +707,8 @@ def run_b200_arm(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None,
                 "traffic": ncu_traffic_per_launch(args.workload, args.X, args.Y),
-                "kernel": wl["kernel"], "bytes_per_node": B,
+                "kernel": ("k_csf_fused (LBM_CSF_FUSED=1: one pass)" if args.workload == "csf_rt" and os.environ.get("LBM_CSF_FUSED") == "1"
+                           else wl["kernel"]), "bytes_per_node": B,
                 "algorithmic_bytes_per_step": B * nodes_per_step,
                 "launches_per_step": dom_n / args.steps if args.steps else 0, "kernel_ms_per_step": dom_ms / args.steps,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0 if achieved else None,

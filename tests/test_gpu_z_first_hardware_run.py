@@ -118,3 +118,30 @@ def test_rk_driver_writes_all_nineteen_reference_files(tmp_path):
                 if s < 12:
                     assert np.abs(a[..., s] - g[key][k]).max() < 1e-12, (fname, s)
     assert np.abs(got["omegas3"] - (got["omegas1"] + got["omegas2"])).max() < 1e-15
+
+
+@pytest.mark.parametrize("R,C,rpb", [(96, 64, 0), (41, 33, 0), (70, 300, 0), (200, 131, 16), (130, 125, 128), (16, 12, 0)])
+def test_csf_single_pass_equals_three_pass(monkeypatch, R, C, rpb):
+    """LBM_CSF_FUSED=1 (k_csf_fused: moments -> ring, normals at lag 2, collision at lag 5, Fs double-buffered) against the
+    three-pass step: populations of both colours and the interfacial tension bit for bit, several strips and bands, a first
+    step out of an import (three-pass) followed by fused steps, getters in between."""
+    from test_gpu_csf import csf_params
+
+    p = csf_params(R, C)
+    st = Oracle().csf_init(p)
+    runs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("LBM_CSF_FUSED", fused)
+        if rpb:
+            monkeypatch.setenv("LBM_TP_RPB", str(rpb))
+        d = cases.csf(R, C)
+        d.init_two_phase(st["r_rho"], st["b_rho"], st["u"])
+        out = []
+        for n in (1, 1, 3, 4):
+            d.step(n)
+            out.append((d.get_f(0), d.get_f(1), d.get_interfacial_tension(), d.get_phase()[0]))
+        runs.append(out)
+        d.close()
+    for a, b in zip(*runs):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)

@@ -27,6 +27,9 @@ except Exception as e:
     print(w, "FAILED", e)
 PY
     done
+    # A/B of the single-pass CSF step (off by default until this line says it is faster)
+    LBM_CSF_FUSED=1 timeout 300 python bench.py --workload csf_rt --steps 30 --warmup 5 2> gpurun_out/bench_csf_rt_fused.err | tail -1 > gpurun_out/bench_csf_rt_fused.json
+    python -c "import json; j=json.load(open('gpurun_out/bench_csf_rt_fused.json')); print('csf_rt fused   %7.2f GLUPS  kernel frac %.3f  whole step %.3f' % (j['value']/1e3, j['roofline']['frac'], j['roofline']['whole_step_frac_per_gpu']))" || echo "csf_rt fused FAILED"
     ;;
   ring)
     n=${2:-2}
