@@ -1781,9 +1781,10 @@ static int csf_build_lists(lbm_domain* d)
   const int Xl = d->g.Xl, Y = d->g.Y;
   std::vector<unsigned char> near2(Xl, 0), near4(Xl, 0);
   auto mark = [&](std::vector<unsigned char>& v, int x) { if (x >= 0 && x < Xl) v[x] = 1; };
-  // the replicate padding of the normals copies rows 0 and Xl-1, whose own normals need the phase of rows 0 .. 2 / Xl-3 .. Xl-1
-  for (int x : {0, Xl - 1}) mark(near2, x);
-  for (int x : {0, 1, 2, Xl - 3, Xl - 2, Xl - 1}) mark(near4, x);
+  // the replicate padding of the normals copies rows 0 and Xl-1 (global edge), and rows 0, 1 / Xl-2, Xl-1 travel to the
+  // neighbouring slab as its normal halo (ring): their own normals need the phase of two more rows each way
+  for (int x : {0, 1, Xl - 2, Xl - 1}) mark(near2, x);
+  for (int x : {0, 1, 2, 3, Xl - 4, Xl - 3, Xl - 2, Xl - 1}) mark(near4, x);
   // listed nodes differentiate the normals of their 5x5 neighbourhood, and those the phase of theirs
   for (int x = 0; x < Xl && x < (int)d->row_has_listed.size(); x++)
     if (d->row_has_listed[x])
@@ -1818,9 +1819,10 @@ static int csf_build_lists(lbm_domain* d)
 
 static bool csf_can_fuse(const lbm_domain* d)
 {
-  // monolithic only: a slab would need four-row halos of the moment planes (the planes carry two)
-  return d->tp->csf_fused && !d->post_stream && d->cfg.x0 == 0 && d->cfg.x1 == d->cfg.X && !d->link_lo && !d->link_hi &&
-         !comm_active(d) && d->g.Xl >= 8 && d->g.Y >= 12;
+  // monolithic domains and the slabs of an NCCL ring (two 2-row halos between the pre-pass stages, like the three-pass
+  // step); linked slabs of one process interleave their phases in csf_step_group and keep the three passes
+  const bool whole = d->cfg.x0 == 0 && d->cfg.x1 == d->cfg.X;
+  return d->tp->csf_fused && !d->post_stream && !d->link_lo && !d->link_hi && (whole || comm_active(d)) && d->g.Xl >= 8 && d->g.Y >= 12;
 }
 
 static int csf_step_fused(lbm_domain* d)
@@ -1837,11 +1839,14 @@ static int csf_step_fused(lbm_domain* d)
     if (d->nb > 0)
       k_csf_moments_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
                                                                               tp->p, table_of(d));
+    const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;  // replicate at the global edges only
     k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
-    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, 1, 1, M_COUNT);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
+    LBM_TRY(comm_exchange_planes(d, tp->mom, M_COUNT));  // ring: rows 0, 1 / Xl-2, Xl-1 (whole rows, in the lists) to the neighbours
     k_csf_normals_nodes<<<cdiv(tp->n_csf_list2, 128), 128, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg, tp->d_csf_list2, tp->n_csf_list2);
     k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
-    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 1, 1, 2);
+    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, lo, hi, 2);
+    LBM_TRY(comm_exchange_planes(d, tp->aux, 2));
     d->launches += 7;
     LBM_CUDA(cudaGetLastError());
   }
@@ -1867,6 +1872,7 @@ static int csf_step_fused(lbm_domain* d)
   d->post_stream = false;
   tp->planes_full = false;
   ProfScope ps(d, LBM_PROF_GHOST);
+  if (comm_active(d)) return comm_exchange(d, d->cur, d->stream);
   return wrap_ghost_rows_local(d, d->cur, d->stream);
 }
 

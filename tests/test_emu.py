@@ -76,11 +76,11 @@ def test_kernels_under_address_sanitizer():
 
 
 @pytest.mark.parametrize("world", [2, 3, 5, 8])
-def test_slab_ring_over_the_nccl_stand_in(emu_lib, world):
+def test_slab_ring_over_the_nccl_stand_in(emu_lib, world, csf_fused="0"):
     """tests/mp_nccl_check.py's own checks (the GPU box runs them under torchrun over real NCCL) with one thread per rank on
     the emulated device: Poiseuille pressure packets across the ring, MRTCG / RK / CSF halos, an immersed body inside one
     slab and across every cut — bit-exact against the monolithic run at ring sizes the GPU budget never reached (8)."""
-    env = dict(os.environ, OMP_WAIT_POLICY="passive", OMP_NUM_THREADS="2", FAKE_NCCL_TIMEOUT_S="120")
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", OMP_NUM_THREADS="2", FAKE_NCCL_TIMEOUT_S="120", LBM_CSF_FUSED=csf_fused)
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "ring_threads.py"), str(world)], cwd=ROOT, env=env, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0 and "failures: []" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
@@ -95,6 +95,11 @@ def test_comm_check_turns_the_missing_marker_list_into_an_error(emu_lib, world):
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "ring_check_misuse.py"), str(world)], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and f"misuse reported on all {world} ranks" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_single_pass_csf_step_on_the_ring(emu_lib):
+    """LBM_CSF_FUSED=1 on the slabs of a ring (two 2-row halos between the pre-pass stages): bit-identical to the monolithic run"""
+    test_slab_ring_over_the_nccl_stand_in(emu_lib, 3, csf_fused="1")
 
 
 def test_every_bench_workload_sets_up_and_steps_on_the_emulated_device(emu_lib):
