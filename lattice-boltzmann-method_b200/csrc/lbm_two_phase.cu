@@ -1820,36 +1820,50 @@ static int csf_build_lists(lbm_domain* d)
 static bool csf_can_fuse(const lbm_domain* d)
 {
   // monolithic domains and the slabs of an NCCL ring (two 2-row halos between the pre-pass stages, like the three-pass
-  // step); linked slabs of one process interleave their phases in csf_step_group and keep the three passes
-  const bool whole = d->cfg.x0 == 0 && d->cfg.x1 == d->cfg.X;
-  return d->tp->csf_fused && !d->post_stream && !d->link_lo && !d->link_hi && (whole || comm_active(d)) && d->g.Xl >= 8 && d->g.Y >= 12;
+  // step) or of a linked group (csf_step_group interleaves the same three stages)
+  const bool whole = d->cfg.x0 == 0 && d->cfg.x1 == d->cfg.X, linked = d->link_lo || d->link_hi;
+  return d->tp->csf_fused && !d->post_stream && (whole || comm_active(d) || linked) && d->g.Xl >= 8 && d->g.Y >= 12;
 }
 
-static int csf_step_fused(lbm_domain* d)
+// the three stages of the single-pass step; between them the slabs of a ring / of a linked group swap two plane rows
+static int csf_fused_moments(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
   LBM_TRY(csf_build_lists(d));
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  const int s = d->cur;
+  // pre-pass: the thin part of the planes that stays authoritative, from the stored post-collision state
+  if (tp->n_csf_list4 > 0)
+    k_csf_moments_nodes<<<cdiv(tp->n_csf_list4, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
+                                                                          tp->p, tp->d_csf_list4, tp->n_csf_list4);
+  if (d->nb > 0)
+    k_csf_moments_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
+                                                                            tp->p, table_of(d));
+  const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;  // replicate at the global edges only
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
+  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
+  d->launches += 4;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+static int csf_fused_normals(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  ProfScope ps(d, LBM_PROF_MOMENTS);
+  const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
+  k_csf_normals_nodes<<<cdiv(tp->n_csf_list2, 128), 128, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg, tp->d_csf_list2, tp->n_csf_list2);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
+  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, lo, hi, 2);
+  d->launches += 3;
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+static int csf_fused_collide(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
   const int s = d->cur, t = d->cur ^ 1, Yi = d->g.Y - 2;
-  {
-    ProfScope ps(d, LBM_PROF_MOMENTS);
-    // pre-pass: the thin part of the planes that stays authoritative, from the stored post-collision state
-    if (tp->n_csf_list4 > 0)
-      k_csf_moments_nodes<<<cdiv(tp->n_csf_list4, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
-                                                                            tp->p, tp->d_csf_list4, tp->n_csf_list4);
-    if (d->nb > 0)
-      k_csf_moments_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
-                                                                              tp->p, table_of(d));
-    const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;  // replicate at the global edges only
-    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
-    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
-    LBM_TRY(comm_exchange_planes(d, tp->mom, M_COUNT));  // ring: rows 0, 1 / Xl-2, Xl-1 (whole rows, in the lists) to the neighbours
-    k_csf_normals_nodes<<<cdiv(tp->n_csf_list2, 128), 128, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg, tp->d_csf_list2, tp->n_csf_list2);
-    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
-    k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, lo, hi, 2);
-    LBM_TRY(comm_exchange_planes(d, tp->aux, 2));
-    d->launches += 7;
-    LBM_CUDA(cudaGetLastError());
-  }
   if (Yi > 0)
   {
     ProfScope ps(d, LBM_PROF_INTERIOR);
@@ -1867,10 +1881,24 @@ static int csf_step_fused(lbm_domain* d)
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
-  std::swap(tp->aux, tp->aux_next);  // the interfacial tension just written is what the next step (and the getters) read
   d->cur ^= 1;
   d->post_stream = false;
   tp->planes_full = false;
+  return LBM_OK;
+}
+
+// the interfacial tension just written is what the next step (and the getters) read.  Its own call: in a linked group a
+// neighbour still copies this step's NORMAL rows out of `aux` after this slab's collision has been enqueued.
+static void csf_fused_swap(lbm_domain* d) { std::swap(d->tp->aux, d->tp->aux_next); }
+
+static int csf_step_fused(lbm_domain* d)
+{
+  LBM_TRY(csf_fused_moments(d));
+  LBM_TRY(comm_exchange_planes(d, d->tp->mom, M_COUNT));  // ring: rows 0, 1 / Xl-2, Xl-1 (whole rows, in the lists) to the neighbours
+  LBM_TRY(csf_fused_normals(d));
+  LBM_TRY(comm_exchange_planes(d, d->tp->aux, 2));
+  LBM_TRY(csf_fused_collide(d));
+  csf_fused_swap(d);
   ProfScope ps(d, LBM_PROF_GHOST);
   if (comm_active(d)) return comm_exchange(d, d->cur, d->stream);
   return wrap_ghost_rows_local(d, d->cur, d->stream);
@@ -1907,10 +1935,12 @@ static int csf_step_group(lbm_domain* const* ds, int n, int n_steps)
   }
   for (int s = 0; s < n_steps; s++)
   {
+    bool fuse = true;  // all slabs or none: the halo rows a slab sends must be the ones its neighbour's stage expects
+    for (int i = 0; i < n; i++) fuse = fuse && csf_can_fuse(ds[i]);
     for (int i = 0; i < n; i++)
     {
       LBM_CUDA(on(ds[i]));
-      LBM_TRY(csf_phase_moments(ds[i]));
+      LBM_TRY(fuse ? csf_fused_moments(ds[i]) : csf_phase_moments(ds[i]));
       LBM_CUDA(cudaEventRecord(ds[i]->ev_ready, ds[i]->stream));
     }
     for (int i = 0; i < n; i++)
@@ -1918,7 +1948,7 @@ static int csf_step_group(lbm_domain* const* ds, int n, int n_steps)
       LBM_CUDA(on(ds[i]));
       LBM_TRY(wait_neighbours(ds[i], &lbm_domain::ev_ready));
       LBM_TRY(tp_link_halo_planes(ds[i], &TwoPhaseState::mom, M_COUNT));
-      LBM_TRY(csf_phase_normals(ds[i]));
+      LBM_TRY(fuse ? csf_fused_normals(ds[i]) : csf_phase_normals(ds[i]));
       LBM_CUDA(cudaEventRecord(ds[i]->ev_packet, ds[i]->stream));
     }
     for (int i = 0; i < n; i++)
@@ -1926,9 +1956,11 @@ static int csf_step_group(lbm_domain* const* ds, int n, int n_steps)
       LBM_CUDA(on(ds[i]));
       LBM_TRY(wait_neighbours(ds[i], &lbm_domain::ev_packet));
       LBM_TRY(tp_link_halo_planes(ds[i], &TwoPhaseState::aux, 2));
-      LBM_TRY(csf_phase_collide(ds[i]));
+      LBM_TRY(fuse ? csf_fused_collide(ds[i]) : csf_phase_collide(ds[i]));
       LBM_CUDA(cudaEventRecord(ds[i]->ev_stage, ds[i]->stream));
     }
+    if (fuse)
+      for (int i = 0; i < n; i++) csf_fused_swap(ds[i]);
     for (int i = 0; i < n; i++)
     {
       lbm_domain* d = ds[i];

@@ -145,3 +145,13 @@ def test_csf_single_pass_equals_three_pass(monkeypatch, R, C, rpb):
     for a, b in zip(*runs):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_csf_single_pass_on_linked_slabs(monkeypatch, orc, P):
+    """the three stages of the single-pass step interleaved across linked slabs (lbm_step_group): bit-identical to the
+    monolithic run, which test_csf_single_pass_equals_three_pass ties to the three-pass step"""
+    import test_gpu_csf
+
+    monkeypatch.setenv("LBM_CSF_FUSED", "1")
+    test_gpu_csf.test_csf_linked_slabs_equal_monolithic(orc, P)
