@@ -56,6 +56,7 @@ struct TwoPhaseState
   int rpb_override = 0;
   // TP_CSF single-pass variant (LBM_CSF_FUSED=1, off by default until it has been measured on the device)
   bool csf_fused = false;
+  bool csf_pipe = false;               // LBM_CSF_PIPE=1: software-pipelined variant of k_csf_fused
   double* aux_next = nullptr;          // second aux set: a fused step reads Fs from aux and writes it here, then the two swap
   unsigned char* d_csf_flags = nullptr;  // [Xl] bit 0: moments of the whole row from the planes; bit 1: normals too
   int* d_csf_list4 = nullptr;          // interior-column nodes whose moments the pre-pass writes to the planes
@@ -767,6 +768,7 @@ int tp_create(lbm_domain* d)
     LBM_CUDA(cudaMalloc(&tp->aux, ab));
     LBM_CUDA(cudaMemset(tp->aux, 0, ab));
     if (const char* e = getenv("LBM_CSF_FUSED")) tp->csf_fused = atoi(e) != 0;
+    if (const char* e = getenv("LBM_CSF_PIPE")) tp->csf_pipe = atoi(e) != 0;
     if (tp->csf_fused)
     {
       LBM_CUDA(cudaMalloc(&tp->aux_next, ab));
@@ -1494,7 +1496,11 @@ k_csf_normals_nodes(const double* __restrict__ mom, double* __restrict__ aux, co
   aux[A_NY * mg.mplane + k] = -gy * inv;
 }
 
-__global__ void __launch_bounds__(TPF_NT, 3)
+// PIPE: the pulls of row r are issued first and finished (moments, ring) after the normal / collision work of the previous
+// iteration, so their DRAM latency hides under that fp64 work (as in k_tp_fused); 36 more live registers, hence two
+// resident blocks instead of three.  Which of the two is faster is a measurement (LBM_CSF_PIPE=1; default off).
+template <bool PIPE>
+__global__ void __launch_bounds__(TPF_NT, PIPE ? 2 : 3)
 k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst, double* __restrict__ bdst,
             const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const double* __restrict__ aux,
             double* __restrict__ aux_out, const TpParams p, const unsigned char* __restrict__ rowflags, int rows_per_block)
@@ -1523,38 +1529,10 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
   __syncthreads();
   auto flag_of = [&](int r) -> int { return sflag[r - (xb - 4)]; };
 
-  for (int r = xb - 4; r <= xe + 4; r++)
-  {
-    // ---- A: moments of (r, y) -> moment ring
-    if (col_ok && r >= -2 && r <= g.Xl + 1)
+  // ---- B of iteration it: normal of (it - 2, y) -> normal ring
+  auto stage_normal = [&](int it) {
     {
-      double rr, rb, ux, uy, ph;
-      const long long k = mom_off(mg, r, y);
-      if (col_plane || (flag_of(r) & 1))
-      {
-        rr = mom[M_RR * mg.mplane + k];
-        rb = mom[M_RB * mg.mplane + k];
-        ux = mom[M_UX * mg.mplane + k];
-        uy = mom[M_UY * mg.mplane + k];
-        ph = mom[M_PH * mg.mplane + k];
-      }
-      else
-      {
-        double fr[9], fb[9];
-        tp_pull_at(rsrc + node_off(g, r, y), g, fr);
-        tp_pull_at(bsrc + node_off(g, r, y), g, fb);
-        tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + k], aux[A_FY * mg.mplane + k]);
-      }
-      const int slot = (r + 4 * NRM) % NRM;
-      const double cq = p.cr * rr + p.cb * rb;
-      M(0, slot, t) = ph;
-      M(1, slot, t) = cq * ux;
-      M(2, slot, t) = cq * uy;
-    }
-    __syncthreads();
-    // ---- B: normal of (r - 2, y) -> normal ring
-    {
-      const int rn = r - C::LAG_N;
+      const int rn = it - C::LAG_N;
       if (col_ok && rn >= xb - 2 && rn <= xe + 1 && rn >= -2 && rn <= g.Xl + 1)
       {
         double nx = 0.0, ny = 0.0;
@@ -1597,9 +1575,12 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
         }
       }
     }
-    // ---- C: collision of (r - 5, y) from moment rows r-7 .. r-3 and normal rows r-7 .. r-3 (written before this barrier)
+  };
+  // ---- C of iteration it: collision of (it - 5, y) from moment rows it-7 .. it-3 and normal rows it-7 .. it-3 (written before
+  //      the barrier that precedes this stage)
+  auto stage_collide = [&](int it) {
     {
-      const int x = r - C::LAG_C;
+      const int x = it - C::LAG_C;
       if (x >= xb && x < xe && collider)
       {
         double fr[9], fb[9];
@@ -1664,8 +1645,62 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
         }
       }
     }
-    // no second barrier: the next iteration writes moment slot (r+1) mod 9 = (r-8) mod 9 and, after ITS barrier, normal slot
-    // (r-1) mod 6 = (r-7) mod 6 — the moment rows read above are r-7 .. r, the normal rows read after that barrier r-6 .. r-2
+  };
+  for (int r = xb - 4; r <= xe + 4 + (PIPE ? 1 : 0); r++)
+  {
+    // ---- A: moments of (r, y) -> moment ring.  Loads first ...
+    const bool want = col_ok && r >= -2 && r <= g.Xl + 1 && r <= xe + 4;
+    const bool plane = want && (col_plane || (flag_of(r) & 1));
+    double fr[9], fb[9];
+    double rr, rb, ux, uy, ph, fsx = 0.0, fsy = 0.0;
+    if (want)
+    {
+      const long long k = mom_off(mg, r, y);
+      if (plane)
+      {
+        rr = mom[M_RR * mg.mplane + k];
+        rb = mom[M_RB * mg.mplane + k];
+        ux = mom[M_UX * mg.mplane + k];
+        uy = mom[M_UY * mg.mplane + k];
+        ph = mom[M_PH * mg.mplane + k];
+      }
+      else
+      {
+        tp_pull_at(rsrc + node_off(g, r, y), g, fr);
+        tp_pull_at(bsrc + node_off(g, r, y), g, fb);
+        fsx = aux[A_FX * mg.mplane + k];
+        fsy = aux[A_FY * mg.mplane + k];
+      }
+    }
+    // ... (pipelined) the previous iteration's normal and collision work while they are in flight ...
+    if constexpr (PIPE)
+    {
+      if (r > xb - 4)
+      {
+        stage_normal(r - 1);
+        stage_collide(r - 1);
+      }
+    }
+    // ... then the moments, published
+    if (want)
+    {
+      if (!plane) tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, fsx, fsy);
+      const int slot = (r + 4 * NRM) % NRM;
+      const double cq = p.cr * rr + p.cb * rb;
+      M(0, slot, t) = ph;
+      M(1, slot, t) = cq * ux;
+      M(2, slot, t) = cq * uy;
+    }
+    __syncthreads();
+    if constexpr (!PIPE)
+    {
+      stage_normal(r);
+      stage_collide(r);
+    }
+    // no second barrier.  Plain: the next iteration writes moment slot (r+1) mod 9 = (r-8) mod 9 and, after ITS barrier, normal
+    // slot (r-1) mod 6 = (r-7) mod 6 — the moment rows read above are r-7 .. r, the normal rows read after that barrier r-6 .. r-2.
+    // Pipelined: the stages of iteration r-1 read moment rows r-8 .. r-1 and normal rows r-8 .. r-4 while this iteration writes
+    // moment slot r mod 9 = (r-9) mod 9 and normal slot (r-3) mod 6 = (r-9) mod 6.
   }
 }
 
@@ -1673,7 +1708,8 @@ static int csf_configure()
 {
   LBM_CUDA(cudaFuncSetAttribute(k_csf_collide_ring<MODE_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfRing::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_csf_collide_ring<MODE_PULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfRing::SMEM));
-  LBM_CUDA(cudaFuncSetAttribute(k_csf_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfFused::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfFused::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfFused::SMEM));
   return LBM_OK;
 }
 
@@ -1869,8 +1905,12 @@ static int csf_fused_collide(lbm_domain* d)
     ProfScope ps(d, LBM_PROF_INTERIOR);
     const int rpb = tp->rpb_override > 0 ? std::min(128, tp->rpb_override) : 64;
     dim3 grid(cdiv(Yi, CsfFused::USEFUL), cdiv(d->g.Xl, rpb));
-    k_csf_fused<<<grid, TPF_NT, CsfFused::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg, tp->mom,
-                                                            tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
+    if (tp->csf_pipe)
+      k_csf_fused<true><<<grid, TPF_NT, CsfFused::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                    tp->mom, tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
+    else
+      k_csf_fused<false><<<grid, TPF_NT, CsfFused::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                     tp->mom, tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
     d->launches++;
   }
   if (d->nb > 0)

@@ -120,8 +120,9 @@ def test_rk_driver_writes_all_nineteen_reference_files(tmp_path):
     assert np.abs(got["omegas3"] - (got["omegas1"] + got["omegas2"])).max() < 1e-15
 
 
+@pytest.mark.parametrize("pipe", ["0", "1"])
 @pytest.mark.parametrize("R,C,rpb", [(96, 64, 0), (41, 33, 0), (70, 300, 0), (200, 131, 16), (130, 125, 128), (16, 12, 0)])
-def test_csf_single_pass_equals_three_pass(monkeypatch, R, C, rpb):
+def test_csf_single_pass_equals_three_pass(monkeypatch, R, C, rpb, pipe):
     """LBM_CSF_FUSED=1 (k_csf_fused: moments -> ring, normals at lag 2, collision at lag 5, Fs double-buffered) against the
     three-pass step: populations of both colours and the interfacial tension bit for bit, several strips and bands, a first
     step out of an import (three-pass) followed by fused steps, getters in between."""
@@ -132,6 +133,7 @@ def test_csf_single_pass_equals_three_pass(monkeypatch, R, C, rpb):
     runs = []
     for fused in ("0", "1"):
         monkeypatch.setenv("LBM_CSF_FUSED", fused)
+        monkeypatch.setenv("LBM_CSF_PIPE", pipe)  # the software-pipelined variant of the kernel (two resident blocks)
         if rpb:
             monkeypatch.setenv("LBM_TP_RPB", str(rpb))
         d = cases.csf(R, C)

@@ -30,6 +30,8 @@ PY
     # A/B of the single-pass CSF step (off by default until this line says it is faster)
     LBM_CSF_FUSED=1 timeout 300 python bench.py --workload csf_rt --steps 30 --warmup 5 2> gpurun_out/bench_csf_rt_fused.err | tail -1 > gpurun_out/bench_csf_rt_fused.json
     python -c "import json; j=json.load(open('gpurun_out/bench_csf_rt_fused.json')); print('csf_rt fused   %7.2f GLUPS  kernel frac %.3f  whole step %.3f' % (j['value']/1e3, j['roofline']['frac'], j['roofline']['whole_step_frac_per_gpu']))" || echo "csf_rt fused FAILED"
+    LBM_CSF_FUSED=1 LBM_CSF_PIPE=1 timeout 300 python bench.py --workload csf_rt --steps 30 --warmup 5 2> gpurun_out/bench_csf_rt_fused_pipe.err | tail -1 > gpurun_out/bench_csf_rt_fused_pipe.json
+    python -c "import json; j=json.load(open('gpurun_out/bench_csf_rt_fused_pipe.json')); print('csf_rt fused+pipe %5.2f GLUPS  kernel frac %.3f  whole step %.3f' % (j['value']/1e3, j['roofline']['frac'], j['roofline']['whole_step_frac_per_gpu']))" || echo "csf_rt fused+pipe FAILED"
     ;;
   ring)
     n=${2:-2}
