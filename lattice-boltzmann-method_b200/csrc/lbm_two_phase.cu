@@ -1947,6 +1947,9 @@ static int csf_step_fused(lbm_domain* d)
 static int csf_step(lbm_domain* d)
 {
   if (csf_can_fuse(d)) return csf_step_fused(d);
+  // a three-pass step out of an import does not swap the aux sets while it flips the population buffers: captured step
+  // pairs (lbm_use_graph) hold the old pairing of the two.  (Never reached inside a capture: those start in steady state.)
+  if (d->tp->csf_fused && d->post_stream) drop_graphs(d);
   LBM_TRY(csf_phase_moments(d));
   LBM_TRY(comm_exchange_planes(d, d->tp->mom, M_COUNT));  // NCCL ring; nothing on a single slab
   LBM_TRY(csf_phase_normals(d));
