@@ -50,6 +50,10 @@ for w in ("cylinder", "mrtcg_rt"):
     except Exception as e:
         print(w, "FAILED", e)
 PY
+    # last, under its own timeout: the checks whose all-to-all groups have only run over the NCCL stand-in so far
+    # (lbm_comm_check, the RK diagnostics' ring-wide max) and the single-pass CSF step on the ring
+    LBM_RING_EXTRA=1 LBM_CSF_FUSED=1 timeout 240 $T --master-port 29514 tests/mp_nccl_check.py 2>&1 | grep -E "ring|rror|Traceback" | tee gpurun_out/mp_nccl_check_extra_n$n.log
+    echo "mp_nccl_check (extra) rc=${PIPESTATUS[0]}"
     ;;
   *) echo "usage: tools/gpu_checks.sh tests|bench|ring N"; exit 2 ;;
 esac
