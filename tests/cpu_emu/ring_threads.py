@@ -10,13 +10,14 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [os.path.join(ROOT, "lattice-boltzmann-method_b200", "python"), os.path.join(ROOT, "tests")]
-os.environ["LBM_NCCL_LIB"] = os.path.join(HERE, "_build", "libnccl_emu.so")
+BUILD = os.path.join(HERE, "_build_asan" if os.environ.get("LBM_EMU_ASAN") == "1" else "_build")  # SAN=1 build: run with libasan preloaded
+os.environ["LBM_NCCL_LIB"] = os.path.join(BUILD, "libnccl_emu.so")
 
 import numpy as np  # noqa: E402
 
 import lbm_b200 as L  # noqa: E402
 
-L.LIB_PATH = os.path.join(HERE, "_build", "liblbm_b200_emu.so")
+L.LIB_PATH = os.path.join(BUILD, "liblbm_b200_emu.so")
 import mp_nccl_check  # noqa: E402
 
 
