@@ -21,6 +21,9 @@ BUDGET = {
     "k_tp_fusedILi0ELb1E": (168, "MRT colour gradient, pipelined: 3 resident blocks"),
     "k_tp_fusedILi1ELb1E": (168, "Rothman-Keller, pipelined: 3 resident blocks"),
     "k_csf_collide_ringILi1E": (168, "CSF collision pass: 3 resident blocks"),
+    "k_csf_fusedILb0E": (168, "CSF single pass, plain: 3 resident blocks"),
+    "k_csf_fusedILb1E": (255, "CSF single pass, pipelined: 2 resident blocks"),
+    "k_bgk_interiorILi1ELi0ELi2ELb1E": (110, "BGK + advection-diffusion lattice + IBM force field (sedimentation_ibm)"),
 }
 
 
