@@ -16,7 +16,8 @@ import lbm_b200 as L
 from oracle_lib import Oracle
 from test_gpu_two_phase import rk_params
 
-pytestmark = pytest.mark.gpu
+# first runs on hardware: a kernel that hangs there must end this process, not the box's whole GPU session
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL_STEP = 1e-12
