@@ -307,7 +307,9 @@ int lbm_profile_read(lbm_domain* d, int prof_class, double* total_ms, long long*
 #define LBM_UNIQUE_ID_BYTES 128
 /* rank 0 creates the id, the launcher broadcasts it (torch.distributed / MPI / file) */
 int lbm_comm_unique_id(char id[LBM_UNIQUE_ID_BYTES]);
-/* joins the slab ring: neighbours are rank-1 and rank+1 (periodic, like solver::advect) */
+/* joins the slab ring: neighbours are rank-1 and rank+1 (periodic, like solver::advect).
+ * Call order: lbm_create -> lbm_comm_init -> rules / markers -> state import -> lbm_step.  A two-phase domain that
+ * already holds state is refused (LBM_ERR_INVALID): its imports swap the moment-plane halos of the cuts when they run. */
 int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank);
 /* Collective consistency check of the ring (optional; every rank calls it after its setup, before the first lbm_step):
  * grids, model, force mode, and that every slab owning rows of an immersed body's ROI was handed that body's marker list —

@@ -97,6 +97,11 @@ static int load_nccl()
   return LBM_OK;
 }
 
+// A failed Send / Recv inside a ncclGroupStart / ncclGroupEnd bracket must not leave this thread's group open (every
+// later NCCL call would nest into it and never launch: a hang instead of LBM_ERR_COMM), so the bracket depth is
+// tracked and closed on the error path.
+static thread_local int t_group_depth = 0;
+
 #define LBM_NCCL(call)                                                                         \
   do                                                                                           \
   {                                                                                            \
@@ -104,8 +109,21 @@ static int load_nccl()
     if (r__ != 0)                                                                              \
     {                                                                                          \
       set_error("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+      for (; t_group_depth > 0; t_group_depth--) g_nccl.GroupEnd();                            \
       return LBM_ERR_COMM;                                                                     \
     }                                                                                          \
+  } while (0)
+#define LBM_NCCL_GROUP_BEGIN()        \
+  do                                  \
+  {                                   \
+    LBM_NCCL(g_nccl.GroupStart());    \
+    t_group_depth++;                  \
+  } while (0)
+#define LBM_NCCL_GROUP_END()          \
+  do                                  \
+  {                                   \
+    t_group_depth--;                  \
+    LBM_NCCL(g_nccl.GroupEnd());      \
   } while (0)
 
 struct CommState
@@ -141,7 +159,7 @@ int comm_exchange(lbm_domain* d, int which, cudaStream_t st)
   const int up = (c->rank + 1) % c->n_ranks, dn = (c->rank + c->n_ranks - 1) % c->n_ranks;
   const SlabGeom& g = d->g;
   const size_t n = (size_t)g.pitch;
-  LBM_NCCL(g_nccl.GroupStart());
+  LBM_NCCL_GROUP_BEGIN();
   for (int l = 0; l < d->nlat; l++)
   {
     double* f = d->buf[l][which];
@@ -164,7 +182,7 @@ int comm_exchange(lbm_domain* d, int which, cudaStream_t st)
       }
     }
   }
-  LBM_NCCL(g_nccl.GroupEnd());
+  LBM_NCCL_GROUP_END();
   d->launches++;
   return LBM_OK;
 }
@@ -180,7 +198,7 @@ int comm_exchange_planes(lbm_domain* d, double* base, int nplanes)
   const int Xl = d->g.Xl;
   const size_t n = (size_t)2 * pm;
   const bool has_dn = d->cfg.x0 > 0, has_up = d->cfg.x1 < d->cfg.X;
-  LBM_NCCL(g_nccl.GroupStart());
+  LBM_NCCL_GROUP_BEGIN();
   for (int f = 0; f < nplanes; f++)
   {
     double* pl = base + (long long)f * mplane;
@@ -196,7 +214,7 @@ int comm_exchange_planes(lbm_domain* d, double* base, int nplanes)
       LBM_NCCL(g_nccl.Recv(pl, n, ncclFloat64, c->rank - 1, c->comm, d->stream));                      // rows -2, -1
     }
   }
-  LBM_NCCL(g_nccl.GroupEnd());
+  LBM_NCCL_GROUP_END();
   d->launches++;
   return LBM_OK;
 }
@@ -212,14 +230,14 @@ int comm_allreduce_max(lbm_domain* d, double* dev_value)
   LBM_CUDA(cudaMalloc(&all, sizeof(double) * P));
   auto run = [&]() -> int {
     LBM_CUDA(cudaMemcpyAsync(all + c->rank, dev_value, sizeof(double), cudaMemcpyDeviceToDevice, d->stream));
-    LBM_NCCL(g_nccl.GroupStart());
+    LBM_NCCL_GROUP_BEGIN();
     for (int k = 0; k < P; k++)
     {
       if (k == c->rank) continue;
       LBM_NCCL(g_nccl.Send(dev_value, 1, ncclFloat64, k, c->comm, d->stream));
       LBM_NCCL(g_nccl.Recv(all + k, 1, ncclFloat64, k, c->comm, d->stream));
     }
-    LBM_NCCL(g_nccl.GroupEnd());
+    LBM_NCCL_GROUP_END();
     std::vector<double> host(P);
     LBM_CUDA(cudaMemcpyAsync(host.data(), all, sizeof(double) * P, cudaMemcpyDeviceToHost, d->stream));
     LBM_CUDA(cudaStreamSynchronize(d->stream));
@@ -249,7 +267,7 @@ int comm_ibm_share(lbm_domain* d, cudaStream_t st)
   CommState* c = d->comm;
   IbmState& ib = d->ibm;
   const int RC = (int)(ib.c1 - ib.c0);
-  LBM_NCCL(g_nccl.GroupStart());
+  LBM_NCCL_GROUP_BEGIN();
   for (int k = 0; k < c->n_ranks; k++)
   {
     if (k == c->rank) continue;
@@ -263,7 +281,7 @@ int comm_ibm_share(lbm_domain* d, cudaStream_t st)
     LBM_NCCL(g_nccl.Recv(ib.d_rho + (size_t)lo * RC, theirs, ncclFloat64, k, c->comm, st));
     LBM_NCCL(g_nccl.Recv(ib.d_u + 2 * (size_t)lo * RC, 2 * theirs, ncclFloat64, k, c->comm, st));
   }
-  LBM_NCCL(g_nccl.GroupEnd());
+  LBM_NCCL_GROUP_END();
   d->launches++;
   return LBM_OK;
 }
@@ -393,6 +411,13 @@ int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks
               x0, x1, d->cfg.x0, d->cfg.x1);
     return LBM_ERR_INVALID;
   }
+  if (d->tp && d->have_state)
+  {
+    // the two-phase imports (lbm_init_two_phase, lbm_set_f, lbm_set_u) swap the moment-plane halos of the cuts when they
+    // run; a ring joined afterwards would take its first step with replicate-padded halos at every cut
+    set_error("lbm_comm_init: a two-phase domain joins the ring BEFORE its state is imported (lbm_init_two_phase / lbm_set_f / lbm_set_u)");
+    return LBM_ERR_INVALID;
+  }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   comm_release(d);
   LBM_TRY(load_nccl());
@@ -434,14 +459,14 @@ int lbm_comm_check(lbm_domain* d)
   LBM_CUDA(cudaMalloc(&dev, sizeof(double) * rec.size()));
   auto exchange = [&]() -> int {
     LBM_CUDA(cudaMemcpyAsync(dev + (size_t)c->rank * NREC, mine, sizeof(double) * NREC, cudaMemcpyHostToDevice, d->stream));
-    LBM_NCCL(g_nccl.GroupStart());
+    LBM_NCCL_GROUP_BEGIN();
     for (int k = 0; k < P; k++)
     {
       if (k == c->rank) continue;
       LBM_NCCL(g_nccl.Send(dev + (size_t)c->rank * NREC, NREC, ncclFloat64, k, c->comm, d->stream));
       LBM_NCCL(g_nccl.Recv(dev + (size_t)k * NREC, NREC, ncclFloat64, k, c->comm, d->stream));
     }
-    LBM_NCCL(g_nccl.GroupEnd());
+    LBM_NCCL_GROUP_END();
     LBM_CUDA(cudaMemcpyAsync(rec.data(), dev, sizeof(double) * rec.size(), cudaMemcpyDeviceToHost, d->stream));
     LBM_CUDA(cudaStreamSynchronize(d->stream));
     return LBM_OK;

@@ -968,18 +968,21 @@ int lbm_create(const lbm_config* cfg, lbm_domain** out)
       }
       cudaMemset(d->buf[l][b], 0, bytes);
     }
-  LBM_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-  {
+  // streams and events: a failure here goes through lbm_destroy like the allocation failures above (no leaked slab)
+  auto make_streams_and_events = [&]() -> int {
+    LBM_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     // the side chain is a string of tiny kernels: give it priority so it slips in between the
     // blocks of the bulk launch instead of queueing behind them
     int lo = 0, hi = 0;
     LBM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     LBM_CUDA(cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, hi));
-  }
-  LBM_CUDA(cudaEventCreate(&d->ev_begin));
-  LBM_CUDA(cudaEventCreate(&d->ev_end));
-  for (cudaEvent_t* e : {&d->ev_ready, &d->ev_early, &d->ev_side, &d->ev_stage, &d->ev_packet, &d->ev_ibm, &d->ev_ibm_got})
-    LBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    LBM_CUDA(cudaEventCreate(&d->ev_begin));
+    LBM_CUDA(cudaEventCreate(&d->ev_end));
+    for (cudaEvent_t* e : {&d->ev_ready, &d->ev_early, &d->ev_side, &d->ev_stage, &d->ev_packet, &d->ev_ibm, &d->ev_ibm_got})
+      LBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return LBM_OK;
+  };
+  if (int s = make_streams_and_events(); s != LBM_OK) { lbm_destroy(d); return s; }
   if (cfg->model == LBM_MODEL_MRTCG || cfg->model == LBM_MODEL_RK || cfg->model == LBM_MODEL_MRT_CSF)
   {
     int s = tp_create(d);
@@ -1300,6 +1303,9 @@ int lbm_synchronize(lbm_domain* d)
   if (!d) { set_error("null domain"); return LBM_ERR_INVALID; }
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   LBM_CUDA(cudaStreamSynchronize(d->stream));
+  // the tail of the last step's side chain (ghost rows, the next step's IBM pre-pass) and a pending snapshot copy
+  if (d->side) LBM_CUDA(cudaStreamSynchronize(d->side));
+  if (d->copy) LBM_CUDA(cudaStreamSynchronize(d->copy));
   return LBM_OK;
 }
 

@@ -193,6 +193,15 @@ def _in(a):
     return a, a.ctypes.data_as(dp)
 
 
+def _shaped(a, shape, what):
+    """contiguous fp64 view of `a` and its pointer; the C ABI takes raw pointers, so a wrong shape (a global array handed
+    to a slab, a short vector) would make the library read host memory out of bounds — refuse it here"""
+    a, p = _in(a)
+    if a.size != int(np.prod(shape)) or (a.ndim == len(shape) and a.shape != tuple(shape)):
+        raise ValueError(f"{what}: expected shape {tuple(shape)}, got {a.shape}")
+    return a, p
+
+
 def version():
     return load().lbm_version().decode()
 
@@ -214,7 +223,7 @@ def default_config(**kw):
     return cfg
 
 
-def bc_op(**kw):
+def bc_op(_rows=None, **kw):
     op = BcOp()
     load().lbm_bc_op_default(C.byref(op))
     keep = None
@@ -222,7 +231,7 @@ def bc_op(**kw):
         if k == "uw":
             op.uw[0], op.uw[1] = v
         elif k == "per_row":
-            keep, ptr = _in(v)
+            keep, ptr = _in(v) if _rows is None else _shaped(v, (_rows,), "bc_add per_row (one value per GLOBAL row)")
             op.per_row = ptr
         else:
             setattr(op, k, v)
@@ -257,7 +266,7 @@ class Domain:
         _chk(self.lib.lbm_bc_clear(self.h))
 
     def bc_add(self, **kw):
-        op = bc_op(**kw)
+        op = bc_op(_rows=self.cfg.X, **kw)
         _chk(self.lib.lbm_bc_add(self.h, C.byref(op)))
 
     def bc_add_solid(self, solid, lattice=0):
@@ -289,7 +298,7 @@ class Domain:
         _chk(self.lib.lbm_preset_free_stream(self.h, uwx, uwy))
 
     def preset_sedimentation(self, u_lb, C_w, R23, C28, C38):
-        a, p = _in(C_w)
+        a, p = _shaped(C_w, (self.cfg.X,), "preset_sedimentation C_w (one value per GLOBAL row)")
         _chk(self.lib.lbm_preset_sedimentation(self.h, u_lb, p, R23, C28, C38))
 
     def preset_mrtcg(self):
@@ -300,8 +309,7 @@ class Domain:
 
     # ---- state
     def set_f(self, f, lattice=0):
-        a, p = _in(f)
-        assert a.shape == (self.Xl, self.Y, 9), a.shape
+        a, p = _shaped(f, (self.Xl, self.Y, 9), "set_f")
         _chk(self.lib.lbm_set_f(self.h, lattice, p))
 
     def get_f(self, lattice=0):
@@ -340,11 +348,11 @@ class Domain:
         _chk(self.lib.lbm_comm_check(self.h))
 
     def set_u(self, u):
-        a, p = _in(u)
+        a, p = _shaped(u, (self.Xl, self.Y, 2), "set_u")
         _chk(self.lib.lbm_set_u(self.h, p))
 
     def init_equilibrium(self, rho, u, kind=EQ_INCOMPRESSIBLE, lattice=0):
-        r, rp = _in(rho); uu, up = _in(u)
+        r, rp = _shaped(rho, (self.Xl, self.Y, 1), "init_equilibrium rho"); uu, up = _shaped(u, (self.Xl, self.Y, 2), "init_equilibrium u")
         _chk(self.lib.lbm_init_equilibrium(self.h, lattice, kind, rp, up))
 
     def get_interfacial_tension(self):
@@ -354,16 +362,19 @@ class Domain:
 
     def set_moments(self, rho, u):
         """MODEL_KBC: m0 / m1 the first step after an import uses (the ulbm drivers' members)"""
-        r, rp = _in(rho); uu, up = _in(u)
+        r, rp = _shaped(rho, (self.Xl, self.Y, 1), "set_moments rho"); uu, up = _shaped(u, (self.Xl, self.Y, 2), "set_moments u")
         _chk(self.lib.lbm_set_moments(self.h, rp, up))
 
     def init_two_phase(self, rho_r, rho_b, u):
-        a, ap = _in(rho_r); b, bp = _in(rho_b); c, cp = _in(u)
+        a, ap = _shaped(rho_r, (self.Xl, self.Y), "init_two_phase rho_r"); b, bp = _shaped(rho_b, (self.Xl, self.Y), "init_two_phase rho_b")
+        c, cp = _shaped(u, (self.Xl, self.Y, 2), "init_two_phase u")
         _chk(self.lib.lbm_init_two_phase(self.h, ap, bp, cp))
 
     # ---- immersed boundary
     def ibm_set_markers(self, xs, ys, m_max=5):
         a, ap = _in(xs); b, bp = _in(ys)
+        if a.ndim != 1 or a.shape != b.shape:
+            raise ValueError(f"ibm_set_markers: xs and ys must be vectors of one length, got {a.shape} and {b.shape}")
         _chk(self.lib.lbm_ibm_set_markers(self.h, ap, bp, len(a), m_max))
 
     def ibm_roi(self):
@@ -380,7 +391,7 @@ class Domain:
     def ibm_force(self, u, rho):
         r0, r1, c0, c1 = self.ibm_roi()
         F = np.empty((r1 - r0, c1 - c0, 2))
-        a, ap = _in(u); b, bp = _in(rho)
+        a, ap = _shaped(u, (self.Xl, self.Y, 2), "ibm_force u"); b, bp = _shaped(rho, (self.Xl, self.Y, 1), "ibm_force rho")
         _chk(self.lib.lbm_ibm_force(self.h, ap, bp, F.ctypes.data_as(dp)))
         return F
 

@@ -326,3 +326,32 @@ def test_sedimentation_golden(orc):
         assert np.abs(rho_g[..., 0] / 3.0 - g["ps"][k]).max() < TOL_STEP, s
         assert np.abs(C_g[..., 0] - g["cs"][k]).max() < TOL_STEP, s
         assert cases.relerr(d.get_f(0), f) < TOL_STEP and cases.relerr(d.get_f(1), gg) < TOL_STEP, s
+
+
+def test_sedimentation_with_immersed_body_vs_oracle(orc):
+    """BASELINE configs[4] as worded ("with immersed-boundary coupling"): driver 15's two lattices plus a body coupled the
+    way test/cylinder_test.cpp couples one.  Not a reference driver; the oracle composes its two pinned steps."""
+    X, Y = 96, 120
+    omega, u_lb, w_s = 1.0 / 0.8, 0.02, 3e-3
+    C_w = np.zeros(X); C_w[-20:] = 1e-3
+    walls = (-30, 70, 90)
+    th = 2 * np.pi * np.arange(40) / 40
+    xs, ys = 30.3 + 7.2 * np.cos(th), 35.6 + 7.2 * np.sin(th)
+    d = cases.sedimentation(X, Y, omega, u_lb, w_s, C_w, walls, ibm=True)
+    d.ibm_set_markers(xs, ys)
+    f, gg, u, rho, Cc = orc.sedimentation_init(X, Y, u_lb, C_w)
+    d.set_f(f, 0)
+    d.set_f(gg, 1)
+    ib = orc.ibm_create(xs, ys)
+    plain_f = f.copy()
+    for n in range(1, 41):
+        orc.sedimentation_step(f, gg, u, rho, Cc, omega, u_lb, w_s, C_w, *walls, ib=ib)
+        d.step(1)
+        if n in (1, 2, 10, 40):
+            assert cases.relerr(d.get_f(0), f) < TOL_STEP and cases.relerr(d.get_f(1), gg) < TOL_STEP, n
+    orc.ibm_destroy(ib)
+    # the body is felt: the state differs from the run without it
+    pf, pg, pu, prho, pC = orc.sedimentation_init(X, Y, u_lb, C_w)
+    for _ in range(40):
+        orc.sedimentation_step(pf, pg, pu, prho, pC, omega, u_lb, w_s, C_w, *walls)
+    assert np.abs(pf - f).max() > 1e-6

@@ -1,13 +1,19 @@
 """GPU parity of the colour-gradient models (MRT colour gradient, Rothman-Keller) against the CPU
 oracle and the reference's golden snapshots."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
+import torch
 
 import cases
 import lbm_b200 as L
 from oracle_lib import MrtcgParams, Oracle, RkParams
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -235,3 +241,67 @@ def test_rk_ragged_and_tiny_grids(orc, Ln):
         orc.rk_step(p, st)
     d.step(6)
     assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12 and cases.relerr(d.get_f(1), st["b_adv"]) < 1e-12
+
+
+def test_rk_diagnostic_fields_vs_oracle_and_golden(orc):
+    """lbm_rk_diagnostics: the fields driver 17 snapshots at the top of every iteration (normal with the 0.1 max|grad|
+    cut, curvature, interfacial tension, eta, kappa, 1/tau, the red colour's omega1/2/3), against the oracle at every
+    step and against the reference driver's own nx / ny / ks / norms / fx / fy / kappas / omegas1 / omegas2 files"""
+    from test_oracle_golden import rk_diag_fields
+
+    g = cases.golden("rk_droplet_101")
+    p = rk_params(101)
+    st = orc.rk_init(p)
+    d = cases.rk(101)
+    d.set_f(st["r_adv"], 0)
+    d.set_f(st["b_adv"], 1)
+    steps = [int(v) for v in g["steps"]]
+    for n in range(steps[-2] + 1):
+        want = orc.rk_diagnostics(p, st)
+        got = d.rk_diagnostics(5e-3)
+        scale = {k: max(float(np.abs(v).max()), 1e-30) for k, v in want.items()}
+        for k in ("phase", "grad", "norm", "n", "K", "Fs", "eta", "kappa", "rparams", "omega1", "omega2", "omega3"):
+            # absolute 1e-12 on O(1) fields, relative on the small ones (Fs ~ 1e-5, omega2 ~ 1e-6)
+            assert np.abs(got[k] - want[k]).max() < 1e-12 * max(scale[k], 1e-3), (n, k)
+        if n in steps:
+            for name, a in rk_diag_fields(got).items():
+                assert np.abs(a - g[name][steps.index(n)]).max() < 1e-12, (n, name)
+        orc.rk_step(p, st)
+        d.step(1)
+    assert cases.relerr(d.get_f(0), st["r_adv"]) < 1e-12  # asking for diagnostics between steps does not disturb the state
+
+
+def test_rk_diagnostics_error_behaviour():
+    d = cases.mrtcg(16, 16, (0.0, 0.0), 0)
+    with pytest.raises(L.LbmError, match="LBM_MODEL_RK"):
+        d.rk_diagnostics()
+    slab = cases.rk(32, x0=0, x1=16)
+    slab.init_two_phase(np.ones((16, 32)), np.ones((16, 32)), np.zeros((16, 32, 2)))
+    with pytest.raises(L.LbmError, match="monolithic domains or the ranks"):
+        slab.rk_diagnostics()  # a slab outside a ring: no way to reduce max|grad| or to swap the normal's halo
+
+
+def test_rk_driver_writes_all_nineteen_reference_files(tmp_path):
+    """drivers/rk_static_droplet mirrors test/rk_static_droplet_test.cpp:617-635 file for file; the diagnostic stacks
+    (normal, curvature, interfacial tension, kappa, omega1/2/3) equal the reference driver's own output"""
+    exe = os.path.join(ROOT, "drivers", "bin", "rk_static_droplet")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "drivers")], stdout=subprocess.DEVNULL)
+    r = subprocess.run([exe, "101", "12"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    g = cases.golden("rk_droplet_101")
+    names = {"r-fs": "r_fs", "b-fs": "b_fs", "ux": "ux", "uy": "uy", "nx": "nx", "ny": "ny", "rho": "rho", "rhon": "rhon", "ks": "ks",
+             "norms": "norms", "fx": "fx", "fy": "fy", "gradx": "gradx", "grady": "grady", "rparams": "rparams", "kappas": "kappas",
+             "omegas1": "omegas1", "omegas2": "omegas2", "omegas3": None}
+    got = {}
+    for fname, key in names.items():
+        path = tmp_path / f"rk-static-droplet-{fname}.pt"
+        assert path.exists(), fname
+        a = list(torch.jit.load(str(path)).parameters())[0].numpy()
+        assert a.shape[:2] == (101, 101) and a.shape[-1] == 12, (fname, a.shape)
+        got[fname] = a
+        if key is not None:
+            for k, s in enumerate(int(s) for s in g["steps"]):
+                if s < 12:
+                    assert np.abs(a[..., s] - g[key][k]).max() < 1e-12, (fname, s)
+    assert np.abs(got["omegas3"] - (got["omegas1"] + got["omegas2"])).max() < 1e-15

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 what=${1:-tests}
 case "$what" in
   tests)
-    timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
+    timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -15
     timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
     ;;
   bench)
