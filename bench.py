@@ -3,18 +3,28 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
     python bench.py --impl reference --steps K --warmup W    (the reference's CPU path, rank 0 only)
-    python bench.py --workload mrtcg_rt|rk_droplet|sedimentation|poiseuille|kbc_shear|csf_rt|cylinder_bb   (the other BASELINE.json configs)
+    python bench.py --workload mrtcg_rt|rk_droplet|sedimentation|...   (one of the other configs as the headline, nothing else)
 
-A "step" is one lattice-Boltzmann time step of the whole grid.  Default workload at every N:
-configs[1] of BASELINE.json — flow past a cylinder, D2Q9 BGK, compressible equilibrium,
-immersed-boundary cylinder (multi-direct forcing), anti-bounce-back inlet/outlet rows, specular
-side columns (test/cylinder_test.cpp of the reference), 8192 x 8192 nodes PER GPU (weak scaling:
-the global grid is (8192 N) x 8192, slab-decomposed along axis 0 like test/decompose_domain.cpp).
-Prints ONE JSON line on rank 0.
+A "step" is one lattice-Boltzmann time step of the whole grid.  Headline workload at every N: configs[1] of BASELINE.json —
+flow past a cylinder, D2Q9 BGK, compressible equilibrium, immersed-boundary cylinder (multi-direct forcing),
+anti-bounce-back inlet/outlet rows, specular side columns (test/cylinder_test.cpp of the reference), 8192 x 8192 nodes PER
+GPU (weak scaling: the global grid is (8192 N) x 8192, slab-decomposed along axis 0 like test/decompose_domain.cpp).
+
+The K-step block is timed with CUDA events on the domain's stream (max over ranks); it is repeated until about half a
+second of device time has been seen (at least 3, at most 50 blocks) and the MEDIAN block is reported — every block is
+exactly K steps.  Rank 0 prints ONE JSON line.  Beside the headline the same line carries
+  other_workloads  N = 1: every other BASELINE.json config at its named size (device-resident value + roofline of its
+                   dominant kernel); every N: `mrtcg_rt_weak`, the MRT colour-gradient step at 8192 x 16384 nodes per GPU —
+                   the model with two-row moment-plane halos — so that the 1 -> 8 GPU records hold a curve for it too
+  ring_parity      N > 1: before anything is timed, every model on a small grid over THIS ring of N ranks against the
+                   monolithic run on rank 0's GPU (bit_exact or the relative error), lbm_comm_check and the ring-wide
+                   max of the RK diagnostics included
+The CPU baseline (N = 1 only) runs after all GPU work, so no GPU idles in a collective while host cores are timed.
 """
 import argparse
 import ctypes
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,6 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "lattice-boltzmann-method_b200", "python"))
 
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md
+CSF_FUSED_DEFAULT = "0"          # the library's default for LBM_CSF_FUSED (csrc/lbm_two_phase.cu: tp_create)
 
 W9 = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
 CX9 = np.array([0, 1, 0, -1, 0, 1, -1, -1, 1], dtype=np.float64)
@@ -55,6 +66,11 @@ WORKLOADS = {
                      driver="test/mrtcg_rayleigh_taylor.cpp",
                      what="MRT colour-gradient Rayleigh-Taylor (mrtcg-rayleigh-taylor-gamma3.toml), two lattices",
                      cpu_sample=512),
+    # configs[2] per slab of a ring: what every N runs beside the headline (two-row moment-plane halos at every cut)
+    "mrtcg_rt_weak": dict(X=8192, Y=16384, bytes=352.0, nlat=2, kernel="k_tp_fused<MRTCG,PIPE>",
+                          driver="test/mrtcg_rayleigh_taylor.cpp",
+                          what="MRT colour-gradient Rayleigh-Taylor (mrtcg-rayleigh-taylor-gamma3.toml), two lattices, 8192 rows of 16384 columns per GPU",
+                          cpu_sample=512),
     # configs[3]
     "rk_droplet": dict(X=4096, Y=4096, bytes=304.0, nlat=2, kernel="k_tp_fused<RK,PIPE>",
                        driver="test/rk_static_droplet_test.cpp",
@@ -89,6 +105,11 @@ RK_BLUE = dict(rho_0=1.0, alpha=0.2, A=1e-4, nu=0.14, beta=-0.7)
 RT_FG = (6.25e-6, 0.0)
 
 
+OTHERS_N1 = ["poiseuille", "mrtcg_rt", "rk_droplet", "sedimentation", "sedimentation_ibm", "kbc_shear", "csf_rt", "cylinder_bb",
+             "mrtcg_rt_weak"]
+OTHERS_RING = ["mrtcg_rt_weak"]
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -102,6 +123,11 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="edge of the square grid the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip other_workloads (they run only beside the default headline)")
+    ap.add_argument("--no-ring-parity", action="store_true")
+    ap.add_argument("--others", default="", help="comma-separated subset of other_workloads")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step pair as a CUDA graph (auto: grids below 2^24 nodes on one GPU, where launches bound the step)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.X = args.X or wl["X"]
@@ -113,12 +139,43 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------
 # workload description (shared by both arms)
 # ---------------------------------------------------------------------------------------------
+PARAMETERS_TOML = os.path.join(ROOT, "configs", "parameters.toml")
+
+
 def lattice_parameters():
-    """omega and u_lb exactly as params::lattice derives them from configs/parameters.toml"""
+    """B200 arm: omega and u_lb as the product's TOML surface derives them (lbm_params_from_toml = params::lattice)"""
     import lbm_b200 as L
 
-    p = L.params_from_toml(os.path.join(ROOT, "configs", "parameters.toml"), False)
+    p = L.params_from_toml(PARAMETERS_TOML, False)
     return p.omega, p.u
+
+
+def reference_lattice_parameters():
+    """CPU arms: the same two numbers WITHOUT the product library — the reference's own params::lattice (oracle/_ref) where it
+    compiled, else the C port fed from a plain TOML read"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    if oracle_lib.have_ref():
+        p = oracle_lib.Ref().params(PARAMETERS_TOML, False)
+        return float(p["omega"]), float(p["u"])
+    import tomllib
+
+    with open(PARAMETERS_TOML, "rb") as fh:
+        t = tomllib.load(fh)
+    fl, la = t["flow"], t["lattice"]
+    p = oracle_lib.Oracle().params_lattice(fl["initial_density"], fl["kinematic_viscosity"], fl["characteristic_velocity"],
+                                           fl["characteristic_length"], la["relaxation_time"], la["lattice_spacing"],
+                                           la["x_multiplier"], la["y_multiplier"])
+    return float(p["omega"]), float(p["u"])
+
+
+def host_threads():
+    """host cores this process may use (the CPU arms set their thread count to this explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def channel_constants(H, W, u_max=0.1030985714):
@@ -190,6 +247,7 @@ def droplet_densities(Ln, radius, r0, r1):
 
 
 def workload_config(args, n):
+    """the `config` object of both arms' lines (identical for one command line)"""
     wl = WORKLOADS[args.workload]
     gb = args.X * args.Y * 72.0 * wl["nlat"] / 1e9
     return {
@@ -198,21 +256,29 @@ def workload_config(args, n):
         "l2": f"inputs larger than L2 (2 x {gb:.1f} GB of populations per GPU), no flush needed" if gb > 0.5 else
               f"populations per GPU: 2 x {gb * 1e3:.0f} MB (fits the 126 MB L2 when below that: reported as such)",
         "reference_driver": wl["driver"],
+        "cpu_sample": f"CPU arms (cpu_baseline, --impl reference) time a {args.cpu_sample}x{args.cpu_sample} crop of this workload, not the full grid",
     }
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU arms
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_mlups(workload, edge, warmup, steps):
-    """The reference's own CPU implementation (oracle/_ref: unmodified sources on CPU libtorch, all host
-    threads) where the harness exposes the workload's loop (cylinder); the plain-C oracle port otherwise.
+def cpu_reference_mlups(workload, edge, warmup, steps, threads=0):
+    """The reference's own CPU implementation (oracle/_ref: unmodified sources on CPU libtorch) where the harness exposes
+    the workload's loop; the plain-C oracle port otherwise.  `threads` host threads (0 = all this process may use), set
+    EXPLICITLY on both libraries: a launcher's OMP_NUM_THREADS=1 (torch.distributed.run exports it) must not shrink the
+    baseline.  Nothing here loads the product library.
     Returns (MLUPS, seconds per step, kind, cores, sample description)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
 
-    omega, u_lb = lattice_parameters()
-    port_cores = os.cpu_count() or 1  # the port's loops are OpenMP-parallel (oracle/Makefile: -fopenmp when available)
+    threads = threads or host_threads()
+    if workload == "mrtcg_rt_weak":
+        workload = "mrtcg_rt"
+    omega, u_lb = reference_lattice_parameters()
+    if oracle_lib.have_ref():
+        oracle_lib.Ref().lib.ref_set_num_threads(threads)
+    port_cores = oracle_lib.Oracle().num_threads(threads)  # the port's loops are OpenMP-parallel (oracle/Makefile: -fopenmp when available)
 
     def timed(step_fn):
         for _ in range(warmup):
@@ -351,16 +417,8 @@ def cpu_baseline_leg(workload, edge, target_seconds=12.0):
            "sample": f"{desc}, {steps} steps after 1 warm-up ({sec * steps:.1f} s of CPU work)", "ms_per_step": sec * 1e3}
     if kind == "reference":
         # the reference also on ONE host thread (at::set_num_threads(1)), a few steps of the same crop
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_lib
-
-        ref = oracle_lib.Ref()
-        ref.lib.ref_set_num_threads(1)
-        try:
-            one, _, _, _, _ = cpu_reference_mlups(workload, edge, 1, int(min(steps, max(2, round(4.0 / max(sec * cores, 1e-6))))))
-            out["single_thread"] = {"value": one, "unit": "MLUPS", "cores": 1}
-        finally:
-            ref.lib.ref_set_num_threads(cores)
+        one, _, _, _, _ = cpu_reference_mlups(workload, edge, 1, int(min(steps, max(2, round(4.0 / max(sec * cores, 1e-6))))), threads=1)
+        out["single_thread"] = {"value": one, "unit": "MLUPS", "cores": 1}
     return out
 
 
@@ -370,7 +428,7 @@ def run_reference_arm(args):
         return
     edge = args.cpu_sample
     mlups, sec, kind, cores, desc = cpu_reference_mlups(args.workload, edge, args.warmup, args.steps)
-    sample = f"{desc}, {args.steps} steps after {args.warmup} warm-up"
+    sample = f"{desc}, {args.steps} steps after {args.warmup} warm-up, {cores} host threads set explicitly"
     line = {
         "impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -477,7 +535,9 @@ class Case:
         self.X, self.Y = args.X, args.Y
         self.Xg = args.X * world
         self.x0, self.x1 = rank * args.X, (rank + 1) * args.X
-        self.name = args.workload
+        self.label = args.workload
+        self.name = "mrtcg_rt" if args.workload == "mrtcg_rt_weak" else args.workload  # same model, per-slab grid
+        self.pin = getattr(args, "pin", True)
         self.omega, self.u_lb = lattice_parameters()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -507,7 +567,8 @@ class Case:
             self.d.comm_init(ident, self.world, self.rank)
 
     def pinned(self, shape):
-        t = self.torch.empty(shape, dtype=self.torch.float64, pin_memory=True)
+        """host buffer of the state: pinned for the headline (its e2e leg times the copies), pageable otherwise"""
+        t = self.torch.empty(shape, dtype=self.torch.float64, pin_memory=self.pin)
         return t, t.numpy()
 
     def setup(self):
@@ -604,6 +665,310 @@ class Case:
         return self.X * (2 * ((self.Y - 3) // 2))
 
 
+# ---------------------------------------------------------------------------------------------
+# B200 arm: one measured workload
+# ---------------------------------------------------------------------------------------------
+class Ctx:
+    """process-wide handles of the B200 arm"""
+
+    def __init__(self, L, torch, dist, rank, world, local):
+        self.L, self.torch, self.dist, self.rank, self.world, self.local = L, torch, dist, rank, world, local
+
+    def fresh_id(self):
+        """one NCCL unique id per ring: rank 0 creates it, everyone receives it"""
+        ident = [self.L.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(ident, src=0)
+        return ident[0]
+
+    def barrier(self, d=None):
+        if d is not None:
+            d.synchronize()
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v):
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_rows(self, a):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, a)
+        return np.concatenate(out, axis=0)
+
+
+def want_graph(mode, X, Y, world):
+    """CUDA-graph replay of the step pair (lbm_use_graph): one process, no ring (the library refuses it there)"""
+    if world > 1 or mode == "off":
+        return False
+    return mode == "on" or X * Y < (1 << 24)
+
+
+def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sampler=None, cpu_sample=0):
+    """Device-resident MLUPS of one workload (median K-step block), the roofline of its dominant kernel and, for the
+    headline, the end-to-end figure through the C ABI with pinned host buffers."""
+    import types
+
+    L, rank, world = ctx.L, ctx.rank, ctx.world
+    wl = WORKLOADS[workload]
+    a = types.SimpleNamespace(workload=workload, X=X, Y=Y, pin=pin, gpus=world, cpu_sample=cpu_sample or wl["cpu_sample"])
+    case = Case(L, ctx.torch, a, rank, world, ctx.local)
+    d = case.d
+    if world > 1:
+        case.comm_init(ctx.fresh_id())
+    case.setup()
+    if world > 1:
+        d.comm_check()  # every rank's setup agrees (grid, model, marker lists of bodies across cuts) or LBM_ERR_COMM — not a hang
+    case.import_state()
+    d.step(warmup)
+    graph = want_graph(graph_mode, X, Y, world)
+    if graph:
+        d.use_graph(True)
+        d.step(4)  # reaches the steady state and captures the pair
+    ctx.barrier(d)
+
+    # ---- device-resident timed region: blocks of exactly K steps, CUDA events on the domain's stream
+    d.profile_enable(not graph)
+    launches0 = d.kernel_launches()
+    block_ms, target = [], None
+    if sampler is not None:
+        sampler.mark_begin()
+    while target is None or len(block_ms) < target:
+        ctx.barrier(d)
+        d.step(steps)
+        d.synchronize()
+        block_ms.append(ctx.max_over_ranks(d.last_step_ms()))
+        if target is None:
+            target = int(min(50, max(3, math.ceil(500.0 / max(block_ms[0], 1e-3)))))
+    ctx.barrier(d)
+    if sampler is not None:
+        sampler.mark_end()
+    nb = len(block_ms)
+    launches = (d.kernel_launches() - launches0) // nb
+    ms = float(np.median(block_ms))
+    prof_steps = steps * nb
+    if graph:
+        # the graph replays without per-kernel events: the dominant kernel's duration comes from one more K-step block of
+        # plain launches of the same kernel (same grid, same launch configuration), right after the timed blocks
+        d.use_graph(False)
+        d.profile_enable(True)
+        d.step(steps)
+        d.synchronize()
+        prof_steps = steps
+    names = [("interior", L.PROF_INTERIOR), ("boundary", L.PROF_BOUNDARY), ("fixup", L.PROF_FIXUP), ("ghost", L.PROF_GHOST),
+             ("ibm", L.PROF_IBM), ("moments", L.PROF_MOMENTS)]
+    prof = {n: d.profile_read(c) for n, c in names}
+    dom_ms, dom_n = prof["interior"]
+    d.profile_enable(False)
+    mlups = (case.Xg * case.Y) * steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers: import the state (H2D), K steps, export rho,u (D2H); median of 3
+    e2e = None
+    if with_e2e:
+        runs = []
+        for _ in range(3):
+            ctx.barrier(d)
+            t0 = time.perf_counter()
+            h2d = case.import_state()
+            t1 = time.perf_counter()
+            d.step(steps)
+            d2h = case.export_moments()
+            d.synchronize()
+            t2 = time.perf_counter()
+            runs.append((ctx.max_over_ranks(t2 - t0), t1 - t0, t2 - t1))
+        sec, imp, rest = sorted(runs)[1]
+        e2e = {"value": (case.Xg * case.Y) * steps / sec / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
+               "what": f"initial fields from pinned host (the drivers' u, rho -> equilibrium; populations for the ADE / two-phase "
+                       f"imports) + lbm_step({steps}) + lbm_get_moments to pinned host, per rank; median of 3 repetitions",
+               "seconds": sec, "import_seconds": imp, "steps_and_export_seconds": rest,
+               "rho_mean": float(case.rho_t.mean())}
+
+    peak, peak_src = measured_hbm_peak()
+    B = wl["bytes"]
+    nodes_per_step = case.dominant_nodes()
+    achieved = B * nodes_per_step * prof_steps / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
+    per_gpu = mlups / world
+    kernel = wl["kernel"]
+    if case.name == "csf_rt" and os.environ.get("LBM_CSF_FUSED", CSF_FUSED_DEFAULT) != CSF_FUSED_DEFAULT:
+        kernel = {"0": "k_csf_collide_ring<PULL> (LBM_CSF_FUSED=0: three passes)", "1": "k_csf_fused (LBM_CSF_FUSED=1: one pass)"}[os.environ["LBM_CSF_FUSED"]]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None,
+                "traffic": ncu_traffic_per_launch(case.name, X, Y),
+                "kernel": kernel, "bytes_per_node": B, "algorithmic_bytes_per_step": B * nodes_per_step,
+                "launches_per_step": dom_n / prof_steps if prof_steps else 0, "kernel_ms_per_step": dom_ms / prof_steps,
+                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0 if achieved else None,
+                "whole_step_frac_per_gpu": B * per_gpu * 1e6 / 1e9 / peak,
+                "whole_step_frac_per_gpu_of_nominal_8TBs": B * per_gpu * 1e6 / 1e9 / 8000.0,
+                "share_of_step": (dom_ms / prof_steps) / (ms / steps),
+                "other_spans_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items() if v[1] and k != "interior"},
+                "timed_in": ("one more K-step block of plain launches after the timed blocks (those replay a CUDA graph)" if graph
+                             else "the timed blocks themselves (CUDA events around every launch of the kernel, rank 0)"),
+                "note": f"achieved = {B:.0f} B x nodes the dominant kernel owns per step / summed duration of its launches; listed "
+                        "nodes, stages, ghost rows and the IBM pre-pass run on a side stream under the bulk launch"}
+    out = {"value": mlups, "ms_per_step": ms / steps, "steps": steps, "blocks": nb, "block_ms": [round(v, 4) for v in block_ms],
+           "cuda_graph": graph, "grid_per_gpu": [X, Y], "global_grid": [case.Xg, Y], "gpu_launches": launches, "roofline": roofline,
+           "e2e": e2e, "what": wl["what"], "reference_driver": wl["driver"]}
+    d.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm, N > 1: the ring against the monolithic run, on this ring, before anything is timed
+# ---------------------------------------------------------------------------------------------
+def ring_parity(ctx):
+    """Every model family on a small grid over the ring of `world` ranks (lbm_comm_init: NCCL send/recv ghost rows, moment
+    and normal halos, pressure packets, an immersed body across every cut) against the monolithic domain on rank 0's GPU.
+    No oracle here: slabs must reproduce the single-GPU run, which the -m gpu tests tie to the oracle.  Returns on rank 0
+    {case: "bit_exact" | relative error}; a rank that waits for a message nobody sends ends the process after 300 s."""
+    L, rank, world, local = ctx.L, ctx.rank, ctx.world, ctx.local
+    t_start = time.perf_counter()
+    dog = threading.Timer(300.0, lambda: (sys.stderr.write("bench.py: ring_parity did not finish within 300 s (a rank waits for a "
+                                                           "message nobody sends)\n"), sys.stderr.flush(), os._exit(3)))
+    dog.daemon = True
+    dog.start()
+    out = {}
+    omega, u_lb = lattice_parameters()
+
+    def verdict(pairs):
+        if all(np.array_equal(a, b) for a, b in pairs):
+            return "bit_exact"
+        return max(float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) for a, b in pairs)
+
+    def run(name, make, init, nsteps, fields):
+        """make(**slab) -> configured Domain (rules, markers); init(d, x0, x1) imports rows [x0, x1); fields(d) -> arrays"""
+        Xg = make.X
+        x0, x1 = L.decompose_rows(Xg, world, rank)
+        d = make(x0=x0, x1=x1, device=local, ring=True)
+        init(d, x0, x1)
+        d.step(nsteps)
+        got = [ctx.gather_rows(a) for a in fields(d)]
+        d.close()
+        if rank == 0:
+            mono = make(x0=0, x1=Xg, device=local, ring=False)
+            init(mono, 0, Xg)
+            mono.step(nsteps)
+            out[name] = verdict(list(zip(got, fields(mono))))
+            mono.close()
+        ctx.barrier()
+
+    class Make:
+        """domain factory: create -> (ring only) lbm_comm_init -> rules -> lbm_comm_check"""
+
+        def __init__(self, X, cfg, rules):
+            self.X, self.cfg, self.rules = X, cfg, rules
+
+        def __call__(self, x0, x1, device, ring):
+            d = L.Domain(L.default_config(X=self.X, x0=x0, x1=x1, device=device, **self.cfg))
+            if ring:
+                d.comm_init(ctx.fresh_id(), world, rank)
+            self.rules(d)
+            if ring:
+                d.comm_check()
+            return d
+
+    rng = np.random.default_rng(11)
+    both = lambda d: (d.get_f(0), d.get_f(1))  # noqa: E731
+
+    # ---- Poiseuille: pressure-periodic packets cross the ring (row 0 <- row X-2, row X-1 <- row 1)
+    X, Y = 8 * world + 5, 33
+    om, rho_in, rho_out = channel_constants(X, Y)
+    f0 = W9 * (1.0 + 0.02 * rng.standard_normal((X, Y, 9)))
+    run("poiseuille", Make(X, dict(model=L.MODEL_BGK, Y=Y, omega=om, equilibrium=L.EQ_INCOMPRESSIBLE), lambda d: d.preset_poiseuille(rho_in, rho_out)),
+        lambda d, a, b: d.set_f(f0[a:b]), 37, lambda d: (d.get_f(),))
+
+    # ---- cylinder: an immersed body whose ROI rows cross every cut of the ring; ABB rows at the two global ends
+    X, Y = 12 * world + 9, 77
+    r = 0.5 * (X - 14)
+    th = 2.0 * np.pi * np.arange(max(16, int(round(2 * np.pi * r)))) / max(16, int(round(2 * np.pi * r)))
+    xs, ys = 0.5 * X + 0.31 + r * np.cos(th), 0.5 * Y + 0.17 + min(r, 30.0) * np.sin(th)
+    fc = W9 * (1.0 + 3.0 * CX9 * u_lb) * (1.0 + 0.01 * rng.standard_normal((X, Y, 9)))
+
+    def cyl_rules(d):
+        d.preset_free_stream(u_lb, 0.0)
+        d.ibm_set_markers(xs, ys)  # every rank gets the list: co-owners of the ROI rows share the solve
+
+    run("cylinder_ibm_across_cuts", Make(X, dict(model=L.MODEL_BGK, Y=Y, omega=omega, equilibrium=L.EQ_COMPRESSIBLE, force=L.FORCE_IBM), cyl_rules),
+        lambda d, a, b: d.set_f(fc[a:b]), 40, lambda d: (d.get_f(),))
+
+    # ---- sedimentation: fluid + advection-diffusion lattice, rectangle walls, inlet column
+    X, Y = 16 * world + 6, 64
+    R23, C28, C38, C_w = sedimentation_geometry(X, Y)
+    R23, C28, C38 = -max(3, X // 4), 20, 26
+    fs = np.broadcast_to((1.0 + 3.0 * CY9 * u_lb) * W9, (X, Y, 9)).copy()
+    cu = CY9 * u_lb
+    gs = np.zeros((X, Y, 9))
+    gs[:, 0, :] = C_w[:, None] * (W9 * (1.0 + 3.0 * cu + 4.5 * cu * cu - 1.5 * u_lb ** 2))[None, :]
+
+    def sed_init(d, a, b):
+        d.set_f(fs[a:b], 0)
+        d.set_f(gs[a:b], 1)
+
+    run("sedimentation_ade", Make(X, dict(model=L.MODEL_BGK_ADE, Y=Y, omega=omega, omega_g=omega, equilibrium=L.EQ_COMPRESSIBLE, w_s=3e-3),
+                                  lambda d: d.preset_sedimentation(u_lb, C_w, R23, C28, C38)), sed_init, 30, both)
+
+    # ---- KBC double shear layer, fully periodic (all nine populations wrap around the ring)
+    X, Y = 8 * world + 4, 40
+    rr_, cc_ = np.arange(X)[:, None] + 0.0 * np.arange(Y)[None, :], np.arange(Y)[None, :] + 0.0 * np.arange(X)[:, None]
+    uk = np.zeros((X, Y, 2))
+    uk[..., 0] = 0.02 * np.tanh(80.0 * (0.25 * X - np.abs(cc_ - 0.5 * X)) / X * 8.0)
+    uk[..., 1] = 0.02 * 0.05 * np.sin(6.2832 * (rr_ + 0.25 * X) / X)
+    ones = np.ones((X, Y, 1))
+
+    def kbc_init(d, a, b):
+        d.init_equilibrium(ones[a:b], uk[a:b], L.EQ_KBC_FRESH)
+        d.set_moments(ones[a:b], uk[a:b])
+
+    run("kbc_periodic", Make(X, dict(model=L.MODEL_KBC, Y=Y, omega=1.0 / (0.5 + 3.0 * 1.70766666e-4)), lambda d: d.preset_periodic()),
+        kbc_init, 30, lambda d: (d.get_f(),))
+
+    # ---- two-phase models: population ghost rows + two-row halos of the moment planes (CSF: and of the normal field)
+    R, C = 16 * world + 6, 40
+    rt = rt_densities(R, C, 0, R)
+    u0 = np.zeros((R, C, 2))
+    tp_init = lambda d, a, b: d.init_two_phase(rt[0][a:b], rt[1][a:b], u0[a:b])  # noqa: E731
+    tp_cfg = dict(Y=C, red=RED, blue=BLUE, sigma=0.1, delta=0.1, Fg=RT_FG, add_force=1)
+    run("mrtcg", Make(R, dict(model=L.MODEL_MRTCG, **tp_cfg), lambda d: d.preset_mrtcg()), tp_init, 12, both)
+    csf_fields = lambda d: both(d) + (d.get_interfacial_tension(),)  # noqa: E731
+    keep = os.environ.get("LBM_CSF_FUSED")
+    for tag, val in (("csf_single_pass", "1"), ("csf_three_pass", "0")):
+        os.environ["LBM_CSF_FUSED"] = val
+        run(tag, Make(R, dict(model=L.MODEL_MRT_CSF, **tp_cfg), lambda d: d.preset_mrtcg()), tp_init, 15, csf_fields)
+    if keep is None:
+        os.environ.pop("LBM_CSF_FUSED", None)
+    else:
+        os.environ["LBM_CSF_FUSED"] = keep
+
+    Ln = 24 * world + 6
+    dr = droplet_densities(Ln, Ln / 4.0, 0, Ln)
+    ur = np.zeros((Ln, Ln, 2))
+    rk_init = lambda d, a, b: d.init_two_phase(dr[0][a:b], dr[1][a:b], ur[a:b])  # noqa: E731
+    rk_make = Make(Ln, dict(model=L.MODEL_RK, Y=Ln, red=RK_RED, blue=RK_BLUE, delta=0.98), lambda d: d.preset_rk())
+    run("rk", rk_make, rk_init, 15, both)
+
+    def rk_diag(d):
+        """the RK driver's diagnostic fields after three steps: max|grad| is reduced over the ring (all-to-all of scalars),
+        the normal planes swap halos"""
+        g = d.rk_diagnostics(5e-3)
+        return tuple(g[k] for k in ("phase", "grad", "norm", "n", "K", "Fs", "kappa", "omega1", "omega2"))
+
+    run("rk_diagnostics_ring_max", rk_make, rk_init, 3, rk_diag)
+
+    dog.cancel()
+    if rank != 0:
+        return None
+    bad = {k: v for k, v in out.items() if v != "bit_exact" and not (isinstance(v, float) and v < 1e-12)}
+    out.update({"ranks": world, "green": not bad, "criterion": "bit_exact, or relative error below 1e-12 against the monolithic run",
+                "seconds": time.perf_counter() - t_start})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
 def run_b200_arm(args):
     import torch
 
@@ -622,118 +987,58 @@ def run_b200_arm(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Ctx(L, torch, dist, rank, world, local)
 
-    wl = WORKLOADS[args.workload]
-    case = Case(L, torch, args, rank, world, local)
-    d = case.d
-    if world > 1:
-        ident = [L.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        case.comm_init(ident[0])
-    case.setup()
-
-    def barrier():
-        d.synchronize()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    ring = None
+    if world > 1 and not args.no_ring_parity:
+        ring = ring_parity(ctx)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    case.import_state()
-    d.step(args.warmup)
-    barrier()
-
-    # ---- device-resident timed region: exactly K steps, CUDA events on the domain's stream
-    launches0 = d.kernel_launches()
-    d.profile_enable(True)
-    barrier()
-    sampler.mark_begin()
-    d.step(args.steps)
-    d.synchronize()
-    ms = d.last_step_ms()
-    barrier()
-    sampler.mark_end()
+    head = measure(ctx, args.workload, args.X, args.Y, args.steps, args.warmup, pin=True, with_e2e=not args.no_e2e,
+                   graph_mode=args.graph, sampler=sampler, cpu_sample=args.cpu_sample)
     clocks = sampler.stop() if rank == 0 else None
-    launches = d.kernel_launches() - launches0
-    prof = {name: d.profile_read(cls) for name, cls in
-            [("interior", L.PROF_INTERIOR), ("boundary", L.PROF_BOUNDARY), ("fixup", L.PROF_FIXUP),
-             ("ghost", L.PROF_GHOST), ("ibm", L.PROF_IBM), ("moments", L.PROF_MOMENTS)]}
-    dom_ms = sum(d.profile_read(c)[0] for c in case.dominant_classes())
-    dom_n = sum(d.profile_read(c)[1] for c in case.dominant_classes())
-    d.profile_enable(False)
-    ms = max_over_ranks(ms)
-    mlups = (case.Xg * case.Y) * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with host buffers: import the state (H2D), K steps, export rho,u (D2H)
-    e2e = None
-    if not args.no_e2e:
-        barrier()
-        t0 = time.perf_counter()
-        h2d = case.import_state()
-        t1 = time.perf_counter()
-        d.step(args.steps)
-        d2h = case.export_moments()
-        d.synchronize()
-        t2 = time.perf_counter()
-        sec = max_over_ranks(t2 - t0)
-        e2e = {"value": (case.Xg * case.Y) * args.steps / sec / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-               "what": f"initial fields from pinned host (the drivers' u, rho -> equilibrium; populations for the ADE / two-phase "
-                       f"imports) + lbm_step({args.steps}) + lbm_get_moments to pinned host, per rank",
-               "seconds": sec, "import_seconds": t1 - t0, "steps_and_export_seconds": t2 - t1,
-               "rho_mean": float(case.rho_t.mean())}
+    # ---- the other configs (device-resident value + roofline), only beside the default headline
+    others = {}
+    if args.workload == "cylinder" and not args.no_others:
+        names = [w for w in args.others.split(",") if w] or (OTHERS_N1 if world == 1 else OTHERS_RING)
+        for w in names:
+            wl = WORKLOADS[w]
+            t0 = time.perf_counter()
+            r = measure(ctx, w, wl["X"], wl["Y"], args.steps, args.warmup, pin=False, with_e2e=False, graph_mode=args.graph)
+            rf = r["roofline"]
+            others[w] = {"value": r["value"], "unit": "MLUPS", "ms_per_step": r["ms_per_step"], "steps": r["steps"], "blocks": r["blocks"],
+                         "grid_per_gpu": r["grid_per_gpu"], "global_grid": r["global_grid"], "cuda_graph": r["cuda_graph"],
+                         "gpu_launches": r["gpu_launches"], "what": r["what"], "reference_driver": r["reference_driver"],
+                         "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "bytes_per_node",
+                                                         "kernel_ms_per_step", "launches_per_step", "whole_step_frac_per_gpu",
+                                                         "frac_of_nominal_8TBs", "share_of_step", "timed_in")},
+                         "setup_and_run_seconds": time.perf_counter() - t0}
 
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel, timed with CUDA events on its own stream inside the timed region above
-    peak, peak_src = measured_hbm_peak()
-    B = wl["bytes"]
-    nodes_per_step = case.dominant_nodes()
-    achieved = B * nodes_per_step * args.steps / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
-    per_gpu_mlups = mlups / world
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None,
-                "traffic": ncu_traffic_per_launch(args.workload, args.X, args.Y),
-                "kernel": ("k_csf_fused (LBM_CSF_FUSED=1: one pass)" if args.workload == "csf_rt" and os.environ.get("LBM_CSF_FUSED") == "1"
-                           else wl["kernel"]), "bytes_per_node": B,
-                "algorithmic_bytes_per_step": B * nodes_per_step,
-                "launches_per_step": dom_n / args.steps if args.steps else 0, "kernel_ms_per_step": dom_ms / args.steps,
-                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0 if achieved else None,
-                "whole_step_frac_per_gpu": B * per_gpu_mlups * 1e6 / 1e9 / peak,
-                "whole_step_frac_per_gpu_of_nominal_8TBs": B * per_gpu_mlups * 1e6 / 1e9 / 8000.0,
-                "share_of_step": dom_ms / ms,
-                "other_spans_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()
-                                            if v[1] and k != "interior"},
-                "note": f"achieved = {B:.0f} B x nodes the dominant kernel owns per step / summed duration of its launches "
-                        "(rank 0); listed nodes, stages, ghost rows and the IBM pre-pass run on a side stream under the bulk launch"}
-
-    cpu_baseline = None
-    if not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_leg(args.workload, args.cpu_sample)
-
-    line = {
-        "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-    }
-    print(json.dumps(line), flush=True)
+    # every GPU is done: ranks other than 0 leave; the CPU baseline (N = 1 only) then runs with no GPU waiting on it
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_leg(args.workload, args.cpu_sample)
+
+    line = {
+        "metric": "MLUPS", "value": head["value"], "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "roofline": head["roofline"], "cpu_baseline": cpu_baseline, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+        "clocks": clocks,
+        "timing": {"blocks": head["blocks"], "block_ms": head["block_ms"], "reported": "median block of exactly K steps",
+                   "cuda_graph": head["cuda_graph"]},
+        "other_workloads": others or None, "ring_parity": ring,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():

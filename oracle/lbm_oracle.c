@@ -28,6 +28,22 @@ static double* dalloc(size_t n)
   return p;
 }
 
+/* host threads of the port's OpenMP loops (1 without OpenMP); n > 0 sets the count first.  bench.py's CPU arms state the
+ * count explicitly: a launcher's OMP_NUM_THREADS=1 (torch.distributed.run exports it) must not shrink the baseline. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+int orc_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 void orc_constants(double* w9, double* c18)
 {
   for (int q = 0; q < 9; q++)

@@ -20,6 +20,7 @@ extern "C" {
 #endif
 
 /* ---- constants: src/solver.cpp:12-21 */
+int orc_num_threads(int n);  /* OpenMP threads of the port (n > 0: set first) */
 void orc_constants(double* w9, double* c18);
 
 /* ---- granular ops: src/solver.cpp:23-131 */

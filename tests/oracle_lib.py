@@ -71,6 +71,10 @@ class Oracle:
         L.orc_ibm_force.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, dp]
         L.orc_cylinder_step.argtypes = [dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, dp]
 
+    def num_threads(self, n=0):
+        """OpenMP threads of the port's loops; n > 0 sets the count first"""
+        return int(self.lib.orc_num_threads(int(n)))
+
     # ---- granular ops
     def constants(self):
         w = np.zeros(9); c = np.zeros((2, 9))

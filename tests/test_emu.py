@@ -97,6 +97,17 @@ def test_comm_check_turns_the_missing_marker_list_into_an_error(emu_lib, world):
     assert r.returncode == 0 and f"misuse reported on all {world} ranks" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_bench_ring_parity_leg_over_the_nccl_stand_in(emu_lib, world):
+    """bench.py's ring_parity (what every multi-GPU bench run checks before its timed region: each model family over the ring
+    against the monolithic run, lbm_comm_check, the ring-wide max of the RK diagnostics) on emulated rings"""
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", OMP_NUM_THREADS="1", FAKE_NCCL_TIMEOUT_S="120")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "bench_ring_threads.py"), str(world)], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "'green': True" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("bit_exact") >= 9, r.stdout
+
+
 def test_single_pass_csf_step_on_the_ring(emu_lib):
     """LBM_CSF_FUSED=1 on the slabs of a ring (two 2-row halos between the pre-pass stages): bit-identical to the monolithic run"""
     test_slab_ring_over_the_nccl_stand_in(emu_lib, 3, csf_fused="1")
