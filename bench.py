@@ -10,8 +10,8 @@ flow past a cylinder, D2Q9 BGK, compressible equilibrium, immersed-boundary cyli
 anti-bounce-back inlet/outlet rows, specular side columns (test/cylinder_test.cpp of the reference), 8192 x 8192 nodes PER
 GPU (weak scaling: the global grid is (8192 N) x 8192, slab-decomposed along axis 0 like test/decompose_domain.cpp).
 
-The K-step block is timed with CUDA events on the domain's stream (max over ranks); it is repeated until about half a
-second of device time has been seen (at least 3, at most 50 blocks) and the MEDIAN block is reported — every block is
+The K-step block is timed with CUDA events on the domain's stream (max over ranks); a block shorter than 0.2 s is
+repeated (at least 5 blocks and a quarter of a second of device time, at most 50; longer blocks: 3) and the MEDIAN block is reported — every block is
 exactly K steps.  Rank 0 prints ONE JSON line.  Beside the headline the same line carries
   other_workloads  N = 1: every other BASELINE.json config at its named size (device-resident value + roofline of its
                    dominant kernel); every N: `mrtcg_rt_weak`, the MRT colour-gradient step at 8192 x 16384 nodes per GPU —
@@ -126,8 +126,9 @@ def parse_args():
     ap.add_argument("--no-others", action="store_true", help="skip other_workloads (they run only beside the default headline)")
     ap.add_argument("--no-ring-parity", action="store_true")
     ap.add_argument("--others", default="", help="comma-separated subset of other_workloads")
+    ap.add_argument("--lib", default="", help="development: another build of the library (path) for an A/B run")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step pair as a CUDA graph (auto: grids below 2^24 nodes on one GPU, where launches bound the step)")
+                    help="replay the step pair as a CUDA graph (auto: grids up to 2^24 nodes on one GPU, where launches bound the step)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.X = args.X or wl["X"]
@@ -704,7 +705,7 @@ def want_graph(mode, X, Y, world):
     """CUDA-graph replay of the step pair (lbm_use_graph): one process, no ring (the library refuses it there)"""
     if world > 1 or mode == "off":
         return False
-    return mode == "on" or X * Y < (1 << 24)
+    return mode == "on" or X * Y <= (1 << 24)
 
 
 def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sampler=None, cpu_sample=0):
@@ -742,7 +743,8 @@ def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sa
         d.synchronize()
         block_ms.append(ctx.max_over_ranks(d.last_step_ms()))
         if target is None:
-            target = int(min(50, max(3, math.ceil(500.0 / max(block_ms[0], 1e-3)))))
+            # K steps shorter than 0.2 s: at least 5 blocks and about a quarter of a second of timed work; else 3 blocks
+            target = 3 if block_ms[0] >= 200.0 else int(min(50, max(5, math.ceil(250.0 / max(block_ms[0], 1e-3)))))
     ctx.barrier(d)
     if sampler is not None:
         sampler.mark_end()
@@ -974,6 +976,8 @@ def run_b200_arm(args):
 
     import lbm_b200 as L
 
+    if args.lib:
+        L.LIB_PATH = os.path.abspath(args.lib)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

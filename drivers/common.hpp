@@ -81,15 +81,20 @@ struct Series
   }
 };
 
-inline bool continue_execution()  // utils::continue_execution (src/utils.cpp:7-19)
+// The reference drivers ask before a long run (utils::continue_execution).  Same question and answers on the terminal;
+// here the answer is read line-wise (so "yes" / "no" work and trailing input does not leak into the next question), end of
+// input means no, and LBM_ASSUME_YES=1 answers for unattended runs (batch queues, the tests).
+inline bool continue_execution()
 {
-  char choice{'a'};
-  while (true)
+  if (const char* yes = std::getenv("LBM_ASSUME_YES"); yes && yes[0] == '1') return true;
+  for (std::string line;;)
   {
-    std::cout << "\nDo you want to continue (y/n)? ";
-    if (!(std::cin >> choice)) return false;
-    if (choice == 'y') return true;
-    else if (choice == 'n') return false;
+    std::cout << "\nDo you want to continue (y/n)? " << std::flush;
+    if (!std::getline(std::cin, line)) return false;
+    const auto first = line.find_first_not_of(" \t\r");
+    const char c = first == std::string::npos ? '\0' : line[first];
+    if (c == 'y' || c == 'Y') return true;
+    if (c == 'n' || c == 'N') return false;
     std::cout << "Invalid input. Please enter 'y' or 'n'." << std::endl;
   }
 }

@@ -26,6 +26,7 @@
 
 #include "lbm_internal.hpp"
 #include "lbm_two_phase.cuh"
+#include "lbm_async.cuh"
 
 // L2 eviction hints of the fused kernel (see tp_pull_at); compile-time switch: 1 = the two reads, 2 = + evict_first
 // stores.  A/B on B200 (MRTCG 8192^2): DRAM reads 185 -> 165 -> 157 B/node (ideal 153), but 15.62 / 15.60 / 15.65 GLUPS
@@ -52,6 +53,9 @@ struct TwoPhaseState
   int n_region = 0;
   int rows_per_block = 64;
   bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
+  bool staged = true;                  // k_tp_staged: population rows staged by bulk async copies (LBM_TP_STAGED=0: k_tp_fused)
+  int stages = 0;                      // LBM_TP_NS: stage slots per block (0 = the model's default)
+  bool stash = false;                  // LBM_TP_STASH=1: resident population rows parked in tensor memory (k_tp_staged<.., STASH>)
   double* aux = nullptr;               // TP_CSF: A_COUNT planes in the moment-plane geometry (normal n, interfacial tension Fs)
   int rpb_override = 0;
   // TP_CSF single-pass variant (LBM_CSF_FUSED=1, off by default until it has been measured on the device)
@@ -486,6 +490,212 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused step with the population rows STAGED in shared memory by bulk asynchronous copies (lbm_async.cuh)
+// ------------------------------------------------------------------------------------------------
+// Same strips, bands, ring and plane rules as k_tp_fused, but nothing is pulled through registers and nothing is read
+// twice: for every row r of the band (and its H warm-up rows on either side) one lane issues 18 bulk copies — population
+// q of both lattices, source row r - c_x(q), the strip's column window widened by two columns on either side — into stage
+// slot r mod NS, completed on that slot's mbarrier.  Iteration r waits for row r, forms its moments out of the slot (the
+// +-1 column shift of the pull is an index offset), and collides row r - H out of ITS slot, which is still resident; the
+// copies of rows r+1 .. r+NS-H-1 are in flight meanwhile, independent of what the fp64 work keeps in registers.
+// rho_k, u of the H+1 rows between moments and collision stay in registers of the thread that formed them (same column).
+//   DRAM: every population row segment once per band (+ 2H warm-up rows per band), results written once.
+//   shared memory (MRTCG): NS x 18 x 132 doubles of stages + 3 x 6 x 128 of ring = 111 KB at NS = 5: two blocks per SM.
+template <int MODEL, int NS>
+struct TpStaged
+{
+  using F = TpFused<MODEL>;
+  static constexpr int H = F::H, NR = F::NR;
+  static constexpr int NF = MODEL == TP_MRTCG ? 3 : 1;       // ring fields: phase [, Q_x, Q_y]
+  static constexpr int W = TPF_NT + 4;                        // staged columns per population row: even start <= ys - 1, end >= ys + 128
+  static constexpr int ROW = 18 * W;                          // doubles per staged row
+  static constexpr int USEFUL = F::USEFUL;
+  static constexpr size_t RING_BYTES = sizeof(double) * NF * NR * TPF_NT;
+  static constexpr size_t STAGE_BYTES = sizeof(double) * NS * ROW;
+  static constexpr size_t SMEM = STAGE_BYTES + RING_BYTES + sizeof(uint64_t) * NS;
+  static constexpr int TMEM_COLS = 128;                       // STASH: (H + 1) rows x 36 columns per thread, rounded up to a power of two
+};
+
+// STASH = false: a stage slot keeps its row until that row has been collided (H + 1 resident rows + the rows in flight:
+//                NS >= H + 2; MRTCG at NS = 5: 111 KB per block, two blocks = 8 warps per SM, which is what bounds it —
+//                ncu: DRAM traffic 293 B/node, the minimum, but 0.4 instructions per cycle and scheduler).
+// STASH = true : the thread parks the 18 populations it has just read in TENSOR MEMORY (its own lane, 36 columns per
+//                row, H + 1 rows) and takes them back H rows later for the collision; the stage slot is free as soon as the
+//                moments are formed, so NS = 3 slots (57 KB) + ring: three or four blocks per SM.
+template <int MODEL, int NS, int MINB, bool STASH>
+__global__ void __launch_bounds__(TPF_NT, MINB)
+k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
+            double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const TpParams p,
+            const unsigned char* __restrict__ rowflag, int rows_per_block)
+{
+  using C = TpStaged<MODEL, NS>;
+  constexpr int H = C::H, NR = C::NR, NT = TPF_NT, W = C::W;
+  constexpr int HOLD = STASH ? 0 : H;  // iterations a stage slot stays resident after its moments have been formed
+  static_assert(NS >= HOLD + 2, "at least one row in flight");
+  extern __shared__ double sm[];  // stages [NS][18][W] | ring [NF][NR][NT] | mbarriers [NS]
+  double* stage = sm;
+  double* ring = sm + NS * C::ROW;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + C::NF * NR * NT);
+  auto S = [&](int f, int slot, int col) -> double& { return ring[(f * NR + slot) * NT + col]; };
+
+  const int t = threadIdx.x;
+  const int ys = 1 + blockIdx.x * C::USEFUL - H;         // column of thread 0
+  const int y = ys + t;
+  const int xb = blockIdx.y * rows_per_block;
+  const int xe = min(xb + rows_per_block, g.Xl);
+  const int r0 = xb - H;                                 // first row of the march
+  const int rs0 = max(r0, 0), rs1 = min(xe + H, g.Xl);   // rows whose populations are staged
+  const bool col_ok = y >= -2 && y <= g.Y + 1;           // inside the padded planes
+  const bool col_plane = y < 1 || y > g.Y - 2;           // edge columns (listed nodes) and the padding
+  const bool collider = t >= H && t < NT - H && y >= 1 && y <= g.Y - 2;
+
+  // staged column window [c0, c0 + W) clamped to the row; c0 even (16-byte aligned copies)
+  const int c0 = (ys - 1) & ~1;                           // floor to even, also for negative ys - 1
+  const int lo = max(c0, 0), hi = min(c0 + W, g.pitch);
+  const unsigned seg_bytes = (unsigned)(hi - lo) * (unsigned)sizeof(double);
+  const int my = t + (ys - c0);                          // this thread's column inside a staged segment (before the -c_y shift)
+
+  __shared__ unsigned char sflag[128 + 2 * H + 2];
+  __shared__ uint32_t tmem_slot;
+  for (int k = t; k < xe - xb + 2 * H; k += NT)
+  {
+    const int r = r0 + k;
+    sflag[k] = (r < 0 || r >= g.Xl) ? 1 : rowflag[r];
+  }
+  if (t == 0)
+  {
+    for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+    mbar_init_fence();
+  }
+  uint32_t tmem = 0;
+  if constexpr (STASH) tmem = tmem_alloc<C::TMEM_COLS>(&tmem_slot);  // (contains the block barrier)
+  else __syncthreads();
+
+  // row rr of the march -> stage slot (rr - r0) % NS; every row of the march uses its slot's barrier once (rows without
+  // populations — outside the slab — complete it with zero bytes), so the parity of a wait is ((rr - r0) / NS) & 1
+  auto issue_row = [&](int rr) {
+    if (t >= 32 || rr >= xe + H) return;
+    const int k = rr - r0, slot = k % NS;
+    const bool staged = rr >= rs0 && rr < rs1;
+    if (t == 0) mbar_arrive_expect_tx(&full[slot], staged ? 18u * seg_bytes : 0u);
+    __syncwarp();
+    if (staged && t < 18)
+    {
+      const int l = t / 9, q = t % 9;
+      const double* src = (l == 0 ? rsrc : bsrc) + (long long)q * g.plane + node_off(g, rr - CX(q), lo);
+      bulk_copy_g2s(stage + (size_t)slot * C::ROW + t * W + (lo - c0), src, seg_bytes, &full[slot]);
+    }
+  };
+  for (int rr = r0; rr < r0 + NS - HOLD - (STASH ? 0 : 1); rr++) issue_row(rr);  // every row the loop's refill rule does not reach
+  __syncthreads();  // once per block: every copy is issued behind a barrier that its waiters pass first
+
+  double mrr[H + 1], mrb[H + 1], mux[H + 1], muy[H + 1];  // rho_r, rho_b, u of rows r, r-1, .. r-H at this thread's column
+#pragma unroll
+  for (int k = 0; k <= H; k++) mrr[k] = mrb[k] = mux[k] = muy[k] = 0.0;
+
+  int slot_ring = 0;
+  for (int r = r0; r < xe + H; r++)
+  {
+    const int k = r - r0, sl = k % NS;
+    const double* st_r = stage + (size_t)sl * C::ROW;
+    mbar_wait(&full[sl], (unsigned)(k / NS) & 1u);
+    // ---- A: moments of (r, y) -> ring, registers
+#pragma unroll
+    for (int j = H; j > 0; j--)
+    {
+      mrr[j] = mrr[j - 1];
+      mrb[j] = mrb[j - 1];
+      mux[j] = mux[j - 1];
+      muy[j] = muy[j - 1];
+    }
+    double fr[9], fb[9];
+    if constexpr (STASH)
+    {
+      // every thread takes its 18 populations out of the slot (rows outside the slab: stale shared memory, never used)
+      // and parks them in its tensor-memory lane for the collision H rows later
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+      {
+        fr[q] = st_r[q * W + my - CY(q)];
+        fb[q] = st_r[(9 + q) * W + my - CY(q)];
+      }
+      tmem_store18(tmem + 36u * (unsigned)(k % (H + 1)), fr, fb);
+    }
+    if (col_ok)
+    {
+      double rr_, rb_, ux_, uy_, ph_;
+      if (col_plane || sflag[k])
+      {
+        const long long km = mom_off(mg, r, y);
+        rr_ = mom[M_RR * mg.mplane + km];
+        rb_ = mom[M_RB * mg.mplane + km];
+        ux_ = mom[M_UX * mg.mplane + km];
+        uy_ = mom[M_UY * mg.mplane + km];
+        ph_ = mom[M_PH * mg.mplane + km];
+      }
+      else
+      {
+        if constexpr (!STASH)
+        {
+#pragma unroll
+          for (int q = 0; q < 9; q++)
+          {
+            fr[q] = st_r[q * W + my - CY(q)];
+            fb[q] = st_r[(9 + q) * W + my - CY(q)];
+          }
+        }
+        tp_moments<MODEL>(p, fr, fb, rr_, rb_, ux_, uy_, ph_);
+      }
+      S(0, slot_ring, t) = ph_;
+      if constexpr (MODEL == TP_MRTCG)
+      {
+        const double cq = p.cr * rr_ + p.cb * rb_;
+        S(1, slot_ring, t) = cq * ux_;
+        S(2, slot_ring, t) = cq * uy_;
+      }
+      mrr[0] = rr_;
+      mrb[0] = rb_;
+      mux[0] = ux_;
+      muy[0] = uy_;
+    }
+    if constexpr (STASH) tmem_store_wait();
+    __syncthreads();
+    // a slot is free now: the one this iteration read (STASH) / the one the previous iteration's collision read last
+    issue_row(r - (STASH ? 0 : 1) - HOLD + NS);
+    // ---- B: collision of row x = r - H out of tensor memory / its stage slot, and the ring rows x-H .. x+H
+    const int x = r - H;
+    if constexpr (STASH) tmem_load18(tmem + 36u * (unsigned)((k + 1) % (H + 1)), fr, fb);  // slot of row r - H: (k - H) mod (H + 1)
+    if (x >= xb && collider)
+    {
+      const int sc = (slot_ring + NR - H) % NR;
+      if constexpr (!STASH)
+      {
+        const double* st_x = stage + (size_t)((k - H) % NS) * C::ROW;
+#pragma unroll
+        for (int q = 0; q < 9; q++)
+        {
+          fr[q] = st_x[q * W + my - CY(q)];
+          fb[q] = st_x[(9 + q) * W + my - CY(q)];
+        }
+      }
+      TpStencil st;
+      tp_ring_stencil<MODEL>(ring, sc, t, st);
+      tp_collide<MODEL>(p, fr, fb, mrr[H], mrb[H], mux[H], muy[H], S(0, sc, t), st);
+      double* wr = rdst + node_off(g, x, y);
+      double* wb = bdst + node_off(g, x, y);
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+      {
+        wr[(long long)q * g.plane] = fr[q];
+        wb[(long long)q * g.plane] = fb[q];
+      }
+    }
+    slot_ring = slot_ring + 1 == NR ? 0 : slot_ring + 1;
+  }
+  if constexpr (STASH) tmem_free<C::TMEM_COLS>(tmem);
+}
+
 // moments of a short list of nodes (plain pull) into the planes: the region around listed nodes,
 // the global edge rows and the rows next to a slab cut
 template <int MODEL>
@@ -779,8 +989,18 @@ int tp_create(lbm_domain* d)
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));
+#define LBM_STAGED_ATTR(MODEL, NS, MINB, STASH) \
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_staged<MODEL, NS, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpStaged<MODEL, NS>::SMEM))
+  LBM_STAGED_ATTR(TP_MRTCG, 4, 2, false); LBM_STAGED_ATTR(TP_MRTCG, 5, 2, false); LBM_STAGED_ATTR(TP_MRTCG, 6, 2, false);
+  LBM_STAGED_ATTR(TP_RK, 3, 3, false); LBM_STAGED_ATTR(TP_RK, 4, 2, false); LBM_STAGED_ATTR(TP_RK, 5, 2, false); LBM_STAGED_ATTR(TP_RK, 6, 2, false);
+  LBM_STAGED_ATTR(TP_MRTCG, 2, 4, true); LBM_STAGED_ATTR(TP_MRTCG, 3, 3, true); LBM_STAGED_ATTR(TP_MRTCG, 4, 2, true);
+  LBM_STAGED_ATTR(TP_RK, 2, 4, true); LBM_STAGED_ATTR(TP_RK, 3, 3, true); LBM_STAGED_ATTR(TP_RK, 4, 2, true);
+#undef LBM_STAGED_ATTR
   LBM_TRY(csf_configure());
   if (const char* e = getenv("LBM_TP_PIPE")) tp->pipe = atoi(e) != 0;
+  if (const char* e = getenv("LBM_TP_STAGED")) tp->staged = atoi(e) != 0;
+  if (const char* e = getenv("LBM_TP_NS")) tp->stages = atoi(e);
+  if (const char* e = getenv("LBM_TP_STASH")) tp->stash = atoi(e) != 0;
   if (const char* e = getenv("LBM_TP_RPB")) tp->rpb_override = atoi(e);
   return LBM_OK;
 }
@@ -944,7 +1164,32 @@ static int tp_launch_fused(lbm_domain* d)
   {
     ProfScope ps(d, LBM_PROF_INTERIOR);
     dim3 grid(cdiv(Yi, C::USEFUL), cdiv(d->g.Xl, tp->rows_per_block));
-    if (tp->pipe)
+    if (tp->staged)
+    {
+      // stage slots: H + 1 resident rows + the rows in flight.  MRTCG: 5 slots = 111 KB, two blocks per SM; 4 = 92 KB.
+      // RK: 5 slots = 97 KB (two blocks), 3 = 60 KB (three blocks)
+      // stage slots.  Without the stash: H + 1 resident rows + the rows in flight (default 5).  With it: rows in flight only (default 3)
+      const int ns = tp->stash ? std::max(2, tp->stages > 0 ? tp->stages : 3) : std::max(TpFused<MODEL>::H + 2, tp->stages > 0 ? tp->stages : 5);
+#define LBM_STAGED_LAUNCH(NS, MINB, STASH)                                                                                           \
+  k_tp_staged<MODEL, NS, MINB, STASH><<<grid, TPF_NT, TpStaged<MODEL, NS>::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t],      \
+                                                                                               d->buf[1][t], d->g, tp->mg, tp->mom, tp->p, \
+                                                                                               tp->d_rowflag, tp->rows_per_block)
+      if (tp->stash)
+      {
+        if (ns <= 2) LBM_STAGED_LAUNCH(2, 4, true);
+        else if (ns == 3) LBM_STAGED_LAUNCH(3, 3, true);
+        else LBM_STAGED_LAUNCH(4, 2, true);
+      }
+      else if (ns <= 3)
+      {
+        if constexpr (TpFused<MODEL>::H + 2 <= 3) LBM_STAGED_LAUNCH(3, 3, false);
+      }
+      else if (ns == 4) LBM_STAGED_LAUNCH(4, 2, false);
+      else if (ns == 5) LBM_STAGED_LAUNCH(5, 2, false);
+      else LBM_STAGED_LAUNCH(6, 2, false);
+#undef LBM_STAGED_LAUNCH
+    }
+    else if (tp->pipe)
       k_tp_fused<MODEL, true><<<grid, TPF_NT, C::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
                                                                     tp->mom, tp->p, tp->d_rowflag, tp->rows_per_block);
     else
@@ -1520,6 +1765,11 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
   const bool normal_thread = t >= 2 && t < NT - 2;  // has the phase of its columns y-2 .. y+2 in the ring
   const bool collider = t >= HC && t < NT - HC && y >= 1 && y <= g.Y - 2;
 
+#if LBM_TP_HINTS
+  const unsigned long long pol_first = l2_policy_evict_last(), pol_second = l2_policy_evict_first();
+#else
+  const unsigned long long pol_first = 0ull, pol_second = 0ull;
+#endif
   __shared__ unsigned char sflag[128 + 16];  // flags of rows xb-4 .. xe+4 (outside the slab: everything from the planes)
   for (int k = t; k < xe - xb + 9; k += NT)
   {
@@ -1584,8 +1834,8 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
       if (x >= xb && x < xe && collider)
       {
         double fr[9], fb[9];
-        tp_pull_at(rsrc + node_off(g, x, y), g, fr);
-        tp_pull_at(bsrc + node_off(g, x, y), g, fb);
+        tp_pull_at(rsrc + node_off(g, x, y), g, fr, pol_second);
+        tp_pull_at(bsrc + node_off(g, x, y), g, fb, pol_second);
         const long long k = mom_off(mg, x, y);
         double rr, rb, ux, uy, ph;
         // the same arithmetic on the same inputs as stage A / the pre-pass: identical values, no ring rows for them
@@ -1640,8 +1890,13 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
 #pragma unroll
         for (int q = 0; q < 9; q++)
         {
+#if LBM_TP_HINTS >= 2
+          asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(rdst + q * g.plane + o), "d"(fr[q]), "l"(pol_second) : "memory");
+          asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(bdst + q * g.plane + o), "d"(fb[q]), "l"(pol_second) : "memory");
+#else
           rdst[q * g.plane + o] = fr[q];
           bdst[q * g.plane + o] = fb[q];
+#endif
         }
       }
     }
@@ -1666,8 +1921,8 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
       }
       else
       {
-        tp_pull_at(rsrc + node_off(g, r, y), g, fr);
-        tp_pull_at(bsrc + node_off(g, r, y), g, fb);
+        tp_pull_at(rsrc + node_off(g, r, y), g, fr, pol_first);
+        tp_pull_at(bsrc + node_off(g, r, y), g, fb, pol_first);
         fsx = aux[A_FX * mg.mplane + k];
         fsy = aux[A_FY * mg.mplane + k];
       }

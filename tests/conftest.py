@@ -28,6 +28,14 @@ if os.environ.get("LBM_EMU") == "1":
     os.environ["LD_LIBRARY_PATH"] = os.path.join(_emu_build, "drv") + ":" + os.environ.get("LD_LIBRARY_PATH", "")
 
 
+# TEST INFRASTRUCTURE: LBM_TEST_LIB=<path> runs the suite against another BUILD of the same library (an experiment variant of
+# lattice-boltzmann-method_b200/Makefile: NOFMA=1, X4=1, HINTS=n) — still the CUDA path, still through the C ABI
+if os.environ.get("LBM_TEST_LIB"):
+    import lbm_b200
+
+    lbm_b200.LIB_PATH = os.path.abspath(os.environ["LBM_TEST_LIB"])
+
+
 # what the emulated runtime does not provide: stream capture (CUDA graphs)
 EMU_SKIPS = ("test_gpu_graph.py", "slabs_and_graph")
 
