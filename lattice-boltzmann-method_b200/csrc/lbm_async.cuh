@@ -123,9 +123,10 @@ __device__ __forceinline__ void tmem_store18(uint32_t taddr, const double (&a)[9
 
 __device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_load18(uint32_t taddr, double (&a)[9], double (&b)[9])
+// the load in two halves, so that its latency can pass under other work: issue (the destination registers are written
+// asynchronously), later wait, then read the registers
+__device__ __forceinline__ void tmem_load18_issue(uint32_t taddr, uint32_t (&r)[36])
 {
-  uint32_t r[36];
 #if LBM_TMEM_X4
 #pragma unroll
   for (int c = 0; c < 36; c += 4)
@@ -142,13 +143,48 @@ __device__ __forceinline__ void tmem_load18(uint32_t taddr, double (&a)[9], doub
       : "memory");
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]) : "r"(taddr + 32u) : "memory");
 #endif
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_load_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_unpack18(uint32_t (&r)[36], double (&a)[9], double (&b)[9])
+{
+  // the registers pass through an empty volatile statement first: nothing may read them ahead of the wait above
+#pragma unroll
+  for (int c = 0; c < 36; c++) asm volatile("" : "+r"(r[c])::"memory");
 #pragma unroll
   for (int q = 0; q < 9; q++)
   {
     a[q] = __hiloint2double((int)r[2 * q + 1], (int)r[2 * q]);
     b[q] = __hiloint2double((int)r[18 + 2 * q + 1], (int)r[18 + 2 * q]);
   }
+}
+__device__ __forceinline__ void tmem_load18(uint32_t taddr, double (&a)[9], double (&b)[9])
+{
+  uint32_t r[36];
+  tmem_load18_issue(taddr, r);
+  tmem_load_wait();
+  tmem_unpack18(r, a, b);
+}
+
+// four doubles = 8 columns
+__device__ __forceinline__ void tmem_store4(uint32_t taddr, double a, double b, double c, double d)
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__double2loint(a)),
+               "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)), "r"(__double2loint(c)), "r"(__double2hiint(c)),
+               "r"(__double2loint(d)), "r"(__double2hiint(d))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_load4(uint32_t taddr, double& a, double& b, double& c, double& d)
+{
+  int r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  a = __hiloint2double(r[1], r[0]);
+  b = __hiloint2double(r[3], r[2]);
+  c = __hiloint2double(r[5], r[4]);
+  d = __hiloint2double(r[7], r[6]);
 }
 
 #else  // ---- tests/cpu_emu: a copy lands when it is issued; a wait on a phase nobody completed is a kernel bug and aborts
@@ -199,9 +235,14 @@ inline void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, 
 }
 inline void mbar_wait(uint64_t* bar, unsigned parity)
 {
-  const EmuMbar* b = (const EmuMbar*)bar;
-  // phase p completed  <=>  the barrier's current phase bit differs from p
-  if ((unsigned)b->phase == (parity & 1u)) emu_async_fail("mbar_wait: the awaited phase was never completed (copies are issued behind a __syncthreads the waiters pass first)");
+  const volatile EmuMbar* b = (const volatile EmuMbar*)bar;
+  // phase p completed  <=>  the barrier's current phase bit differs from p.  Poll like the device does, handing the host
+  // thread to the block's other fibers; a phase nobody ever completes is a kernel bug and aborts instead of spinning for ever
+  for (long spins = 0; (unsigned)b->phase == (parity & 1u); spins++)
+  {
+    if (spins > (1L << 22)) emu_async_fail("mbar_wait: the awaited phase is never completed (no thread of the block issues the copy)");
+    emu::spin_yield();
+  }
 }
 
 // tensor memory: one 512-column lane per thread of the block (static thread_local like __shared__: one block at a time per host thread)
@@ -232,6 +273,31 @@ inline void tmem_load18(uint32_t taddr, double (&a)[9], double (&b)[9])
   const uint32_t* c = emu_tmem()[threadIdx.x] + taddr;
   std::memcpy(a, c, 72);
   std::memcpy(b, c + 18, 72);
+}
+
+inline void tmem_load18_issue(uint32_t taddr, uint32_t (&r)[36])
+{
+  if (taddr + 36u > 512u || threadIdx.x >= 128u) emu_async_fail("tmem_load18_issue: outside the thread's 512 columns");
+  std::memcpy(r, emu_tmem()[threadIdx.x] + taddr, 144);
+}
+inline void tmem_load_wait() {}
+inline void tmem_unpack18(uint32_t (&r)[36], double (&a)[9], double (&b)[9])
+{
+  std::memcpy(a, r, 72);
+  std::memcpy(b, r + 18, 72);
+}
+inline void tmem_store4(uint32_t taddr, double a, double b, double c, double d)
+{
+  if (taddr + 8u > 512u || threadIdx.x >= 128u) emu_async_fail("tmem_store4: outside the thread's 512 columns");
+  const double v[4] = {a, b, c, d};
+  std::memcpy(emu_tmem()[threadIdx.x] + taddr, v, 32);
+}
+inline void tmem_load4(uint32_t taddr, double& a, double& b, double& c, double& d)
+{
+  if (taddr + 8u > 512u || threadIdx.x >= 128u) emu_async_fail("tmem_load4: outside the thread's 512 columns");
+  double v[4];
+  std::memcpy(v, emu_tmem()[threadIdx.x] + taddr, 32);
+  a = v[0]; b = v[1]; c = v[2]; d = v[3];
 }
 
 #endif

@@ -55,12 +55,14 @@ struct TwoPhaseState
   bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
   bool staged = true;                  // k_tp_staged: population rows staged by bulk async copies (LBM_TP_STAGED=0: k_tp_fused)
   int stages = 0;                      // LBM_TP_NS: stage slots per block (0 = the model's default)
-  bool stash = false;                  // LBM_TP_STASH=1: resident population rows parked in tensor memory (k_tp_staged<.., STASH>)
+  bool stash = true;                   // resident population rows parked in tensor memory (k_tp_staged<.., STASH>); LBM_TP_STASH=0: in the stage slots
   double* aux = nullptr;               // TP_CSF: A_COUNT planes in the moment-plane geometry (normal n, interfacial tension Fs)
   int rpb_override = 0;
   // TP_CSF single-pass variant (LBM_CSF_FUSED=1, off by default until it has been measured on the device)
   bool csf_fused = false;
   bool csf_pipe = false;               // LBM_CSF_PIPE=1: software-pipelined variant of k_csf_fused
+  int csf_rows = 0;                    // band height of k_csf_staged (pick_band_rows, once per rule set)
+  int csf_staged = 0;                  // LBM_CSF_STAGED=1: k_csf_staged (bulk-async staging); 2: + tensor-memory stash
   double* aux_next = nullptr;          // second aux set: a fused step reads Fs from aux and writes it here, then the two swap
   unsigned char* d_csf_flags = nullptr;  // [Xl] bit 0: moments of the whole row from the planes; bit 1: normals too
   int* d_csf_list4 = nullptr;          // interior-column nodes whose moments the pre-pass writes to the planes
@@ -70,6 +72,54 @@ struct TwoPhaseState
 };
 
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+constexpr int TPF_NT = 128;  // threads per block of the row-marching kernels = columns of a strip including its halo columns
+
+// Rows per band of the row-marching kernels.  Tall bands amortise the warm-up rows above and below a band (their
+// populations are read and their moments formed a second time), but the grid should also come out as whole WAVES of
+// resident blocks: at 4096^2 the old rule (6 waves' worth of blocks, rounded up) launched 6.02 waves — a seventh pass
+// over the SMs for 9 blocks, 14 % of the kernel's time.  Model: time ~ ceil(blocks / resident) * (rows + c * warm-up rows).
+static int pick_band_rows(int Xl, int strips, int resident_blocks, int warmup_rows, int cap = 128)
+{
+  if (Xl <= 24) return std::max(Xl, 1);
+  double best = 1e300;
+  int best_rpb = std::min(cap, Xl);
+  for (int rpb = std::min(cap, Xl); rpb >= 24; rpb--)
+  {
+    const long long blocks = (long long)strips * cdiv(Xl, rpb);
+    const double waves = std::ceil((double)blocks / std::max(resident_blocks, 1));
+    const double t = waves * (rpb + 0.6 * warmup_rows);
+    if (t < best * (1.0 - 1e-9))
+    {
+      best = t;
+      best_rpb = rpb;
+    }
+  }
+  return best_rpb;
+}
+
+// blocks of `kernel` (TPF_NT threads, `smem` dynamic bytes) the device keeps resident at once.  From the kernel's own
+// resource use and the SM's limits rather than the occupancy calculator, whose answer depends on the shared-memory
+// carve-out in force when it is asked (it said one block per SM for a kernel that runs two).
+template <class K>
+static int resident_blocks_of(const lbm_domain* d, K kernel, size_t smem)
+{
+  int sms = 0, smem_sm = 0, regs_sm = 0;
+  cudaFuncAttributes fa{};
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->cfg.device) != cudaSuccess || sms < 1) sms = 148;
+  if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->cfg.device) != cudaSuccess || smem_sm < 1) smem_sm = 233472;
+  if (cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, d->cfg.device) != cudaSuccess || regs_sm < 1) regs_sm = 65536;
+  int per_sm = 2;
+  if (cudaFuncGetAttributes(&fa, (const void*)kernel) == cudaSuccess && fa.numRegs > 0)
+  {
+    const int regs_thread = (fa.numRegs + 7) / 8 * 8;  // allocation granularity
+    const int by_regs = regs_sm / (regs_thread * TPF_NT);
+    const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));  // 1 KB per block is the system's
+    per_sm = std::max(1, std::min({by_regs, by_smem, 16}));
+  }
+  cudaGetLastError();
+  return per_sm * sms;
+}
 
 constexpr int TILE_X = 8, TILE_Y = 32, HALO = 2;
 constexpr int SM_X = TILE_X + 2 * HALO, SM_Y = TILE_Y + 2 * HALO;
@@ -288,7 +338,6 @@ k_tp_collide_interior(const double* __restrict__ rsrc, const double* __restrict_
 // ------------------------------------------------------------------------------------------------
 // fused step: moments of row r+H into a shared-memory ring, collision of row r out of it
 // ------------------------------------------------------------------------------------------------
-constexpr int TPF_NT = 128;  // threads per block = columns of a strip including the 2H halo columns
 
 template <int MODEL>
 struct TpFused
@@ -315,7 +364,7 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
 #pragma unroll
     for (int a = -1; a <= 1; a++)
     {
-      const int sa = (sc + NR + a) % NR;
+      const int sa = sc + a < 0 ? sc + a + NR : (sc + a >= NR ? sc + a - NR : sc + a);  // (sc + a) mod NR without a division
 #pragma unroll
       for (int b = -1; b <= 1; b++)
       {
@@ -331,7 +380,7 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
 #pragma unroll
     for (int a = -2; a <= 2; a++)
     {
-      const int sa = (sc + NR + a) % NR;
+      const int sa = sc + a < 0 ? sc + a + NR : (sc + a >= NR ? sc + a - NR : sc + a);  // (sc + a) mod NR without a division
 #pragma unroll
       for (int b = -2; b <= 2; b++)
       {
@@ -573,33 +622,35 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
   else __syncthreads();
 
   // row rr of the march -> stage slot (rr - r0) % NS; every row of the march uses its slot's barrier once (rows without
-  // populations — outside the slab — complete it with zero bytes), so the parity of a wait is ((rr - r0) / NS) & 1
-  auto issue_row = [&](int rr) {
+  // populations — outside the slab — complete it with zero bytes), so the parity of a wait is ((rr - r0) / NS) & 1.
+  // Lanes 0 .. 17 of warp 0 own one population row segment each: source pointer at row 0 and shared-memory offset once,
+  // so that issuing a row costs that warp a dozen instructions (the other warps wait for it at the next barrier).
+  const int lane_q = (t < 18 ? t : 0) % 9;
+  const double* lane_src = (t < 9 ? rsrc : bsrc) + (long long)lane_q * g.plane + node_off(g, -CX(lane_q), lo);
+  double* lane_dst = stage + (t < 18 ? t : 0) * W + (lo - c0);
+  auto issue_row = [&](int rr, int slot) {
     if (t >= 32 || rr >= xe + H) return;
-    const int k = rr - r0, slot = k % NS;
     const bool staged = rr >= rs0 && rr < rs1;
     if (t == 0) mbar_arrive_expect_tx(&full[slot], staged ? 18u * seg_bytes : 0u);
     __syncwarp();
-    if (staged && t < 18)
-    {
-      const int l = t / 9, q = t % 9;
-      const double* src = (l == 0 ? rsrc : bsrc) + (long long)q * g.plane + node_off(g, rr - CX(q), lo);
-      bulk_copy_g2s(stage + (size_t)slot * C::ROW + t * W + (lo - c0), src, seg_bytes, &full[slot]);
-    }
+    if (staged && t < 18) bulk_copy_g2s(lane_dst + (size_t)slot * C::ROW, lane_src + (long long)rr * g.pitch, seg_bytes, &full[slot]);
   };
-  for (int rr = r0; rr < r0 + NS - HOLD - (STASH ? 0 : 1); rr++) issue_row(rr);  // every row the loop's refill rule does not reach
-  __syncthreads();  // once per block: every copy is issued behind a barrier that its waiters pass first
+  constexpr int AHEAD = NS - HOLD - (STASH ? 0 : 1);  // rows issued before the march starts = distance of the loop's refill rule
+  for (int j = 0; j < AHEAD; j++) issue_row(r0 + j, j);
+  __syncthreads();
 
   double mrr[H + 1], mrb[H + 1], mux[H + 1], muy[H + 1];  // rho_r, rho_b, u of rows r, r-1, .. r-H at this thread's column
 #pragma unroll
   for (int k = 0; k <= H; k++) mrr[k] = mrb[k] = mux[k] = muy[k] = 0.0;
 
-  int slot_ring = 0;
+  // counters instead of k % NS, k / NS, k % (H + 1): slot and parity of row r, slot of the row to refill, tensor-memory slot
+  int slot_ring = 0, sl = 0, sl_x = (NS - H % NS) % NS, sl_fill = AHEAD % NS, ts = 0;
+  unsigned par = 0;
   for (int r = r0; r < xe + H; r++)
   {
-    const int k = r - r0, sl = k % NS;
+    const int k = r - r0;
     const double* st_r = stage + (size_t)sl * C::ROW;
-    mbar_wait(&full[sl], (unsigned)(k / NS) & 1u);
+    mbar_wait(&full[sl], par);
     // ---- A: moments of (r, y) -> ring, registers
 #pragma unroll
     for (int j = H; j > 0; j--)
@@ -620,7 +671,7 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
         fr[q] = st_r[q * W + my - CY(q)];
         fb[q] = st_r[(9 + q) * W + my - CY(q)];
       }
-      tmem_store18(tmem + 36u * (unsigned)(k % (H + 1)), fr, fb);
+      tmem_store18(tmem + 36u * (unsigned)ts, fr, fb);
     }
     if (col_ok)
     {
@@ -659,19 +710,31 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
       mux[0] = ux_;
       muy[0] = uy_;
     }
-    if constexpr (STASH) tmem_store_wait();
+    // the park has landed before the barrier (measured: waiting for it behind the barrier, right before the collision's
+    // tcgen05.ld, cost the MRT kernel 4 %), and the collided row's populations are on their way back under the barrier
+    [[maybe_unused]] uint32_t tr[36];
+    if constexpr (STASH)
+    {
+      ts = ts == H ? 0 : ts + 1;  // now the slot of row r - H: (k - H) mod (H + 1) = (k + 1) mod (H + 1)
+      tmem_load18_issue(tmem + 36u * (unsigned)ts, tr);
+      tmem_store_wait();
+    }
     __syncthreads();
     // a slot is free now: the one this iteration read (STASH) / the one the previous iteration's collision read last
-    issue_row(r - (STASH ? 0 : 1) - HOLD + NS);
+    issue_row(r + AHEAD, sl_fill);
     // ---- B: collision of row x = r - H out of tensor memory / its stage slot, and the ring rows x-H .. x+H
     const int x = r - H;
-    if constexpr (STASH) tmem_load18(tmem + 36u * (unsigned)((k + 1) % (H + 1)), fr, fb);  // slot of row r - H: (k - H) mod (H + 1)
+    if constexpr (STASH)
+    {
+      tmem_load_wait();
+      tmem_unpack18(tr, fr, fb);
+    }
     if (x >= xb && collider)
     {
       const int sc = (slot_ring + NR - H) % NR;
       if constexpr (!STASH)
       {
-        const double* st_x = stage + (size_t)((k - H) % NS) * C::ROW;
+        const double* st_x = stage + (size_t)sl_x * C::ROW;
 #pragma unroll
         for (int q = 0; q < 9; q++)
         {
@@ -692,6 +755,13 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
       }
     }
     slot_ring = slot_ring + 1 == NR ? 0 : slot_ring + 1;
+    sl_x = sl_x + 1 == NS ? 0 : sl_x + 1;
+    sl_fill = sl_fill + 1 == NS ? 0 : sl_fill + 1;
+    if (++sl == NS)
+    {
+      sl = 0;
+      par ^= 1u;
+    }
   }
   if constexpr (STASH) tmem_free<C::TMEM_COLS>(tmem);
 }
@@ -979,6 +1049,7 @@ int tp_create(lbm_domain* d)
     LBM_CUDA(cudaMemset(tp->aux, 0, ab));
     if (const char* e = getenv("LBM_CSF_FUSED")) tp->csf_fused = atoi(e) != 0;
     if (const char* e = getenv("LBM_CSF_PIPE")) tp->csf_pipe = atoi(e) != 0;
+    if (const char* e = getenv("LBM_CSF_STAGED")) tp->csf_staged = atoi(e);
     if (tp->csf_fused)
     {
       LBM_CUDA(cudaMalloc(&tp->aux_next, ab));
@@ -989,8 +1060,9 @@ int tp_create(lbm_domain* d)
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_MRTCG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_MRTCG>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_tp_fused<TP_RK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpFused<TP_RK>::SMEM));
-#define LBM_STAGED_ATTR(MODEL, NS, MINB, STASH) \
-  LBM_CUDA(cudaFuncSetAttribute(k_tp_staged<MODEL, NS, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpStaged<MODEL, NS>::SMEM))
+#define LBM_STAGED_ATTR(MODEL, NS, MINB, STASH)                                                                                             \
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_staged<MODEL, NS, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpStaged<MODEL, NS>::SMEM)); \
+  LBM_CUDA(cudaFuncSetAttribute(k_tp_staged<MODEL, NS, MINB, STASH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
   LBM_STAGED_ATTR(TP_MRTCG, 4, 2, false); LBM_STAGED_ATTR(TP_MRTCG, 5, 2, false); LBM_STAGED_ATTR(TP_MRTCG, 6, 2, false);
   LBM_STAGED_ATTR(TP_RK, 3, 3, false); LBM_STAGED_ATTR(TP_RK, 4, 2, false); LBM_STAGED_ATTR(TP_RK, 5, 2, false); LBM_STAGED_ATTR(TP_RK, 6, 2, false);
   LBM_STAGED_ATTR(TP_MRTCG, 2, 4, true); LBM_STAGED_ATTR(TP_MRTCG, 3, 3, true); LBM_STAGED_ATTR(TP_MRTCG, 4, 2, true);
@@ -1142,13 +1214,7 @@ static int tp_build_region(lbm_domain* d)
     LBM_CUDA(cudaMalloc(&tp->d_region, sizeof(int) * nodes.size()));
     LBM_CUDA(cudaMemcpy(tp->d_region, nodes.data(), sizeof(int) * nodes.size(), cudaMemcpyHostToDevice));
   }
-  // enough blocks for several waves over 148 SMs, bands as tall as that allows (the 2H warm-up rows
-  // of a band are recomputed by the band above)
-  const int useful = tp->model == TP_MRTCG ? TpFused<TP_MRTCG>::USEFUL : TpFused<TP_RK>::USEFUL;
-  const int strips = cdiv(std::max(Y - 2, 1), useful);
-  const int bands = std::max(1, cdiv(148 * 3 * 6, strips));
-  tp->rows_per_block = std::min(128, std::max(16, cdiv(Xl, bands)));
-  if (tp->rpb_override > 0) tp->rows_per_block = std::min(128, tp->rpb_override);  // k_tp_fused stages <= 128 + 2H row flags
+  tp->rows_per_block = 0;  // chosen at the next launch, from the occupancy of the kernel that runs (pick_band_rows)
   tp->region_dirty = false;
   return LBM_OK;
 }
@@ -1162,40 +1228,39 @@ static int tp_launch_fused(lbm_domain* d)
   const int Yi = d->g.Y - 2;
   if (Yi > 0)
   {
-    ProfScope ps(d, LBM_PROF_INTERIOR);
-    dim3 grid(cdiv(Yi, C::USEFUL), cdiv(d->g.Xl, tp->rows_per_block));
+    const int strips = cdiv(Yi, C::USEFUL);
+    // one launcher per kernel variant: band height from that variant's occupancy (once per rule set), then the launch
+    auto run = [&](auto kernel, size_t smem) {
+      if (tp->rows_per_block <= 0)
+        tp->rows_per_block = tp->rpb_override > 0 ? std::min(128, tp->rpb_override)  // the kernels stage <= 128 + 2H row flags
+                                                  : pick_band_rows(d->g.Xl, strips, resident_blocks_of(d, kernel, smem), 2 * C::H);
+      ProfScope ps(d, LBM_PROF_INTERIOR);
+      dim3 grid(strips, cdiv(d->g.Xl, tp->rows_per_block));
+      kernel<<<grid, TPF_NT, smem, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg, tp->mom, tp->p,
+                                                tp->d_rowflag, tp->rows_per_block);
+      d->launches++;
+    };
     if (tp->staged)
     {
-      // stage slots: H + 1 resident rows + the rows in flight.  MRTCG: 5 slots = 111 KB, two blocks per SM; 4 = 92 KB.
-      // RK: 5 slots = 97 KB (two blocks), 3 = 60 KB (three blocks)
-      // stage slots.  Without the stash: H + 1 resident rows + the rows in flight (default 5).  With it: rows in flight only (default 3)
-      const int ns = tp->stash ? std::max(2, tp->stages > 0 ? tp->stages : 3) : std::max(TpFused<MODEL>::H + 2, tp->stages > 0 ? tp->stages : 5);
-#define LBM_STAGED_LAUNCH(NS, MINB, STASH)                                                                                           \
-  k_tp_staged<MODEL, NS, MINB, STASH><<<grid, TPF_NT, TpStaged<MODEL, NS>::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t],      \
-                                                                                               d->buf[1][t], d->g, tp->mg, tp->mom, tp->p, \
-                                                                                               tp->d_rowflag, tp->rows_per_block)
+      // stage slots.  Without the stash: H + 1 resident rows + the rows in flight (default 5).  With it: rows in flight only
+      const int ns = tp->stash ? std::max(2, tp->stages > 0 ? tp->stages : (MODEL == TP_MRTCG ? 3 : 4))
+                               : std::max(C::H + 2, tp->stages > 0 ? tp->stages : 5);
       if (tp->stash)
       {
-        if (ns <= 2) LBM_STAGED_LAUNCH(2, 4, true);
-        else if (ns == 3) LBM_STAGED_LAUNCH(3, 3, true);
-        else LBM_STAGED_LAUNCH(4, 2, true);
+        if (ns <= 2) run(k_tp_staged<MODEL, 2, 4, true>, TpStaged<MODEL, 2>::SMEM);
+        else if (ns == 3) run(k_tp_staged<MODEL, 3, 3, true>, TpStaged<MODEL, 3>::SMEM);
+        else run(k_tp_staged<MODEL, 4, 2, true>, TpStaged<MODEL, 4>::SMEM);
       }
       else if (ns <= 3)
       {
-        if constexpr (TpFused<MODEL>::H + 2 <= 3) LBM_STAGED_LAUNCH(3, 3, false);
+        if constexpr (C::H + 2 <= 3) run(k_tp_staged<MODEL, 3, 3, false>, TpStaged<MODEL, 3>::SMEM);
       }
-      else if (ns == 4) LBM_STAGED_LAUNCH(4, 2, false);
-      else if (ns == 5) LBM_STAGED_LAUNCH(5, 2, false);
-      else LBM_STAGED_LAUNCH(6, 2, false);
-#undef LBM_STAGED_LAUNCH
+      else if (ns == 4) run(k_tp_staged<MODEL, 4, 2, false>, TpStaged<MODEL, 4>::SMEM);
+      else if (ns == 5) run(k_tp_staged<MODEL, 5, 2, false>, TpStaged<MODEL, 5>::SMEM);
+      else run(k_tp_staged<MODEL, 6, 2, false>, TpStaged<MODEL, 6>::SMEM);
     }
-    else if (tp->pipe)
-      k_tp_fused<MODEL, true><<<grid, TPF_NT, C::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
-                                                                    tp->mom, tp->p, tp->d_rowflag, tp->rows_per_block);
-    else
-      k_tp_fused<MODEL, false><<<grid, TPF_NT, C::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
-                                                                     tp->mom, tp->p, tp->d_rowflag, tp->rows_per_block);
-    d->launches++;
+    else if (tp->pipe) run(k_tp_fused<MODEL, true>, C::SMEM);
+    else run(k_tp_fused<MODEL, false>, C::SMEM);
   }
   if (d->nb > 0)
   {
@@ -1579,7 +1644,7 @@ __device__ __forceinline__ void csf_ring_diff5(const double* __restrict__ sm, in
 #pragma unroll
   for (int a = -2; a <= 2; a++)
   {
-    const int sa = (sc + NR + a) % NR;
+    const int sa = sc + a < 0 ? sc + a + NR : (sc + a >= NR ? sc + a - NR : sc + a);  // (sc + a) mod NR without a division
 #pragma unroll
     for (int b = -2; b <= 2; b++)
     {
@@ -1959,12 +2024,313 @@ k_csf_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The single pass with the population rows STAGED by bulk asynchronous copies and (STASH) parked in tensor memory —
+// k_csf_fused's march, rings and plane rules; what changes is where the populations come from.  k_csf_fused pulls every
+// row twice through registers, five rows apart, and on the B200 the second pull misses L2 (ncu: 322 B/node read against
+// 160, long-scoreboard stalls on top).  Here every row is copied ONCE into a stage slot (18 bulk copies of the strip's
+// column window per row, one mbarrier per slot), read out of it when its moments are formed, and kept for the collision
+// five rows later
+//   STASH = true : in the thread's own tensor-memory lane — 6 rows x 36 columns of populations + 5 rows x 8 columns of
+//                  rho_r, rho_b, u (256 columns per block, two blocks per SM); the slot is free at once: NS = 3;
+//   STASH = false: in the stage slot itself (6 resident rows + the rows in flight: NS = 7, 172 KB, one block per SM).
+// Arithmetic per node exactly as k_csf_fused (same device functions, same summation order): the moments of the collided
+// node are the ones formed when its row entered instead of a second evaluation of the same expression.
+template <int NS>
+struct CsfStaged
+{
+  using F = CsfFused;
+  static constexpr int W = TPF_NT + 4, ROW = 18 * W;
+  static constexpr size_t RING_BYTES = F::SMEM;
+  static constexpr size_t SMEM = sizeof(double) * NS * ROW + RING_BYTES + sizeof(uint64_t) * NS;
+  static constexpr int TMEM_COLS = 256, T_MOM = 6 * 36;  // columns: populations of 6 rows, then rho_r, rho_b, u_x, u_y of 5 rows
+};
+
+template <int NS, bool STASH>
+__global__ void __launch_bounds__(TPF_NT, STASH ? 2 : 1)
+k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst, double* __restrict__ bdst,
+             const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const double* __restrict__ aux,
+             double* __restrict__ aux_out, const TpParams p, const unsigned char* __restrict__ rowflags, int rows_per_block)
+{
+  using F = CsfFused;
+  using C = CsfStaged<NS>;
+  constexpr int NT = TPF_NT, NRM = F::NRM, NRN = F::NRN, HC = F::HC, W = C::W, LAG = F::LAG_C;
+  constexpr int HOLD = STASH ? 0 : LAG;
+  static_assert(NS >= HOLD + 2, "at least one row in flight");
+  extern __shared__ double sm[];  // stages [NS][18][W] | moments ring [3][NRM][NT] | normals ring [2][NRN][NT] | mbarriers [NS]
+  double* stage = sm;
+  double* smm = sm + NS * C::ROW;
+  double* smn = smm + 3 * NRM * NT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smn + 2 * NRN * NT);
+  auto M = [&](int f, int slot, int col) -> double& { return smm[(f * NRM + slot) * NT + col]; };
+  auto N = [&](int f, int slot, int col) -> double& { return smn[(f * NRN + slot) * NT + col]; };
+  const int t = threadIdx.x;
+  const int ys = 1 + blockIdx.x * F::USEFUL - HC;
+  const int y = ys + t;
+  const int xb = blockIdx.y * rows_per_block;
+  const int xe = min(xb + rows_per_block, g.Xl);
+  const int r0 = xb - 4, r_end = xe + 4 + 1;          // rows r0 .. r_end - 1 are marched (the last iteration only collides)
+  const int rs0 = max(r0, 0), rs1 = min(xe + 4, g.Xl); // rows whose populations are staged
+  const bool col_ok = y >= -2 && y <= g.Y + 1;      // inside the padded planes
+  const bool col_plane = y < 1 || y > g.Y - 2;      // listed edge columns and the padding
+  const bool normal_thread = t >= 2 && t < NT - 2;  // has the phase of its columns y-2 .. y+2 in the ring
+  const bool collider = t >= HC && t < NT - HC && y >= 1 && y <= g.Y - 2;
+  const int c0 = (ys - 1) & ~1;
+  const int lo = max(c0, 0), hi = min(c0 + W, g.pitch);
+  const unsigned seg_bytes = (unsigned)(hi - lo) * (unsigned)sizeof(double);
+  const int my = t + (ys - c0);
+
+  __shared__ unsigned char sflag[128 + 16];  // flags of rows xb-4 .. xe+4 (outside the slab: everything from the planes)
+  __shared__ uint32_t tmem_slot;
+  for (int k = t; k < xe - xb + 9; k += NT)
+  {
+    const int r = r0 + k;
+    sflag[k] = (r < 0 || r >= g.Xl) ? 3 : rowflags[r];
+  }
+  if (t == 0)
+  {
+    for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+    mbar_init_fence();
+  }
+  uint32_t tmem = 0;
+  if constexpr (STASH) tmem = tmem_alloc<C::TMEM_COLS>(&tmem_slot);
+  else __syncthreads();
+  auto flag_of = [&](int r) -> int { return sflag[r - r0]; };
+
+  // lanes 0 .. 17 of warp 0 own one population row segment each (source pointer at row 0, shared-memory offset)
+  const int lane_q = (t < 18 ? t : 0) % 9;
+  const double* lane_src = (t < 9 ? rsrc : bsrc) + (long long)lane_q * g.plane + node_off(g, -CX(lane_q), lo);
+  double* lane_dst = stage + (t < 18 ? t : 0) * W + (lo - c0);
+  auto issue_row = [&](int rr, int slot) {
+    if (t >= 32 || rr >= r_end) return;
+    const bool staged = rr >= rs0 && rr < rs1;
+    if (t == 0) mbar_arrive_expect_tx(&full[slot], staged ? 18u * seg_bytes : 0u);
+    __syncwarp();
+    if (staged && t < 18) bulk_copy_g2s(lane_dst + (size_t)slot * C::ROW, lane_src + (long long)rr * g.pitch, seg_bytes, &full[slot]);
+  };
+  constexpr int AHEAD = NS - HOLD - (STASH ? 0 : 1);  // rows issued before the march starts = distance of the loop's refill rule
+  for (int j = 0; j < AHEAD; j++) issue_row(r0 + j, j);
+  __syncthreads();
+
+  // !STASH: rho_r, rho_b, u of rows r .. r-5 at this thread's column ride in registers
+  double mrr[LAG + 1], mrb[LAG + 1], mux[LAG + 1], muy[LAG + 1];
+#pragma unroll
+  for (int k = 0; k <= LAG; k++) mrr[k] = mrb[k] = mux[k] = muy[k] = 0.0;
+
+  // counters instead of k % NS, k / NS, k % 6, k % 5 and the ring slots' modulo arithmetic
+  int sl = 0, sl_x = (NS - LAG % NS) % NS, sl_fill = AHEAD % NS, ts = 0, tm = 0;
+  int ms = (r0 + 4 * NRM) % NRM;  // moment-ring slot of row r
+  int ns = (r0 - F::LAG_N + 4 * NRN) % NRN;  // normal-ring slot of row r - 2
+  unsigned par = 0;
+  auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };  // v mod n for -n <= v < 2n
+  for (int r = r0; r < r_end; r++)
+  {
+    const int k = r - r0;
+    const double* st_r = stage + (size_t)sl * C::ROW;
+    mbar_wait(&full[sl], par);
+    // ---- A: moments of (r, y) -> moment ring
+    const bool want = col_ok && r >= -2 && r <= g.Xl + 1 && r <= xe + 3;  // (row xe + 4 only collides row xe - 1)
+    const bool plane = want && (col_plane || (flag_of(r) & 1));
+    double fr[9], fb[9];
+    double rr = 0.0, rb = 0.0, ux = 0.0, uy = 0.0, ph = 0.0;
+    if (STASH || (want && !plane))
+    {
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+      {
+        fr[q] = st_r[q * W + my - CY(q)];
+        fb[q] = st_r[(9 + q) * W + my - CY(q)];
+      }
+    }
+    if constexpr (STASH) tmem_store18(tmem + 36u * (unsigned)ts, fr, fb);
+    if (want)
+    {
+      const long long km = mom_off(mg, r, y);
+      if (plane)
+      {
+        rr = mom[M_RR * mg.mplane + km];
+        rb = mom[M_RB * mg.mplane + km];
+        ux = mom[M_UX * mg.mplane + km];
+        uy = mom[M_UY * mg.mplane + km];
+        ph = mom[M_PH * mg.mplane + km];
+      }
+      else
+        tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + km], aux[A_FY * mg.mplane + km]);
+      const double cq = p.cr * rr + p.cb * rb;
+      M(0, ms, t) = ph;
+      M(1, ms, t) = cq * ux;
+      M(2, ms, t) = cq * uy;
+    }
+    if constexpr (!STASH)
+    {
+#pragma unroll
+      for (int j = LAG; j > 0; j--)
+      {
+        mrr[j] = mrr[j - 1];
+        mrb[j] = mrb[j - 1];
+        mux[j] = mux[j - 1];
+        muy[j] = muy[j - 1];
+      }
+      mrr[0] = rr; mrb[0] = rb; mux[0] = ux; muy[0] = uy;
+    }
+    if constexpr (STASH) tmem_store_wait();  // both parks (this row's populations, the previous row's moments) have landed
+    __syncthreads();
+    issue_row(r + AHEAD, sl_fill);
+    // the collided row's populations start their way back from tensor memory under the normal's arithmetic
+    [[maybe_unused]] uint32_t tr[36];
+    if constexpr (STASH) tmem_load18_issue(tmem + 36u * (unsigned)(ts == 5 ? 0 : ts + 1), tr);  // row r - 5: slot (k - 5) mod 6 = (k + 1) mod 6
+
+    // ---- B: normal of (r - 2, y) -> normal ring
+    {
+      const int rn = r - F::LAG_N;
+      if (col_ok && rn >= xb - 2 && rn <= xe + 1 && rn >= -2 && rn <= g.Xl + 1)
+      {
+        double nx = 0.0, ny = 0.0;
+        bool have = false;
+        if (col_plane || (flag_of(rn) & 2))
+        {
+          const long long kn = mom_off(mg, rn, y);
+          nx = aux[A_NX * mg.mplane + kn];
+          ny = aux[A_NY * mg.mplane + kn];
+          have = true;
+        }
+        else if (normal_thread)
+        {
+          // the summation order of diff5_at (k_csf_normals): rows, then columns, separately rounded products and sums
+          double gx = 0.0, gy = 0.0;
+#pragma unroll
+          for (int a = -2; a <= 2; a++)
+          {
+            const int sa = wrap(ms - F::LAG_N + a, NRM);  // moment row rn + a
+#pragma unroll
+            for (int b = -2; b <= 2; b++)
+            {
+              if (a == 0 && b == 0) continue;
+              const double v = M(0, sa, t + b);
+              const double w = XI5(a, b);
+              if (a != 0) gx = __dadd_rn(gx, __dmul_rn(w * (double)a, v));
+              if (b != 0) gy = __dadd_rn(gy, __dmul_rn(w * (double)b, v));
+            }
+          }
+          const double inv = 1.0 / (1e-20 + sqrt(gx * gx + gy * gy));
+          nx = -gx * inv;
+          ny = -gy * inv;
+          have = true;
+        }
+        if (have)
+        {
+          N(0, ns, t) = nx;
+          N(1, ns, t) = ny;
+        }
+      }
+    }
+    // ---- C: collision of (r - 5, y) from moment rows r-7 .. r-3 and normal rows r-7 .. r-3 (written before this iteration's barrier)
+    const int x = r - LAG;
+    double crr, crb, cux, cuy;  // moments of the collided node, formed when its row entered
+    if constexpr (STASH)
+    {
+      tmem_load_wait();
+      tmem_unpack18(tr, fr, fb);
+      tmem_load4(tmem + (unsigned)C::T_MOM + 8u * (unsigned)tm, crr, crb, cux, cuy);      // and its moments: slot (k - 5) mod 5 = k mod 5
+    }
+    else
+    {
+      crr = mrr[LAG]; crb = mrb[LAG]; cux = mux[LAG]; cuy = muy[LAG];
+    }
+    if (x >= xb && x < xe && collider)
+    {
+      if constexpr (!STASH)
+      {
+        const double* st_x = stage + (size_t)sl_x * C::ROW;
+#pragma unroll
+        for (int q = 0; q < 9; q++)
+        {
+          fr[q] = st_x[q * W + my - CY(q)];
+          fb[q] = st_x[(9 + q) * W + my - CY(q)];
+        }
+      }
+      const long long kx = mom_off(mg, x, y);
+      TpStencil st;
+      st.gx = st.gy = st.DxQx = st.DyQy = 0.0;
+      double dx_nx = 0.0, dy_nx = 0.0, dx_ny = 0.0, dy_ny = 0.0;
+#pragma unroll
+      for (int a = -2; a <= 2; a++)
+      {
+        const int sa = wrap(ms - LAG + a, NRM);  // moment row x + a
+#pragma unroll
+        for (int b = -2; b <= 2; b++)
+        {
+          if (a == 0 && b == 0) continue;
+          const double w = XI5(a, b);
+          if (a != 0)
+          {
+            st.gx += (w * (double)a) * M(0, sa, t + b);
+            st.DxQx += (w * (double)a) * M(1, sa, t + b);
+          }
+          if (b != 0)
+          {
+            st.gy += (w * (double)b) * M(0, sa, t + b);
+            st.DyQy += (w * (double)b) * M(2, sa, t + b);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = -2; a <= 2; a++)
+      {
+        const int na = wrap(ns - (LAG - F::LAG_N) + a, NRN);  // normal row x + a
+#pragma unroll
+        for (int b = -2; b <= 2; b++)
+        {
+          if (a == 0 && b == 0) continue;
+          const double w = XI5(a, b);
+          const double vx = N(0, na, t + b), vy = N(1, na, t + b);
+          if (a != 0) { dx_nx += (w * (double)a) * vx; dx_ny += (w * (double)a) * vy; }
+          if (b != 0) { dy_nx += (w * (double)b) * vx; dy_ny += (w * (double)b) * vy; }
+        }
+      }
+      const int nc = wrap(ns - (LAG - F::LAG_N), NRN);
+      const double nx = N(0, nc, t), ny = N(1, nc, t);
+      const double K = nx * ny * (dy_nx + dx_ny) - (nx * nx) * dy_ny - (ny * ny) * dx_nx;  // eval_local_curvature (:355-364)
+      st.Fsx = (-0.5 * p.sigma) * K * st.gx;                                              // interf_tension (:510)
+      st.Fsy = (-0.5 * p.sigma) * K * st.gy;
+      aux_out[A_FX * mg.mplane + kx] = st.Fsx;
+      aux_out[A_FY * mg.mplane + kx] = st.Fsy;
+      tp_collide<TP_CSF>(p, fr, fb, crr, crb, cux, cuy, M(0, wrap(ms - LAG, NRM), t), st);
+      const long long o = node_off(g, x, y);
+#pragma unroll
+      for (int q = 0; q < 9; q++)
+      {
+        rdst[q * g.plane + o] = fr[q];
+        bdst[q * g.plane + o] = fb[q];
+      }
+    }
+    // this row's moments take the tensor-memory slot the collided row's have just left
+    if constexpr (STASH) tmem_store4(tmem + (unsigned)C::T_MOM + 8u * (unsigned)tm, rr, rb, ux, uy);
+    ts = ts == 5 ? 0 : ts + 1;
+    tm = tm == 4 ? 0 : tm + 1;
+    ms = ms + 1 == NRM ? 0 : ms + 1;
+    ns = ns + 1 == NRN ? 0 : ns + 1;
+    sl_x = sl_x + 1 == NS ? 0 : sl_x + 1;
+    sl_fill = sl_fill + 1 == NS ? 0 : sl_fill + 1;
+    if (++sl == NS)
+    {
+      sl = 0;
+      par ^= 1u;
+    }
+  }
+  if constexpr (STASH) tmem_free<C::TMEM_COLS>(tmem);
+}
+
 static int csf_configure()
 {
   LBM_CUDA(cudaFuncSetAttribute(k_csf_collide_ring<MODE_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfRing::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_csf_collide_ring<MODE_PULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfRing::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_csf_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfFused::SMEM));
   LBM_CUDA(cudaFuncSetAttribute(k_csf_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfFused::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_staged<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfStaged<3>::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_staged<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CsfStaged<7>::SMEM));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_staged<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  LBM_CUDA(cudaFuncSetAttribute(k_csf_staged<7, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return LBM_OK;
 }
 
@@ -2105,6 +2471,7 @@ static int csf_build_lists(lbm_domain* d)
   LBM_CUDA(cudaMemcpy(tp->d_csf_list4, list4.data(), sizeof(int) * list4.size(), cudaMemcpyHostToDevice));
   LBM_CUDA(cudaMemcpy(tp->d_csf_list2, list2.data(), sizeof(int) * list2.size(), cudaMemcpyHostToDevice));
   tp->csf_lists_dirty = false;
+  tp->csf_rows = 0;
   return LBM_OK;
 }
 
@@ -2158,9 +2525,23 @@ static int csf_fused_collide(lbm_domain* d)
   if (Yi > 0)
   {
     ProfScope ps(d, LBM_PROF_INTERIOR);
-    const int rpb = tp->rpb_override > 0 ? std::min(128, tp->rpb_override) : 64;
-    dim3 grid(cdiv(Yi, CsfFused::USEFUL), cdiv(d->g.Xl, rpb));
-    if (tp->csf_pipe)
+    const int strips = cdiv(Yi, CsfFused::USEFUL);
+    auto band_rows = [&](auto kernel, size_t smem) {
+      if (tp->rpb_override > 0) return std::min(128, tp->rpb_override);
+      if (tp->csf_rows <= 0) tp->csf_rows = pick_band_rows(d->g.Xl, strips, resident_blocks_of(d, kernel, smem), 8);
+      return tp->csf_rows;
+    };
+    int rpb = tp->rpb_override > 0 ? std::min(128, tp->rpb_override) : 64;
+    if (tp->csf_staged == 2) rpb = band_rows(k_csf_staged<3, true>, CsfStaged<3>::SMEM);
+    else if (tp->csf_staged == 1) rpb = band_rows(k_csf_staged<7, false>, CsfStaged<7>::SMEM);
+    dim3 grid(strips, cdiv(d->g.Xl, rpb));
+    if (tp->csf_staged == 2)
+      k_csf_staged<3, true><<<grid, TPF_NT, CsfStaged<3>::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                            tp->mom, tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
+    else if (tp->csf_staged == 1)
+      k_csf_staged<7, false><<<grid, TPF_NT, CsfStaged<7>::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
+                                                                             tp->mom, tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
+    else if (tp->csf_pipe)
       k_csf_fused<true><<<grid, TPF_NT, CsfFused::SMEM, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg,
                                                                     tp->mom, tp->aux, tp->aux_next, tp->p, tp->d_csf_flags, rpb);
     else

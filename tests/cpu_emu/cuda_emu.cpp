@@ -274,6 +274,9 @@ void sync_threads()
   f->wait.gen = nullptr;
 }
 
+// a thread that polls for something another thread of its block will do (an mbarrier phase): let the others run
+void spin_yield() { yield_to_main(*tl_block); }
+
 static void warp_barrier(Block& b, WarpState& w)
 {
   if (++w.arrived == w.alive)
@@ -392,6 +395,18 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.
 cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+// a small "device" on purpose: the band-height rule (pick_band_rows) then cuts even the tests' grids into several bands
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int)
+{
+  *v = a == cudaDevAttrMultiProcessorCount ? 3 : a == cudaDevAttrMaxRegistersPerMultiprocessor ? 65536 : a == cudaDevAttrMaxSharedMemoryPerMultiprocessor ? 233472 : 0;
+  return cudaSuccess;
+}
+cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* fa, const void*)
+{
+  std::memset(fa, 0, sizeof(*fa));
+  fa->numRegs = 160;
+  return cudaSuccess;
+}
 // stream capture is not emulated: lbm_use_graph reports the error, plain stepping is what the emulated tests run
 cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
 cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }

@@ -38,6 +38,7 @@ struct LaunchCfg
 void run_grid(const LaunchCfg& cfg, const std::function<void()>& thread_body);
 void* dyn_smem();
 void sync_threads();
+void spin_yield();  // polling loops (mbarrier waits) hand the host thread to the block's other fibers
 uint64_t warp_exchange(uint64_t mine, int src_lane_delta, bool up, int width);
 
 template <class... P, class... A>
