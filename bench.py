@@ -38,7 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "lattice-boltzmann-method_b200", "python"))
 
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md
-CSF_FUSED_DEFAULT = "0"          # the library's default for LBM_CSF_FUSED (csrc/lbm_two_phase.cu: tp_create)
+CSF_FUSED_DEFAULT = "1"          # the library's default for LBM_CSF_FUSED (csrc/lbm_two_phase.cu: the single pass, k_csf_staged)
 
 W9 = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
 CX9 = np.array([0, 1, 0, -1, 0, 1, -1, -1, 1], dtype=np.float64)
@@ -86,9 +86,9 @@ WORKLOADS = {
                               driver="test/rectangle_sedimentation_test.cpp + ibm as in test/cylinder_test.cpp",
                               what="rectangle sedimentation with an immersed cylinder: fluid (Guo-forced) + advection-diffusion lattice",
                               cpu_sample=1024),
-    # not a BASELINE.json config: SURVEY §8(f) rank 2, the continuum-surface-force variant (three passes per step; bytes =
+    # not a BASELINE.json config: SURVEY §8(f) rank 2, the continuum-surface-force variant (one pass per step; bytes =
     # both colours' populations read + written once (288) + the carried interfacial tension read + written (32))
-    "csf_rt": dict(X=8192, Y=8192, bytes=320.0, nlat=2, kernel="k_csf_collide_ring<PULL>",
+    "csf_rt": dict(X=8192, Y=8192, bytes=320.0, nlat=2, kernel="k_csf_staged<3,STASH>",
                    driver="test/mrt_rayleigh_taylor.cpp",
                    what="MRT colour-gradient Rayleigh-Taylor with continuum surface force (curvature from nested 5x5 differences)",
                    cpu_sample=512),
@@ -675,6 +675,8 @@ class Ctx:
     def __init__(self, L, torch, dist, rank, world, local):
         self.L, self.torch, self.dist, self.rank, self.world, self.local = L, torch, dist, rank, world, local
 
+    anchor = None  # the domain that holds this process's ring communicator (join_ring)
+
     def fresh_id(self):
         """one NCCL unique id per ring: rank 0 creates it, everyone receives it"""
         ident = [self.L.comm_unique_id() if self.rank == 0 else None]
@@ -701,6 +703,18 @@ class Ctx:
         return np.concatenate(out, axis=0)
 
 
+def join_ring(ctx, d):
+    """d joins the ring of this run.  ONE NCCL communicator per process, created on a tiny anchor domain the first time and
+    shared from then on (lbm_comm_share): ncclCommInitRank costs seconds on eight ranks, and this run joins a dozen domains"""
+    L = ctx.L
+    if getattr(ctx, "anchor", None) is None:
+        X = 4 * ctx.world
+        x0, x1 = L.decompose_rows(X, ctx.world, ctx.rank)
+        ctx.anchor = L.Domain(L.default_config(model=L.MODEL_BGK, X=X, Y=8, x0=x0, x1=x1, omega=1.0, device=ctx.local))
+        ctx.anchor.comm_init(ctx.fresh_id(), ctx.world, ctx.rank)
+    d.comm_share(ctx.anchor)
+
+
 def want_graph(mode, X, Y, world):
     """CUDA-graph replay of the step pair (lbm_use_graph): one process, no ring (the library refuses it there)"""
     if world > 1 or mode == "off":
@@ -719,7 +733,7 @@ def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sa
     case = Case(L, ctx.torch, a, rank, world, ctx.local)
     d = case.d
     if world > 1:
-        case.comm_init(ctx.fresh_id())
+        join_ring(ctx, d)
     case.setup()
     if world > 1:
         d.comm_check()  # every rank's setup agrees (grid, model, marker lists of bodies across cuts) or LBM_ERR_COMM — not a hang
@@ -796,7 +810,7 @@ def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sa
     per_gpu = mlups / world
     kernel = wl["kernel"]
     if case.name == "csf_rt" and os.environ.get("LBM_CSF_FUSED", CSF_FUSED_DEFAULT) != CSF_FUSED_DEFAULT:
-        kernel = {"0": "k_csf_collide_ring<PULL> (LBM_CSF_FUSED=0: three passes)", "1": "k_csf_fused (LBM_CSF_FUSED=1: one pass)"}[os.environ["LBM_CSF_FUSED"]]
+        kernel = "k_csf_collide_ring<PULL> (LBM_CSF_FUSED=0: three passes)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None,
                 "traffic": ncu_traffic_per_launch(case.name, X, Y),
@@ -866,7 +880,7 @@ def ring_parity(ctx):
         def __call__(self, x0, x1, device, ring):
             d = L.Domain(L.default_config(X=self.X, x0=x0, x1=x1, device=device, **self.cfg))
             if ring:
-                d.comm_init(ctx.fresh_id(), world, rank)
+                join_ring(ctx, d)
             self.rules(d)
             if ring:
                 d.comm_check()
@@ -1022,6 +1036,8 @@ def run_b200_arm(args):
                          "setup_and_run_seconds": time.perf_counter() - t0}
 
     # every GPU is done: ranks other than 0 leave; the CPU baseline (N = 1 only) then runs with no GPU waiting on it
+    if ctx.anchor is not None:
+        ctx.anchor.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

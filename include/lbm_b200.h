@@ -311,6 +311,11 @@ int lbm_comm_unique_id(char id[LBM_UNIQUE_ID_BYTES]);
  * Call order: lbm_create -> lbm_comm_init -> rules / markers -> state import -> lbm_step.  A two-phase domain that
  * already holds state is refused (LBM_ERR_INVALID): its imports swap the moment-plane halos of the cuts when they run. */
 int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank);
+/* d joins the ring `member` belongs to, on member's communicator (no second ncclCommInitRank: seconds on eight ranks).  For
+ * drivers that keep several domains on the same slabs — the reference's drivers hold fluid, sediment and colour lattices in
+ * separate tensors over one decomposition (test/decompose_domain.cpp:60-95) — and for running cases one after the other.
+ * Same device, same decomposition rule and call order as lbm_comm_init; step the sharing domains one at a time. */
+int lbm_comm_share(lbm_domain* d, lbm_domain* member);
 /* Collective consistency check of the ring (optional; every rank calls it after its setup, before the first lbm_step):
  * grids, model, force mode, and that every slab owning rows of an immersed body's ROI was handed that body's marker list —
  * the misuse that otherwise leaves ranks waiting for a row exchange nobody posts.  LBM_ERR_COMM on every rank, with the

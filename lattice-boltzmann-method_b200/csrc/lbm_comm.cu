@@ -19,6 +19,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 #include "lbm_internal.hpp"
@@ -126,9 +127,22 @@ static thread_local int t_group_depth = 0;
     LBM_NCCL(g_nccl.GroupEnd());      \
   } while (0)
 
-struct CommState
+// the NCCL communicator of a ring, shared by every domain of this process that joined it (lbm_comm_init creates it,
+// lbm_comm_share hands it on: a driver that advances several fields on the same slabs, or a bench that runs one workload
+// after the other, pays ncclCommInitRank — seconds on eight ranks — once)
+struct CommHandle
 {
   ncclComm_t comm = nullptr;
+  ~CommHandle()
+  {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+  }
+};
+
+struct CommState
+{
+  std::shared_ptr<CommHandle> handle;
+  ncclComm_t comm = nullptr;  // = handle->comm
   int n_ranks = 1, rank = 0;
 };
 
@@ -137,8 +151,7 @@ bool comm_active(const lbm_domain* d) { return d->comm != nullptr && d->comm->n_
 int comm_release(lbm_domain* d)
 {
   if (!d->comm) return LBM_OK;
-  if (d->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm->comm);
-  delete d->comm;
+  delete d->comm;  // the communicator goes with its last holder
   d->comm = nullptr;
   return LBM_OK;
 }
@@ -424,15 +437,51 @@ int lbm_comm_init(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks
   CommState* c = new CommState();
   c->n_ranks = n_ranks;
   c->rank = rank;
+  c->handle = std::make_shared<CommHandle>();
   ncclUniqueId u;
   std::memcpy(&u, id, sizeof(u));
-  ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, u, rank);
+  ncclResult_t r = g_nccl.CommInitRank(&c->handle->comm, n_ranks, u, rank);
   if (r != 0)
   {
     set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    c->handle->comm = nullptr;
     delete c;
     return LBM_ERR_COMM;
   }
+  c->comm = c->handle->comm;
+  d->comm = c;
+  d->side_ready = false;
+  return LBM_OK;
+}
+
+// d joins the ring `member` already belongs to, on the same communicator.  Same conditions as lbm_comm_init: d owns the
+// rows lbm_decompose_rows gives this rank, and a two-phase domain joins before its state is imported.  Both domains live
+// on the same device; they may be stepped one after the other, not concurrently from several host threads.
+int lbm_comm_share(lbm_domain* d, lbm_domain* member)
+{
+  if (!d || !member || !member->comm || !member->comm->handle) { set_error("lbm_comm_share: the second domain has not joined a ring"); return LBM_ERR_INVALID; }
+  if (d->cfg.device != member->cfg.device) { set_error("lbm_comm_share: the two domains live on different devices"); return LBM_ERR_INVALID; }
+  const int n_ranks = member->comm->n_ranks, rank = member->comm->rank;
+  int x0 = 0, x1 = 0;
+  LBM_TRY(lbm_decompose_rows(d->cfg.X, n_ranks, rank, &x0, &x1));
+  if (x0 != d->cfg.x0 || x1 != d->cfg.x1)
+  {
+    set_error("lbm_comm_share: rank %d of %d must own rows [%d,%d) (lbm_decompose_rows), the domain has [%d,%d)", rank, n_ranks, x0, x1,
+              d->cfg.x0, d->cfg.x1);
+    return LBM_ERR_INVALID;
+  }
+  if (d->tp && d->have_state)
+  {
+    set_error("lbm_comm_share: a two-phase domain joins the ring BEFORE its state is imported (lbm_init_two_phase / lbm_set_f / lbm_set_u)");
+    return LBM_ERR_INVALID;
+  }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  comm_release(d);
+  CommState* c = new CommState();
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  c->handle = member->comm->handle;
+  c->comm = c->handle->comm;
   d->comm = c;
   d->side_ready = false;
   return LBM_OK;

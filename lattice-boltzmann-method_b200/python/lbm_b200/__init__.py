@@ -105,7 +105,7 @@ EXPORTS = [
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
     "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension", "lbm_link_face", "lbm_set_force_region",
-    "lbm_rk_diagnostics", "lbm_comm_check",
+    "lbm_rk_diagnostics", "lbm_comm_check", "lbm_comm_share",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
 
@@ -156,6 +156,7 @@ def load():
         _lib.lbm_profile_read.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_longlong)]
         _lib.lbm_comm_unique_id.argtypes = [C.c_char_p]
         _lib.lbm_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        _lib.lbm_comm_share.argtypes = [C.c_void_p, C.c_void_p]
         _lib.lbm_link_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.lbm_link_face.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         _lib.lbm_set_force_region.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -431,6 +432,10 @@ class Domain:
     # ---- multi-GPU
     def comm_init(self, unique_id, n_ranks, rank):
         _chk(self.lib.lbm_comm_init(self.h, unique_id, n_ranks, rank))
+
+    def comm_share(self, member):
+        """join the ring `member` belongs to, on its communicator"""
+        _chk(self.lib.lbm_comm_share(self.h, member.h))
 
     def link_face(self, side, row_begin, n_rows, other, other_row_begin):
         """bind rows [row_begin, row_begin + n_rows) of the first (side 0) / last (side 1) column to the facing column of `other`"""

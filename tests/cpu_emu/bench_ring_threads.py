@@ -27,7 +27,7 @@ def main(world):
 
     class ThreadCtx:
         def __init__(self, rank):
-            self.L, self.rank, self.world, self.local = L, rank, world, 0
+            self.L, self.rank, self.world, self.local, self.anchor = L, rank, world, 0, None
 
         def fresh_id(self):
             if self.rank == 0:

@@ -48,8 +48,8 @@ def main(seed, rounds):
             ("kbc ragged", lambda R, C: kbc.test_tiny_and_ragged_grids(orc, R, C), (pick(3, 140), pick(3, 140))),
             ("kbc shear", lambda R, C: kbc.test_double_shear_flow_vs_oracle(orc, R, C), (pick(8, 90), pick(8, 150))),
             ("csf", lambda R, C: csf.test_csf_vs_oracle(orc, R, C), (pick(12, 100), pick(9, 270))),
-            ("csf single pass", lambda R, C, rpb, pipe: csf.test_csf_single_pass_equals_three_pass_without_contraction(R, C, rpb, pipe),
-             (pick(8, 150), pick(12, 400), int(rng.choice([0, 16, 32, 128])), str(pick(0, 1)))),
+            ("csf single pass", lambda R, C, rpb, kernel: csf.test_csf_single_pass_equals_three_pass_without_contraction(R, C, rpb, kernel),
+             (pick(8, 150), pick(12, 400), int(rng.choice([0, 16, 32, 128])), str(rng.choice(csf.KERNELS)))),
         ]
         for name, fn, args in cases:
             try:

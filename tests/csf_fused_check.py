@@ -1,4 +1,4 @@
-"""The single-pass CSF step (LBM_CSF_FUSED=1, k_csf_fused) against the three-pass step — helper of tests/test_gpu_csf.py.
+"""The single-pass CSF step (k_csf_staged / k_csf_fused) against the three-pass step (LBM_CSF_FUSED=0) — helper of tests/test_gpu_csf.py.
 
 Both steps state the same arithmetic in two differently shaped kernels.  With floating-point contraction off they agree
 bit for bit (hardware: liblbm_b200_nofma.so, `make NOFMA=1`; the emulated device never contracts); in the product build
@@ -6,7 +6,7 @@ nvcc picks the multiply-adds it fuses per kernel, and the two differ in the last
 the B200: 1e-16 relative, growing to 7e-16 over nine steps; the same kernel against itself — run twice, other band heights,
 the software-pipelined instantiation — stays bit-identical, so there is no race behind it).
 
-As a script:  python tests/csf_fused_check.py --lib <path or suffix> R C rpb pipe   -> exit 0 iff bit-identical
+As a script:  python tests/csf_fused_check.py --lib <path or suffix> R C rpb kernel   -> exit 0 iff bit-identical
 TEST INFRASTRUCTURE."""
 import os
 import sys
@@ -22,13 +22,23 @@ SCHEDULE = (1, 1, 3, 4)  # a first step out of an import (three passes either wa
 NAMES = ("f_red", "f_blue", "Fs", "phase")
 
 
-def run(R, C, fused, pipe="0", rpb=0, schedule=SCHEDULE):
-    """[(f_red, f_blue, Fs, phase)] after every entry of the schedule; the switches are read when the domain is created"""
+# the single-pass kernels: name -> (LBM_CSF_STAGED, LBM_CSF_PIPE)
+KERNELS = {"staged+stash": ("2", "0"),   # k_csf_staged<3, STASH>: bulk-async staging + tensor-memory stash (the default)
+           "staged": ("1", "0"),         # k_csf_staged<7, false>: rows resident in the stage slots
+           "fused": ("0", "0"),          # k_csf_fused<false>: two pulls through registers
+           "fused+pipe": ("0", "1")}     # k_csf_fused<true>: software-pipelined
+
+
+def run(R, C, fused, pipe="0", rpb=0, schedule=SCHEDULE, kernel=None):
+    """[(f_red, f_blue, Fs, phase)] after every entry of the schedule; the switches are read when the domain is created.
+    kernel: one of KERNELS (overrides pipe); None leaves LBM_CSF_STAGED at the library's default"""
     import cases
     from oracle_lib import Oracle
     from test_gpu_csf import csf_params
 
-    old = {k: os.environ.get(k) for k in ("LBM_CSF_FUSED", "LBM_CSF_PIPE", "LBM_TP_RPB")}
+    old = {k: os.environ.get(k) for k in ("LBM_CSF_FUSED", "LBM_CSF_PIPE", "LBM_TP_RPB", "LBM_CSF_STAGED")}
+    if kernel is not None:
+        os.environ["LBM_CSF_STAGED"], pipe = KERNELS[kernel]
     os.environ["LBM_CSF_FUSED"], os.environ["LBM_CSF_PIPE"] = str(fused), str(pipe)
     if rpb:
         os.environ["LBM_TP_RPB"] = str(rpb)
@@ -77,7 +87,7 @@ if __name__ == "__main__":
     if argv[:1] == ["--lib"]:
         L.LIB_PATH = argv[1] if "/" in argv[1] else os.path.join(L.PKG_DIR, f"liblbm_b200_{argv[1]}.so")
         argv = argv[2:]
-    R, C, rpb, pipe = int(argv[0]), int(argv[1]), int(argv[2]), argv[3]
-    diff = first_difference(run(R, C, 1, pipe, rpb), run(R, C, 0, pipe, rpb))
-    print(f"{os.path.basename(L.LIB_PATH)} {R}x{C} rpb={rpb} pipe={pipe}: " + (diff or "single pass == three passes, bit for bit"))
+    R, C, rpb, kernel = int(argv[0]), int(argv[1]), int(argv[2]), argv[3]
+    diff = first_difference(run(R, C, 1, rpb=rpb, kernel=kernel), run(R, C, 0, rpb=rpb))
+    print(f"{os.path.basename(L.LIB_PATH)} {R}x{C} rpb={rpb} {kernel}: " + (diff or "single pass == three passes, bit for bit"))
     sys.exit(1 if diff else 0)

@@ -129,33 +129,35 @@ def test_csf_linked_slabs_equal_monolithic(orc, P):
     assert np.array_equal(np.concatenate([g[1] for g in got], axis=0), u)
 
 
-# ---- the single-pass step (LBM_CSF_FUSED=1: k_csf_fused — moments -> ring, normals at lag 2, collision at lag 5, Fs
-#      double-buffered).  What "equal to the three-pass step" can mean on a device that contracts: csf_fused_check.py
+# ---- the single-pass step (the default: k_csf_staged — moments -> ring, normals at lag 2, collision at lag 5, Fs
+#      double-buffered; populations staged by bulk async copies and parked in tensor memory) and its predecessors.
+#      What "equal to the three-pass step" can mean on a device that contracts: csf_fused_check.py
 FUSED_SHAPES = [(96, 64, 0), (41, 33, 0), (70, 300, 0), (200, 131, 16), (130, 125, 128), (16, 12, 0)]
+KERNELS = ["staged+stash", "staged", "fused", "fused+pipe"]
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("R,C,rpb", FUSED_SHAPES)
-def test_csf_single_pass_is_one_function_of_its_input(R, C, rpb):
-    """the same kernel whatever the launch shape: run twice, 16-row bands, the software-pipelined instantiation — bit for
-    bit (several strips and bands; a missing barrier around the two rings or a plane / ring mix-up shows here)"""
+def test_csf_single_pass_is_one_function_of_its_input(R, C, rpb, kernel):
+    """the same kernel whatever the launch shape: run twice and with 16-row bands — bit for bit (several strips and bands; a
+    missing barrier around the rings, a stage slot refilled too early or a plane / ring mix-up shows here)"""
     import csf_fused_check as K
 
-    base = K.run(R, C, 1, "0", rpb)
-    for what, other in (("again", K.run(R, C, 1, "0", rpb)), ("16-row bands", K.run(R, C, 1, "0", 16)),
-                        ("pipelined", K.run(R, C, 1, "1", rpb))):
+    base = K.run(R, C, 1, rpb=rpb, kernel=kernel)
+    for what, other in (("again", K.run(R, C, 1, rpb=rpb, kernel=kernel)), ("16-row bands", K.run(R, C, 1, rpb=16, kernel=kernel))):
         assert K.first_difference(other, base) is None, (what, K.first_difference(other, base))
 
 
-@pytest.mark.parametrize("pipe", ["0", "1"])
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("R,C,rpb", FUSED_SHAPES)
-def test_csf_single_pass_vs_three_pass_and_oracle(orc, R, C, rpb, pipe):
+def test_csf_single_pass_vs_three_pass_and_oracle(orc, R, C, rpb, kernel):
     """product build: the first step (three passes either way) bit for bit, afterwards the two steps part only by where the
     compiler contracted — a few ulp per step (measured 1e-16 .. 7e-16 over nine steps), bounded here by 1e-13 + 20 x the
     oracle's own distance to a 1e-15-perturbed twin; and the single-pass run holds the oracle bound of test_csf_vs_oracle"""
     import csf_fused_check as K
 
     schedule = (1, 1, 1, 3, 4)
-    fused, three = K.run(R, C, 1, pipe, rpb, schedule), K.run(R, C, 0, pipe, rpb, schedule)
+    fused, three = K.run(R, C, 1, rpb=rpb, schedule=schedule, kernel=kernel), K.run(R, C, 0, rpb=rpb, schedule=schedule)
     assert K.first_difference(fused[:1], three[:1]) is None
     p = csf_params(R, C)
     st, twin = orc.csf_init(p), orc.csf_init(p)
@@ -170,20 +172,21 @@ def test_csf_single_pass_vs_three_pass_and_oracle(orc, R, C, rpb, pipe):
         assert cases.relerr(fused[k][0], st["r_adv"]) < tol and cases.relerr(fused[k][1], st["b_adv"]) < tol, (k, own)
 
 
-@pytest.mark.parametrize("R,C,rpb,pipe", [(96, 64, 0, "0"), (200, 131, 16, "0"), (70, 300, 0, "1"), (16, 12, 0, "0")])
-def test_csf_single_pass_equals_three_pass_without_contraction(R, C, rpb, pipe):
+@pytest.mark.parametrize("R,C,rpb,kernel", [(96, 64, 0, "staged+stash"), (200, 131, 16, "staged+stash"), (16, 12, 0, "staged+stash"),
+                                            (70, 300, 0, "staged"), (96, 64, 0, "fused"), (70, 300, 0, "fused+pipe")])
+def test_csf_single_pass_equals_three_pass_without_contraction(R, C, rpb, kernel):
     """the same sources compiled with -fmad=false (liblbm_b200_nofma.so, built by __graft_entry__.build()): populations of
-    both colours, interfacial tension and phase bit for bit — the two kernels are the same computation.  On the emulated
-    device (LBM_EMU=1) nothing contracts, so the loaded library itself is held to it."""
+    both colours, interfacial tension and phase bit for bit — every single-pass kernel is the same computation as the three
+    passes.  On the emulated device (LBM_EMU=1) nothing contracts, so the loaded library itself is held to it."""
     import csf_fused_check as K
 
     if os.environ.get("LBM_EMU") == "1":
-        assert K.first_difference(K.run(R, C, 1, pipe, rpb), K.run(R, C, 0, pipe, rpb)) is None
+        assert K.first_difference(K.run(R, C, 1, rpb=rpb, kernel=kernel), K.run(R, C, 0, rpb=rpb)) is None
         return
     lib = os.path.join(L.PKG_DIR, "liblbm_b200_nofma.so")
     assert os.path.exists(lib), f"{lib} is missing: make -C lattice-boltzmann-method_b200 NOFMA=1"
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "csf_fused_check.py"), "--lib", lib,
-                        str(R), str(C), str(rpb), pipe], capture_output=True, text=True, timeout=300)
+                        str(R), str(C), str(rpb), kernel], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -192,4 +195,11 @@ def test_csf_single_pass_on_linked_slabs(monkeypatch, orc, P):
     """the three stages of the single-pass step interleaved across linked slabs (lbm_step_group): bit-identical to the
     monolithic single-pass run (same kernel, same operands per node)"""
     monkeypatch.setenv("LBM_CSF_FUSED", "1")
+    test_csf_linked_slabs_equal_monolithic(orc, P)
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_csf_three_pass_on_linked_slabs(monkeypatch, orc, P):
+    """LBM_CSF_FUSED=0: the three-pass step across linked slabs, bit-identical to the monolithic three-pass run"""
+    monkeypatch.setenv("LBM_CSF_FUSED", "0")
     test_csf_linked_slabs_equal_monolithic(orc, P)

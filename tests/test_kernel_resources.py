@@ -18,6 +18,10 @@ BUDGET = {
     "k_bgk_interiorILi1ELi1ELi0ELb0E": (80, "BGK pull, incompressible (Poiseuille)"),
     "k_bgk_interiorILi1ELi0ELi0ELb1E": (100, "BGK + advection-diffusion lattice (sedimentation)"),
     "k_bgk_interiorILi1ELi2ELi0ELb0E": (128, "KBC: 4 resident blocks of 128 threads"),
+    "k_tp_stagedILi0ELi3ELi3ELb1E": (168, "MRT colour gradient, staged rows + tensor-memory stash (the default): 3 resident blocks"),
+    "k_tp_stagedILi1ELi4ELi2ELb1E": (168, "Rothman-Keller, staged rows + tensor-memory stash (the default): 2 resident blocks by shared memory"),
+    "k_tp_stagedILi0ELi5ELi2ELb0E": (255, "MRT colour gradient, rows resident in the stage slots (LBM_TP_STASH=0): 2 resident blocks"),
+    "k_csf_stagedILi3ELb1E": (208, "CSF single pass, staged rows + tensor-memory stash (the default): 2 resident blocks"),
     "k_tp_fusedILi0ELb1E": (168, "MRT colour gradient, pipelined: 3 resident blocks"),
     "k_tp_fusedILi1ELb1E": (168, "Rothman-Keller, pipelined: 3 resident blocks"),
     "k_csf_collide_ringILi1E": (168, "CSF collision pass: 3 resident blocks"),
