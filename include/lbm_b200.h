@@ -296,10 +296,14 @@ typedef enum
   LBM_PROF_GHOST = 3,    /* ghost-row wrap / exchange */
   LBM_PROF_IBM = 4,      /* immersed-boundary pre-pass */
   LBM_PROF_MOMENTS = 5,  /* two-phase models: stream + moments kernel */
-  LBM_PROF_CLASSES = 6
+  LBM_PROF_EARLY = 6,    /* single-phase family: the same kernel over the EARLY rows, on the side stream beside the bulk launch */
+  LBM_PROF_CLASSES = 7
 } lbm_prof_class;
 int lbm_profile_enable(lbm_domain* d, int enable);
 int lbm_profile_read(lbm_domain* d, int prof_class, double* total_ms, long long* launches);
+/* single-phase family: how the step splits the slab's rows between the early launch (first / last row, rows with listed nodes
+ * in interior columns or feeding a stage, the immersed body's ROI rows) and the bulk launch; both run k_bgk_interior */
+int lbm_row_split(lbm_domain* d, int* n_early_rows, int* n_bulk_rows);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU slabs (test/decompose_domain.cpp:181-187 generalised to P slabs along axis 0)

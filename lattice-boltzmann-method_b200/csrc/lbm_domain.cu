@@ -109,7 +109,13 @@ struct LaunchArgs
   cudaStream_t stream;
   double* snap_rho = nullptr;  // MODE_PULL_ONLY: write moments here instead of the AoS populations
   double* snap_u = nullptr;
+  int prof_cls = LBM_PROF_INTERIOR;  // profiling class of the interior launch
 };
+
+// Threads per block of the side chain's kernels (listed nodes, stages, ghost rows).  (32-thread blocks, so that a pending
+// block of the high-priority side stream fits the hole any retiring bulk block leaves, were measured: no difference — the
+// listed-node kernel takes 79 us beside the bulk launch of a 2700 x 2100 grid against 13 us alone either way.)
+constexpr int SIDE_NT = 128;
 
 template <int MODE, int EQ, int FORCE, bool ADE>
 static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
@@ -133,7 +139,7 @@ static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
   p.snap_u = a.snap_u;
   if (a.rows && d->npairs > 0 && a.n_rows > 0)
   {
-    ProfScope ps(d, LBM_PROF_INTERIOR, a.stream);
+    ProfScope ps(d, a.prof_cls, a.stream);
     // block size among 64 / 96 / 128 that wastes the fewest threads in a row's last block (Y = 2100: 1048 pairs are
     // 8.2 blocks of 128 but 10.9 blocks of 96)
     int bs = 128;
@@ -154,7 +160,7 @@ static int launch_bgk(lbm_domain* d, const LaunchArgs& a)
     bt.ent = d->d_ent;
     bt.mom_prev = d->d_mom[d->mom_cur];
     bt.mom_cur = MODE == MODE_PULL_ONLY ? nullptr : d->d_mom[d->mom_cur ^ 1];
-    k_bgk_boundary<MODE, EQ, FORCE, ADE><<<cdiv(d->nb, 128), 128, 0, a.stream>>>(d->buf[0][a.s], d->buf[0][a.t], d->buf[1][a.s],
+    k_bgk_boundary<MODE, EQ, FORCE, ADE><<<cdiv(d->nb, SIDE_NT), SIDE_NT, 0, a.stream>>>(d->buf[0][a.s], d->buf[0][a.t], d->buf[1][a.s],
                                                                                 d->buf[1][a.t], d->g, p, bt, d->d_aos[0], d->d_aos[1]);
     d->launches++;
   }
@@ -201,7 +207,7 @@ int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st)
 {
   for (int l = 0; l < d->nlat; l++)
   {
-    k_wrap_ghost_rows<<<cdiv(d->g.pitch, 128), 128, 0, st>>>(d->buf[l][which], d->g, d->wrap_all_q ? 1 : 0);
+    k_wrap_ghost_rows<<<cdiv(d->g.pitch, SIDE_NT), SIDE_NT, 0, st>>>(d->buf[l][which], d->g, d->wrap_all_q ? 1 : 0);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
@@ -214,6 +220,7 @@ int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st)
 //   main stream : [wait side chain of the previous step]  EARLY rows  ->  ev_early  ->  BULK rows
 //   side stream : [wait ev_early] listed nodes -> pre-stream stages -> ghost rows of the new buffer
 //                 (local wrap / NCCL ring) -> IBM pre-pass for the NEXT step -> ev_side
+//   (no bulk rows at all: the early launch opens the side chain instead, see step_early)
 //
 // EARLY rows are the few rows whose results something else needs soon: the first and last row
 // (ghost exchange), rows owning a listed node in an interior column or feeding a stage (the listed
@@ -280,13 +287,29 @@ int step_prologue(lbm_domain* d, bool exchange_local, bool with_ibm)
   return LBM_OK;
 }
 
+// Early rows.  With a bulk launch to overlap: on the main stream, ahead of it (the side chain starts from ev_early and runs
+// beside the bulk rows).  WITHOUT one — every row is an early row, e.g. the sedimentation driver, whose outlet stage reads
+// every row — the step is a serial chain anyway, and the launch opens the side chain itself: one cross-stream hop per step
+// instead of two, +5.7 % on the 4096 x 8192 sedimentation workload.  (Moving the early rows to the side stream in
+// general was measured too: same speed at 8192^2, -5 % on the 2700 x 2100 Poiseuille grid, whose side chain is its
+// critical path, and per-kernel times that no longer add up because the two launches share the SMs.)
 int step_early(lbm_domain* d)
 {
   LBM_TRY(step_rows(d));
   const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
-  if (!d->skip_side_wait) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+  if (!d->skip_side_wait) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));  // main: the previous side chain
   d->skip_side_wait = false;
+  d->early_on_side = d->n_bulk == 0;
+  if (d->early_on_side)
+  {
+    LBM_CUDA(cudaEventRecord(d->ev_early, d->stream));
+    LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_early, 0));
+    LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_early, d->n_early, false, d->ibm.next_slot, d->side};
+    a.prof_cls = LBM_PROF_EARLY;
+    return dispatch_mode(d, mode, a);
+  }
   LaunchArgs a{d->cur, d->cur ^ 1, d->d_rows_early, d->n_early, false, d->ibm.next_slot, d->stream};
+  a.prof_cls = LBM_PROF_EARLY;
   LBM_TRY(dispatch_mode(d, mode, a));
   LBM_CUDA(cudaEventRecord(d->ev_early, d->stream));
   return LBM_OK;
@@ -295,7 +318,7 @@ int step_early(lbm_domain* d)
 int step_listed(lbm_domain* d)
 {
   const int mode = d->post_stream ? MODE_LOCAL : MODE_PULL;
-  LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_early, 0));
+  if (!d->early_on_side) LBM_CUDA(cudaStreamWaitEvent(d->side, d->ev_early, 0));
   LaunchArgs a{d->cur, d->cur ^ 1, nullptr, 0, true, d->ibm.next_slot, d->side};
   return dispatch_mode(d, mode, a);
 }
@@ -306,7 +329,7 @@ int stage_pack(lbm_domain* d, size_t k)
   if (sg.kind != 1 || !sg.own_src || sg.y_hi <= sg.y_lo) return LBM_OK;
   ProfScope ps(d, LBM_PROF_FIXUP, d->side);
   const int t = d->cur ^ 1;
-  k_pressure_pack<<<cdiv(sg.y_hi - sg.y_lo, 128), 128, 0, d->side>>>(d->buf[0][t], d->g, sg.src_gx - d->cfg.x0, sg.d_src_bidx,
+  k_pressure_pack<<<cdiv(sg.y_hi - sg.y_lo, SIDE_NT), SIDE_NT, 0, d->side>>>(d->buf[0][t], d->g, sg.src_gx - d->cfg.x0, sg.d_src_bidx,
                                                                     d->d_mom[d->mom_cur ^ 1], sg.d_packet, sg.y_lo, sg.y_hi);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
@@ -321,19 +344,19 @@ int stage_apply(lbm_domain* d, size_t k)
   if (sg.kind == 0)
   {
     if (sg.n == 0) return LBM_OK;
-    k_fix_copy<<<cdiv(sg.n, 128), 128, 0, d->side>>>(d->buf[0][t], d->buf[1][t], d->g, sg.d_entries, sg.n);
+    k_fix_copy<<<cdiv(sg.n, SIDE_NT), SIDE_NT, 0, d->side>>>(d->buf[0][t], d->buf[1][t], d->g, sg.d_entries, sg.n);
     d->launches++;
   }
   else
   {
     if (!sg.own_dst || sg.y_hi <= sg.y_lo) return LBM_OK;
-    const int lx = sg.dst_gx - d->cfg.x0, nblk = cdiv(sg.y_hi - sg.y_lo, 128);
+    const int lx = sg.dst_gx - d->cfg.x0, nblk = cdiv(sg.y_hi - sg.y_lo, SIDE_NT);
     if (d->cfg.model == LBM_MODEL_KBC)
-      k_pressure_apply<EQ_KBC><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+      k_pressure_apply<EQ_KBC><<<nblk, SIDE_NT, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     else if (d->cfg.equilibrium == EQ_INCOMP)
-      k_pressure_apply<EQ_INCOMP><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+      k_pressure_apply<EQ_INCOMP><<<nblk, SIDE_NT, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     else
-      k_pressure_apply<EQ_COMP><<<nblk, 128, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
+      k_pressure_apply<EQ_COMP><<<nblk, SIDE_NT, 0, d->side>>>(d->buf[0][t], d->g, lx, sg.d_packet, sg.rho_bc, sg.y_lo, sg.y_hi);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
@@ -345,16 +368,16 @@ static int stage_local(lbm_domain* d, size_t k)
   Stage& sg = d->stages[k];
   if (sg.y_hi <= sg.y_lo) return LBM_OK;
   ProfScope ps(d, LBM_PROF_FIXUP, d->side);
-  const int t = d->cur ^ 1, nblk = cdiv(sg.y_hi - sg.y_lo, 128);
+  const int t = d->cur ^ 1, nblk = cdiv(sg.y_hi - sg.y_lo, SIDE_NT);
   const int src_lx = sg.src_gx - d->cfg.x0, dst_lx = sg.dst_gx - d->cfg.x0;
   double* f = d->buf[0][t];
   const double* mom = d->d_mom[d->mom_cur ^ 1];
   if (d->cfg.model == LBM_MODEL_KBC)
-    k_pressure_local<EQ_KBC><<<nblk, 128, 0, d->side>>>(f, d->g, src_lx, dst_lx, sg.d_src_bidx, mom, sg.rho_bc, sg.y_lo, sg.y_hi);
+    k_pressure_local<EQ_KBC><<<nblk, SIDE_NT, 0, d->side>>>(f, d->g, src_lx, dst_lx, sg.d_src_bidx, mom, sg.rho_bc, sg.y_lo, sg.y_hi);
   else if (d->cfg.equilibrium == EQ_INCOMP)
-    k_pressure_local<EQ_INCOMP><<<nblk, 128, 0, d->side>>>(f, d->g, src_lx, dst_lx, sg.d_src_bidx, mom, sg.rho_bc, sg.y_lo, sg.y_hi);
+    k_pressure_local<EQ_INCOMP><<<nblk, SIDE_NT, 0, d->side>>>(f, d->g, src_lx, dst_lx, sg.d_src_bidx, mom, sg.rho_bc, sg.y_lo, sg.y_hi);
   else
-    k_pressure_local<EQ_COMP><<<nblk, 128, 0, d->side>>>(f, d->g, src_lx, dst_lx, sg.d_src_bidx, mom, sg.rho_bc, sg.y_lo, sg.y_hi);
+    k_pressure_local<EQ_COMP><<<nblk, SIDE_NT, 0, d->side>>>(f, d->g, src_lx, dst_lx, sg.d_src_bidx, mom, sg.rho_bc, sg.y_lo, sg.y_hi);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
@@ -832,12 +855,30 @@ int commit_boundary_tables(lbm_domain* d)
 int host_staging(lbm_domain* d, double** out)
 {
   const long long N = (long long)d->g.Xl * d->g.Y;
-  if (!d->d_mom_out) LBM_CUDA(cudaMalloc(&d->d_mom_out, 6 * N * sizeof(double)));
   if (d->copy_pending)
   {
-    LBM_CUDA(cudaEventSynchronize(d->ev_copied));
-    d->copy_pending = false;
+    if (cudaEventQuery(d->ev_copied) == cudaSuccess) d->copy_pending = false;
+    else
+    {
+      // an asynchronous snapshot is still on its way to the host out of d_mom_out: the import takes a second staging area
+      // (4 N doubles: the largest import, rho_r, rho_b, u) instead of waiting, so that its host->device copy runs beside the
+      // snapshot's device->host copy — PCIe is full duplex.  Out of memory: wait after all.
+      cudaGetLastError();
+      if (!d->d_stage_in && cudaMalloc(&d->d_stage_in, 4 * N * sizeof(double)) != cudaSuccess)
+      {
+        cudaGetLastError();
+        d->d_stage_in = nullptr;
+        LBM_CUDA(cudaEventSynchronize(d->ev_copied));
+        d->copy_pending = false;
+      }
+      else
+      {
+        *out = d->d_stage_in;
+        return LBM_OK;
+      }
+    }
   }
+  if (!d->d_mom_out) LBM_CUDA(cudaMalloc(&d->d_mom_out, 6 * N * sizeof(double)));
   *out = d->d_mom_out;
   return LBM_OK;
 }
@@ -1009,6 +1050,7 @@ int lbm_destroy(lbm_domain* d)
     cudaFree(d->d_aos[l]);
   }
   cudaFree(d->d_mom_out);
+  cudaFree(d->d_stage_in);
   cudaFree(d->d_mom_in);
   if (d->copy)
   {
@@ -1372,6 +1414,18 @@ int lbm_profile_read(lbm_domain* d, int cls, double* total_ms, long long* launch
   }
   *total_ms = sum;
   *launches = n;
+  return LBM_OK;
+}
+
+int lbm_row_split(lbm_domain* d, int* n_early_rows, int* n_bulk_rows)
+{
+  if (!d || !n_early_rows || !n_bulk_rows) { set_error("lbm_row_split: null argument"); return LBM_ERR_INVALID; }
+  if (d->tp) { set_error("lbm_row_split: the two-phase models march row bands, they have no early / bulk split"); return LBM_ERR_UNSUPPORTED; }
+  if (!d->committed) { set_error("lbm_row_split: call lbm_bc_commit first"); return LBM_ERR_INVALID; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  LBM_TRY(step_rows(d));
+  *n_early_rows = d->n_early;
+  *n_bulk_rows = d->n_bulk;
   return LBM_OK;
 }
 

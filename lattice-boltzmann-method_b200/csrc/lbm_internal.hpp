@@ -152,6 +152,7 @@ struct lbm_domain
   // row lists of the interior kernel
   bool rows_dirty = true;
   int n_early = 0, n_bulk = 0;
+  bool early_on_side = false;  // this step's early rows were launched on the side stream (no bulk rows to overlap)
   int *d_rows_all = nullptr, *d_rows_early = nullptr, *d_rows_bulk = nullptr;
   std::vector<char> row_has_listed;  // row owns a listed node in an interior column, or feeds a stage
   float last_ms = 0.f;
@@ -176,6 +177,7 @@ struct lbm_domain
   // snapshot staging: [6][Xl*Y] rho, u (2), phase, rho_r, rho_b — filled on `stream`, drained either on `stream`
   // (lbm_get_moments / lbm_get_phase) or on `copy` while later steps run (lbm_snapshot_async)
   double* d_mom_out = nullptr;
+  double* d_stage_in = nullptr;  // second import staging area, used while an async snapshot still reads d_mom_out
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
   bool copy_pending = false;

@@ -55,7 +55,7 @@ struct TwoPhaseState
   bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
   bool staged = true;                  // k_tp_staged: population rows staged by bulk async copies (LBM_TP_STAGED=0: k_tp_fused)
   int stages = 0;                      // LBM_TP_NS: stage slots per block (0 = the model's default)
-  bool stash = true;                   // resident population rows parked in tensor memory (k_tp_staged<.., STASH>); LBM_TP_STASH=0: in the stage slots
+  bool stash = true;                   // resident population rows parked in tensor memory (k_tp_staged<.., STASH>): default for MRTCG; LBM_TP_STASH=0/1
   double* aux = nullptr;               // TP_CSF: A_COUNT planes in the moment-plane geometry (normal n, interfacial tension Fs)
   int rpb_override = 0;
   // TP_CSF single-pass variant (LBM_CSF_FUSED=1, off by default until it has been measured on the device)
@@ -76,9 +76,12 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 constexpr int TPF_NT = 128;  // threads per block of the row-marching kernels = columns of a strip including its halo columns
 
 // Rows per band of the row-marching kernels.  Tall bands amortise the warm-up rows above and below a band (their
-// populations are read and their moments formed a second time), but the grid should also come out as whole WAVES of
-// resident blocks: at 4096^2 the old rule (6 waves' worth of blocks, rounded up) launched 6.02 waves — a seventh pass
-// over the SMs for 9 blocks, 14 % of the kernel's time.  Model: time ~ ceil(blocks / resident) * (rows + c * warm-up rows).
+// populations are read and their moments formed a second time) and the per-block set-up; short bands shorten the tail:
+// the last blocks of the grid end at different times and nothing fills the SMs they leave.  Model, fitted to a sweep of
+// the RK kernel at 4096^2 on the B200 (24 .. 128 rows: 0.867, 0.856, 0.857, 0.860, 0.870, 0.884, 0.908, 0.971 ms):
+//     time ~ (blocks / resident) * d + 0.84 * d,   d = rows + 0.6 * warm-up rows + 1.5   (rows' worth of work per block)
+// Round 1's rule (six waves' worth of blocks) and a first whole-waves rule both chose 51 .. 84 rows there; the minimum
+// is at 32 .. 40.  Large grids (MRTCG 16384^2: 38 waves at 128 rows) are flat within 1 % and keep tall bands.
 static int pick_band_rows(int Xl, int strips, int resident_blocks, int warmup_rows, int cap = 128)
 {
   if (Xl <= 24) return std::max(Xl, 1);
@@ -86,9 +89,9 @@ static int pick_band_rows(int Xl, int strips, int resident_blocks, int warmup_ro
   int best_rpb = std::min(cap, Xl);
   for (int rpb = std::min(cap, Xl); rpb >= 24; rpb--)
   {
-    const long long blocks = (long long)strips * cdiv(Xl, rpb);
-    const double waves = std::ceil((double)blocks / std::max(resident_blocks, 1));
-    const double t = waves * (rpb + 0.6 * warmup_rows);
+    const double blocks = (double)strips * cdiv(Xl, rpb);
+    const double d = rpb + 0.6 * warmup_rows + 1.5;
+    const double t = blocks / std::max(resident_blocks, 1) * d + 0.84 * d;
     if (t < best * (1.0 - 1e-9))
     {
       best = t;
@@ -1072,6 +1075,9 @@ int tp_create(lbm_domain* d)
   if (const char* e = getenv("LBM_TP_PIPE")) tp->pipe = atoi(e) != 0;
   if (const char* e = getenv("LBM_TP_STAGED")) tp->staged = atoi(e) != 0;
   if (const char* e = getenv("LBM_TP_NS")) tp->stages = atoi(e);
+  // MRTCG (H = 2): the stash frees shared memory for a third block per SM (+17 %).  RK (H = 1) runs two blocks either way
+  // and is 1 % faster with its two resident rows left in the stage slots
+  tp->stash = tp->model == TP_MRTCG;
   if (const char* e = getenv("LBM_TP_STASH")) tp->stash = atoi(e) != 0;
   if (const char* e = getenv("LBM_TP_RPB")) tp->rpb_override = atoi(e);
   return LBM_OK;
@@ -2125,7 +2131,6 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
   auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };  // v mod n for -n <= v < 2n
   for (int r = r0; r < r_end; r++)
   {
-    const int k = r - r0;
     const double* st_r = stage + (size_t)sl * C::ROW;
     mbar_wait(&full[sl], par);
     // ---- A: moments of (r, y) -> moment ring

@@ -105,9 +105,9 @@ EXPORTS = [
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
     "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension", "lbm_link_face", "lbm_set_force_region",
-    "lbm_rk_diagnostics", "lbm_comm_check", "lbm_comm_share",
+    "lbm_rk_diagnostics", "lbm_comm_check", "lbm_comm_share", "lbm_row_split",
 ]
-PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS = range(6)
+PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS, PROF_EARLY = range(7)
 
 _lib = None
 
@@ -154,6 +154,7 @@ def load():
         _lib.lbm_use_graph.argtypes = [C.c_void_p, C.c_int]
         _lib.lbm_profile_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.lbm_profile_read.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_longlong)]
+        _lib.lbm_row_split.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.lbm_comm_unique_id.argtypes = [C.c_char_p]
         _lib.lbm_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.lbm_comm_share.argtypes = [C.c_void_p, C.c_void_p]
@@ -425,6 +426,12 @@ class Domain:
         ms = C.c_double(); n = C.c_longlong()
         _chk(self.lib.lbm_profile_read(self.h, prof_class, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def row_split(self):
+        """(early rows, bulk rows) of the single-phase step's two interior launches"""
+        a, b = C.c_int(), C.c_int()
+        _chk(self.lib.lbm_row_split(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def use_graph(self, enable=True):
         _chk(self.lib.lbm_use_graph(self.h, 1 if enable else 0))

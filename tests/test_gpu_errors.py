@@ -78,3 +78,22 @@ def test_linked_slab_refuses_plain_step():
     st, msg = status_of(lambda: a.step(1))
     assert st == 1 and "lbm_step_group" in msg
     L.step_group([a, b], 2)
+
+
+def test_row_split_and_ring_calls_out_of_order():
+    """lbm_row_split reports the step's early / bulk rows (single-phase family only); lbm_comm_share needs a ring member;
+    the binding refuses arrays of the wrong shape before their pointers cross the C ABI"""
+    d, _ = cases.poiseuille(40, 33)
+    assert d.row_split() == (4, 36)          # rows 0, 1, X-2, X-1 feed the pressure-periodic stages
+    tp = cases.mrtcg(24, 20, (0.0, 0.0), 0)
+    st, msg = status_of(lambda: tp.row_split())
+    assert st == 4 and "two-phase" in msg
+    other = L.Domain(L.default_config(model=L.MODEL_BGK, X=12, Y=12))
+    st, msg = status_of(lambda: d.comm_share(other))
+    assert st == 1 and "has not joined a ring" in msg
+    with pytest.raises(ValueError, match="expected shape"):
+        d.set_f(np.zeros((40, 32, 9)))
+    with pytest.raises(ValueError, match="expected shape"):
+        tp.init_two_phase(np.ones((24, 20)), np.ones((24, 20)), np.zeros((24, 21, 2)))
+    with pytest.raises(ValueError, match="one length"):
+        cases.cylinder(40, 40, 1.2, 0.05, np.zeros(5), np.zeros(4))
