@@ -786,7 +786,7 @@ def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sa
     #      snapshot rho, u (D2H into pinned host).  Two measurements of the same traffic:
     #        blocking  : lbm_get_moments returns when the copy is done (what round 1 reported) — median of 3 blocks
     #        streaming : lbm_snapshot_async stages rho, u on the device and copies them on the library's copy stream while the
-    #                    next block's import and steps run (PCIe is full duplex), lbm_snapshot_wait at the very end — three
+    #                    next block's import and steps run (PCIe is full duplex), lbm_snapshot_wait at the very end — five
     #                    consecutive blocks timed as one region, every byte moved and waited for inside it.  This is how the
     #                    drivers of this repo snapshot (drivers/common.hpp), and it is the `e2e.value` of the line.
     e2e = None
@@ -803,7 +803,7 @@ def measure(ctx, workload, X, Y, steps, warmup, *, pin, with_e2e, graph_mode, sa
             t2 = time.perf_counter()
             runs.append((ctx.max_over_ranks(t2 - t0), t1 - t0, t2 - t1))
         sec_blocking, imp, rest = sorted(runs)[1]
-        R = 3
+        R = 5
         ctx.barrier(d)
         t0 = time.perf_counter()
         for _ in range(R):
