@@ -173,18 +173,22 @@ __device__ __forceinline__ void tmem_store4(uint32_t taddr, double a, double b, 
                "r"(__double2loint(d)), "r"(__double2hiint(d))
                : "memory");
 }
-__device__ __forceinline__ void tmem_load4(uint32_t taddr, double& a, double& b, double& c, double& d)
+__device__ __forceinline__ void tmem_load4_issue(uint32_t taddr, uint32_t (&r)[8])
 {
-  int r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  a = __hiloint2double(r[1], r[0]);
-  b = __hiloint2double(r[3], r[2]);
-  c = __hiloint2double(r[5], r[4]);
-  d = __hiloint2double(r[7], r[6]);
+}
+// after tmem_load_wait()
+__device__ __forceinline__ void tmem_unpack4(uint32_t (&r)[8], double& a, double& b, double& c, double& d)
+{
+#pragma unroll
+  for (int k = 0; k < 8; k++) asm volatile("" : "+r"(r[k])::"memory");
+  a = __hiloint2double((int)r[1], (int)r[0]);
+  b = __hiloint2double((int)r[3], (int)r[2]);
+  c = __hiloint2double((int)r[5], (int)r[4]);
+  d = __hiloint2double((int)r[7], (int)r[6]);
 }
 
 #else  // ---- tests/cpu_emu: a copy lands when it is issued; a wait on a phase nobody completed is a kernel bug and aborts
@@ -292,11 +296,15 @@ inline void tmem_store4(uint32_t taddr, double a, double b, double c, double d)
   const double v[4] = {a, b, c, d};
   std::memcpy(emu_tmem()[threadIdx.x] + taddr, v, 32);
 }
-inline void tmem_load4(uint32_t taddr, double& a, double& b, double& c, double& d)
+inline void tmem_load4_issue(uint32_t taddr, uint32_t (&r)[8])
 {
-  if (taddr + 8u > 512u || threadIdx.x >= 128u) emu_async_fail("tmem_load4: outside the thread's 512 columns");
+  if (taddr + 8u > 512u || threadIdx.x >= 128u) emu_async_fail("tmem_load4_issue: outside the thread's 512 columns");
+  std::memcpy(r, emu_tmem()[threadIdx.x] + taddr, 32);
+}
+inline void tmem_unpack4(uint32_t (&r)[8], double& a, double& b, double& c, double& d)
+{
   double v[4];
-  std::memcpy(v, emu_tmem()[threadIdx.x] + taddr, 32);
+  std::memcpy(v, r, 32);
   a = v[0]; b = v[1]; c = v[2]; d = v[3];
 }
 

@@ -2046,7 +2046,7 @@ template <int NS>
 struct CsfStaged
 {
   using F = CsfFused;
-  static constexpr int W = TPF_NT + 4, ROW = 18 * W;
+  static constexpr int W = TPF_NT + 4, ROW = 20 * W;  // 18 population row segments + the carried interfacial tension (Fs_x, Fs_y)
   static constexpr size_t RING_BYTES = F::SMEM;
   static constexpr size_t SMEM = sizeof(double) * NS * ROW + RING_BYTES + sizeof(uint64_t) * NS;
   static constexpr int TMEM_COLS = 256, T_MOM = 6 * 36;  // columns: populations of 6 rows, then rho_r, rho_b, u_x, u_y of 5 rows
@@ -2103,16 +2103,22 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
   else __syncthreads();
   auto flag_of = [&](int r) -> int { return sflag[r - r0]; };
 
-  // lanes 0 .. 17 of warp 0 own one population row segment each (source pointer at row 0, shared-memory offset)
+  // lanes 0 .. 17 of warp 0 own one population row segment each (source pointer at row 0, shared-memory offset); lanes 18, 19
+  // the same column window of the carried interfacial tension's two planes (moment-plane geometry: two cells of padding)
   const int lane_q = (t < 18 ? t : 0) % 9;
-  const double* lane_src = (t < 9 ? rsrc : bsrc) + (long long)lane_q * g.plane + node_off(g, -CX(lane_q), lo);
-  double* lane_dst = stage + (t < 18 ? t : 0) * W + (lo - c0);
+  const int alo = max(c0 + 2, 0), ahi = min(c0 + 2 + W, mg.pm);   // plane columns [c0 + 2, c0 + 2 + W) hold grid columns [c0, c0 + W)
+  const unsigned aux_bytes = (unsigned)(ahi - alo) * (unsigned)sizeof(double);
+  const double* lane_src = t < 18 ? (t < 9 ? rsrc : bsrc) + (long long)lane_q * g.plane + node_off(g, -CX(lane_q), lo)
+                                  : aux + (long long)(t == 18 ? A_FX : A_FY) * mg.mplane + 2LL * mg.pm + alo;  // (row 0 of the slab)
+  double* lane_dst = stage + (t < 20 ? t : 0) * W + (t < 18 ? lo - c0 : alo - (c0 + 2));
+  const long long lane_pitch = t < 18 ? g.pitch : mg.pm;
+  const unsigned lane_bytes = t < 18 ? seg_bytes : aux_bytes;
   auto issue_row = [&](int rr, int slot) {
     if (t >= 32 || rr >= r_end) return;
     const bool staged = rr >= rs0 && rr < rs1;
-    if (t == 0) mbar_arrive_expect_tx(&full[slot], staged ? 18u * seg_bytes : 0u);
+    if (t == 0) mbar_arrive_expect_tx(&full[slot], staged ? 18u * seg_bytes + 2u * aux_bytes : 0u);
     __syncwarp();
-    if (staged && t < 18) bulk_copy_g2s(lane_dst + (size_t)slot * C::ROW, lane_src + (long long)rr * g.pitch, seg_bytes, &full[slot]);
+    if (staged && t < 20) bulk_copy_g2s(lane_dst + (size_t)slot * C::ROW, lane_src + (long long)rr * lane_pitch, lane_bytes, &full[slot]);
   };
   constexpr int AHEAD = NS - HOLD - (STASH ? 0 : 1);  // rows issued before the march starts = distance of the loop's refill rule
   for (int j = 0; j < AHEAD; j++) issue_row(r0 + j, j);
@@ -2160,7 +2166,7 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
         ph = mom[M_PH * mg.mplane + km];
       }
       else
-        tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, aux[A_FX * mg.mplane + km], aux[A_FY * mg.mplane + km]);
+        tp_moments<TP_CSF>(p, fr, fb, rr, rb, ux, uy, ph, st_r[18 * W + my], st_r[19 * W + my]);  // Fs of the previous step, staged with the row
       const double cq = p.cr * rr + p.cb * rb;
       M(0, ms, t) = ph;
       M(1, ms, t) = cq * ux;
@@ -2182,8 +2188,12 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
     __syncthreads();
     issue_row(r + AHEAD, sl_fill);
     // the collided row's populations start their way back from tensor memory under the normal's arithmetic
-    [[maybe_unused]] uint32_t tr[36];
-    if constexpr (STASH) tmem_load18_issue(tmem + 36u * (unsigned)(ts == 5 ? 0 : ts + 1), tr);  // row r - 5: slot (k - 5) mod 6 = (k + 1) mod 6
+    [[maybe_unused]] uint32_t tr[36], tq[8];
+    if constexpr (STASH)
+    {
+      tmem_load18_issue(tmem + 36u * (unsigned)(ts == 5 ? 0 : ts + 1), tr);       // row r - 5: slot (k - 5) mod 6 = (k + 1) mod 6
+      tmem_load4_issue(tmem + (unsigned)C::T_MOM + 8u * (unsigned)tm, tq);        // and its moments: slot (k - 5) mod 5 = k mod 5
+    }
 
     // ---- B: normal of (r - 2, y) -> normal ring
     {
@@ -2236,7 +2246,7 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
     {
       tmem_load_wait();
       tmem_unpack18(tr, fr, fb);
-      tmem_load4(tmem + (unsigned)C::T_MOM + 8u * (unsigned)tm, crr, crb, cux, cuy);      // and its moments: slot (k - 5) mod 5 = k mod 5
+      tmem_unpack4(tq, crr, crb, cux, cuy);
     }
     else
     {

@@ -396,6 +396,8 @@ cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaS
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 // a small "device" on purpose: the band-height rule (pick_band_rows) then cuts even the tests' grids into several bands
+// a small "device" on purpose: persistent launches then stride over their tiles even on the tests' grids
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 3; return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int)
 {
   *v = a == cudaDevAttrMultiProcessorCount ? 3 : a == cudaDevAttrMaxRegistersPerMultiprocessor ? 65536 : a == cudaDevAttrMaxSharedMemoryPerMultiprocessor ? 233472 : 0;
