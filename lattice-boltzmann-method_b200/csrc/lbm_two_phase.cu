@@ -666,6 +666,10 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
     double fr[9], fb[9];
     if constexpr (STASH)
     {
+      // the previous rows' parks have landed (tcgen05.wait::st, a whole iteration after they were issued: nothing to wait
+      // for in practice; measured alternatives: in front of the barrier the same, right before the collision's load -4 %).
+      // A row is taken back H >= 1 iterations after its park, so every load has at least one such wait behind it.
+      tmem_store_wait();
       // every thread takes its 18 populations out of the slot (rows outside the slab: stale shared memory, never used)
       // and parks them in its tensor-memory lane for the collision H rows later
 #pragma unroll
@@ -713,14 +717,12 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
       mux[0] = ux_;
       muy[0] = uy_;
     }
-    // the park has landed before the barrier (measured: waiting for it behind the barrier, right before the collision's
-    // tcgen05.ld, cost the MRT kernel 4 %), and the collided row's populations are on their way back under the barrier
+    // the collided row's populations are on their way back from tensor memory under the barrier
     [[maybe_unused]] uint32_t tr[36];
     if constexpr (STASH)
     {
       ts = ts == H ? 0 : ts + 1;  // now the slot of row r - H: (k - H) mod (H + 1) = (k + 1) mod (H + 1)
       tmem_load18_issue(tmem + 36u * (unsigned)ts, tr);
-      tmem_store_wait();
     }
     __syncthreads();
     // a slot is free now: the one this iteration read (STASH) / the one the previous iteration's collision read last
@@ -2153,7 +2155,11 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
         fb[q] = st_r[(9 + q) * W + my - CY(q)];
       }
     }
-    if constexpr (STASH) tmem_store18(tmem + 36u * (unsigned)ts, fr, fb);
+    if constexpr (STASH)
+    {
+      tmem_store_wait();  // the previous iterations' parks have landed (they are taken back five iterations after they were issued)
+      tmem_store18(tmem + 36u * (unsigned)ts, fr, fb);
+    }
     if (want)
     {
       const long long km = mom_off(mg, r, y);
@@ -2184,7 +2190,6 @@ k_csf_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, d
       }
       mrr[0] = rr; mrb[0] = rb; mux[0] = ux; muy[0] = uy;
     }
-    if constexpr (STASH) tmem_store_wait();  // both parks (this row's populations, the previous row's moments) have landed
     __syncthreads();
     issue_row(r + AHEAD, sl_fill);
     // the collided row's populations start their way back from tensor memory under the normal's arithmetic

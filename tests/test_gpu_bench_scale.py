@@ -287,3 +287,43 @@ def test_slabs_equal_monolithic_at_8192():
         x0, x1 = L.decompose_rows(X, 3, r)
         assert np.array_equal(d.get_f(), want[x0:x1]), r
         d.close()
+
+
+def test_sedimentation_ade_at_4096x8192(orc):
+    """BASELINE configs[4]'s grid, fluid + advection-diffusion lattice (k_bgk_interior<PULL,COMP,NONE,ADE>; every row of this
+    driver is an early row, so the one launch over all rows runs on the side stream): inlet column, extrapolated outlet,
+    zero-gradient copies and the rectangle's walls stay within one tile of the grid's edges for 40 steps"""
+    X, Y = (full(4096), full(8192)) if not EMU else (4 * T, 4 * T)
+    omega, u_lb, w_s, steps = 1.0 / 0.55, 0.02, 3e-3, 40
+    walls = (-20, 10, 30)                       # rectangle_sedimentation_test.cpp:73-75: rows from the end, two wall columns
+    rho_t, u_t = tile_fields()
+    u_t = u_t * 0.5
+    u_t[..., 1] += u_lb                         # the driver's stream runs along axis 1
+    C_t = 1e-3 * (1.0 + 0.3 * np.sin(2 * np.pi * np.arange(T)[:, None] / T) * np.cos(4 * np.pi * np.arange(T)[None, :] / T))[..., None]
+    f_t = orc.equilibrium(u_t, rho_t)
+    g_t = orc.equilibrium(u_t + w_s, C_t)       # rectangle_sedimentation_test.cpp:123-131: the sediment settles with u + w_s
+
+    def run_gpu(nx, ny):
+        C_w = np.zeros(nx * T); C_w[-10:] = 1e-3
+        d = cases.sedimentation(nx * T, ny * T, omega, u_lb, w_s, C_w, walls)
+        d.set_f(tiled(f_t, nx, ny), 0)
+        d.set_f(tiled(g_t, nx, ny), 1)
+        d.step(steps)
+        out = d.get_f(0), d.get_f(1)
+        d.close()
+        return out
+
+    gf, gg = run_gpu(X // T, Y // T)
+    ref_f = assert_tiles_identical(gf, 1, "fluid populations")
+    ref_g = assert_tiles_identical(gg, 1, "sediment populations")
+    del gf, gg
+    n = 3 * T
+    C_w = np.zeros(n); C_w[-10:] = 1e-3
+    f, g = tiled(f_t, 3, 3), tiled(g_t, 3, 3)
+    rho = orc.calc_rho(f)
+    u = orc.calc_u(f, rho)
+    Cc = orc.calc_rho(g)
+    for _ in range(steps):
+        orc.sedimentation_step(f, g, u, rho, Cc, omega, u_lb, w_s, C_w, *walls)
+    assert cases.relerr(ref_f, f[T:2 * T, T:2 * T]) < 1e-12
+    assert cases.relerr(ref_g, g[T:2 * T, T:2 * T]) < 1e-12
