@@ -340,6 +340,19 @@ int lbm_step_group(lbm_domain* const* domains, int n_domains, int n_steps);
  * Blocks keep their own coordinates and rule lists (like the reference's `domain A{L, L4}; domain B{L4, L2}; ...`), must own
  * all their rows, and are advanced together with lbm_step_group.  Call lbm_bc_commit after the last binding. */
 int lbm_link_face(lbm_domain* d, int side, int row_begin, int n_rows, lbm_domain* other, int other_row_begin);
+/* The same binding between blocks that live in DIFFERENT processes (one block per GPU), over NCCL send/recv:
+ *   lbm_comm_init_blocks   joins the block communicator (rank 0 makes the id with lbm_comm_unique_id); unlike lbm_comm_init
+ *                          the members are independent grids, there is no slab ring
+ *   lbm_link_face_rank     like lbm_link_face, the facing block named by the rank that owns it; one call per direction ON THE
+ *                          READING RANK only
+ *   lbm_comm_faces_commit  collective, after the last lbm_link_face_rank of every rank and before lbm_bc_commit / lbm_step:
+ *                          the ranks exchange their link lists, so that each learns which rows of its edge columns the others
+ *                          read and sends them every step
+ * then plain lbm_step on every rank, the same number of steps everywhere (each step holds one grouped exchange).
+ * test/decompose_domain_loop.cpp:232-261 with A, B, C, D on four ranks. */
+int lbm_comm_init_blocks(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank);
+int lbm_link_face_rank(lbm_domain* d, int side, int row_begin, int n_rows, int peer_rank, int peer_row_begin);
+int lbm_comm_faces_commit(lbm_domain* d);
 /* bit-exact decomposition indexing: rows [x0,x1) for `rank` of `n_ranks` over X rows */
 int lbm_decompose_rows(int X, int n_ranks, int rank, int* x0, int* x1);
 

@@ -144,9 +144,11 @@ struct CommState
   std::shared_ptr<CommHandle> handle;
   ncclComm_t comm = nullptr;  // = handle->comm
   int n_ranks = 1, rank = 0;
+  bool blocks = false;        // lbm_comm_init_blocks: independent blocks bound across column faces, not the slabs of one grid
 };
 
-bool comm_active(const lbm_domain* d) { return d->comm != nullptr && d->comm->n_ranks > 1; }
+bool comm_active(const lbm_domain* d) { return d->comm != nullptr && d->comm->n_ranks > 1 && !d->comm->blocks; }
+bool comm_blocks(const lbm_domain* d) { return d->comm != nullptr && d->comm->blocks; }
 
 int comm_release(lbm_domain* d)
 {
@@ -382,6 +384,17 @@ int comm_link_refresh(lbm_domain* d)
   return LBM_OK;
 }
 
+// packet[lattice][qi][k] = f_coll(lattice)[row0 + k, col, face_q(side, qi)]
+__global__ void k_face_pack(const double* __restrict__ f0, const double* __restrict__ f1, const SlabGeom g, int col, int row0,
+                            int n, int side, int nlat, double* __restrict__ packet)
+{
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nlat * 3 * n) return;
+  const int k = idx % n, qi = (idx / n) % 3, l = idx / (3 * n);
+  const double* f = l == 0 ? f0 : f1;
+  packet[idx] = f[(long long)face_q(side, qi) * g.plane + node_off(g, row0 + k, col)];
+}
+
 int faces_release(lbm_domain* d)
 {
   for (auto& fl : d->faces)
@@ -392,6 +405,46 @@ int faces_release(lbm_domain* d)
   }
   d->faces.clear();
   cudaSetDevice(d->cfg.device);
+  for (auto& sv : d->serves) cudaFree(sv.d_packet);
+  d->serves.clear();
+  d->faces_remote_ready = false;
+  return LBM_OK;
+}
+
+// Bound column faces between blocks on DIFFERENT ranks (lbm_link_face_rank): on the side stream, behind the listed-node
+// kernel that wrote the edge columns of buffer `w` — pack the rows remote readers asked for, then one NCCL group: send the
+// packets, receive this block's face tails straight into place (3 x nlat contiguous pieces per link).  Between two ranks
+// sends and receives match in order: the reader enumerates its links to that peer by index, the server the same links out
+// of the reader's descriptors (lbm_comm_faces_commit), each link as [lattice][qi].
+int faces_exchange_remote(lbm_domain* d, bool new_buffer)
+{
+  if (!comm_blocks(d)) return LBM_OK;
+  CommState* c = d->comm;
+  const int w = new_buffer ? d->cur ^ 1 : d->cur;
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  for (auto& sv : d->serves)
+  {
+    const int total = d->nlat * 3 * sv.n;
+    k_face_pack<<<(total + 127) / 128, 128, 0, d->side>>>(d->buf[0][w], d->buf[1][w], d->g, sv.reader_side == 0 ? d->g.Y - 1 : 0, sv.rb, sv.n,
+                                                         sv.reader_side, d->nlat, sv.d_packet);
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  ProfScope ps(d, LBM_PROF_GHOST, d->side);
+  LBM_NCCL_GROUP_BEGIN();
+  for (auto& sv : d->serves)
+    for (int l = 0; l < d->nlat; l++)
+      for (int qi = 0; qi < 3; qi++)
+        LBM_NCCL(g_nccl.Send(sv.d_packet + (size_t)(l * 3 + qi) * sv.n, (size_t)sv.n, ncclFloat64, sv.peer_rank, c->comm, d->side));
+  for (auto& fl : d->faces)
+  {
+    if (fl.peer_rank < 0) continue;
+    for (int l = 0; l < d->nlat; l++)
+      for (int qi = 0; qi < 3; qi++)
+        LBM_NCCL(g_nccl.Recv(d->buf[l][w] + face_tail_off(d->g, fl.side, qi, fl.rb), (size_t)fl.n, ncclFloat64, fl.peer_rank, c->comm, d->side));
+  }
+  LBM_NCCL_GROUP_END();
+  d->launches++;
   return LBM_OK;
 }
 
@@ -638,16 +691,133 @@ int lbm_link_face(lbm_domain* d, int side, int row_begin, int n_rows, lbm_domain
   return LBM_OK;
 }
 
-// packet[lattice][qi][k] = f_coll(lattice)[row0 + k, col, face_q(side, qi)]
-__global__ void k_face_pack(const double* __restrict__ f0, const double* __restrict__ f1, const SlabGeom g, int col, int row0,
-                            int n, int side, int nlat, double* __restrict__ packet)
+// ---- the same binding between blocks on different ranks.  One process per block: lbm_comm_init_blocks makes the
+// communicator (no slab ring: the blocks are independent grids), lbm_link_face_rank declares what THIS block reads, and
+// lbm_comm_faces_commit — collective — lets every rank learn which of its rows the others read.
+int lbm_comm_init_blocks(lbm_domain* d, const char id[LBM_UNIQUE_ID_BYTES], int n_ranks, int rank)
 {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nlat * 3 * n) return;
-  const int k = idx % n, qi = (idx / n) % 3, l = idx / (3 * n);
-  const double* f = l == 0 ? f0 : f1;
-  packet[idx] = f[(long long)face_q(side, qi) * g.plane + node_off(g, row0 + k, col)];
+  if (!d || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) { set_error("lbm_comm_init_blocks: bad argument"); return LBM_ERR_INVALID; }
+  if (d->tp) { set_error("lbm_comm_init_blocks: column faces are built for the single-phase models"); return LBM_ERR_UNSUPPORTED; }
+  if (d->cfg.x0 != 0 || d->cfg.x1 != d->cfg.X) { set_error("lbm_comm_init_blocks: a block owns all of its rows (no row slabs)"); return LBM_ERR_UNSUPPORTED; }
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  comm_release(d);
+  LBM_TRY(load_nccl());
+  CommState* c = new CommState();
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  c->blocks = true;
+  c->handle = std::make_shared<CommHandle>();
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  ncclResult_t r = g_nccl.CommInitRank(&c->handle->comm, n_ranks, u, rank);
+  if (r != 0)
+  {
+    set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    c->handle->comm = nullptr;
+    delete c;
+    return LBM_ERR_COMM;
+  }
+  c->comm = c->handle->comm;
+  d->comm = c;
+  d->side_ready = false;
+  return LBM_OK;
 }
+
+int lbm_link_face_rank(lbm_domain* d, int side, int row_begin, int n_rows, int peer_rank, int peer_row_begin)
+{
+  if (!d || (side != 0 && side != 1) || n_rows < 1 || peer_row_begin < 0) { set_error("lbm_link_face_rank: bad argument"); return LBM_ERR_INVALID; }
+  if (!comm_blocks(d)) { set_error("lbm_link_face_rank: call lbm_comm_init_blocks first"); return LBM_ERR_INVALID; }
+  if (peer_rank < 0 || peer_rank >= d->comm->n_ranks || peer_rank == d->comm->rank)
+  {
+    set_error("lbm_link_face_rank: peer rank %d of %d (this is rank %d; bind blocks of one process with lbm_link_face)", peer_rank, d->comm->n_ranks,
+              d->comm->rank);
+    return LBM_ERR_INVALID;
+  }
+  if (row_begin < 0 || row_begin + n_rows > d->cfg.X) { set_error("lbm_link_face_rank: rows [%d,%d) outside the block", row_begin, row_begin + n_rows); return LBM_ERR_INVALID; }
+  for (const auto& fl : d->faces)
+    if (fl.side == side && row_begin < fl.rb + fl.n && fl.rb < row_begin + n_rows)
+    {
+      set_error("lbm_link_face_rank: rows [%d,%d) of side %d are already bound", row_begin, row_begin + n_rows, side);
+      return LBM_ERR_INVALID;
+    }
+  FaceLink fl;
+  fl.side = side; fl.rb = row_begin; fl.n = n_rows; fl.orb = peer_row_begin; fl.other = nullptr; fl.peer_rank = peer_rank;
+  fl.other_device = d->cfg.device;
+  d->faces.push_back(fl);
+  d->committed = false;  // the edge-column programs change: lbm_bc_commit again
+  d->side_ready = false;
+  d->faces_remote_ready = false;
+  drop_graphs(d);
+  return LBM_OK;
+}
+
+// Collective over the block communicator, after every rank's lbm_link_face_rank calls: each rank hands every other its list
+// of remote links (side, rows, the peer's rows); a rank finds the links that name it and from now on packs and sends those
+// rows of its facing edge column every step.  Checks that the rows exist on the serving block.
+int lbm_comm_faces_commit(lbm_domain* d)
+{
+  if (!d) { set_error("lbm_comm_faces_commit: null domain"); return LBM_ERR_INVALID; }
+  if (!comm_blocks(d)) { set_error("lbm_comm_faces_commit: call lbm_comm_init_blocks first"); return LBM_ERR_INVALID; }
+  CommState* c = d->comm;
+  constexpr int MAXF = 16, NREC = 1 + 5 * MAXF;  // count, then (side, rb, n, orb, peer) per link
+  const int P = c->n_ranks;
+  LBM_CUDA(cudaSetDevice(d->cfg.device));
+  std::vector<double> rec((size_t)P * NREC, 0.0);
+  double* mine = rec.data() + (size_t)c->rank * NREC;
+  int nf = 0;
+  for (const auto& fl : d->faces)
+  {
+    if (fl.peer_rank < 0) continue;
+    if (nf == MAXF) { set_error("lbm_comm_faces_commit: more than %d remote links on one block", MAXF); return LBM_ERR_UNSUPPORTED; }
+    double* r = mine + 1 + 5 * nf++;
+    r[0] = fl.side; r[1] = fl.rb; r[2] = fl.n; r[3] = fl.orb; r[4] = fl.peer_rank;
+  }
+  mine[0] = nf;
+  double* dev = nullptr;
+  LBM_CUDA(cudaMalloc(&dev, sizeof(double) * rec.size()));
+  auto exchange = [&]() -> int {
+    LBM_CUDA(cudaMemcpyAsync(dev + (size_t)c->rank * NREC, mine, sizeof(double) * NREC, cudaMemcpyHostToDevice, d->stream));
+    LBM_NCCL_GROUP_BEGIN();
+    for (int k = 0; k < P; k++)
+    {
+      if (k == c->rank) continue;
+      LBM_NCCL(g_nccl.Send(dev + (size_t)c->rank * NREC, NREC, ncclFloat64, k, c->comm, d->stream));
+      LBM_NCCL(g_nccl.Recv(dev + (size_t)k * NREC, NREC, ncclFloat64, k, c->comm, d->stream));
+    }
+    LBM_NCCL_GROUP_END();
+    LBM_CUDA(cudaMemcpyAsync(rec.data(), dev, sizeof(double) * rec.size(), cudaMemcpyDeviceToHost, d->stream));
+    LBM_CUDA(cudaStreamSynchronize(d->stream));
+    return LBM_OK;
+  };
+  const int rc = exchange();
+  cudaFree(dev);
+  if (rc != LBM_OK) return rc;
+  for (auto& sv : d->serves) cudaFree(sv.d_packet);
+  d->serves.clear();
+  for (int k = 0; k < P; k++)  // readers in rank order, their links in index order: the order both sides send / receive in
+  {
+    if (k == c->rank) continue;
+    const double* r = rec.data() + (size_t)k * NREC;
+    for (int j = 0; j < (int)r[0]; j++)
+    {
+      const double* q = r + 1 + 5 * j;
+      if ((int)q[4] != c->rank) continue;
+      FaceServe sv;
+      sv.reader_side = (int)q[0]; sv.n = (int)q[2]; sv.rb = (int)q[3]; sv.peer_rank = k;
+      if (sv.rb < 0 || sv.rb + sv.n > d->cfg.X)
+      {
+        set_error("lbm_comm_faces_commit: rank %d binds rows [%d,%d) of this block, which has %d rows", k, sv.rb, sv.rb + sv.n, d->cfg.X);
+        return LBM_ERR_COMM;
+      }
+      LBM_CUDA(cudaMalloc(&sv.d_packet, sizeof(double) * d->nlat * 3 * sv.n));
+      d->serves.push_back(sv);
+    }
+  }
+  d->faces_remote_ready = true;
+  d->side_ready = false;
+  return LBM_OK;
+}
+
 
 // Face tails of every bound block: the facing edge columns of the other blocks (written by their listed-node kernels on
 // their side streams) packed there, copied here on this block's side stream ahead of its next listed-node kernel.
@@ -659,6 +829,7 @@ static int group_faces(lbm_domain* const* ds, int n, bool new_buffer)
     lbm_domain* d = ds[i];
     for (auto& fl : d->faces)
     {
+      if (fl.peer_rank >= 0) continue;  // a block on another rank: faces_exchange_remote
       lbm_domain* o = fl.other;
       bool member = false;
       for (int j = 0; j < n; j++) member = member || ds[j] == o;
@@ -762,7 +933,7 @@ int lbm_step_group(lbm_domain* const* ds, int n, int n_steps)
   for (int i = 0; i < n; i++)
     for (const auto& fl : ds[i]->faces)
     {
-      bool member = false;
+      bool member = fl.peer_rank >= 0;  // (blocks on other ranks are not advanced by a group)
       for (int j = 0; j < n; j++) member = member || ds[j] == fl.other;
       if (!member) { set_error("lbm_step_group: block %d is bound across a column face to a block outside the group", i); return LBM_ERR_INVALID; }
     }

@@ -419,9 +419,20 @@ int step_bulk(lbm_domain* d)
 
 static int bgk_step_once(lbm_domain* d)
 {
-  if (!d->faces.empty())
+  bool remote_faces = false;
+  for (const auto& fl : d->faces)
   {
-    set_error("lbm_step: this block is bound to others across a column face; advance the set with lbm_step_group");
+    if (fl.peer_rank < 0)
+    {
+      set_error("lbm_step: this block is bound to others across a column face; advance the set with lbm_step_group");
+      return LBM_ERR_INVALID;
+    }
+    remote_faces = true;
+  }
+  remote_faces = remote_faces || !d->serves.empty();
+  if (comm_blocks(d) && !d->faces_remote_ready)
+  {
+    set_error("lbm_step: blocks bound across ranks: call lbm_comm_faces_commit (every rank) after the last lbm_link_face_rank");
     return LBM_ERR_INVALID;
   }
   if (uses_ibm(d) && d->ibm.split && !comm_active(d))
@@ -434,9 +445,17 @@ static int bgk_step_once(lbm_domain* d)
     set_error("lbm_step: this slab is linked to neighbours; advance the set with lbm_step_group");
     return LBM_ERR_INVALID;
   }
+  const bool unprepared = !d->side_ready;
   LBM_TRY(step_prologue(d, true, true));
+  if (remote_faces && unprepared && !d->post_stream)
+  {
+    // a stored state no step has prepared (after an export): the face tails of the CURRENT buffers, like lbm_step_group
+    LBM_TRY(faces_exchange_remote(d, false));
+    LBM_CUDA(cudaEventRecord(d->ev_side, d->side));
+  }
   LBM_TRY(step_early(d));
   LBM_TRY(step_listed(d));
+  if (remote_faces) LBM_TRY(faces_exchange_remote(d, true));  // the edge columns just written feed the bound blocks' next step
   for (size_t k = 0; k < d->stages.size(); k++)
   {
     const Stage& sg = d->stages[k];

@@ -116,10 +116,20 @@ namespace lbm
 struct FaceLink
 {
   int side = 0, rb = 0, n = 0, orb = 0;
-  lbm_domain* other = nullptr;
+  lbm_domain* other = nullptr;  // the facing block in this process (lbm_link_face) ...
+  int peer_rank = -1;           // ... or the rank that owns it (lbm_link_face_rank): its column arrives over NCCL
   int other_device = 0;        // kept separately: `other` may be destroyed before this block is
   double* d_packet = nullptr;  // [lattice][3][n] on other's device
   cudaEvent_t ev = nullptr;    // packet packed (other's side stream)
+};
+// what this block packs and sends so that a block on another rank can read it through ITS face link (the mirror image of
+// that rank's FaceLink, derived from the descriptors the ranks exchange in lbm_comm_faces_commit)
+struct FaceServe
+{
+  int reader_side = 0;         // the READER's side: 0 = it reads our last column (populations 2, 5, 6), 1 = our first (4, 7, 8)
+  int rb = 0, n = 0;           // our rows
+  int peer_rank = 0;
+  double* d_packet = nullptr;  // [lattice][3][n]
 };
 // the three populations that enter through the first (side 0: c_y = +1) / last (side 1: c_y = -1) column
 __host__ __device__ inline int face_q(int side, int qi) { return side == 0 ? (qi == 0 ? 2 : (qi == 1 ? 5 : 6)) : (qi == 0 ? 4 : (qi == 1 ? 7 : 8)); }
@@ -188,6 +198,8 @@ struct lbm_domain
   // column-face bindings to other blocks (lbm_link_face): the populations entering through an edge column are read
   // from a tail appended to every lattice buffer, [side][3 populations][Xl] behind the nine planes
   std::vector<lbm::FaceLink> faces;
+  std::vector<lbm::FaceServe> serves;   // remote readers of this block's edge columns (lbm_comm_faces_commit)
+  bool faces_remote_ready = false;       // the descriptors have been exchanged since the last lbm_link_face_rank
   lbm::TwoPhaseState* tp = nullptr;
   lbm::CommState* comm = nullptr;
   lbm_domain *link_lo = nullptr, *link_hi = nullptr;
@@ -257,6 +269,8 @@ int comm_exchange_planes(lbm_domain* d, double* base, int nplanes);  // 2 ghost 
 int comm_allreduce_max(lbm_domain* d, double* dev_value);  // ring-wide max of one non-negative device double (diagnostics)
 int comm_exchange_moments(lbm_domain* d);  // two-phase: 2 ghost rows of the moment planes at slab cuts
 int comm_stage_transfer(lbm_domain* d, size_t k, cudaStream_t st);  // pressure packet of stage k between ranks
-int comm_link_refresh(lbm_domain* d);                             // linked slabs: ghost rows of buf[cur] outside lbm_step_group               // pressure packet of stage k between ranks
+bool comm_blocks(const lbm_domain* d);                              // member of a block communicator (lbm_comm_init_blocks): no slab ring
+int faces_exchange_remote(lbm_domain* d, bool new_buffer);           // side stream: pack what remote readers need, send / receive the face tails
+int comm_link_refresh(lbm_domain* d);                               // linked slabs: ghost rows of buf[cur] outside lbm_step_group
 double* tp_moment_planes(lbm_domain* d, int* pm, long long* mplane);
 }  // namespace lbm

@@ -105,7 +105,7 @@ EXPORTS = [
     "lbm_markers_from_toml", "lbm_preset_poiseuille", "lbm_preset_specular_channel", "lbm_preset_free_stream",
     "lbm_preset_sedimentation", "lbm_preset_mrtcg", "lbm_preset_rk", "lbm_preset_periodic",
     "lbm_profile_enable", "lbm_profile_read", "lbm_step_group", "lbm_save_pt", "lbm_snapshot_async", "lbm_snapshot_wait", "lbm_set_moments", "lbm_get_interfacial_tension", "lbm_link_face", "lbm_set_force_region",
-    "lbm_rk_diagnostics", "lbm_comm_check", "lbm_comm_share", "lbm_row_split",
+    "lbm_rk_diagnostics", "lbm_comm_check", "lbm_comm_share", "lbm_row_split", "lbm_comm_init_blocks", "lbm_link_face_rank", "lbm_comm_faces_commit",
 ]
 PROF_INTERIOR, PROF_BOUNDARY, PROF_FIXUP, PROF_GHOST, PROF_IBM, PROF_MOMENTS, PROF_EARLY = range(7)
 
@@ -158,6 +158,9 @@ def load():
         _lib.lbm_comm_unique_id.argtypes = [C.c_char_p]
         _lib.lbm_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         _lib.lbm_comm_share.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.lbm_comm_init_blocks.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        _lib.lbm_link_face_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.lbm_comm_faces_commit.argtypes = [C.c_void_p]
         _lib.lbm_link_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.lbm_link_face.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         _lib.lbm_set_force_region.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -439,6 +442,17 @@ class Domain:
     # ---- multi-GPU
     def comm_init(self, unique_id, n_ranks, rank):
         _chk(self.lib.lbm_comm_init(self.h, unique_id, n_ranks, rank))
+
+    def comm_init_blocks(self, unique_id, n_ranks, rank):
+        """join the communicator of independent blocks bound across column faces (one block per process)"""
+        _chk(self.lib.lbm_comm_init_blocks(self.h, unique_id, n_ranks, rank))
+
+    def link_face_rank(self, side, row_begin, n_rows, peer_rank, peer_row_begin):
+        """link_face with the facing block on another rank (call on the reading rank)"""
+        _chk(self.lib.lbm_link_face_rank(self.h, side, row_begin, n_rows, peer_rank, peer_row_begin))
+
+    def comm_faces_commit(self):
+        _chk(self.lib.lbm_comm_faces_commit(self.h))
 
     def comm_share(self, member):
         """join the ring `member` belongs to, on its communicator"""

@@ -151,3 +151,47 @@ def loop_blocks(Ln, omega, F=(3e-3, 0.0), device=0):
     for d in dom.values():
         d.bc_commit()
     return dom
+
+
+LOOP_BLOCKS = ("A", "B", "C", "D")
+
+
+def loop_block_on_rank(Ln, omega, rank, unique_id, F=(3e-3, 0.0), device=0):
+    """The same channel with ONE block per process (rank 0..3 = A..D): the column faces are bound across ranks
+    (lbm_comm_init_blocks, lbm_link_face_rank; every rank then calls comm_faces_commit() and bc_commit())."""
+    L4, L2, END = Ln // 4, Ln // 2, L.LBM_END
+    shapes = {"A": (Ln, L4), "B": (L4, L2), "C": (Ln, L4), "D": (L4, L2)}
+    k = LOOP_BLOCKS[rank]
+    R, Cc = shapes[k]
+    d = L.Domain(L.default_config(model=L.MODEL_BGK, X=R, Y=Cc, omega=omega, equilibrium=L.EQ_COMPRESSIBLE,
+                                  force=L.FORCE_IBM if k == "A" else L.FORCE_NONE, device=device))
+    d.comm_init_blocks(unique_id, 4, rank)
+
+    def wall(xb, xe, yb, ye, pairs):
+        for q, qs in pairs:
+            d.bc_add(kind=L.BC_LINEAR, lattice=0, x_begin=xb, x_end=xe, y_begin=yb, y_end=ye, dst_q=q, src_q=qs, coef=1.0)
+
+    top, bottom = [(8, 6), (1, 3), (5, 7)], [(7, 5), (3, 1), (6, 8)]
+    left, right = [(2, 4), (5, 7), (6, 8)], [(4, 2), (7, 5), (8, 6)]
+    d.bc_clear()
+    wall(0, 1, 0, END, top)
+    wall(-1, END, 0, END, bottom)
+    A, B, Cb, D = 0, 1, 2, 3
+    if k == "A":
+        wall(L4, -L4, 0, 1, left)
+        wall(1, -1, -1, END, right)
+        d.link_face_rank(0, Ln - L4, L4, B, 0)     # A-B
+        d.link_face_rank(0, 0, L4, D, 0)           # D-A
+        d.set_force_region(L4 + 5, L4 + 55, 0, END, F[0], F[1], 3.0, 9.0)
+    elif k == "B":
+        d.link_face_rank(1, 0, L4, A, Ln - L4)     # A-B
+        d.link_face_rank(0, 0, L4, Cb, Ln - L4)    # B-C
+    elif k == "C":
+        wall(1, -1, 0, 1, left)
+        wall(L4, -L4, -1, END, right)
+        d.link_face_rank(1, Ln - L4, L4, B, 0)     # B-C
+        d.link_face_rank(1, 0, L4, D, 0)           # C-D
+    else:
+        d.link_face_rank(0, 0, L4, Cb, 0)          # C-D
+        d.link_face_rank(1, 0, L4, A, 0)           # D-A
+    return d

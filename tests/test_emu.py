@@ -108,6 +108,15 @@ def test_bench_ring_parity_leg_over_the_nccl_stand_in(emu_lib, world):
     assert r.stdout.count("bit_exact") >= 9, r.stdout
 
 
+def test_blocks_bound_across_ranks_over_the_nccl_stand_in(emu_lib):
+    """test/decompose_domain_loop.cpp's four blocks, one per rank (lbm_comm_init_blocks, lbm_link_face_rank,
+    lbm_comm_faces_commit, plain lbm_step): bit-identical to the blocks linked inside one process"""
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", OMP_NUM_THREADS="1", FAKE_NCCL_TIMEOUT_S="60")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "blocks_ring_threads.py")], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "bit-exact vs linked blocks = True" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_single_pass_csf_step_on_the_ring(emu_lib):
     """LBM_CSF_FUSED=1 on the slabs of a ring (two 2-row halos between the pre-pass stages): bit-identical to the monolithic run"""
     test_slab_ring_over_the_nccl_stand_in(emu_lib, 3, csf_fused="1")

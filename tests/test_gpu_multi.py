@@ -26,3 +26,12 @@ def test_nccl_slab_ring_two_ranks():
     for case in ("poiseuille", "mrtcg", "rk", "csf", "cylinder"):
         assert f"{case} ring of 2" in r.stdout
     assert "cylinder across the cuts, ring of 2: bit-exact vs monolithic = True" in r.stdout
+
+
+@pytest.mark.skipif("n_devices() < 4")
+def test_blocks_bound_across_four_ranks():
+    """column faces bound across ranks (NCCL send / recv of the face tails): bit-identical to the linked blocks of one process"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", "29518", os.path.join(ROOT, "tests", "mp_blocks_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "bit-exact vs linked blocks after 65 steps = True" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
