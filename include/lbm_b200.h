@@ -246,7 +246,10 @@ int lbm_set_u(lbm_domain* d, const double* u_aos);
 int lbm_set_moments(lbm_domain* d, const double* rho, const double* u);
 /* initial condition helpers that mirror the drivers' own initialisation:
  *   BGK       f = incomp_equilibrium(u0, rho0)              (cylinder_test.cpp:86)
- *   two-phase adv_f = eq(rho_r, rho_b, u)                   (mrtcg_rayleigh_taylor.cpp:407-410)     */
+ *   two-phase adv_f = eq(rho_r, rho_b, u)                   (mrtcg_rayleigh_taylor.cpp:407-410)
+ * lbm_init_equilibrium returns once the HOST buffers have been read (they may be reused); the copy runs on its own stream,
+ * beside whatever the domain is still doing, and the equilibrium kernel is ordered behind both — feeding one initial state
+ * after the other overlaps the copy with the previous run's steps and with its asynchronous snapshot. */
 int lbm_init_equilibrium(lbm_domain* d, int lattice, int equilibrium_kind, const double* rho, const double* u);
 int lbm_init_two_phase(lbm_domain* d, const double* rho_r, const double* rho_b, const double* u);
 

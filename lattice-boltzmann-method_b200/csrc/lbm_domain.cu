@@ -883,6 +883,7 @@ int host_staging(lbm_domain* d, double** out)
       // (4 N doubles: the largest import, rho_r, rho_b, u) instead of waiting, so that its host->device copy runs beside the
       // snapshot's device->host copy — PCIe is full duplex.  Out of memory: wait after all.
       cudaGetLastError();
+      if (d->stage_in_busy) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_stage_free, 0));  // (an lbm_init_equilibrium's kernel may still read it)
       if (!d->d_stage_in && cudaMalloc(&d->d_stage_in, 4 * N * sizeof(double)) != cudaSuccess)
       {
         cudaGetLastError();
@@ -1070,6 +1071,13 @@ int lbm_destroy(lbm_domain* d)
   }
   cudaFree(d->d_mom_out);
   cudaFree(d->d_stage_in);
+  if (d->copyin)
+  {
+    cudaStreamSynchronize(d->copyin);
+    cudaEventDestroy(d->ev_h2d);
+    cudaEventDestroy(d->ev_stage_free);
+    cudaStreamDestroy(d->copyin);
+  }
   cudaFree(d->d_mom_in);
   if (d->copy)
   {
@@ -1238,15 +1246,29 @@ int lbm_init_equilibrium(lbm_domain* d, int lattice, int eq_kind, const double* 
   LBM_CUDA(cudaSetDevice(d->cfg.device));
   const long long N = (long long)d->g.Xl * d->g.Y;
   if (eq_kind < LBM_EQ_COMPRESSIBLE || eq_kind > LBM_EQ_KBC_FRESH) { set_error("lbm_init_equilibrium: unknown equilibrium kind %d", eq_kind); return LBM_ERR_INVALID; }
-  double* stage = nullptr;
-  LBM_TRY(host_staging(d, &stage));
-  double *d_rho = stage, *d_u = stage + N;
-  LBM_CUDA(cudaMemcpyAsync(d_rho, rho, N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-  LBM_CUDA(cudaMemcpyAsync(d_u, u, 2 * N * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  // The host->device copy runs on its own stream into an import staging area, so that it overlaps whatever the domain's
+  // stream is still doing (the previous run's steps, a snapshot's staging) — a driver that feeds one initial state after
+  // the other keeps the copy engine, the SMs and the snapshot's device->host copy busy at once.  The call returns when the
+  // HOST buffers have been consumed; the equilibrium kernel is ordered behind both the copy and the stream's earlier work.
+  if (!d->copyin)
+  {
+    LBM_CUDA(cudaStreamCreateWithFlags(&d->copyin, cudaStreamNonBlocking));
+    LBM_CUDA(cudaEventCreateWithFlags(&d->ev_h2d, cudaEventDisableTiming));
+    LBM_CUDA(cudaEventCreateWithFlags(&d->ev_stage_free, cudaEventDisableTiming));
+  }
+  if (!d->d_stage_in) LBM_CUDA(cudaMalloc(&d->d_stage_in, 4 * N * sizeof(double)));
+  double *d_rho = d->d_stage_in, *d_u = d->d_stage_in + N;
+  if (d->stage_in_busy) LBM_CUDA(cudaStreamWaitEvent(d->copyin, d->ev_stage_free, 0));  // the previous import's kernel has read the area
+  LBM_CUDA(cudaMemcpyAsync(d_rho, rho, N * sizeof(double), cudaMemcpyHostToDevice, d->copyin));
+  LBM_CUDA(cudaMemcpyAsync(d_u, u, 2 * N * sizeof(double), cudaMemcpyHostToDevice, d->copyin));
+  LBM_CUDA(cudaEventRecord(d->ev_h2d, d->copyin));
+  LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_h2d, 0));
   k_init_equilibrium<<<cdiv(N, 256), 256, 0, d->stream>>>(d->buf[lattice][d->cur], d->g, eq_kind, d_rho, d_u);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
-  LBM_CUDA(cudaStreamSynchronize(d->stream));
+  LBM_CUDA(cudaEventRecord(d->ev_stage_free, d->stream));
+  d->stage_in_busy = true;
+  LBM_CUDA(cudaEventSynchronize(d->ev_h2d));
   d->post_stream = true;
   d->have_state = true;
   d->side_ready = false;

@@ -187,7 +187,10 @@ struct lbm_domain
   // snapshot staging: [6][Xl*Y] rho, u (2), phase, rho_r, rho_b — filled on `stream`, drained either on `stream`
   // (lbm_get_moments / lbm_get_phase) or on `copy` while later steps run (lbm_snapshot_async)
   double* d_mom_out = nullptr;
-  double* d_stage_in = nullptr;  // second import staging area, used while an async snapshot still reads d_mom_out
+  double* d_stage_in = nullptr;  // import staging area (lbm_init_equilibrium always; the other imports while an async snapshot still reads d_mom_out)
+  cudaStream_t copyin = nullptr;  // host->device copies of lbm_init_equilibrium, beside the domain's stream
+  cudaEvent_t ev_h2d = nullptr, ev_stage_free = nullptr;
+  bool stage_in_busy = false;
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
   bool copy_pending = false;
