@@ -354,20 +354,20 @@ struct TpFused
   static constexpr size_t SMEM = sizeof(double) * NF * NR * TPF_NT;
 };
 
-// stencil of row-slot sc, column t, out of the ring
-template <int MODEL>
-__device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, int sc, int t, TpStencil& st)
+// stencil at column t out of the ring; row_of(a) = element offset (slot * NT) of the ring row a rows from the centre
+template <int MODEL, class RowOf>
+__device__ __forceinline__ void tp_ring_stencil_at(const double* __restrict__ sm, RowOf row_of, int t, TpStencil& st)
 {
   using C = TpFused<MODEL>;
   constexpr int NR = C::NR, NT = TPF_NT;
-  auto S = [&](int f, int slot, int col) -> double { return sm[(f * NR + slot) * NT + col]; };
+  auto S = [&](int f, int off, int col) -> double { return sm[f * NR * NT + off + col]; };
   st.gx = st.gy = st.DxQx = st.DyQy = 0.0;
   if constexpr (MODEL == TP_RK)
   {
 #pragma unroll
     for (int a = -1; a <= 1; a++)
     {
-            const int sa = (sc + NR + a) % NR;  // (a compare-and-wrap instead of the constant division measured 0 - 1.5 % slower)
+      const int sa = row_of(a);
 #pragma unroll
       for (int b = -1; b <= 1; b++)
       {
@@ -383,7 +383,7 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
 #pragma unroll
     for (int a = -2; a <= 2; a++)
     {
-            const int sa = (sc + NR + a) % NR;  // (a compare-and-wrap instead of the constant division measured 0 - 1.5 % slower)
+      const int sa = row_of(a);
 #pragma unroll
       for (int b = -2; b <= 2; b++)
       {
@@ -402,6 +402,15 @@ __device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, i
       }
     }
   }
+}
+
+// stencil of row-slot sc, column t, out of the ring
+template <int MODEL>
+__device__ __forceinline__ void tp_ring_stencil(const double* __restrict__ sm, int sc, int t, TpStencil& st)
+{
+  constexpr int NR = TpFused<MODEL>::NR;
+  // (a compare-and-wrap instead of the constant division measured 0 - 1.5 % slower)
+  tp_ring_stencil_at<MODEL>(sm, [&](int a) { return ((sc + NR + a) % NR) * TPF_NT; }, t, st);
 }
 
 // grid: x = strips of USEFUL columns starting at column 1, y = bands of rows_per_block rows.
@@ -589,7 +598,6 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
   double* stage = sm;
   double* ring = sm + NS * C::ROW;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + C::NF * NR * NT);
-  auto S = [&](int f, int slot, int col) -> double& { return ring[(f * NR + slot) * NT + col]; };
 
   const int t = threadIdx.x;
   const int ys = 1 + blockIdx.x * C::USEFUL - H;         // column of thread 0
@@ -648,6 +656,11 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
 
   // counters instead of k % NS, k / NS, k % (H + 1): slot and parity of row r, slot of the row to refill, tensor-memory slot
   int slot_ring = 0, sl = 0, sl_x = (NS - H % NS) % NS, sl_fill = AHEAD % NS, ts = 0;
+  // rrow[j] = element offset of the ring row of row r - j: rotated once per iteration (2H register moves) instead of
+  // one (slot mod NR) * NT per stencil row
+  int rrow[2 * H + 1];
+#pragma unroll
+  for (int j = 0; j <= 2 * H; j++) rrow[j] = ((NR - j) % NR) * NT;
   unsigned par = 0;
   for (int r = r0; r < xe + H; r++)
   {
@@ -705,12 +718,12 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
         }
         tp_moments<MODEL>(p, fr, fb, rr_, rb_, ux_, uy_, ph_);
       }
-      S(0, slot_ring, t) = ph_;
+      ring[rrow[0] + t] = ph_;
       if constexpr (MODEL == TP_MRTCG)
       {
         const double cq = p.cr * rr_ + p.cb * rb_;
-        S(1, slot_ring, t) = cq * ux_;
-        S(2, slot_ring, t) = cq * uy_;
+        ring[NR * NT + rrow[0] + t] = cq * ux_;
+        ring[2 * NR * NT + rrow[0] + t] = cq * uy_;
       }
       mrr[0] = rr_;
       mrb[0] = rb_;
@@ -736,7 +749,6 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
     }
     if (x >= xb && collider)
     {
-      const int sc = (slot_ring + NR - H) % NR;
       if constexpr (!STASH)
       {
         const double* st_x = stage + (size_t)sl_x * C::ROW;
@@ -748,8 +760,8 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
         }
       }
       TpStencil st;
-      tp_ring_stencil<MODEL>(ring, sc, t, st);
-      tp_collide<MODEL>(p, fr, fb, mrr[H], mrb[H], mux[H], muy[H], S(0, sc, t), st);
+      tp_ring_stencil_at<MODEL>(ring, [&](int a) { return rrow[H - a]; }, t, st);  // row x + a = r - (H - a)
+      tp_collide<MODEL>(p, fr, fb, mrr[H], mrb[H], mux[H], muy[H], ring[rrow[H] + t], st);
       double* wr = rdst + node_off(g, x, y);
       double* wb = bdst + node_off(g, x, y);
 #pragma unroll
@@ -760,6 +772,9 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
       }
     }
     slot_ring = slot_ring + 1 == NR ? 0 : slot_ring + 1;
+#pragma unroll
+    for (int j = 2 * H; j > 0; j--) rrow[j] = rrow[j - 1];
+    rrow[0] = slot_ring * NT;
     sl_x = sl_x + 1 == NS ? 0 : sl_x + 1;
     sl_fill = sl_fill + 1 == NS ? 0 : sl_fill + 1;
     if (++sl == NS)
