@@ -54,7 +54,7 @@ extern thread_local dim3 blockDim, gridDim;
 constexpr int warpSize = 32;
 
 inline void __syncthreads() { emu::sync_threads(); }
-inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline void __syncwarp(unsigned = 0xffffffffu) { (void)emu::warp_exchange(0, 0, false, 32); }  // a real barrier of the warp's fibers (all lanes must call it)
 
 template <class T>
 inline T __ldg(const T* p) { return *p; }
