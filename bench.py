@@ -62,17 +62,17 @@ WORKLOADS = {
                        what="horizontal Poiseuille, D2Q9 BGK incompressible, pressure-periodic rows, bounce-back walls",
                        cpu_sample=1024),
     # configs[2]
-    "mrtcg_rt": dict(X=16384, Y=16384, bytes=352.0, nlat=2, kernel="k_tp_fused<MRTCG,PIPE>",
+    "mrtcg_rt": dict(X=16384, Y=16384, bytes=352.0, nlat=2, kernel="k_tp_staged<MRTCG,3,3,STASH>",
                      driver="test/mrtcg_rayleigh_taylor.cpp",
                      what="MRT colour-gradient Rayleigh-Taylor (mrtcg-rayleigh-taylor-gamma3.toml), two lattices",
                      cpu_sample=512),
     # configs[2] per slab of a ring: what every N runs beside the headline (two-row moment-plane halos at every cut)
-    "mrtcg_rt_weak": dict(X=8192, Y=16384, bytes=352.0, nlat=2, kernel="k_tp_fused<MRTCG,PIPE>",
+    "mrtcg_rt_weak": dict(X=8192, Y=16384, bytes=352.0, nlat=2, kernel="k_tp_staged<MRTCG,3,3,STASH>",
                           driver="test/mrtcg_rayleigh_taylor.cpp",
                           what="MRT colour-gradient Rayleigh-Taylor (mrtcg-rayleigh-taylor-gamma3.toml), two lattices, 8192 rows of 16384 columns per GPU",
                           cpu_sample=512),
     # configs[3]
-    "rk_droplet": dict(X=4096, Y=4096, bytes=304.0, nlat=2, kernel="k_tp_fused<RK,PIPE>",
+    "rk_droplet": dict(X=4096, Y=4096, bytes=304.0, nlat=2, kernel="k_tp_staged<RK,4,2>",
                        driver="test/rk_static_droplet_test.cpp",
                        what="Rothman-Keller static droplet, R = L/4, two lattices", cpu_sample=512),
     # configs[4]
@@ -973,6 +973,25 @@ def ring_parity(ctx):
     tp_init = lambda d, a, b: d.init_two_phase(rt[0][a:b], rt[1][a:b], u0[a:b])  # noqa: E731
     tp_cfg = dict(Y=C, red=RED, blue=BLUE, sigma=0.1, delta=0.1, Fg=RT_FG, add_force=1)
     run("mrtcg", Make(R, dict(model=L.MODEL_MRTCG, **tp_cfg), lambda d: d.preset_mrtcg()), tp_init, 12, both)
+
+    def with_band_rows(rows, *case):
+        """a case with LBM_TP_OVERLAP=1 and slabs that march in bands of `rows` rows (LBM_TP_RPB; both read at lbm_create): every
+        slab then has edge and interior bands and lbm_step sends both halo exchanges of a two-phase step behind the interior
+        bands (tp_steps_ring).  That path is off by default (over NCCL it measured slower than the in-line exchange, DESIGN
+        3.3); the ring keeps it honest on every multi-GPU run"""
+        keep = os.environ.get("LBM_TP_RPB")
+        os.environ["LBM_TP_RPB"] = str(rows)
+        os.environ["LBM_TP_OVERLAP"] = "1"
+        ctx.barrier()
+        run(*case)
+        os.environ.pop("LBM_TP_OVERLAP", None)
+        if keep is None:
+            os.environ.pop("LBM_TP_RPB", None)
+        else:
+            os.environ["LBM_TP_RPB"] = keep
+        ctx.barrier()
+
+    with_band_rows(4, "mrtcg_halos_behind_interior_bands", Make(R, dict(model=L.MODEL_MRTCG, **tp_cfg), lambda d: d.preset_mrtcg()), tp_init, 12, both)
     csf_fields = lambda d: both(d) + (d.get_interfacial_tension(),)  # noqa: E731
     keep = os.environ.get("LBM_CSF_FUSED")
     for tag, val in (("csf_single_pass", "1"), ("csf_three_pass", "0")):
@@ -989,6 +1008,7 @@ def ring_parity(ctx):
     rk_init = lambda d, a, b: d.init_two_phase(dr[0][a:b], dr[1][a:b], ur[a:b])  # noqa: E731
     rk_make = Make(Ln, dict(model=L.MODEL_RK, Y=Ln, red=RK_RED, blue=RK_BLUE, delta=0.98), lambda d: d.preset_rk())
     run("rk", rk_make, rk_init, 15, both)
+    with_band_rows(7, "rk_halos_behind_interior_bands", rk_make, rk_init, 15, both)
 
     def rk_diag(d):
         """the RK driver's diagnostic fields after three steps: max|grad| is reduced over the ring (all-to-all of scalars),

@@ -203,9 +203,10 @@ int comm_exchange(lbm_domain* d, int which, cudaStream_t st)
 }
 
 // two ghost rows of `nplanes` planes in the moment-plane geometry across every INTERNAL cut (the global edge replicates)
-int comm_exchange_planes(lbm_domain* d, double* base, int nplanes)
+int comm_exchange_planes(lbm_domain* d, double* base, int nplanes, cudaStream_t st)
 {
   if (!d->tp || !comm_active(d)) return LBM_OK;
+  if (!st) st = d->stream;
   CommState* c = d->comm;
   int pm = 0;
   long long mplane = 0;
@@ -220,13 +221,13 @@ int comm_exchange_planes(lbm_domain* d, double* base, int nplanes)
     // storage row r holds slab row r - 2
     if (has_up)
     {
-      LBM_NCCL(g_nccl.Send(pl + (long long)Xl * pm, n, ncclFloat64, c->rank + 1, c->comm, d->stream));        // rows Xl-2, Xl-1
-      LBM_NCCL(g_nccl.Recv(pl + (long long)(Xl + 2) * pm, n, ncclFloat64, c->rank + 1, c->comm, d->stream));  // rows Xl, Xl+1
+      LBM_NCCL(g_nccl.Send(pl + (long long)Xl * pm, n, ncclFloat64, c->rank + 1, c->comm, st));        // rows Xl-2, Xl-1
+      LBM_NCCL(g_nccl.Recv(pl + (long long)(Xl + 2) * pm, n, ncclFloat64, c->rank + 1, c->comm, st));  // rows Xl, Xl+1
     }
     if (has_dn)
     {
-      LBM_NCCL(g_nccl.Send(pl + (long long)2 * pm, n, ncclFloat64, c->rank - 1, c->comm, d->stream));  // rows 0, 1
-      LBM_NCCL(g_nccl.Recv(pl, n, ncclFloat64, c->rank - 1, c->comm, d->stream));                      // rows -2, -1
+      LBM_NCCL(g_nccl.Send(pl + (long long)2 * pm, n, ncclFloat64, c->rank - 1, c->comm, st));  // rows 0, 1
+      LBM_NCCL(g_nccl.Recv(pl, n, ncclFloat64, c->rank - 1, c->comm, st));                      // rows -2, -1
     }
   }
   LBM_NCCL_GROUP_END();

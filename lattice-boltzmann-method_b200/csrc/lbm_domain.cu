@@ -1376,6 +1376,16 @@ int lbm_step(lbm_domain* d, int n_steps)
       if (!d->tp) LBM_CUDA(cudaEventRecord(d->ev_side, d->stream));
     }
   }
+  if (d->tp && comm_active(d) && !(d->link_lo || d->link_hi))
+  {
+    // ring ranks: the first step after an import in line, the others with their halo exchanges behind the interior bands
+    while (s < n_steps && d->post_stream) { LBM_TRY(step_once(d)); s++; }
+    if (n_steps - s >= 2 && tp_ring_overlap_ok(d))
+    {
+      LBM_TRY(tp_steps_ring(d, n_steps - s));
+      s = n_steps;
+    }
+  }
   for (; s < n_steps; s++) LBM_TRY(step_once(d));
   LBM_CUDA(cudaEventRecord(d->ev_end, d->stream));
   return LBM_OK;

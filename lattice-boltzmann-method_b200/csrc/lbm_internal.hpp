@@ -257,6 +257,8 @@ int faces_release(lbm_domain* d);                      // NCCL: ROI row segments
 int tp_create(lbm_domain* d);
 int tp_destroy(lbm_domain* d);
 int tp_step(lbm_domain* d);
+bool tp_ring_overlap_ok(lbm_domain* d);   // ring rank in the steady state whose halos can travel behind the interior bands
+int tp_steps_ring(lbm_domain* d, int n);  // n such steps (both exchanges on the side stream; joined into d->stream at the end)
 int tp_step_group(lbm_domain* const* ds, int n, int n_steps);  // linked two-phase slabs in lock step
 int tp_commit(lbm_domain* d);
 int tp_export(lbm_domain* d);
@@ -268,7 +270,7 @@ int comm_release(lbm_domain* d);
 bool comm_active(const lbm_domain* d);
 int link_exchange(lbm_domain* d, int which, cudaStream_t st);  // ghost rows from linked neighbours
 int comm_exchange(lbm_domain* d, int which, cudaStream_t st);  // population ghost rows over NCCL
-int comm_exchange_planes(lbm_domain* d, double* base, int nplanes);  // 2 ghost rows of planes in the moment-plane geometry
+int comm_exchange_planes(lbm_domain* d, double* base, int nplanes, cudaStream_t st = nullptr);  // 2 ghost rows of planes in the moment-plane geometry
 int comm_allreduce_max(lbm_domain* d, double* dev_value);  // ring-wide max of one non-negative device double (diagnostics)
 int comm_exchange_moments(lbm_domain* d);  // two-phase: 2 ghost rows of the moment planes at slab cuts
 int comm_stage_transfer(lbm_domain* d, size_t k, cudaStream_t st);  // pressure packet of stage k between ranks

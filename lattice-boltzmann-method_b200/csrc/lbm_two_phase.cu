@@ -49,8 +49,10 @@ struct TwoPhaseState
   bool planes_full = false;            // planes hold the moments of every own node of the current state
   bool region_dirty = true;            // (re)build the lists below
   unsigned char* d_rowflag = nullptr;  // [Xl] 1 = every node of the row takes its moments from the planes
-  int* d_region = nullptr;             // [n_region] local node ids x * Y + y the region kernel recomputes
+  int* d_region = nullptr;             // [n_region] local node ids x * Y + y the region kernel recomputes, by rows
   int n_region = 0;
+  int n_region_lo = 0, n_region_hi = 0;  // how many of them lie in rows 0, 1 (the head of the list) and Xl-2, Xl-1 (its tail)
+  bool ring_overlap = false;           // LBM_TP_OVERLAP=1: the ranks of a ring send their halos behind the interior bands (tp_steps_ring)
   int rows_per_block = 64;
   bool pipe = true;                    // software-pipelined variant of the fused kernel (LBM_TP_PIPE=0: plain)
   bool staged = true;                  // k_tp_staged: population rows staged by bulk async copies (LBM_TP_STAGED=0: k_tp_fused)
@@ -432,7 +434,7 @@ template <int MODEL, bool PIPE>
 __global__ void __launch_bounds__(TPF_NT, MODEL == TP_MRTCG ? (PIPE ? LBM_TPF_MINB : LBM_TPF_MINB + 1) : LBM_TPF_MINB_RK)
 k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
            double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const TpParams p,
-           const unsigned char* __restrict__ rowflag, int rows_per_block)
+           const unsigned char* __restrict__ rowflag, int rows_per_block, int band_lo, int band_jump)
 {
   using C = TpFused<MODEL>;
   constexpr int H = C::H, NR = C::NR, NT = TPF_NT, LAG = PIPE ? H + 1 : H;
@@ -441,7 +443,7 @@ k_tp_fused(const double* __restrict__ rsrc, const double* __restrict__ bsrc, dou
 
   const int t = threadIdx.x;
   const int y = 1 + blockIdx.x * C::USEFUL - H + t;
-  const int xb = blockIdx.y * rows_per_block;
+  const int xb = ((int)blockIdx.y < band_lo ? (int)blockIdx.y : (int)blockIdx.y + band_jump) * rows_per_block;  // (0, 0): every band; see tp_launch_fused
   const int xe = min(xb + rows_per_block, g.Xl);
   const bool col_ok = y >= -2 && y <= g.Y + 1;           // inside the padded planes
   const bool col_plane = y < 1 || y > g.Y - 2;           // edge columns (listed nodes) and the padding
@@ -588,7 +590,7 @@ template <int MODEL, int NS, int MINB, bool STASH>
 __global__ void __launch_bounds__(TPF_NT, MINB)
 k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, double* __restrict__ rdst,
             double* __restrict__ bdst, const SlabGeom g, const MomGeom mg, const double* __restrict__ mom, const TpParams p,
-            const unsigned char* __restrict__ rowflag, int rows_per_block)
+            const unsigned char* __restrict__ rowflag, int rows_per_block, int band_lo, int band_jump)
 {
   using C = TpStaged<MODEL, NS>;
   constexpr int H = C::H, NR = C::NR, NT = TPF_NT, W = C::W;
@@ -602,7 +604,7 @@ k_tp_staged(const double* __restrict__ rsrc, const double* __restrict__ bsrc, do
   const int t = threadIdx.x;
   const int ys = 1 + blockIdx.x * C::USEFUL - H;         // column of thread 0
   const int y = ys + t;
-  const int xb = blockIdx.y * rows_per_block;
+  const int xb = ((int)blockIdx.y < band_lo ? (int)blockIdx.y : (int)blockIdx.y + band_jump) * rows_per_block;  // (0, 0): every band; see tp_launch_fused
   const int xe = min(xb + rows_per_block, g.Xl);
   const int r0 = xb - H;                                 // first row of the march
   const int rs0 = max(r0, 0), rs1 = min(xe + H, g.Xl);   // rows whose populations are staged
@@ -876,11 +878,13 @@ template <int MODEL, int MODE>
 __global__ void __launch_bounds__(128)
 k_tp_moments_listed(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
                     double* __restrict__ mom, const TpParams p, const BoundaryTable t, double* __restrict__ out_r,
-                    double* __restrict__ out_b)
+                    double* __restrict__ out_b, int sel)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.n) return;
   const int x = t.x[i], y = t.y[i];
+  // sel 1: only the rows next to a slab cut / the global edge (0, 1, Xl-2, Xl-1); sel 2: every other row (tp_pre_part)
+  if (sel != 0 && ((x < 2 || x >= g.Xl - 2) != (sel == 1))) return;
   double fr[9], fb[9];
   tp_load_listed<MODE>(rsrc, g, t, 0, i, x, y, fr);
   tp_load_listed<MODE>(bsrc, g, t, 1, i, x, y, fb);
@@ -907,10 +911,10 @@ k_tp_moments_listed(const double* __restrict__ rsrc, const double* __restrict__ 
 }
 
 // replicate padding of the moment planes: columns first (all owned rows), then rows (whole padded width)
-__global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int nplanes)
+__global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int nplanes, int x_begin, int x_end)
 {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= g.Xl) return;
+  const int x = x_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= g.Xl || x >= x_end) return;
   for (int f = 0; f < nplanes; f++)
   {
     double* pl = mom + f * mg.mplane;
@@ -1097,6 +1101,7 @@ int tp_create(lbm_domain* d)
   tp->stash = tp->model == TP_MRTCG;
   if (const char* e = getenv("LBM_TP_STASH")) tp->stash = atoi(e) != 0;
   if (const char* e = getenv("LBM_TP_RPB")) tp->rpb_override = atoi(e);
+  if (const char* e = getenv("LBM_TP_OVERLAP")) tp->ring_overlap = atoi(e) != 0;  // (off by default: see tp_steps_ring)
   return LBM_OK;
 }
 
@@ -1138,7 +1143,7 @@ static BoundaryTable table_of(lbm_domain* d)
 int tp_pad(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT, 0, d->g.Xl);
   const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
   k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
   d->launches += 2;
@@ -1188,7 +1193,7 @@ static int tp_launch_moments(lbm_domain* d, int which, double* out_r, double* ou
   if (d->nb > 0)
   {
     k_tp_moments_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][which], d->buf[1][which], d->g, tp->mg,
-                                                                                  tp->mom, tp->p, table_of(d), out_r, out_b);
+                                                                                  tp->mom, tp->p, table_of(d), out_r, out_b, 0);
     d->launches++;
   }
   LBM_CUDA(cudaGetLastError());
@@ -1232,6 +1237,12 @@ static int tp_build_region(lbm_domain* d)
   LBM_CUDA(cudaMalloc(&tp->d_rowflag, Xl));
   LBM_CUDA(cudaMemcpy(tp->d_rowflag, flag.data(), Xl, cudaMemcpyHostToDevice));
   tp->n_region = (int)nodes.size();
+  tp->n_region_lo = tp->n_region_hi = 0;
+  for (int id : nodes)
+  {
+    if (id / Y < 2) tp->n_region_lo++;
+    else if (id / Y >= Xl - 2) tp->n_region_hi++;
+  }
   if (tp->n_region > 0)
   {
     LBM_CUDA(cudaMalloc(&tp->d_region, sizeof(int) * nodes.size()));
@@ -1242,8 +1253,19 @@ static int tp_build_region(lbm_domain* d)
   return LBM_OK;
 }
 
+// which bands a launch of the fused kernel covers.  TP_BANDS_EDGE = band 0 and the last band (the last two when the last one
+// has fewer than four rows): the rows whose results travel to the neighbouring ranks and whose stencils read the planes'
+// halo rows; TP_BANDS_INTERIOR = the others; TP_BANDS_NONE only fixes the band height (tp->rows_per_block)
+enum { TP_BANDS_ALL = 0, TP_BANDS_EDGE = 1, TP_BANDS_INTERIOR = 2, TP_BANDS_NONE = 3 };
+
+static int tp_edge_bands_hi(const lbm_domain* d)
+{
+  const int rpb = d->tp->rows_per_block, nb = cdiv(d->g.Xl, rpb);
+  return d->g.Xl - (nb - 1) * rpb < 4 ? 2 : 1;
+}
+
 template <int MODEL>
-static int tp_launch_fused(lbm_domain* d)
+static int tp_launch_fused(lbm_domain* d, int part = TP_BANDS_ALL)
 {
   TwoPhaseState* tp = d->tp;
   using C = TpFused<MODEL>;
@@ -1257,10 +1279,16 @@ static int tp_launch_fused(lbm_domain* d)
       if (tp->rows_per_block <= 0)
         tp->rows_per_block = tp->rpb_override > 0 ? std::min(128, tp->rpb_override)  // the kernels stage <= 128 + 2H row flags
                                                   : pick_band_rows(d->g.Xl, strips, resident_blocks_of(d, kernel, smem), 2 * C::H);
+      if (part == TP_BANDS_NONE) return;
       ProfScope ps(d, LBM_PROF_INTERIOR);
-      dim3 grid(strips, cdiv(d->g.Xl, tp->rows_per_block));
+      // grid row j works on band j < band_lo ? j : j + band_jump
+      const int nb = cdiv(d->g.Xl, tp->rows_per_block), k_hi = tp_edge_bands_hi(d);
+      int ny = nb, band_lo = 0, band_jump = 0;
+      if (part == TP_BANDS_EDGE) { ny = 1 + k_hi; band_lo = 1; band_jump = nb - k_hi - 1; }
+      if (part == TP_BANDS_INTERIOR) { ny = nb - 1 - k_hi; band_jump = 1; }
+      dim3 grid(strips, ny);
       kernel<<<grid, TPF_NT, smem, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t], d->buf[1][t], d->g, tp->mg, tp->mom, tp->p,
-                                                tp->d_rowflag, tp->rows_per_block);
+                                                tp->d_rowflag, tp->rows_per_block, band_lo, band_jump);
       d->launches++;
     };
     if (tp->staged)
@@ -1285,7 +1313,9 @@ static int tp_launch_fused(lbm_domain* d)
     else if (tp->pipe) run(k_tp_fused<MODEL, true>, C::SMEM);
     else run(k_tp_fused<MODEL, false>, C::SMEM);
   }
-  if (d->nb > 0)
+  // listed nodes after the bands that hold them (a band writes every node of its rows' interior columns; with the bands split,
+  // tp_ring_overlap_ok has checked that only the edge bands hold any)
+  if (d->nb > 0 && part <= TP_BANDS_EDGE)
   {
     ProfScope ps(d, LBM_PROF_BOUNDARY);
     k_tp_collide_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->buf[0][t],
@@ -1318,9 +1348,9 @@ static int tp_phase_pre(lbm_domain* d)
   if (d->nb > 0)
   {
     if (tp->model == TP_MRTCG)
-      k_tp_moments_listed<TP_MRTCG, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr);
+      k_tp_moments_listed<TP_MRTCG, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr, 0);
     else
-      k_tp_moments_listed<TP_RK, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr);
+      k_tp_moments_listed<TP_RK, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr, 0);
     d->launches++;
   }
   LBM_TRY(tp_pad(d));
@@ -1346,6 +1376,135 @@ static int tp_phase_main(lbm_domain* d)
   d->post_stream = false;
   tp->planes_full = false;
   return LBM_OK;
+}
+
+// ---- the ranks of a ring: both halo exchanges of a step behind the interior bands --------------------------------------
+// tp_step on a ring is a chain: region moments -> moment-plane halo (NCCL) -> all bands -> ghost rows (NCCL), 0.3 - 0.4 ms of
+// exposed exchange per step at 8192 x 16384 per GPU.  What crosses a cut is produced and consumed by the EDGE bands alone:
+//   ghost rows of the new populations   <- rows 0, Xl-1 of this step             (edge bands + listed nodes)
+//   moments of rows 0, 1, Xl-2, Xl-1    <- pull from rows -1 .. 2, Xl-3 .. Xl     (edge bands + those ghost rows)
+//   moment-plane rows -2, -1, Xl, Xl+1  -> read by the stencils of rows 0, 1, Xl-2, Xl-1 of the NEXT step's edge bands
+// so within one lbm_step(n) call the steps are run as
+//   main stream:  region moments of rows 2 .. Xl-3 | wait side | edge bands, listed nodes | record | interior bands
+//   side stream:  wait record | ghost rows | region moments of the four cut rows of the new state | moment-plane halo | record
+// and the side chain of step i runs under the interior bands of step i; only the first step's cut rows are exchanged in line.
+// Same kernels, same values: bit-identical to tp_step on the emulated rings and over NCCL on two B200s (tests/mp_nccl_check.py,
+// bench.py's ring_parity force this path on).
+// OFF by default (LBM_TP_OVERLAP=1 turns it on): measured on two B200s at 8192 x 16384 per GPU it is 0.4 - 1 % SLOWER than the
+// in-line chain (7.55 ms in line; 7.63 overlapped; 7.58 with the side chain at the main stream's priority; 7.55 with
+// NCCL_MAX_CTAS=1 - profiles/r02_ab_same_box.md).  The exchanges do leave the critical path (0.23 -> 0.10 ms outside the kernel)
+// but NCCL's send/receive kernels are blocks of 512+ threads that need a nearly empty SM: beside a launch whose 128-thread
+// blocks live for 0.1 ms and fill every SM they wait 0.5 - 1 ms for room and cost the interior bands 0.15 - 0.25 ms of
+// throughput while they do.  What would make this pay is a transport without resident blocks (copy-engine peer copies
+// between the ranks' buffers, which needs the ranks' allocations opened to each other) - the band split, the cut / rest
+// split of the region pass and the event chain below are what such a transport plugs into.
+enum { TP_PRE_ALL = 0, TP_PRE_CUT = 1, TP_PRE_REST = 2 };
+
+// the authoritative thin region of the moment planes (tp_phase_pre) for the cut rows 0, 1, Xl-2, Xl-1 or for all the others
+template <int MODEL>
+static int tp_pre_part(lbm_domain* d, int part, cudaStream_t st)
+{
+  TwoPhaseState* tp = d->tp;
+  ProfScope ps(d, LBM_PROF_MOMENTS, st);
+  const int s = d->cur, Xl = d->g.Xl;
+  auto nodes = [&](const int* list, int n) {
+    if (n <= 0) return;
+    k_tp_moments_nodes<MODEL><<<cdiv(n, 128), 128, 0, st>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, list, n);
+    d->launches++;
+  };
+  if (part == TP_PRE_CUT)
+  {
+    nodes(tp->d_region, tp->n_region_lo);
+    nodes(tp->d_region + (tp->n_region - tp->n_region_hi), tp->n_region_hi);
+  }
+  else
+    nodes(tp->d_region + tp->n_region_lo, tp->n_region - tp->n_region_lo - tp->n_region_hi);
+  if (d->nb > 0)
+  {
+    k_tp_moments_listed<MODEL, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, st>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d),
+                                                                           nullptr, nullptr, part == TP_PRE_CUT ? 1 : 2);
+    d->launches++;
+  }
+  if (part == TP_PRE_CUT)
+  {
+    k_tp_pad_cols<<<1, 128, 0, st>>>(tp->mom, d->g, tp->mg, M_COUNT, 0, 2);
+    k_tp_pad_cols<<<1, 128, 0, st>>>(tp->mom, d->g, tp->mg, M_COUNT, Xl - 2, Xl);
+    const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;  // the global edge replicates rows 0 / Xl-1 (padded width: after the columns)
+    if (lo || hi) k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, st>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
+    d->launches += 2 + (lo || hi);
+  }
+  else
+  {
+    k_tp_pad_cols<<<cdiv(Xl - 4, 128), 128, 0, st>>>(tp->mom, d->g, tp->mg, M_COUNT, 2, Xl - 2);
+    d->launches++;
+  }
+  LBM_CUDA(cudaGetLastError());
+  return LBM_OK;
+}
+
+// can lbm_step run the remaining steps through tp_steps_ring?
+bool tp_ring_overlap_ok(lbm_domain* d)
+{
+  TwoPhaseState* tp = d->tp;
+  if (!tp || tp->model == TP_CSF || !tp->ring_overlap || !comm_active(d) || d->post_stream || d->g.Xl < 16 || d->g.Y < 3) return false;
+  if (tp_build_region(d) != LBM_OK) return false;
+  if (tp->rows_per_block <= 0)
+  {
+    if (tp->model == TP_MRTCG) tp_launch_fused<TP_MRTCG>(d, TP_BANDS_NONE);
+    else tp_launch_fused<TP_RK>(d, TP_BANDS_NONE);
+  }
+  const int rpb = tp->rows_per_block, nb = cdiv(d->g.Xl, rpb);
+  if (rpb < 4 || nb < 4) return false;
+  // a band overwrites the listed nodes of its rows' interior columns until the listed-node kernel has run: interior bands must hold none
+  const int k_hi = tp_edge_bands_hi(d);
+  for (int x = rpb; x < (nb - k_hi) * rpb && x < (int)d->row_has_listed.size(); x++)
+    if (d->row_has_listed[x]) return false;
+  return true;
+}
+
+template <int MODEL>
+static int tp_steps_ring_t(lbm_domain* d, int n)
+{
+  TwoPhaseState* tp = d->tp;
+  cudaStream_t side = d->side;
+  // the first step's cut rows: in line
+  LBM_TRY(tp_pre_part<MODEL>(d, TP_PRE_CUT, d->stream));
+  {
+    ProfScope ps(d, LBM_PROF_MOMENTS);
+    LBM_TRY(comm_exchange_moments(d));
+  }
+  for (int i = 0; i < n; i++)
+  {
+    LBM_TRY(tp_pre_part<MODEL>(d, TP_PRE_REST, d->stream));
+    if (i > 0) LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));  // ghost rows and cut-row moments of this state
+    LBM_TRY(tp_launch_fused<MODEL>(d, TP_BANDS_EDGE));
+    LBM_CUDA(cudaEventRecord(d->ev_early, d->stream));
+    LBM_CUDA(cudaStreamWaitEvent(side, d->ev_early, 0));
+    {
+      // queued before the interior bands (its blocks find an idle GPU; measured the same as queued after them)
+      ProfScope ps(d, LBM_PROF_GHOST, side);
+      LBM_TRY(comm_exchange(d, d->cur ^ 1, side));
+    }
+    LBM_TRY(tp_launch_fused<MODEL>(d, TP_BANDS_INTERIOR));
+    d->cur ^= 1;
+    tp->planes_full = false;
+    if (i + 1 < n)
+    {
+      LBM_TRY(tp_pre_part<MODEL>(d, TP_PRE_CUT, side));
+      ProfScope ps(d, LBM_PROF_MOMENTS, side);
+      int pm = 0;
+      long long mplane = 0;
+      LBM_TRY(comm_exchange_planes(d, tp_moment_planes(d, &pm, &mplane), M_COUNT, side));
+    }
+    LBM_CUDA(cudaEventRecord(d->ev_side, side));
+  }
+  LBM_CUDA(cudaStreamWaitEvent(d->stream, d->ev_side, 0));
+  return LBM_OK;
+}
+
+int tp_steps_ring(lbm_domain* d, int n)
+{
+  return d->tp->model == TP_MRTCG ? tp_steps_ring_t<TP_MRTCG>(d, n) : tp_steps_ring_t<TP_RK>(d, n);
 }
 
 static int csf_step(lbm_domain* d);
@@ -2427,7 +2586,7 @@ static int csf_phase_moments(lbm_domain* d)
   TwoPhaseState* tp = d->tp;
   if (!d->post_stream && !tp->planes_full) LBM_TRY(csf_fill_planes(d));  // (post-stream state: the import's planes, the caller's u)
   ProfScope ps(d, LBM_PROF_MOMENTS);
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT, 0, d->g.Xl);
   d->launches++;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
@@ -2441,7 +2600,7 @@ static int csf_phase_normals(lbm_domain* d)
   k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
   const long long N = (long long)d->g.Xl * d->g.Y;
   k_csf_normals<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg);
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2, 0, d->g.Xl);
   d->launches += 3;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
@@ -2533,7 +2692,7 @@ static int csf_fused_moments(lbm_domain* d)
     k_csf_moments_listed<MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->aux,
                                                                             tp->p, table_of(d));
   const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;  // replicate at the global edges only
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT, 0, d->g.Xl);
   k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
   d->launches += 4;
   LBM_CUDA(cudaGetLastError());
@@ -2546,7 +2705,7 @@ static int csf_fused_normals(lbm_domain* d)
   ProfScope ps(d, LBM_PROF_MOMENTS);
   const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
   k_csf_normals_nodes<<<cdiv(tp->n_csf_list2, 128), 128, 0, d->stream>>>(tp->mom, tp->aux, d->g, tp->mg, tp->d_csf_list2, tp->n_csf_list2);
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2);
+  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, 2, 0, d->g.Xl);
   k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->aux, d->g, tp->mg, lo, hi, 2);
   d->launches += 3;
   LBM_CUDA(cudaGetLastError());
@@ -2885,7 +3044,7 @@ int lbm_rk_diagnostics(lbm_domain* d, double sigma, const lbm_rk_diag* out)
     k_rk_diag_grad<<<cdiv(N, 256), 256, 0, d->stream>>>(tp->mom, d->g, mg, tp->p, grad, norm, gmax);
     LBM_TRY(comm_allreduce_max(d, reinterpret_cast<double*>(gmax)));  // grad_norm.max() over the whole grid
     k_rk_diag_normal<<<cdiv(N, 256), 256, 0, d->stream>>>(grad, norm, d->g, mg, gmax, npl);
-    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(npl, d->g, mg, 2);
+    k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(npl, d->g, mg, 2, 0, d->g.Xl);
     k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(npl, d->g, mg, d->cfg.x0 == 0, d->cfg.x1 == d->cfg.X, 2);
     LBM_TRY(comm_exchange_planes(d, npl, 2));  // the curvature differentiates the normal across the cuts
     k_rk_diag_final<<<cdiv(N, 128), 128, 0, d->stream>>>(tp->mom, npl, grad, norm, d->d_aos[0], d->g, mg, tp->p, sigma, o);

@@ -21,6 +21,30 @@ import lbm_b200 as L  # noqa: E402
 print = functools.partial(print, flush=True)  # the launcher's pipe would hold the lines back until exit
 
 
+class band_rows:
+    """LBM_TP_RPB and LBM_TP_OVERLAP=1 (read when a domain is created) for the domains created inside; the ranks may be
+    threads of one process"""
+
+    def __init__(self, barrier, rows):
+        self.barrier, self.rows = barrier, rows
+
+    def __enter__(self):
+        self.barrier()
+        self.old = os.environ.get("LBM_TP_RPB")
+        os.environ["LBM_TP_RPB"] = str(self.rows)
+        os.environ["LBM_TP_OVERLAP"] = "1"  # (off by default: slower than the in-line exchange over NCCL, DESIGN 3.3)
+        self.barrier()
+
+    def __exit__(self, *exc):
+        self.barrier()
+        os.environ.pop("LBM_TP_OVERLAP", None)
+        if self.old is None:
+            os.environ.pop("LBM_TP_RPB", None)
+        else:
+            os.environ["LBM_TP_RPB"] = self.old
+        self.barrier()
+
+
 def run_checks(rank, world, local, fresh_id, gather, barrier, extra=False):
     """Every check of the ring on one rank.  fresh_id() hands all ranks one new communicator id, gather(a) returns the
     row-concatenation of every rank's array, barrier() joins the ranks — torch.distributed under torchrun (main below),
@@ -68,6 +92,7 @@ def run_checks(rank, world, local, fresh_id, gather, barrier, extra=False):
     p.Fg[0], p.Fg[1] = Fg
     p.add_force = 1
     st = orc.mrtcg_init(p, "rt")
+    st0 = {k: np.array(st[k], copy=True) for k in ("r_rho", "b_rho", "u")}
     x0, x1 = L.decompose_rows(R, world, rank)
     d = cases.mrtcg(R, C, Fg, 1, x0=x0, x1=x1, device=local)
     d.comm_init(fresh_id(), world, rank)
@@ -81,6 +106,21 @@ def run_checks(rank, world, local, fresh_id, gather, barrier, extra=False):
         print(f"mrtcg ring of {world}: rel err vs oracle after 12 steps = {e:.2e}")
         if not e < 1e-12:
             failures.append("mrtcg")
+    d.close()
+    # the same run with LBM_TP_OVERLAP=1 and bands of four rows: every slab has edge and interior bands and lbm_step sends both
+    # halo exchanges behind the interior bands (tp_steps_ring; off by default) — in three calls, so that the in-line
+    # prologue and the join at the end of a call are crossed twice
+    with band_rows(barrier, 4):
+        d = cases.mrtcg(R, C, Fg, 1, x0=x0, x1=x1, device=local)
+    d.comm_init(fresh_id(), world, rank)
+    d.init_two_phase(st0["r_rho"][x0:x1], st0["b_rho"][x0:x1], st0["u"][x0:x1])
+    for n in (5, 1, 6):
+        d.step(n)
+    ok = np.array_equal(gather(d.get_f(0)), fr) and np.array_equal(gather(d.get_f(1)), fb)
+    if rank == 0:
+        print(f"mrtcg halos behind the interior bands, ring of {world}: bit-exact vs the in-line exchange = {ok}")
+        if not ok:
+            failures.append("mrtcg-overlap")
     d.close()
 
     # ---- Rothman-Keller droplet: 1-row moment halo of the 3x3 differences, all-9 wrap rules
@@ -100,6 +140,16 @@ def run_checks(rank, world, local, fresh_id, gather, barrier, extra=False):
     d.set_f(rst["b_adv"][x0:x1], 1)
     d.step(15)
     fr, fb = gather(d.get_f(0)), gather(d.get_f(1))
+    d.close()
+    with band_rows(barrier, 7):  # (24 or 25 rows in three bands and a rest of three or four: the last TWO bands / the last band are edge bands)
+        d = cases.rk(Ln, x0=x0, x1=x1, device=local)
+    d.comm_init(fresh_id(), world, rank)
+    d.set_f(rst["r_adv"][x0:x1], 0)
+    d.set_f(rst["b_adv"][x0:x1], 1)
+    for n in (7, 8):
+        d.step(n)
+    ok = np.array_equal(gather(d.get_f(0)), fr) and np.array_equal(gather(d.get_f(1)), fb)
+    d.close()
     if rank == 0:
         for _ in range(15):
             orc.rk_step(rp, rst)
@@ -107,7 +157,9 @@ def run_checks(rank, world, local, fresh_id, gather, barrier, extra=False):
         print(f"rk ring of {world}: rel err vs oracle after 15 steps = {e:.2e}")
         if not e < 1e-12:
             failures.append("rk")
-    d.close()
+        print(f"rk halos behind the interior bands, ring of {world}: bit-exact vs the in-line exchange = {ok}")
+        if not ok:
+            failures.append("rk-overlap")
 
     # ---- continuum-surface-force variant: halos of the moment planes and of the normal field across the ring
     R, Cc = 96, 40
