@@ -499,10 +499,11 @@ k_pressure_local(double* __restrict__ f, const SlabGeom g, int src_lx, int dst_l
 // ghost rows of a single slab that is its own neighbour (periodic wrap of solver::advect along
 // axis 0): row -1 <- row Xl-1 for c_x = +1 populations, row Xl <- row 0 for c_x = -1 populations.
 // With all_q != 0 every population is copied (models whose boundary rules read a whole opposite row).
-static __global__ void k_wrap_ghost_rows(double* __restrict__ f, const SlabGeom g, int all_q)
+static __global__ void k_wrap_ghost_rows(double* __restrict__ f0, double* __restrict__ f1, const SlabGeom g, int all_q)
 {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
   if (y >= g.pitch) return;
+  double* __restrict__ f = blockIdx.y == 0 ? f0 : f1;  // grid row = lattice
   const long long lo = y, hi = (long long)(g.Xl + 1) * g.pitch + y;
   const long long first = (long long)g.pitch + y, last = (long long)g.Xl * g.pitch + y;
 #pragma unroll

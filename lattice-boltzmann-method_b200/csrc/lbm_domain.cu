@@ -205,11 +205,10 @@ static int dispatch_mode(lbm_domain* d, int mode, const LaunchArgs& a)
 
 int wrap_ghost_rows_local(lbm_domain* d, int which, cudaStream_t st)
 {
-  for (int l = 0; l < d->nlat; l++)
-  {
-    k_wrap_ghost_rows<<<cdiv(d->g.pitch, SIDE_NT), SIDE_NT, 0, st>>>(d->buf[l][which], d->g, d->wrap_all_q ? 1 : 0);
-    d->launches++;
-  }
+  // one launch for both lattices (grid row = lattice)
+  k_wrap_ghost_rows<<<dim3(cdiv(d->g.pitch, SIDE_NT), d->nlat), SIDE_NT, 0, st>>>(d->buf[0][which], d->nlat > 1 ? d->buf[1][which] : nullptr, d->g,
+                                                                                d->wrap_all_q ? 1 : 0);
+  d->launches++;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
 }
@@ -805,10 +804,12 @@ int commit_boundary_tables(lbm_domain* d)
 
   // rows the interior kernel must finish before the listed-node kernel / the stages touch them
   d->row_has_listed.assign(Xl, 0);
-  for (auto& kv : index)
+  d->listed_ids.clear();
+  for (auto& kv : index)  // (ordered map: ascending ids)
   {
     const int lx = (int)(kv.first / Y), y = (int)(kv.first % Y);
     if (y >= y_int_begin && y < y_int_end) d->row_has_listed[lx] = 1;
+    d->listed_ids.push_back((int)kv.first);
   }
   for (auto& hs : host_stages)
   {

@@ -165,6 +165,7 @@ struct lbm_domain
   bool early_on_side = false;  // this step's early rows were launched on the side stream (no bulk rows to overlap)
   int *d_rows_all = nullptr, *d_rows_early = nullptr, *d_rows_bulk = nullptr;
   std::vector<char> row_has_listed;  // row owns a listed node in an interior column, or feeds a stage
+  std::vector<int> listed_ids;       // local node ids x * Y + y of the listed nodes, ascending (commit_boundary_tables)
   float last_ms = 0.f;
   long long launches = 0;
 

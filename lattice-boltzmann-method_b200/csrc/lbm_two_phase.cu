@@ -910,6 +910,44 @@ k_tp_moments_listed(const double* __restrict__ rsrc, const double* __restrict__ 
   mom[M_PH * mg.mplane + k] = ph;
 }
 
+// the region pass in ONE launch: blocks 0 .. ceil(n / 128) - 1 take the node list (plain pull), the others the listed nodes
+// (pull through their rules).  The two sets are disjoint (tp_build_region).
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+k_tp_moments_region(const double* __restrict__ rsrc, const double* __restrict__ bsrc, const SlabGeom g, const MomGeom mg,
+                    double* __restrict__ mom, const TpParams p, const int* __restrict__ nodes, int n, const BoundaryTable t)
+{
+  const int node_blocks = (n + 127) / 128;
+  int x, y;
+  double fr[9], fb[9];
+  if ((int)blockIdx.x < node_blocks)
+  {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    x = nodes[i] / g.Y;
+    y = nodes[i] % g.Y;
+    tp_load_interior<MODE_PULL>(rsrc, g, x, y, fr);
+    tp_load_interior<MODE_PULL>(bsrc, g, x, y, fb);
+  }
+  else
+  {
+    const int i = ((int)blockIdx.x - node_blocks) * 128 + threadIdx.x;
+    if (i >= t.n) return;
+    x = t.x[i];
+    y = t.y[i];
+    tp_load_listed<MODE_PULL>(rsrc, g, t, 0, i, x, y, fr);
+    tp_load_listed<MODE_PULL>(bsrc, g, t, 1, i, x, y, fb);
+  }
+  double rr, rb, ux, uy, ph;
+  tp_moments<MODEL>(p, fr, fb, rr, rb, ux, uy, ph);
+  const long long k = mom_off(mg, x, y);
+  mom[M_RR * mg.mplane + k] = rr;
+  mom[M_RB * mg.mplane + k] = rb;
+  mom[M_UX * mg.mplane + k] = ux;
+  mom[M_UY * mg.mplane + k] = uy;
+  mom[M_PH * mg.mplane + k] = ph;
+}
+
 // replicate padding of the moment planes: columns first (all owned rows), then rows (whole padded width)
 __global__ void k_tp_pad_cols(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int nplanes, int x_begin, int x_end)
 {
@@ -945,6 +983,45 @@ __global__ void k_tp_pad_rows(double* __restrict__ mom, const SlabGeom g, const 
     if (hi_global)
     {
       const double v = pl[mom_off(mg, g.Xl - 1, y)];
+      pl[mom_off(mg, g.Xl, y)] = v;
+      pl[mom_off(mg, g.Xl + 1, y)] = v;
+    }
+  }
+}
+
+// both paddings in one launch: threads 0 .. Xl-1 pad the columns of their row, threads Xl .. Xl+Y+3 the rows of their padded
+// column (reading the edge rows at the column clamped into the grid: the value k_tp_pad_cols would have put there)
+__global__ void k_tp_pad(double* __restrict__ mom, const SlabGeom g, const MomGeom mg, int lo_global, int hi_global, int nplanes)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.Xl)
+  {
+    for (int f = 0; f < nplanes; f++)
+    {
+      double* pl = mom + f * mg.mplane;
+      const double lo = pl[mom_off(mg, i, 0)], hi = pl[mom_off(mg, i, g.Y - 1)];
+      pl[mom_off(mg, i, -1)] = lo;
+      pl[mom_off(mg, i, -2)] = lo;
+      pl[mom_off(mg, i, g.Y)] = hi;
+      pl[mom_off(mg, i, g.Y + 1)] = hi;
+    }
+    return;
+  }
+  const int j = i - g.Xl;
+  if (j >= g.Y + 4) return;
+  const int y = j - 2, yc = min(max(y, 0), g.Y - 1);
+  for (int f = 0; f < nplanes; f++)
+  {
+    double* pl = mom + f * mg.mplane;
+    if (lo_global)
+    {
+      const double v = pl[mom_off(mg, 0, yc)];
+      pl[mom_off(mg, -1, y)] = v;
+      pl[mom_off(mg, -2, y)] = v;
+    }
+    if (hi_global)
+    {
+      const double v = pl[mom_off(mg, g.Xl - 1, yc)];
       pl[mom_off(mg, g.Xl, y)] = v;
       pl[mom_off(mg, g.Xl + 1, y)] = v;
     }
@@ -1143,10 +1220,9 @@ static BoundaryTable table_of(lbm_domain* d)
 int tp_pad(lbm_domain* d)
 {
   TwoPhaseState* tp = d->tp;
-  k_tp_pad_cols<<<cdiv(d->g.Xl, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, M_COUNT, 0, d->g.Xl);
   const int lo = d->cfg.x0 == 0, hi = d->cfg.x1 == d->cfg.X;
-  k_tp_pad_rows<<<cdiv(d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
-  d->launches += 2;
+  k_tp_pad<<<cdiv(d->g.Xl + d->g.Y + 4, 128), 128, 0, d->stream>>>(tp->mom, d->g, tp->mg, lo, hi, M_COUNT);
+  d->launches++;
   LBM_CUDA(cudaGetLastError());
   return LBM_OK;
 }
@@ -1214,19 +1290,22 @@ static int tp_build_region(lbm_domain* d)
   for (int x = 0; x < Xl && x < (int)d->row_has_listed.size(); x++)
     if (d->row_has_listed[x])
       for (int k = -2; k <= 2; k++) mark(x + k);
+  // (listed nodes are left out: the listed half of k_tp_moments_region forms their moments through their rules, and the two
+  // halves of that launch must not write the same cell)
   std::vector<int> nodes;
+  auto add = [&](int id) { if (!std::binary_search(d->listed_ids.begin(), d->listed_ids.end(), id)) nodes.push_back(id); };
   for (int x = 0; x < Xl; x++)
   {
     if (flag[x])
     {
-      for (int y = 1; y <= Y - 2; y++) nodes.push_back(x * Y + y);
+      for (int y = 1; y <= Y - 2; y++) add(x * Y + y);
       continue;
     }
     int last = 0;
     for (int y : {1, 2, Y - 3, Y - 2})
       if (y >= 1 && y <= Y - 2 && y > last)
       {
-        nodes.push_back(x * Y + y);
+        add(x * Y + y);
         last = y;
       }
   }
@@ -1337,20 +1416,13 @@ static int tp_phase_pre(lbm_domain* d)
   if (d->post_stream) return LBM_OK;  // first step after an import: the planes are full and hold the caller's u
   ProfScope ps(d, LBM_PROF_MOMENTS);
   const int s = d->cur;
-  if (tp->n_region > 0)
+  if (tp->n_region > 0 || d->nb > 0)
   {
+    const int blocks = cdiv(tp->n_region, 128) + cdiv(d->nb, 128);
     if (tp->model == TP_MRTCG)
-      k_tp_moments_nodes<TP_MRTCG><<<cdiv(tp->n_region, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, tp->d_region, tp->n_region);
+      k_tp_moments_region<TP_MRTCG><<<blocks, 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, tp->d_region, tp->n_region, table_of(d));
     else
-      k_tp_moments_nodes<TP_RK><<<cdiv(tp->n_region, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, tp->d_region, tp->n_region);
-    d->launches++;
-  }
-  if (d->nb > 0)
-  {
-    if (tp->model == TP_MRTCG)
-      k_tp_moments_listed<TP_MRTCG, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr, 0);
-    else
-      k_tp_moments_listed<TP_RK, MODE_PULL><<<cdiv(d->nb, 128), 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, table_of(d), nullptr, nullptr, 0);
+      k_tp_moments_region<TP_RK><<<blocks, 128, 0, d->stream>>>(d->buf[0][s], d->buf[1][s], d->g, tp->mg, tp->mom, tp->p, tp->d_region, tp->n_region, table_of(d));
     d->launches++;
   }
   LBM_TRY(tp_pad(d));
