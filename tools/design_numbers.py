@@ -5,7 +5,7 @@ import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = lambda n: json.load(open(os.path.join(ROOT, "profiles", n)))  # noqa: E731
-j, n2, n8 = P("r02_bench_n1_full.json"), P("r02_bench_n2.json"), P("r02_bench_n8.json")
+j, n2, n8 = P("r02_bench_n1_full_final_lib.json"), P("r02_bench_n2_final_lib.json"), P("r02_bench_n8.json")  # N = 1, 2: the last library of the round
 o = j["other_workloads"]
 names = {"poiseuille": ("poiseuille (configs[0])", "2700x2100"), "mrtcg_rt": ("mrtcg_rt (configs[2])", "16384^2"),
          "rk_droplet": ("rk_droplet (configs[3])", "4096^2"), "sedimentation": ("sedimentation (configs[4], the reference driver)", "4096x8192"),
