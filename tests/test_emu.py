@@ -117,6 +117,15 @@ def test_blocks_bound_across_ranks_over_the_nccl_stand_in(emu_lib):
     assert r.returncode == 0 and "bit-exact vs linked blocks = True" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_two_phase_halos_behind_the_interior_bands_over_random_rings(emu_lib):
+    """LBM_TP_OVERLAP=1 (tp_steps_ring: edge bands, then both halo exchanges on the side stream under the interior bands) over
+    random ring sizes, slab heights, band heights and lbm_step call patterns: bit-identical to the monolithic run"""
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", OMP_NUM_THREADS="1", FAKE_NCCL_TIMEOUT_S="60")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "ring_overlap_fuzz.py"), "7", "10"], cwd=ROOT, env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "10 of 10 cases bit-exact" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_single_pass_csf_step_on_the_ring(emu_lib):
     """LBM_CSF_FUSED=1 on the slabs of a ring (two 2-row halos between the pre-pass stages): bit-identical to the monolithic run"""
     test_slab_ring_over_the_nccl_stand_in(emu_lib, 3, csf_fused="1")
