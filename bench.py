@@ -72,7 +72,7 @@ WORKLOADS = {
                           what="MRT colour-gradient Rayleigh-Taylor (mrtcg-rayleigh-taylor-gamma3.toml), two lattices, 8192 rows of 16384 columns per GPU",
                           cpu_sample=512),
     # configs[3]
-    "rk_droplet": dict(X=4096, Y=4096, bytes=304.0, nlat=2, kernel="k_tp_staged<RK,4,2>",
+    "rk_droplet": dict(X=4096, Y=4096, bytes=304.0, nlat=2, kernel="k_tp_staged<RK,5,2>",
                        driver="test/rk_static_droplet_test.cpp",
                        what="Rothman-Keller static droplet, R = L/4, two lattices", cpu_sample=512),
     # configs[4]
